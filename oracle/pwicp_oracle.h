@@ -1,0 +1,145 @@
+/*
+ * pwicp_oracle.h -- CPU ORACLE for the Piecewise-ICP inner registration loop.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it, and
+ * only as the checker / CPU baseline.  The product path (piecewise-icp_b200/) never links,
+ * imports or calls it.
+ *
+ * PARITY UNPINNED: the reference's arithmetic for this path lives in PCL 1.8.1 (+FLANN, Eigen),
+ * which is neither vendored in /root/reference nor installable here, and the reference ships no
+ * test, fixture or golden vector at the hot-path boundary.  This file is a
+ * plain restatement of (i) the reference's own statements in src/Registration.cpp and
+ * src/CommonFunc.cpp and (ii) the published PCL 1.8.1 algorithms those statements call.  It is
+ * cross-checked only against independent implementations (brute force, scipy cKDTree, numpy
+ * float64 algebra) and against end-to-end properties (recovering a known rigid motion).
+ *
+ * Every function cites the reference file:line it follows (paths relative to /root/reference).
+ * Matrices are row-major.  All point arrays are packed xyz float32 (n x 3).
+ */
+#ifndef PWICP_ORACLE_H
+#define PWICP_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- A1: exact 1-NN (pcl::registration::CorrespondenceEstimation::determineCorrespondences,
+ * call sites src/Registration.cpp:737-747, :1293-1297, src/CommonFunc.cpp:269-273).
+ * Distance = ((dx*dx)+dy*dy)+dz*dz in float32, no FMA (flann::L2_Simple<float>).  Exact ties
+ * resolve to the LOWEST target index (documented deviation: FLANN returns the first visited). */
+int orc_nn(const float* tgt, int n1, const float* qry, int nq, int* idx, float* d2);
+int orc_nn_brute(const float* tgt, int n1, const float* qry, int nq, int* idx, float* d2);
+/* reusable tree handle (the bench's CPU baseline builds once, queries many times) */
+void* orc_tree_build(const float* tgt, int n1);
+void  orc_tree_query(const void* tree, const float* qry, int nq, int* idx, float* d2);
+void  orc_tree_free(void* tree);
+
+/* ---- A5: pcl::transformPointCloud (src/Registration.cpp:943-954), float, left-to-right, in place */
+void orc_transform(float* pts, int n, const float* T16);
+
+/* ---- A4: TransformationEstimationPointToPlaneLLS::estimateRigidTransformation
+ * (reached from src/Registration.cpp:1266).  reduce_mode 0 = sequential double sums in
+ * correspondence order (what PCL does); reduce_mode 1 = the summation order of the CUDA kernel
+ * (grid_blocks x warps_per_block warps, 32-point batches; see DESIGN.md "reduction geometry"),
+ * used to prove the GPU loop bit-exactly. Outputs: ATA (36), ATb (6), x (6), T (16 f32). */
+int orc_lls_step(const float* src, const int* match, int n, const float* tgt, const float* nrm,
+                 int reduce_mode, int grid_blocks, int warps_per_block,
+                 double* ATA36, double* ATb6, double* x6, float* T16);
+
+/* ---- A3 + A6: P2PICPwithPatchNormal (src/Registration.cpp:1255-1269) =
+ * pcl::IterativeClosestPointWithNormals::align with tf-eps 1e-8, fitness-eps, max 100 iters. */
+typedef struct {
+    int    max_iter;        /* 100  (src/Registration.cpp:1264) */
+    double tf_eps;          /* 1e-8 (src/Registration.cpp:1262) */
+    double fit_eps;         /* 1e-6 (src/Registration.cpp:877, :1263) */
+    int    force_iters;     /* !=0: benchmark mode, run exactly max_iter iterations */
+    int    reduce_mode;     /* see orc_lls_step */
+    int    grid_blocks;
+    int    warps_per_block;
+    int    rot_thr_default; /* !=0: leave the rotation threshold at PCL's default 0.99999 */
+} orc_icp_params;
+
+/* conv_state: 0 not converged, 1 ITERATIONS, 2 TRANSFORM, 3 ABS_MSE, 4 REL_MSE, 5 NO_CORRESPONDENCES.
+ * Optional traces (may be NULL): mse_trace[max_iter], T_trace[max_iter*16],
+ * idx_trace[max_iter*n2s] (correspondence indices of every inner iteration). */
+int orc_icp_p2plane(const float* tgt, const float* nrm, int n1, const float* src, int n2s,
+                    const orc_icp_params* prm, float* T_final16, int* n_iter, int* conv_state,
+                    double* mse_trace, float* T_trace, int* idx_trace);
+
+/* ---- A7 pieces */
+/* pcl::octree::OctreePointCloudSearch(res): defineBoundingBox + getBoundingBox
+ * (src/Registration.cpp:881-886).  bb6 = min_x,min_y,min_z,max_x,max_y,max_z. */
+void  orc_octree_bbox(const float* pts, int n, double res, double* bb6);
+/* calBoundingBoxCornerChange (src/CommonFunc.cpp:410-419) */
+float orc_bbox_corner_change(const double* bb6, const float* T16);
+/* calPercentileDistBetween2PC (src/CommonFunc.cpp:266-281, :174-179) */
+double orc_percentile_nn(const float* cloud1, int m1, const float* cloud2, int m2, float pct);
+
+/* ---- A8: calTransParaVCM (src/Registration.cpp:1273-1343). Returns 0; *singular = |det|<1e-9 */
+int orc_vcm(const float* tgt, const float* nrm, int n1, const float* src_stable, int n2s,
+            double* vcm36, int* singular);
+
+/* ---- A9: calPatchNormal (src/CommonFunc.cpp:284-333) incl. pcl::computePointNormal/eigen33.
+ * Returns 1 on success (normal written), 0 on failure (normal = 0,0,1). */
+int orc_patch_normal(const float* pts, int n, float* n3);
+
+/* ---- A10: matrix2angle (src/CommonFunc.cpp:385-407) */
+void orc_matrix2angle(const float* T16, float* ang3);
+
+/* ---- A2 + A7: one outer iteration, PwICP_singleIteration (src/Registration.cpp:704-972), at
+ * the centroid-level boundary: patch generation has already happened, target normals are
+ * pre-computed once (they are constants of the pair). */
+typedef struct {
+    /* target side (read only) */
+    const float* cloud1; int m1;          /* full pre-processed target cloud */
+    const float* ct1;    int n1;          /* patch centroids */
+    const float* nrm1;                    /* patch normals (n1 x 3) */
+    const unsigned char* nrm1_ok;         /* calPatchNormal success per patch (may be NULL = all 1) */
+    const float* ctstd1;                  /* CTstd1 (n1) */
+    /* source side (mutated in place by every outer iteration) */
+    float* cloud2; int m2;
+    float* ct2;    int n2;
+    float* bp2;                           /* 6*n2 x 3, ordered 6 per patch */
+    const float* bpstd2;                  /* n2 */
+    const int* patch_off2;                /* n2+1 offsets into patch_pts2 */
+    float* patch_pts2;                    /* concatenated patch points */
+    /* parameters */
+    float Res1, Res2, SVRes1, SVRes2, DTmin;
+} orc_pair;
+
+typedef struct {
+    float currDT, BBchange_1, BBchange_2;
+    int   toStage2, toStage3;             /* the reference's globals g_toStage2/3 (:11-12) */
+} orc_state;
+
+typedef struct {
+    int   n_stable;                       /* stable patches */
+    int   n_stable_pts;                   /* points in stablePC2 */
+    int   icp_iters, icp_state;
+    float LoDet_min, LoDet_max, maxBBchange;
+    double P75;                           /* stage-1 percentile, NaN when not evaluated */
+    double bb6[6];
+} orc_iter_stats;
+
+/* Returns 0 ok, -1 fewer than 4 patches, -2 fewer than 4 stable patches (the reference exits).
+ * stable_flags (n2, may be NULL) receives the classification; vcm36 is written when stage 3 was
+ * reached in this call (vcm_written=1). icp may be NULL for the reference's settings. */
+int orc_single_iteration(orc_pair* pr, orc_state* st, const orc_icp_params* icp,
+                         float* T16, double* vcm36, int* vcm_written,
+                         unsigned char* stable_flags, orc_iter_stats* stats);
+
+/* Piecewise_ICP (src/Registration.cpp:618-700) from the centroid-level boundary on.
+ * isManualDTinit==0 -> DTinit = 3 * P75(cloud1, cloud2).  DTseries must hold max_outer+1 floats.
+ * Returns the number of outer iterations done (>0) or a negative error from the iteration. */
+int orc_piecewise_icp(orc_pair* pr, int isManualDTinit, float DTinit, const orc_icp_params* icp,
+                      int max_outer, float* DTseries, int* n_series, float* T16, double* vcm36,
+                      orc_iter_stats* stats_per_iter);
+
+/* 4x4 float product C = A*B, Eigen order (used for transMat = cur * transMat, :687, :319) */
+void orc_mat4_mul(const float* A, const float* B, float* C);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,494 @@
+// capi.cu -- the extern "C" boundary of libpwicp.so (declared in include/pwicp.h).
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <mutex>
+
+#include "common.cuh"
+#include "nn_search.cuh"
+#include "small_algebra.cuh"
+
+namespace pwicp {
+
+static std::string g_last_error;
+static std::mutex g_err_mu;
+
+void set_error(Ctx* c, const std::string& msg) {
+    if (c) c->err = msg;
+    std::lock_guard<std::mutex> lk(g_err_mu);
+    g_last_error = msg;
+}
+
+// nx,ny,nz,ctstd and ok flags gathered into level-0 order
+__global__ void gather_aux_kernel(const float* __restrict__ nrm, const float* __restrict__ ctstd,
+                                  const unsigned char* __restrict__ ok, const uint32_t* __restrict__ perm,
+                                  int n, float4* aux, unsigned char* ok_sorted) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t o = perm[i];
+    aux[i] = make_float4(nrm[3 * (size_t)o], nrm[3 * (size_t)o + 1], nrm[3 * (size_t)o + 2], ctstd ? ctstd[o] : 0.f);
+    ok_sorted[i] = ok ? ok[o] : (unsigned char)1;
+}
+
+__global__ void expand_f4_kernel(const float* __restrict__ xyz, int n, float4* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_float4(xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2], 0.f);
+}
+
+__global__ void pack_f4_kernel(const float4* __restrict__ in, int n, float* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { float4 v = in[i]; out[3 * (size_t)i] = v.x; out[3 * (size_t)i + 1] = v.y; out[3 * (size_t)i + 2] = v.z; }
+}
+
+__global__ void patch_id_kernel(const int* __restrict__ off, int n2, int m, int* pid) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    int lo = 0, hi = n2;               // largest i with off[i] <= j
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (off[mid] <= j) lo = mid; else hi = mid; }
+    pid[j] = lo;
+}
+
+__global__ void count_below_kernel(const float* __restrict__ d2, int n, float thr, unsigned long long* cnt) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool below = (i < n) && (sqrtf(d2[i]) < thr);
+    unsigned m = __ballot_sync(0xffffffffu, below);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(cnt, (unsigned long long)__popc(m));
+}
+
+__global__ void fill_kernel(uint4* p, size_t n, unsigned v) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = make_uint4(v, v, v, v);
+}
+
+static int upload_checked(Ctx* ctx, DevBuf& buf, const float* host, size_t n_floats, const char* what) {
+    if (!host && n_floats) { set_error(ctx, std::string(what) + ": null pointer"); return PWICP_ERR_ARG; }
+    PW_TRY(upload_packed(ctx, buf, host, n_floats));
+    bool ok = true;
+    PW_TRY(check_finite_dev(ctx, buf.as<float>(), n_floats, &ok));
+    if (!ok) { set_error(ctx, std::string(what) + ": non-finite value in input"); return PWICP_ERR_NONFINITE; }
+    return PWICP_OK;
+}
+
+}  // namespace pwicp
+
+using namespace pwicp;
+
+extern "C" {
+
+int pwicp_version(void) { return 100; }
+
+int pwicp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* pwicp_last_error(const pwicp_ctx* c) {
+    if (c) return reinterpret_cast<const Ctx*>(c)->err.c_str();
+    return g_last_error.c_str();
+}
+
+int pwicp_ctx_create(int device, pwicp_ctx** out) {
+    Ctx* ctx = nullptr;
+    if (!out) return PWICP_ERR_ARG;
+    *out = nullptr;
+    int ndev = pwicp_device_count();
+    if (ndev < 1) { set_error(nullptr, "no CUDA device available (libpwicp has no CPU fallback)"); return PWICP_ERR_CUDA; }
+    if (device < 0 || device >= ndev) { set_error(nullptr, "device index out of range"); return PWICP_ERR_ARG; }
+    PW_CUDA(cudaSetDevice(device));
+    Ctx* c = new Ctx();
+    c->device = device;
+    ctx = c;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; set_error(nullptr, "cudaGetDeviceProperties failed"); return PWICP_ERR_CUDA; }
+    if (prop.major < 10) {
+        delete c;
+        set_error(nullptr, "libpwicp is built for sm_100a (B200) only");
+        return PWICP_ERR_CUDA;
+    }
+    c->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
+        delete c; set_error(nullptr, "stream/event creation failed"); return PWICP_ERR_CUDA;
+    }
+    *out = reinterpret_cast<pwicp_ctx*>(c);
+    return PWICP_OK;
+}
+
+void pwicp_ctx_destroy(pwicp_ctx* p) {
+    if (!p) return;
+    Ctx* c = reinterpret_cast<Ctx*>(p);
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->tgt.release(); c->c1.release();
+    DevBuf* bufs[] = {&c->tgt_aux, &c->tgt_ok, &c->ct2, &c->bp2, &c->bpstd2, &c->patch_xyz, &c->patch_id,
+                      &c->patch_off, &c->cloud2, &c->icp_src, &c->icp_work, &c->icp_partials, &c->icp_out,
+                      &c->icp_idx, &c->keys, &c->vals, &c->keys2, &c->vals2, &c->cub_tmp, &c->scratch_a,
+                      &c->scratch_b, &c->scratch_c, &c->scratch_d, &c->flags, &c->pos, &c->l2flush};
+    for (DevBuf* b : bufs) b->release();
+    if (c->pinned) cudaFreeHost(c->pinned);
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+float pwicp_last_device_ms(const pwicp_ctx* p) { return p ? reinterpret_cast<const Ctx*>(p)->last_ms : 0.f; }
+long long pwicp_launch_count(const pwicp_ctx* p) { return p ? reinterpret_cast<const Ctx*>(p)->launches : 0; }
+
+int pwicp_sync(pwicp_ctx* p) {
+    Ctx* ctx = reinterpret_cast<Ctx*>(p);
+    if (!ctx) return PWICP_ERR_ARG;
+    PW_CUDA(cudaSetDevice(ctx->device));
+    PW_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PWICP_OK;
+}
+
+int pwicp_flush_l2(pwicp_ctx* p) {
+    Ctx* ctx = reinterpret_cast<Ctx*>(p);
+    if (!ctx) return PWICP_ERR_ARG;
+    PW_CUDA(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)384 << 20;           // 3x the 126 MB L2
+    PW_TRY(ctx->l2flush.reserve(ctx, bytes));
+    fill_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(ctx->l2flush.as<uint4>(), bytes / 16, (unsigned)ctx->launches);
+    ctx->launches++;
+    PW_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PWICP_OK;
+}
+
+int pwicp_set_cells_per_point(pwicp_ctx* p, float cpp) {
+    Ctx* ctx = reinterpret_cast<Ctx*>(p);
+    if (!ctx || !(cpp > 0.01f) || cpp > 1024.f) return PWICP_ERR_ARG;
+    ctx->cells_per_point = cpp;
+    return PWICP_OK;
+}
+
+void pwicp_icp_default_params(pwicp_icp_params* p) {
+    if (!p) return;
+    p->max_iter = 100; p->tf_eps = 1e-8; p->fit_eps = 1e-6; p->force_iters = 0; p->rot_thr_default = 0;
+}
+
+// ---- uploads -------------------------------------------------------------------------------
+int pwicp_target_upload(pwicp_ctx* p, const float* ct_xyz, const float* nrm, const unsigned char* nrm_ok,
+                        const float* ct_std, int n1) {
+    Ctx* ctx = reinterpret_cast<Ctx*>(p);
+    if (!ctx || n1 < 1 || !ct_xyz) { set_error(ctx, "target_upload: bad arguments"); return PWICP_ERR_ARG; }
+    PW_CUDA(cudaSetDevice(ctx->device));
+    ctx->n1 = 0;
+    PW_TRY(upload_checked(ctx, ctx->scratch_a, ct_xyz, (size_t)3 * n1, "target centroids"));
+    PW_TRY(grid_build(ctx, ctx->tgt, ctx->scratch_a.as<float>(), n1));
+    // normals / sigma / ok flags into level-0 order
+    PW_TRY(ctx->tgt_aux.reserve(ctx, (size_t)n1 * sizeof(float4)));
+    PW_TRY(ctx->tgt_ok.reserve(ctx, (size_t)n1));
+    if (nrm) {
+        PW_TRY(upload_checked(ctx, ctx->scratch_b, nrm, (size_t)3 * n1, "target normals"));
+    } else {
+        PW_TRY(ctx->scratch_b.reserve(ctx, (size_t)3 * n1 * 4));
+        PW_CUDA(cudaMemsetAsync(ctx->scratch_b.p, 0, (size_t)3 * n1 * 4, ctx->stream));
+    }
+    float* std_dev = nullptr;
+    if (ct_std) { PW_TRY(upload_checked(ctx, ctx->scratch_c, ct_std, (size_t)n1, "CTstd1")); std_dev = ctx->scratch_c.as<float>(); }
+    unsigned char* ok_dev = nullptr;
+    if (nrm_ok) {
+        PW_TRY(ctx->keys.reserve(ctx, (size_t)n1));
+        PW_CUDA(cudaMemcpyAsync(ctx->keys.p, nrm_ok, (size_t)n1, cudaMemcpyHostToDevice, ctx->stream));
+        ok_dev = ctx->keys.as<unsigned char>();
+    }
+    gather_aux_kernel<<<(n1 + 255) / 256, 256, 0, ctx->stream>>>(ctx->scratch_b.as<float>(), std_dev, ok_dev,
+                                                                 ctx->tgt.perm0, n1, ctx->tgt_aux.as<float4>(),
+                                                                 ctx->tgt_ok.as<unsigned char>());
+    ctx->launches++;
+    PW_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->n1 = n1;
+    return PWICP_OK;
+}
+
+int pwicp_source_upload(pwicp_ctx* p, const float* ct_xyz, const float* bp_xyz, const float* bp_std,
+                        const int* patch_off, const float* patch_xyz, int n2) {
+    Ctx* ctx = reinterpret_cast<Ctx*>(p);
+    if (!ctx || n2 < 1 || !ct_xyz) { set_error(ctx, "source_upload: bad arguments"); return PWICP_ERR_ARG; }
+    PW_CUDA(cudaSetDevice(ctx->device));
+    ctx->n2 = 0;
+    PW_TRY(upload_checked(ctx, ctx->scratch_a, ct_xyz, (size_t)3 * n2, "source centroids"));
+    PW_TRY(ctx->ct2.reserve(ctx, (size_t)n2 * sizeof(float4)));
+    expand_f4_kernel<<<(n2 + 255) / 256, 256, 0, ctx->stream>>>(ctx->scratch_a.as<float>(), n2, ctx->ct2.as<float4>());
+    ctx->launches++;
+    PW_TRY(ctx->bp2.reserve(ctx, (size_t)6 * n2 * sizeof(float4)));
+    if (bp_xyz) {
+        PW_TRY(upload_checked(ctx, ctx->scratch_b, bp_xyz, (size_t)18 * n2, "source boundary points"));
+        expand_f4_kernel<<<(6 * n2 + 255) / 256, 256, 0, ctx->stream>>>(ctx->scratch_b.as<float>(), 6 * n2, ctx->bp2.as<float4>());
+        ctx->launches++;
+    }
+    PW_TRY(ctx->bpstd2.reserve(ctx, (size_t)n2 * 4));
+    if (bp_std) { PW_TRY(upload_checked(ctx, ctx->bpstd2, bp_std, (size_t)n2, "BPstd2")); }
+    else PW_CUDA(cudaMemsetAsync(ctx->bpstd2.p, 0, (size_t)n2 * 4, ctx->stream));
+    PW_TRY(ctx->patch_off.reserve(ctx, (size_t)(n2 + 1) * 4));
+    int mp = 0;
+    if (patch_off) {
+        mp = patch_off[n2];
+        if (mp < 0 || patch_off[0] != 0) { set_error(ctx, "source_upload: bad patch offsets"); return PWICP_ERR_ARG; }
+        PW_CUDA(cudaMemcpyAsync(ctx->patch_off.p, patch_off, (size_t)(n2 + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        PW_CUDA(cudaMemsetAsync(ctx->patch_off.p, 0, (size_t)(n2 + 1) * 4, ctx->stream));
+    }
+    ctx->mp2 = mp;
+    if (mp > 0) {
+        PW_TRY(upload_checked(ctx, ctx->patch_xyz, patch_xyz, (size_t)3 * mp, "source patch points"));
+        PW_TRY(ctx->patch_id.reserve(ctx, (size_t)mp * 4));
+        patch_id_kernel<<<(mp + 255) / 256, 256, 0, ctx->stream>>>(ctx->patch_off.as<int>(), n2, mp, ctx->patch_id.as<int>());
+        ctx->launches++;
+    }
+    PW_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->n2 = n2;
+    return PWICP_OK;
+}
+
+int pwicp_clouds_upload(pwicp_ctx* p, const float* cloud1, int m1, const float* cloud2, int m2) {
+    Ctx* ctx = reinterpret_cast<Ctx*>(p);
+    if (!ctx || m1 < 1 || m2 < 1 || !cloud1 || !cloud2) { set_error(ctx, "clouds_upload: bad arguments"); return PWICP_ERR_ARG; }
+    PW_CUDA(cudaSetDevice(ctx->device));
+    ctx->m1 = ctx->m2 = 0;
+    PW_TRY(upload_checked(ctx, ctx->scratch_a, cloud1, (size_t)3 * m1, "cloud1"));
+    PW_TRY(grid_build(ctx, ctx->c1, ctx->scratch_a.as<float>(), m1));
+    PW_TRY(upload_checked(ctx, ctx->cloud2, cloud2, (size_t)3 * m2, "cloud2"));
+    ctx->m1 = m1; ctx->m2 = m2;
+    return PWICP_OK;
+}
+
+int pwicp_source_download(pwicp_ctx* p, float* cloud2, float* ct_xyz, float* bp_xyz, float* patch_xyz) {
+    Ctx* ctx = reinterpret_cast<Ctx*>(p);
+    if (!ctx) return PWICP_ERR_ARG;
+    PW_CUDA(cudaSetDevice(ctx->device));
+    if (cloud2 && ctx->m2) PW_CUDA(cudaMemcpyAsync(cloud2, ctx->cloud2.p, (size_t)3 * ctx->m2 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (patch_xyz && ctx->mp2) PW_CUDA(cudaMemcpyAsync(patch_xyz, ctx->patch_xyz.p, (size_t)3 * ctx->mp2 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    const int n2 = ctx->n2;
+    if ((ct_xyz || bp_xyz) && n2) {
+        PW_TRY(ctx->scratch_b.reserve(ctx, (size_t)21 * n2 * 4));
+        float* tmp = ctx->scratch_b.as<float>();
+        if (ct_xyz) {
+            pack_f4_kernel<<<(n2 + 255) / 256, 256, 0, ctx->stream>>>(ctx->ct2.as<float4>(), n2, tmp);
+            PW_CUDA(cudaMemcpyAsync(ct_xyz, tmp, (size_t)3 * n2 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        if (bp_xyz) {
+            pack_f4_kernel<<<(6 * n2 + 255) / 256, 256, 0, ctx->stream>>>(ctx->bp2.as<float4>(), 6 * n2, tmp + (size_t)3 * n2);
+            PW_CUDA(cudaMemcpyAsync(bp_xyz, tmp + (size_t)3 * n2, (size_t)18 * n2 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        ctx->launches += 2;
+    }
+    PW_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PWICP_OK;
+}
+
+// ---- A1 --------------------------------------------------------------------------------------
+int pwicp_nn(pwicp_ctx* p, int which, const float* qry, int nq, int* idx, float* d2) {
+    Ctx* ctx = reinterpret_cast<Ctx*>(p);
+    if (!ctx || nq < 0 || (nq && !qry)) { set_error(ctx, "nn: bad arguments"); return PWICP_ERR_ARG; }
+    PW_CUDA(cudaSetDevice(ctx->device));
+    const GridOwner& g = (which == PWICP_TGT_CLOUD1) ? ctx->c1 : ctx->tgt;
+    if (!g.dev.nlevels) { set_error(ctx, "nn: target not uploaded"); return PWICP_ERR_ARG; }
+    if (nq == 0) return PWICP_OK;
+    PW_TRY(upload_checked(ctx, ctx->scratch_a, qry, (size_t)3 * nq, "nn queries"));
+    PW_TRY(ctx->scratch_b.reserve(ctx, (size_t)nq * 8));
+    int* idx_d = ctx->scratch_b.as<int>();
+    float* d2_d = reinterpret_cast<float*>(idx_d + nq);
+    PW_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    PW_TRY(nn_query_packed(ctx, g.dev, ctx->scratch_a.as<float>(), nq, idx_d, d2_d));
+    PW_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    if (idx) PW_CUDA(cudaMemcpyAsync(idx, idx_d, (size_t)nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (d2) PW_CUDA(cudaMemcpyAsync(d2, d2_d, (size_t)nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PW_CUDA(cudaStreamSynchronize(ctx->stream));
+    PW_CUDA(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    return PWICP_OK;
+}
+
+// ---- A3-A6 -----------------------------------------------------------------------------------
+int pwicp_icp_source_upload(pwicp_ctx* p, const float* src, int n) {
+    Ctx* ctx = reinterpret_cast<Ctx*>(p);
+    if (!ctx || n < 1 || !src) { set_error(ctx, "icp_source_upload: bad arguments"); return PWICP_ERR_ARG; }
+    PW_CUDA(cudaSetDevice(ctx->device));
+    PW_TRY(upload_checked(ctx, ctx->scratch_a, src, (size_t)3 * n, "icp source"));
+    PW_TRY(icp_expand_source(ctx, ctx->scratch_a.as<float>(), n));
+    PW_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PWICP_OK;
+}
+
+int pwicp_icp_source_all(pwicp_ctx* p) {
+    Ctx* ctx = reinterpret_cast<Ctx*>(p);
+    if (!ctx || ctx->n2 < 1) { set_error(ctx, "icp_source_all: no source uploaded"); return PWICP_ERR_ARG; }
+    PW_CUDA(cudaSetDevice(ctx->device));
+    PW_TRY(ctx->icp_src.reserve(ctx, (size_t)ctx->n2 * sizeof(float4)));
+    PW_CUDA(cudaMemcpyAsync(ctx->icp_src.p, ctx->ct2.p, (size_t)ctx->n2 * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->n_icp = ctx->n2;
+    PW_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PWICP_OK;
+}
+
+int pwicp_icp_run(pwicp_ctx* p, const pwicp_icp_params* prm, float* T16, pwicp_icp_result* res,
+                  double* mse_trace, float* T_trace, int* idx_trace) {
+    Ctx* ctx = reinterpret_cast<Ctx*>(p);
+    if (!ctx) return PWICP_ERR_ARG;
+    PW_CUDA(cudaSetDevice(ctx->device));
+    pwicp_icp_params d; pwicp_icp_default_params(&d);
+    return icp_run_device(ctx, prm ? *prm : d, T16, res, mse_trace, T_trace, idx_trace);
+}
+
+int pwicp_icp_p2plane(pwicp_ctx* p, const float* tgt_xyz, const float* tgt_nrm, int n1, const float* src_xyz,
+                      int n2, const pwicp_icp_params* prm, float* T16, pwicp_icp_result* res) {
+    PW_TRY(pwicp_target_upload(p, tgt_xyz, tgt_nrm, nullptr, nullptr, n1));
+    PW_TRY(pwicp_icp_source_upload(p, src_xyz, n2));
+    return pwicp_icp_run(p, prm, T16, res, nullptr, nullptr, nullptr);
+}
+
+// ---- outer iteration / loop -------------------------------------------------------------------
+int pwicp_single_iteration(pwicp_ctx* p, const pwicp_pair_params* pp, pwicp_state* st,
+                           const pwicp_icp_params* icp, float* T16, double* vcm36,
+                           unsigned char* stable_flags, pwicp_iter_stats* stats) {
+    Ctx* ctx = reinterpret_cast<Ctx*>(p);
+    if (!ctx || !pp || !st || !T16) { set_error(ctx, "single_iteration: bad arguments"); return PWICP_ERR_ARG; }
+    PW_CUDA(cudaSetDevice(ctx->device));
+    pwicp_icp_params d; pwicp_icp_default_params(&d);
+    return outer_single_iteration(ctx, *pp, st, icp ? *icp : d, T16, vcm36, stable_flags, stats);
+}
+
+int pwicp_piecewise_icp(pwicp_ctx* p, const pwicp_pair_params* pp, int is_manual, float DTinit,
+                        const pwicp_icp_params* icp, int max_outer, float* DTseries, int* n_series,
+                        float* T16, double* vcm36, int* n_outer, pwicp_iter_stats* stats_per_iter) {
+    Ctx* ctx = reinterpret_cast<Ctx*>(p);
+    if (!ctx || !pp || !DTseries || !n_series || !T16 || max_outer < 1) { set_error(ctx, "piecewise_icp: bad arguments"); return PWICP_ERR_ARG; }
+    PW_CUDA(cudaSetDevice(ctx->device));
+    pwicp_state st;
+    st.toStage2 = 0; st.toStage3 = 0;                                       // :623-624
+    if (!is_manual) {
+        if (!ctx->c1.dev.nlevels || ctx->m2 < 1) { set_error(ctx, "piecewise_icp: clouds not uploaded"); return PWICP_ERR_ARG; }
+        double Dist75 = 0;
+        PW_TRY(percentile_dev(ctx, ctx->c1.dev, ctx->cloud2.as<float>(), ctx->m2, nullptr, nullptr, ctx->m2, 0.75f, &Dist75));
+        DTinit = Dist75 * 3.0;                                              // :627-630
+    }
+    st.currDT = DTinit; st.BBchange_1 = 0.f; st.BBchange_2 = 0.f;
+    float transMat[16];
+    for (int k = 0; k < 16; ++k) transMat[k] = (k % 5 == 0) ? 1.f : 0.f;
+    int ns = 0, count = 0;
+    DTseries[ns++] = st.currDT;
+    float total_ms = 0.f;
+    pwicp_icp_params ip;
+    pwicp_icp_default_params(&ip);
+    if (icp) ip = *icp;
+    while (!st.toStage3 && count < max_outer) {
+        float cur[16];
+        int rc = outer_single_iteration(ctx, *pp, &st, ip, cur, vcm36, nullptr,
+                                        stats_per_iter ? stats_per_iter + count : nullptr);
+        if (rc != PWICP_OK) { *n_series = ns; if (n_outer) *n_outer = count; memcpy(T16, transMat, sizeof(transMat)); return rc; }
+        total_ms += ctx->last_ms;
+        mat4_mul(cur, transMat, transMat);                                  // transMat = cur * transMat, :687
+        DTseries[ns++] = st.currDT;
+        ++count;
+    }
+    ctx->last_ms = total_ms;
+    *n_series = ns;
+    if (n_outer) *n_outer = count;
+    memcpy(T16, transMat, sizeof(transMat));
+    return PWICP_OK;
+}
+
+// ---- stand-alone pieces -------------------------------------------------------------------------
+int pwicp_percentile_nn(pwicp_ctx* p, const float* cloud1, int m1, const float* cloud2, int m2,
+                        float pct, double* out) {
+    Ctx* ctx = reinterpret_cast<Ctx*>(p);
+    if (!ctx || m1 < 1 || m2 < 1 || !out) { set_error(ctx, "percentile_nn: bad arguments"); return PWICP_ERR_ARG; }
+    PW_CUDA(cudaSetDevice(ctx->device));
+    GridOwner g;
+    PW_TRY(upload_checked(ctx, ctx->scratch_a, cloud1, (size_t)3 * m1, "cloud1"));
+    int rc = grid_build(ctx, g, ctx->scratch_a.as<float>(), m1);
+    if (rc == PWICP_OK) rc = upload_checked(ctx, ctx->scratch_c, cloud2, (size_t)3 * m2, "cloud2");
+    if (rc == PWICP_OK) rc = percentile_dev(ctx, g.dev, ctx->scratch_c.as<float>(), m2, nullptr, nullptr, m2, pct, out);
+    g.release();
+    return rc;
+}
+
+int pwicp_overlap_ratio(pwicp_ctx* p, const float* cloud1, int m1, const float* cloud2, int m2,
+                        float DTinit, float* out) {
+    Ctx* ctx = reinterpret_cast<Ctx*>(p);
+    if (!ctx || m1 < 1 || m2 < 1 || !out) { set_error(ctx, "overlap_ratio: bad arguments"); return PWICP_ERR_ARG; }
+    PW_CUDA(cudaSetDevice(ctx->device));
+    GridOwner g;
+    PW_TRY(upload_checked(ctx, ctx->scratch_a, cloud1, (size_t)3 * m1, "cloud1"));
+    int rc = grid_build(ctx, g, ctx->scratch_a.as<float>(), m1);
+    if (rc == PWICP_OK) rc = upload_checked(ctx, ctx->scratch_c, cloud2, (size_t)3 * m2, "cloud2");
+    unsigned long long cnt = 0;
+    if (rc == PWICP_OK) rc = ctx->scratch_b.reserve(ctx, (size_t)m2 * 4 + 64);
+    if (rc == PWICP_OK) {
+        float* d2 = ctx->scratch_b.as<float>();
+        unsigned long long* cd = reinterpret_cast<unsigned long long*>(ctx->scratch_d.p);
+        cudaMemsetAsync(cd, 0, 8, ctx->stream);
+        rc = nn_query_packed(ctx, g.dev, ctx->scratch_c.as<float>(), m2, nullptr, d2);
+        if (rc == PWICP_OK) {
+            count_below_kernel<<<(m2 + 255) / 256, 256, 0, ctx->stream>>>(d2, m2, DTinit, cd);
+            ctx->launches++;
+            if (cudaMemcpyAsync(&cnt, cd, 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                cudaStreamSynchronize(ctx->stream) != cudaSuccess) { set_error(ctx, "overlap_ratio: copy failed"); rc = PWICP_ERR_CUDA; }
+        }
+    }
+    g.release();
+    if (rc == PWICP_OK) *out = float((int)cnt) / float(m2);        // :613
+    return rc;
+}
+
+int pwicp_vcm(pwicp_ctx* p, const float* src, int n, double* vcm36, int* singular) {
+    Ctx* ctx = reinterpret_cast<Ctx*>(p);
+    if (!ctx || !src || !vcm36 || n < 1) { set_error(ctx, "vcm: bad arguments"); return PWICP_ERR_ARG; }
+    PW_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->tgt.dev.nlevels) { set_error(ctx, "vcm: target not uploaded"); return PWICP_ERR_ARG; }
+    PW_TRY(upload_checked(ctx, ctx->scratch_a, src, (size_t)3 * n, "vcm source"));
+    PW_TRY(ctx->scratch_b.reserve(ctx, (size_t)n * sizeof(float4)));
+    expand_f4_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->scratch_a.as<float>(), n, ctx->scratch_b.as<float4>());
+    ctx->launches++;
+    return vcm_dev(ctx, ctx->scratch_b.as<float4>(), n, vcm36, singular);
+}
+
+int pwicp_transform(pwicp_ctx* p, float* xyz, int n, const float* T16) {
+    Ctx* ctx = reinterpret_cast<Ctx*>(p);
+    if (!ctx || !xyz || n < 0 || !T16) { set_error(ctx, "transform: bad arguments"); return PWICP_ERR_ARG; }
+    if (n == 0) return PWICP_OK;
+    PW_CUDA(cudaSetDevice(ctx->device));
+    PW_TRY(upload_packed(ctx, ctx->scratch_a, xyz, (size_t)3 * n));
+    PW_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    PW_TRY(transform_packed_dev(ctx, ctx->scratch_a.as<float>(), (size_t)n, T16));
+    PW_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    PW_CUDA(cudaMemcpyAsync(xyz, ctx->scratch_a.p, (size_t)3 * n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PW_CUDA(cudaStreamSynchronize(ctx->stream));
+    PW_CUDA(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    return PWICP_OK;
+}
+
+int pwicp_octree_bbox(pwicp_ctx* p, const float* xyz, int n, double res, double* bb6) {
+    Ctx* ctx = reinterpret_cast<Ctx*>(p);
+    if (!ctx || !xyz || n < 1 || !bb6) { set_error(ctx, "octree_bbox: bad arguments"); return PWICP_ERR_ARG; }
+    PW_CUDA(cudaSetDevice(ctx->device));
+    PW_TRY(upload_packed(ctx, ctx->scratch_a, xyz, (size_t)3 * n));
+    float mn[3], mx[3];
+    PW_TRY(bbox_packed_dev(ctx, ctx->scratch_a.as<float>(), (size_t)n, mn, mx));
+    octree_cube(mn, mx, res, bb6);
+    return PWICP_OK;
+}
+
+float pwicp_bbox_corner_change(const double* bb6, const float* T16) { return bbox_corner_change_host(bb6, T16); }
+
+void pwicp_matrix2angle(const float* T, float* ang) {
+    double ax, ay, az;
+    if (T[8] == 1 || T[8] == -1) {
+        az = 0;
+        const double dlta = std::atan2(T[1], T[2]);
+        if (T[8] == -1) { ay = M_PI / 2; ax = az + dlta; }
+        else { ay = -M_PI / 2; ax = -az + dlta; }
+    } else {
+        ay = -std::asin(T[8]);
+        ax = std::atan2(T[9] / std::cos(ay), T[10] / std::cos(ay));
+        az = std::atan2(T[4] / std::cos(ay), T[0] / std::cos(ay));
+    }
+    ang[0] = (float)ax; ang[1] = (float)ay; ang[2] = (float)az;
+}
+
+void pwicp_mat4_mul(const float* A, const float* B, float* C) { mat4_mul(A, B, C); }
+
+}  // extern "C"

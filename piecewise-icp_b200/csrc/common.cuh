@@ -1,0 +1,131 @@
+// common.cuh -- shared declarations of libpwicp.so (sm_100a only; compiled with -fmad=false).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/pwicp.h"
+
+namespace pwicp {
+
+constexpr int kMaxLevels = 3;      // grid pyramid: cell sizes h, 8h, 64h
+constexpr int kLevelFactor = 8;
+constexpr int kRingsPerLevel = 2;  // rings searched on a level before moving to the coarser one
+constexpr int kIcpThreads = 256;   // 8 warps per CTA (reduction geometry)
+constexpr int kIcpWarps = kIcpThreads / 32;
+constexpr int kNumVals = 28;       // 21 ATA + 6 ATb + sum d2
+constexpr int kMaxIcpIter = 1024;
+
+struct GridLevel {
+    const float4* pts;           // cell-sorted targets: x, y, z, original index (int bits)
+    const uint32_t* cell_start;  // ncells + 1
+    int dx, dy, dz;
+    float inv_h, inv_h2;         // 1/h, 1/h^2
+};
+
+struct GridDev {
+    float ox, oy, oz;
+    int nlevels;
+    int n;
+    GridLevel lv[kMaxLevels];
+    const uint32_t* inv_perm;    // original index -> position in level 0
+};
+
+// Owns the device memory of one grid pyramid.
+struct GridOwner {
+    GridDev dev{};
+    void* pts[kMaxLevels] = {nullptr, nullptr, nullptr};
+    void* cells[kMaxLevels] = {nullptr, nullptr, nullptr};
+    void* inv_perm = nullptr;
+    uint32_t* perm0 = nullptr;   // level-0 order: position -> original index
+    float h0 = 0.f;
+    int n = 0;
+    void release();
+};
+
+struct Ctx;
+
+// error helpers ---------------------------------------------------------------------------
+void set_error(Ctx* c, const std::string& msg);
+#define PW_CUDA(call)                                                                        \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess) {                                                            \
+            set_error(ctx, std::string(#call) + ": " + cudaGetErrorString(e__));            \
+            return PWICP_ERR_CUDA;                                                           \
+        }                                                                                    \
+    } while (0)
+#define PW_TRY(call)                                                                         \
+    do {                                                                                     \
+        int s__ = (call);                                                                    \
+        if (s__ != PWICP_OK) return s__;                                                     \
+    } while (0)
+
+// simple device buffer that grows on demand
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(Ctx* ctx, size_t bytes);
+    void release();
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    float last_ms = 0.f;
+    long long launches = 0;
+    float cells_per_point = 4.0f;
+    int num_sms = 0;
+
+    // target (centroids)
+    GridOwner tgt;
+    DevBuf tgt_aux;      // float4 per target in level-0 order: nx, ny, nz, ctstd
+    DevBuf tgt_ok;       // uint8 per target in level-0 order (calPatchNormal success)
+    int n1 = 0;
+    // full cloud1
+    GridOwner c1;
+    int m1 = 0;
+    // source
+    DevBuf ct2, bp2, bpstd2, patch_xyz, patch_id, patch_off, cloud2;
+    int n2 = 0, m2 = 0, mp2 = 0;
+    // inner loop
+    DevBuf icp_src, icp_work, icp_partials, icp_out, icp_idx;
+    int n_icp = 0;
+    // scratch
+    DevBuf keys, vals, keys2, vals2, cub_tmp, scratch_a, scratch_b, scratch_c, scratch_d, flags, pos;
+    DevBuf l2flush;
+    void* pinned = nullptr;   // small pinned staging area
+    size_t pinned_cap = 0;
+};
+
+// grid.cu
+int grid_build(Ctx* ctx, GridOwner& g, const float* xyz_dev_packed, int n);
+int nn_query_packed(Ctx* ctx, const GridDev& g, const float* q_dev_packed, int nq, int* idx_dev,
+                    float* d2_dev);
+int upload_packed(Ctx* ctx, DevBuf& buf, const float* host_xyz, size_t n_floats);
+int check_finite_dev(Ctx* ctx, const float* dev, size_t n_floats, bool* ok);
+
+// icp.cu
+int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_result* res,
+                   double* mse_trace, float* T_trace, int* idx_trace);
+
+// outer.cu
+int outer_single_iteration(Ctx* ctx, const pwicp_pair_params& pp, pwicp_state* st,
+                           const pwicp_icp_params& icp, float* T16, double* vcm36,
+                           unsigned char* stable_flags, pwicp_iter_stats* stats);
+int percentile_dev(Ctx* ctx, const GridDev& g, const float* q_packed_dev, int nq,
+                   const int* patch_id_dev, const int* flags_dev, long long n_valid,
+                   float pct, double* out);
+float bbox_corner_change_host(const double* bb6, const float* T16);
+int icp_expand_source(Ctx* ctx, const float* packed_dev, int n);
+int vcm_dev(Ctx* ctx, const float4* src_dev, int n, double* vcm36, int* singular);
+int transform_packed_dev(Ctx* ctx, float* xyz_dev, size_t n, const float* T16);
+int bbox_packed_dev(Ctx* ctx, const float* xyz_dev, size_t n, float* mn3, float* mx3);
+void octree_cube(const float* mn, const float* mx, double res, double* bb6);
+
+}  // namespace pwicp

@@ -1,0 +1,291 @@
+// grid.cu -- device-side build of the cell-sorted grid pyramid + the batched exact 1-NN kernel.
+//
+// One build per target replaces the reference's repeated KD-tree builds over the same cloud
+// (five per outer iteration over CTcloud1: src/Registration.cpp:738, :744, :1294 and two inside
+// pcl::IterativeClosestPoint; one per stage-1 iteration over cloud1: src/CommonFunc.cpp:269-273).
+#include <cub/cub.cuh>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+#include "nn_search.cuh"
+
+namespace pwicp {
+
+// ---- small utilities ----------------------------------------------------------------------
+void GridOwner::release() {
+    for (int l = 0; l < kMaxLevels; ++l) {
+        if (pts[l]) cudaFree(pts[l]);
+        if (cells[l]) cudaFree(cells[l]);
+        pts[l] = cells[l] = nullptr;
+    }
+    if (inv_perm) cudaFree(inv_perm);
+    if (perm0) cudaFree(perm0);
+    inv_perm = nullptr; perm0 = nullptr; n = 0;
+    dev = GridDev{};
+}
+
+int DevBuf::reserve(Ctx* ctx, size_t bytes) {
+    if (bytes <= cap && p) return PWICP_OK;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    size_t want = bytes < 256 ? 256 : bytes;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+        p = nullptr;
+        set_error(ctx, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        cudaGetLastError();
+        return PWICP_ERR_NOMEM;
+    }
+    cap = want;
+    return PWICP_OK;
+}
+void DevBuf::release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+
+static int ensure_pinned(Ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->pinned_cap) return PWICP_OK;
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    ctx->pinned = nullptr; ctx->pinned_cap = 0;
+    PW_CUDA(cudaMallocHost(&ctx->pinned, bytes));
+    ctx->pinned_cap = bytes;
+    return PWICP_OK;
+}
+
+int upload_packed(Ctx* ctx, DevBuf& buf, const float* host_xyz, size_t n_floats) {
+    PW_TRY(buf.reserve(ctx, n_floats * sizeof(float) + 64));
+    if (n_floats)
+        PW_CUDA(cudaMemcpyAsync(buf.p, host_xyz, n_floats * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    return PWICP_OK;
+}
+
+__global__ void finite_kernel(const float* __restrict__ v, size_t n, int* bad) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    int b = 0;
+    for (; i < n; i += stride) {
+        float x = v[i];
+        if (!(fabsf(x) <= FLT_MAX)) b = 1;
+    }
+    if (b) atomicOr(bad, 1);
+}
+
+int check_finite_dev(Ctx* ctx, const float* dev, size_t n_floats, bool* ok) {
+    PW_TRY(ensure_pinned(ctx, 4096));
+    PW_TRY(ctx->scratch_d.reserve(ctx, 256));
+    int* flag = ctx->scratch_d.as<int>();
+    PW_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+    if (n_floats) {
+        int blocks = (int)std::min<size_t>((n_floats + 255) / 256, (size_t)ctx->num_sms * 8);
+        finite_kernel<<<blocks, 256, 0, ctx->stream>>>(dev, n_floats, flag);
+        ctx->launches++;
+    }
+    PW_CUDA(cudaMemcpyAsync(ctx->pinned, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PW_CUDA(cudaStreamSynchronize(ctx->stream));
+    *ok = (*(int*)ctx->pinned == 0);
+    return PWICP_OK;
+}
+
+// ---- bounding box -------------------------------------------------------------------------
+__device__ __forceinline__ int float_to_ordered(float f) {
+    int i = __float_as_int(f);
+    return (i >= 0) ? i : i ^ 0x7fffffff;
+}
+__host__ __device__ __forceinline__ float ordered_to_float(int i) {
+    int j = (i >= 0) ? i : i ^ 0x7fffffff;
+#ifdef __CUDA_ARCH__
+    return __int_as_float(j);
+#else
+    float f; memcpy(&f, &j, 4); return f;
+#endif
+}
+
+// min/max over packed xyz.  out[0..2] = ordered-int min, out[3..5] = ordered-int max.
+__global__ void bbox_kernel(const float* __restrict__ xyz, size_t n, int* out) {
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+        mn[0] = fminf(mn[0], x); mx[0] = fmaxf(mx[0], x);
+        mn[1] = fminf(mn[1], y); mx[1] = fmaxf(mx[1], y);
+        mn[2] = fminf(mn[2], z); mx[2] = fmaxf(mx[2], z);
+    }
+    for (int c = 0; c < 3; ++c)
+        for (int o = 16; o; o >>= 1) {
+            mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
+            mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
+        }
+    if ((threadIdx.x & 31) == 0)
+        for (int c = 0; c < 3; ++c) {
+            atomicMin(out + c, float_to_ordered(mn[c]));
+            atomicMax(out + 3 + c, float_to_ordered(mx[c]));
+        }
+}
+
+__global__ void bbox_init_kernel(int* out) {
+    if (threadIdx.x < 3) out[threadIdx.x] = 0x7fffffff;
+    else if (threadIdx.x < 6) out[threadIdx.x] = (int)0x80000000;
+}
+
+int bbox_packed_dev(Ctx* ctx, const float* xyz_dev, size_t n, float* mn3, float* mx3) {
+    PW_TRY(ensure_pinned(ctx, 4096));
+    PW_TRY(ctx->scratch_d.reserve(ctx, 256));
+    int* out = ctx->scratch_d.as<int>();
+    bbox_init_kernel<<<1, 32, 0, ctx->stream>>>(out);
+    int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)ctx->num_sms * 8);
+    if (blocks < 1) blocks = 1;
+    bbox_kernel<<<blocks, 256, 0, ctx->stream>>>(xyz_dev, n, out);
+    ctx->launches += 2;
+    PW_CUDA(cudaMemcpyAsync(ctx->pinned, out, 6 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PW_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int* h = (const int*)ctx->pinned;
+    for (int c = 0; c < 3; ++c) { mn3[c] = ordered_to_float(h[c]); mx3[c] = ordered_to_float(h[3 + c]); }
+    return PWICP_OK;
+}
+
+// ---- build ---------------------------------------------------------------------------------
+__global__ void cell_key_kernel(const float* __restrict__ xyz, int n, float ox, float oy, float oz,
+                                float inv_h, int dx, int dy, int dz, uint32_t* keys, uint32_t* vals,
+                                uint32_t* counts) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float x = xyz[3 * (size_t)i], y = xyz[3 * (size_t)i + 1], z = xyz[3 * (size_t)i + 2];
+    // identical expression to search_level(): (p - origin) * inv_h, floor, clamp
+    float fx = (x - ox) * inv_h, fy = (y - oy) * inv_h, fz = (z - oz) * inv_h;
+    int cx = min(max((int)floorf(fx), 0), dx - 1);
+    int cy = min(max((int)floorf(fy), 0), dy - 1);
+    int cz = min(max((int)floorf(fz), 0), dz - 1);
+    uint32_t key = ((uint32_t)cz * (uint32_t)dy + (uint32_t)cy) * (uint32_t)dx + (uint32_t)cx;
+    keys[i] = key;
+    vals[i] = (uint32_t)i;
+    atomicAdd(counts + key, 1u);
+}
+
+__global__ void gather_sorted_kernel(const float* __restrict__ xyz, const uint32_t* __restrict__ order,
+                                     int n, float4* out, uint32_t* inv_perm) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t o = order[i];
+    out[i] = make_float4(xyz[3 * (size_t)o], xyz[3 * (size_t)o + 1], xyz[3 * (size_t)o + 2],
+                         __int_as_float((int)o));
+    if (inv_perm) inv_perm[o] = (uint32_t)i;
+}
+
+static int bits_for(uint64_t v) { int b = 1; while ((1ull << b) < v && b < 32) ++b; return b; }
+
+int grid_build(Ctx* ctx, GridOwner& g, const float* xyz, int n) {
+    g.release();
+    if (n < 1) { set_error(ctx, "grid_build: empty target"); return PWICP_ERR_ARG; }
+    float mn[3], mx[3];
+    PW_TRY(bbox_packed_dev(ctx, xyz, (size_t)n, mn, mx));
+    double ext[3];
+    for (int c = 0; c < 3; ++c) ext[c] = std::max((double)mx[c] - (double)mn[c], 0.0);
+    double emax = std::max(ext[0], std::max(ext[1], ext[2]));
+    if (!(emax > 0)) emax = 1.0;
+    // finest cell size: about cells_per_point cells per point over the bounding box, where
+    // degenerate (flat) axes count as one cell
+    const double budget = std::max(64.0, (double)ctx->cells_per_point * (double)n);
+    double h = emax / 1024.0;
+    {
+        // solve prod(max(1, ext/h)) ~= budget by bisection on log h
+        double lo = emax * 1e-7, hi = emax * 2.0;
+        for (int it = 0; it < 80; ++it) {
+            double mid = std::sqrt(lo * hi);
+            double cells = 1.0;
+            for (int c = 0; c < 3; ++c) cells *= std::max(1.0, std::ceil(ext[c] / mid + 1e-9));
+            if (cells > budget) lo = mid; else hi = mid;
+        }
+        h = hi;
+    }
+    // keep the coordinates in cell units small enough for float (|f| * 4e-6 margin stays tiny)
+    h = std::max(h, emax / 30000.0);
+
+    g.h0 = (float)h;
+    g.n = n;
+    g.dev.ox = mn[0]; g.dev.oy = mn[1]; g.dev.oz = mn[2];
+    g.dev.n = n;
+    int nlev = 0;
+    double hl = h;
+    for (int l = 0; l < kMaxLevels; ++l) {
+        int d[3];
+        for (int c = 0; c < 3; ++c) d[c] = (int)std::max(1.0, std::floor(ext[c] / hl) + 1.0);
+        uint64_t ncells = (uint64_t)d[0] * d[1] * d[2];
+        if (ncells > 0x7fffffffull) { set_error(ctx, "grid_build: too many cells"); return PWICP_ERR_ARG; }
+        float inv_h = (float)(1.0 / hl);
+
+        PW_TRY(ctx->keys.reserve(ctx, (size_t)n * 4));
+        PW_TRY(ctx->vals.reserve(ctx, (size_t)n * 4));
+        PW_TRY(ctx->keys2.reserve(ctx, (size_t)n * 4));
+        PW_TRY(ctx->vals2.reserve(ctx, (size_t)n * 4));
+        uint32_t* cells = nullptr;
+        PW_CUDA(cudaMalloc(&cells, (ncells + 1) * sizeof(uint32_t)));
+        g.cells[l] = cells;
+        PW_CUDA(cudaMemsetAsync(cells, 0, (ncells + 1) * sizeof(uint32_t), ctx->stream));
+        int blocks = (n + 255) / 256;
+        cell_key_kernel<<<blocks, 256, 0, ctx->stream>>>(xyz, n, mn[0], mn[1], mn[2], inv_h, d[0], d[1], d[2],
+                                                         ctx->keys.as<uint32_t>(), ctx->vals.as<uint32_t>(), cells);
+        ctx->launches++;
+        // exclusive scan of the counts -> cell_start (in place)
+        size_t tmp_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cells, cells, (int)(ncells + 1), ctx->stream);
+        size_t tmp2 = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp2, ctx->keys.as<uint32_t>(), ctx->keys2.as<uint32_t>(),
+                                        ctx->vals.as<uint32_t>(), ctx->vals2.as<uint32_t>(), n, 0,
+                                        bits_for(ncells), ctx->stream);
+        PW_TRY(ctx->cub_tmp.reserve(ctx, std::max(tmp_bytes, tmp2)));
+        size_t cap = ctx->cub_tmp.cap;
+        PW_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, cap, cells, cells, (int)(ncells + 1), ctx->stream));
+        // stable radix sort by cell key: points of one cell stay in ascending original index
+        cap = ctx->cub_tmp.cap;
+        PW_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, cap, ctx->keys.as<uint32_t>(),
+                                                ctx->keys2.as<uint32_t>(), ctx->vals.as<uint32_t>(),
+                                                ctx->vals2.as<uint32_t>(), n, 0, bits_for(ncells), ctx->stream));
+        ctx->launches += 6;
+        float4* pts = nullptr;
+        PW_CUDA(cudaMalloc(&pts, (size_t)n * sizeof(float4)));
+        g.pts[l] = pts;
+        uint32_t* invp = nullptr;
+        if (l == 0) {
+            PW_CUDA(cudaMalloc(&g.inv_perm, (size_t)n * sizeof(uint32_t)));
+            PW_CUDA(cudaMalloc(&g.perm0, (size_t)n * sizeof(uint32_t)));
+            invp = (uint32_t*)g.inv_perm;
+            PW_CUDA(cudaMemcpyAsync(g.perm0, ctx->vals2.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        gather_sorted_kernel<<<blocks, 256, 0, ctx->stream>>>(xyz, ctx->vals2.as<uint32_t>(), n, pts, invp);
+        ctx->launches++;
+
+        GridLevel& L = g.dev.lv[l];
+        L.pts = pts; L.cell_start = cells;
+        L.dx = d[0]; L.dy = d[1]; L.dz = d[2];
+        L.inv_h = inv_h; L.inv_h2 = inv_h * inv_h;
+        nlev = l + 1;
+        if (d[0] <= 4 && d[1] <= 4 && d[2] <= 4) break;
+        hl *= kLevelFactor;
+    }
+    g.dev.nlevels = nlev;
+    g.dev.inv_perm = (const uint32_t*)g.inv_perm;
+    PW_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PWICP_OK;
+}
+
+// ---- batched query -------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+nn_kernel(GridDev g, const float* __restrict__ q, int nq, int* __restrict__ idx, float* __restrict__ d2) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    float px = q[3 * (size_t)i], py = q[3 * (size_t)i + 1], pz = q[3 * (size_t)i + 2];
+    Best b = nn_search(g, px, py, pz);
+    if (idx) idx[i] = b.idx;
+    if (d2) d2[i] = b.d2;
+}
+
+int nn_query_packed(Ctx* ctx, const GridDev& g, const float* q_dev, int nq, int* idx_dev, float* d2_dev) {
+    if (nq <= 0) return PWICP_OK;
+    int blocks = (nq + 255) / 256;
+    nn_kernel<<<blocks, 256, 0, ctx->stream>>>(g, q_dev, nq, idx_dev, d2_dev);
+    ctx->launches++;
+    PW_CUDA(cudaGetLastError());
+    return PWICP_OK;
+}
+
+}  // namespace pwicp
