@@ -67,6 +67,9 @@ int  pwicp_set_cells_per_point(pwicp_ctx* ctx, float cpp);
  * success per patch (NULL = all ok), ct_std = CTstd1 (src/Segmentation.cpp:319). */
 int pwicp_target_upload(pwicp_ctx* ctx, const float* ct_xyz, const float* nrm,
                         const unsigned char* nrm_ok, const float* ct_std, int n1);
+/* Rebuilds the grid from the device-resident copy of the target centroids (same result as
+ * pwicp_target_upload without the host copy; what the device-resident bench step times). */
+int pwicp_target_rebuild(pwicp_ctx* ctx);
 /* CTcloud2, BPcloud2 (6 per patch), BPstd2 and the patch point lists SVcloud2[] as one
  * concatenated array with n2+1 offsets (src/Registration.cpp:646-664). */
 int pwicp_source_upload(pwicp_ctx* ctx, const float* ct_xyz, const float* bp_xyz,

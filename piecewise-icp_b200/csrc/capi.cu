@@ -125,7 +125,7 @@ void pwicp_ctx_destroy(pwicp_ctx* p) {
     c->tgt.release(); c->c1.release();
     DevBuf* bufs[] = {&c->tgt_aux, &c->tgt_ok, &c->ct2, &c->bp2, &c->bpstd2, &c->patch_xyz, &c->patch_id,
                       &c->patch_off, &c->cloud2, &c->icp_src, &c->icp_work, &c->icp_partials, &c->icp_out,
-                      &c->icp_idx, &c->keys, &c->vals, &c->keys2, &c->vals2, &c->cub_tmp, &c->scratch_a,
+                      &c->icp_idx, &c->tgt_xyz, &c->tgt_nrm_raw, &c->tgt_std_raw, &c->tgt_ok_raw, &c->keys, &c->vals, &c->keys2, &c->vals2, &c->cub_tmp, &c->scratch_a,
                       &c->scratch_b, &c->scratch_c, &c->scratch_d, &c->flags, &c->pos, &c->l2flush};
     for (DevBuf* b : bufs) b->release();
     if (c->pinned) cudaFreeHost(c->pinned);
@@ -170,37 +170,56 @@ void pwicp_icp_default_params(pwicp_icp_params* p) {
 }
 
 // ---- uploads -------------------------------------------------------------------------------
+static int target_build_resident(Ctx* ctx, int n1) {
+    PW_TRY(grid_build(ctx, ctx->tgt, ctx->tgt_xyz.as<float>(), n1));
+    // normals / sigma / ok flags into level-0 order
+    PW_TRY(ctx->tgt_aux.reserve(ctx, (size_t)n1 * sizeof(float4)));
+    PW_TRY(ctx->tgt_ok.reserve(ctx, (size_t)n1));
+    gather_aux_kernel<<<(n1 + 255) / 256, 256, 0, ctx->stream>>>(
+        ctx->tgt_nrm_raw.as<float>(), ctx->tgt_has_std ? ctx->tgt_std_raw.as<float>() : nullptr,
+        ctx->tgt_has_ok ? ctx->tgt_ok_raw.as<unsigned char>() : nullptr, ctx->tgt.perm0, n1,
+        ctx->tgt_aux.as<float4>(), ctx->tgt_ok.as<unsigned char>());
+    ctx->launches++;
+    PW_CUDA(cudaGetLastError());
+    return PWICP_OK;
+}
+
 int pwicp_target_upload(pwicp_ctx* p, const float* ct_xyz, const float* nrm, const unsigned char* nrm_ok,
                         const float* ct_std, int n1) {
     Ctx* ctx = reinterpret_cast<Ctx*>(p);
     if (!ctx || n1 < 1 || !ct_xyz) { set_error(ctx, "target_upload: bad arguments"); return PWICP_ERR_ARG; }
     PW_CUDA(cudaSetDevice(ctx->device));
     ctx->n1 = 0;
-    PW_TRY(upload_checked(ctx, ctx->scratch_a, ct_xyz, (size_t)3 * n1, "target centroids"));
-    PW_TRY(grid_build(ctx, ctx->tgt, ctx->scratch_a.as<float>(), n1));
-    // normals / sigma / ok flags into level-0 order
-    PW_TRY(ctx->tgt_aux.reserve(ctx, (size_t)n1 * sizeof(float4)));
-    PW_TRY(ctx->tgt_ok.reserve(ctx, (size_t)n1));
+    PW_TRY(upload_checked(ctx, ctx->tgt_xyz, ct_xyz, (size_t)3 * n1, "target centroids"));
     if (nrm) {
-        PW_TRY(upload_checked(ctx, ctx->scratch_b, nrm, (size_t)3 * n1, "target normals"));
+        PW_TRY(upload_checked(ctx, ctx->tgt_nrm_raw, nrm, (size_t)3 * n1, "target normals"));
     } else {
-        PW_TRY(ctx->scratch_b.reserve(ctx, (size_t)3 * n1 * 4));
-        PW_CUDA(cudaMemsetAsync(ctx->scratch_b.p, 0, (size_t)3 * n1 * 4, ctx->stream));
+        PW_TRY(ctx->tgt_nrm_raw.reserve(ctx, (size_t)3 * n1 * 4));
+        PW_CUDA(cudaMemsetAsync(ctx->tgt_nrm_raw.p, 0, (size_t)3 * n1 * 4, ctx->stream));
     }
-    float* std_dev = nullptr;
-    if (ct_std) { PW_TRY(upload_checked(ctx, ctx->scratch_c, ct_std, (size_t)n1, "CTstd1")); std_dev = ctx->scratch_c.as<float>(); }
-    unsigned char* ok_dev = nullptr;
+    ctx->tgt_has_std = ct_std != nullptr;
+    if (ct_std) PW_TRY(upload_checked(ctx, ctx->tgt_std_raw, ct_std, (size_t)n1, "CTstd1"));
+    ctx->tgt_has_ok = nrm_ok != nullptr;
     if (nrm_ok) {
-        PW_TRY(ctx->keys.reserve(ctx, (size_t)n1));
-        PW_CUDA(cudaMemcpyAsync(ctx->keys.p, nrm_ok, (size_t)n1, cudaMemcpyHostToDevice, ctx->stream));
-        ok_dev = ctx->keys.as<unsigned char>();
+        PW_TRY(ctx->tgt_ok_raw.reserve(ctx, (size_t)n1));
+        PW_CUDA(cudaMemcpyAsync(ctx->tgt_ok_raw.p, nrm_ok, (size_t)n1, cudaMemcpyHostToDevice, ctx->stream));
     }
-    gather_aux_kernel<<<(n1 + 255) / 256, 256, 0, ctx->stream>>>(ctx->scratch_b.as<float>(), std_dev, ok_dev,
-                                                                 ctx->tgt.perm0, n1, ctx->tgt_aux.as<float4>(),
-                                                                 ctx->tgt_ok.as<unsigned char>());
-    ctx->launches++;
+    PW_TRY(target_build_resident(ctx, n1));
     PW_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->n1 = n1;
+    return PWICP_OK;
+}
+
+int pwicp_target_rebuild(pwicp_ctx* p) {
+    Ctx* ctx = reinterpret_cast<Ctx*>(p);
+    if (!ctx || ctx->n1 < 1) { set_error(ctx, "target_rebuild: no target uploaded"); return PWICP_ERR_ARG; }
+    PW_CUDA(cudaSetDevice(ctx->device));
+    const int n1 = ctx->n1;
+    PW_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    PW_TRY(target_build_resident(ctx, n1));
+    PW_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    PW_CUDA(cudaStreamSynchronize(ctx->stream));
+    PW_CUDA(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
     return PWICP_OK;
 }
 

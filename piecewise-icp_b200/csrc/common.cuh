@@ -86,6 +86,8 @@ struct Ctx {
     GridOwner tgt;
     DevBuf tgt_aux;      // float4 per target in level-0 order: nx, ny, nz, ctstd
     DevBuf tgt_ok;       // uint8 per target in level-0 order (calPatchNormal success)
+    DevBuf tgt_xyz, tgt_nrm_raw, tgt_std_raw, tgt_ok_raw;   // original-order copies (rebuild)
+    bool tgt_has_std = false, tgt_has_ok = false;
     int n1 = 0;
     // full cloud1
     GridOwner c1;

@@ -57,7 +57,7 @@ class IterStats(C.Structure):
 EXPORTS = [
     "pwicp_version", "pwicp_device_count", "pwicp_ctx_create", "pwicp_ctx_destroy",
     "pwicp_last_error", "pwicp_last_device_ms", "pwicp_launch_count", "pwicp_flush_l2",
-    "pwicp_sync", "pwicp_set_cells_per_point", "pwicp_target_upload", "pwicp_source_upload",
+    "pwicp_sync", "pwicp_set_cells_per_point", "pwicp_target_upload", "pwicp_target_rebuild", "pwicp_source_upload",
     "pwicp_clouds_upload", "pwicp_source_download", "pwicp_nn", "pwicp_icp_default_params",
     "pwicp_icp_source_upload", "pwicp_icp_source_all", "pwicp_icp_run", "pwicp_icp_p2plane",
     "pwicp_single_iteration", "pwicp_piecewise_icp", "pwicp_percentile_nn", "pwicp_overlap_ratio",
@@ -92,6 +92,7 @@ def load_library(path=None):
     L.pwicp_sync.argtypes = [vp]
     L.pwicp_set_cells_per_point.argtypes = [vp, C.c_float]
     L.pwicp_target_upload.argtypes = [vp, vp, vp, vp, vp, C.c_int]
+    L.pwicp_target_rebuild.argtypes = [vp]
     L.pwicp_source_upload.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int]
     L.pwicp_clouds_upload.argtypes = [vp, vp, C.c_int, vp, C.c_int]
     L.pwicp_source_download.argtypes = [vp, vp, vp, vp, vp]
@@ -210,6 +211,10 @@ class Context:
         ok = None if nrm_ok is None else np.ascontiguousarray(nrm_ok, np.uint8)
         self._chk(self.L.pwicp_target_upload(self.h, _ptr(ct), _ptr(nrm), _ptr(ok), _ptr(ctstd), len(ct)))
         self.n1 = len(ct)
+
+    def target_rebuild(self):
+        self._chk(self.L.pwicp_target_rebuild(self.h))
+        return self.last_device_ms()
 
     def source_upload(self, ct, bp=None, bpstd=None, patch_off=None, patch_xyz=None):
         ct = _f32(ct)

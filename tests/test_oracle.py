@@ -1,0 +1,222 @@
+"""CPU tests of the oracle (no GPU): independent cross-checks + the committed golden vectors.
+
+The reference pins nothing at this boundary, so the oracle is checked against
+independent implementations (brute force, scipy, numpy float64 algebra) and physical properties.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from pwicp_b200 import synth
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pair2k.npz")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD)
+
+
+@pytest.fixture(scope="module")
+def pair2k():
+    return synth.make_pair(2000, seed=20250606)
+
+
+def test_nn_matches_brute_force_and_scipy(oracle):
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(0)
+    for n1, nq in [(1, 10), (7, 50), (16, 40), (500, 700), (5000, 3000)]:
+        tgt = rng.normal(0, 1, (n1, 3)).astype(np.float32)
+        qry = rng.normal(0, 1.5, (nq, 3)).astype(np.float32)
+        i1, d1 = oracle.nn(tgt, qry)
+        i2, d2 = oracle.nn(tgt, qry, brute=True)
+        assert np.array_equal(i1, i2) and np.array_equal(d1, d2)
+        dd, ii = cKDTree(tgt.astype(np.float64)).query(qry.astype(np.float64))
+        assert (ii == i1).mean() > 0.999          # float32 vs float64 may differ on near ties
+        assert np.allclose(np.sqrt(d1), dd, rtol=1e-5, atol=1e-7)
+
+
+def test_nn_ties_resolve_to_lowest_index(oracle):
+    tgt = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [1, 0, 0]], np.float32)
+    idx, d2 = oracle.nn(tgt, np.zeros((1, 3), np.float32))
+    assert idx[0] == 0 and d2[0] == 1.0
+    big = np.tile(tgt, (40, 1))                   # duplicates spread over several leaves
+    idx, _ = oracle.nn(big, np.zeros((3, 3), np.float32))
+    assert (idx == 0).all()
+
+
+def test_nn_distance_is_float32_left_to_right(oracle):
+    rng = np.random.default_rng(1)
+    tgt = rng.normal(0, 3, (200, 3)).astype(np.float32)
+    qry = rng.normal(0, 3, (100, 3)).astype(np.float32)
+    idx, d2 = oracle.nn(tgt, qry)
+    d = qry - tgt[idx]
+    expect = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+    assert np.array_equal(d2, expect.astype(np.float32))
+
+
+def test_transform_is_float32_in_order(oracle):
+    rng = np.random.default_rng(2)
+    p = rng.normal(0, 10, (1000, 3)).astype(np.float32)
+    T = synth.rigid_matrix(0.1, -0.2, 0.3, 1, 2, 3).astype(np.float32)
+    out = oracle.transform(p, T)
+    exp = np.empty_like(p)
+    for r in range(3):
+        exp[:, r] = ((T[r, 0] * p[:, 0] + T[r, 1] * p[:, 1]) + T[r, 2] * p[:, 2]) + T[r, 3]
+    assert np.array_equal(out, exp)
+
+
+def test_lls_step_matches_float64_least_squares(oracle, pair2k):
+    d = pair2k
+    idx, _ = oracle.nn(d["ct1"], d["ct2"])
+    ATA, ATb, x, T = oracle.lls_step(d["ct2"], idx, d["ct1"], d["nrm1"])
+    s, q, n = d["ct2"].astype(np.float64), d["ct1"][idx].astype(np.float64), d["nrm1"][idx].astype(np.float64)
+    A = np.concatenate([np.cross(s, n), n], 1)
+    b = ((q - s) * n).sum(1)
+    assert np.allclose(ATA, A.T @ A, rtol=1e-5)
+    xs = np.linalg.lstsq(A, b, rcond=None)[0]
+    assert np.allclose(x, xs, rtol=1e-3, atol=1e-7)
+    assert np.allclose(ATA, ATA.T)
+    assert T.dtype == np.float32 and np.allclose(T[:3, :3] @ T[:3, :3].T, np.eye(3), atol=1e-6)
+
+
+def test_gpu_summation_order_is_equivalent(oracle, pair2k):
+    d = pair2k
+    idx, _ = oracle.nn(d["ct1"], d["ct2"])
+    a = oracle.lls_step(d["ct2"], idx, d["ct1"], d["nrm1"], 0)
+    for g, w in [(1, 8), (7, 8), (63, 8), (444, 8)]:
+        b = oracle.lls_step(d["ct2"], idx, d["ct1"], d["nrm1"], 1, g, w)
+        assert np.allclose(a[0], b[0], rtol=1e-12) and np.allclose(a[2], b[2], rtol=1e-9, atol=1e-15)
+        assert np.abs(a[3] - b[3]).max() <= 6e-8      # one float ulp at most
+
+
+def test_icp_recovers_a_known_rigid_motion(oracle):
+    d = synth.make_pair(2500, changed=0.0, motion=(0.002, -0.001, 0.0015, 0.003, -0.002, 0.001))
+    T = np.eye(4, dtype=np.float32)
+    src = d["ct2"].copy()
+    for _ in range(6):                                # the reference restarts ICP every outer iteration
+        r = oracle.icp(d["ct1"], d["nrm1"], src)
+        src = oracle.transform(src, r["T"])
+        T = oracle.mat4_mul(r["T"], T)
+    err = np.abs(T.astype(np.float64) - d["T_true"]).max()
+    assert err < 2e-4, err
+    assert r["state"] in (2, 3, 4)
+
+
+def test_icp_forced_iterations_and_states(oracle, pair2k):
+    d = pair2k
+    r = oracle.icp(d["ct1"], d["nrm1"], d["ct2"], oracle.icp_params(max_iter=7, force_iters=1), trace=True)
+    assert r["n_iter"] == 7 and r["state"] == 1 and len(r["mse"]) == 7
+    r1 = oracle.icp(d["ct1"], d["nrm1"], d["ct2"], oracle.icp_params(max_iter=1))
+    assert r1["n_iter"] == 1 and r1["state"] == 1
+    # final transform is the ordered product of the incremental ones (final = T * final)
+    F = np.eye(4, dtype=np.float32)
+    for Tk in r["T_trace"]:
+        F = oracle.mat4_mul(Tk, F)
+    assert np.array_equal(F, r["T"])
+
+
+def test_octree_bbox_is_a_padded_cube(oracle):
+    rng = np.random.default_rng(5)
+    for scale in [(10, 4, 1), (0.3, 0.3, 0.3), (50, 2, 7)]:
+        p = (rng.uniform(-1, 1, (3000, 3)) * scale).astype(np.float32)
+        for res in (0.01, 0.25, 2.0):
+            bb = oracle.octree_bbox(p, res)
+            side = bb[3:] - bb[:3]
+            assert np.allclose(side, side[0], rtol=1e-9)
+            k = np.log2(side[0] / res)
+            assert abs(k - round(k)) < 1e-6 and side[0] >= 2 * res - 1e-9
+            assert (p >= bb[:3] - 1e-6).all() and (p <= bb[3:] + 1e-6).all()
+            c = (p.max(0).astype(np.float64) + p.min(0)) / 2
+            assert np.allclose((bb[:3] + bb[3:]) / 2, c, atol=1e-3)
+
+
+def test_percentile_matches_numpy(oracle, pair2k):
+    d = pair2k
+    v = oracle.percentile_nn(d["cloud1"], d["cloud2"], 0.75)
+    _, d2 = oracle.nn(d["cloud1"], d["cloud2"])
+    s = np.sort(np.sqrt(d2).astype(np.float64))
+    assert v == s[int(np.float32(len(s)) * np.float32(0.75))]
+
+
+def test_vcm_matches_numpy(oracle, pair2k):
+    d = pair2k
+    src = d["ct2"][~d["changed"]][:400]
+    V, sing = oracle.vcm(d["ct1"], d["nrm1"], src)
+    idx, _ = oracle.nn(d["ct1"], src)
+    Q, P, N = src.astype(np.float64), d["ct1"][idx].astype(np.float64), d["nrm1"][idx].astype(np.float64)
+    A = np.concatenate([np.cross(Q, N), N], 1)
+    L = (N * (P - Q)).sum(1)
+    Qxx = np.linalg.inv(A.T @ A)
+    X = Qxx @ A.T @ L
+    v = A @ X - L
+    D = (v @ v) / (len(src) - 6) * Qxx
+    assert np.allclose(V, D, rtol=1e-6, atol=0) and not sing
+    assert np.allclose(V, V.T, rtol=1e-9)
+
+
+def test_patch_normal_matches_eigh(oracle):
+    rng = np.random.default_rng(9)
+    for _ in range(50):
+        n = rng.normal(0, 1, 3); n /= np.linalg.norm(n)
+        u = np.cross(n, [1, 0, 0]); u /= np.linalg.norm(u); v = np.cross(n, u)
+        c = rng.uniform(-3, 3, 3)
+        ab = rng.uniform(-0.03, 0.03, (40, 2))
+        pts = (c + ab[:, :1] * u + ab[:, 1:] * v + rng.normal(0, 5e-4, (40, 1)) * n).astype(np.float32)
+        est, ok = oracle.patch_normal(pts)
+        assert ok and abs(np.linalg.norm(est) - 1) < 1e-5
+        w, V = np.linalg.eigh(np.cov(pts.astype(np.float64).T))
+        assert abs(abs(est @ V[:, 0]) - 1) < 2e-3
+    est, ok = oracle.patch_normal(np.zeros((4, 3), np.float32))     # <= 4 points -> (0,0,1), failure
+    assert not ok and np.array_equal(est, [0, 0, 1])
+
+
+def test_matrix2angle_roundtrip(oracle):
+    rng = np.random.default_rng(4)
+    for _ in range(50):
+        a = rng.uniform(-1.2, 1.2, 3)
+        T = synth.rigid_matrix(*a, 0, 0, 0).astype(np.float32)
+        assert np.allclose(oracle.matrix2angle(T), a, atol=2e-6)
+
+
+def test_outer_loop_properties(oracle, pair2k):
+    d = pair2k
+    pd = oracle.PairData(d)
+    res = oracle.piecewise_icp(pd, 1, 0.05)
+    s = res["DTseries"]
+    assert res["rc"] > 0 and len(s) == res["rc"] + 1
+    assert (np.diff(s) <= 0).all()                       # monotonically decreasing DT (:907)
+    assert s[-1] == np.float32(d["DTmin"])               # ends at LoDet_min = DTmin
+    assert np.abs(res["T"].astype(np.float64) - d["T_true"]).max() < 2e-4
+    # changed patches are rejected, unchanged ones kept
+    st = oracle.State(0.004, 0, 0, 1, 0)
+    rc, T, V, flags, stats = oracle.single_iteration(pd, st)
+    assert rc == 0 and flags[d["changed"]].mean() < 0.05 and flags[~d["changed"]].mean() > 0.9
+    assert np.sqrt(np.diag(res["VCM"])).max() < 1e-3
+
+
+def test_outer_loop_error_codes(oracle, pair2k):
+    d = dict(pair2k)
+    few = {k: (v[:3] if k in ("ct2", "bpstd2") else v) for k, v in d.items()}
+    few["bp2"] = d["bp2"][:18]; few["patch_off2"] = d["patch_off2"][:4]
+    rc, *_ = oracle.single_iteration(oracle.PairData(few), oracle.State(0.05, 0, 0, 0, 0))
+    assert rc == -1                                       # < 4 patches (:728-731)
+    far = dict(d); far["ct2"] = d["ct2"] + np.float32(5.0)
+    rc, *_ = oracle.single_iteration(oracle.PairData(far), oracle.State(0.05, 0, 0, 0, 0))
+    assert rc == -2                                       # < 4 stable patches (:864-867)
+
+
+def test_golden_vectors(oracle, gold, pair2k):
+    d = pair2k
+    q = np.concatenate([d["ct2"], d["bp2"]])
+    i, d2 = oracle.nn(d["ct1"], q)
+    assert np.array_equal(i, gold["nn_pair_idx"]) and np.array_equal(d2, gold["nn_pair_d2"])
+    r = oracle.icp(d["ct1"], d["nrm1"], d["ct2"], oracle.icp_params(max_iter=10, force_iters=1), trace=True)
+    assert np.array_equal(r["T_trace"], gold["icp_T_trace"]) and np.array_equal(r["mse"], gold["icp_mse"])
+    res = oracle.piecewise_icp(oracle.PairData(d), 1, 0.05)
+    assert np.array_equal(res["DTseries"], gold["outer_DTseries"])
+    assert np.array_equal(res["T"], gold["outer_T"])
+    assert np.allclose(res["VCM"], gold["outer_VCM"], rtol=1e-12)
+    res2 = oracle.piecewise_icp(oracle.PairData(d), 0, 0.0)
+    assert np.array_equal(res2["DTseries"], gold["outer_auto_DTseries"])
