@@ -117,6 +117,11 @@ int pwicp_icp_source_all(pwicp_ctx* ctx);
  * idx_trace[max_iter*n] (int, correspondence indices of every inner iteration). */
 int pwicp_icp_run(pwicp_ctx* ctx, const pwicp_icp_params* prm, float* T16, pwicp_icp_result* res,
                   double* mse_trace, float* T_trace, int* idx_trace);
+/* Processing order of the last pwicp_icp_run: perm[k] = index (in the uploaded source set) of the
+ * k-th point in the order the device accumulated the normal equations (source points are sorted
+ * by the target-grid cell they start in).  Only the order of the double sums depends on it; the
+ * bit-exact parity test feeds the oracle the same order.  perm holds n_source ints. */
+int pwicp_icp_order(pwicp_ctx* ctx, int* perm);
 /* Host-buffer convenience with the call shape of P2PICPwithPatchNormal(target, source, eps):
  * uploads both clouds, builds the grid, runs the loop (this is the path `e2e` times). */
 int pwicp_icp_p2plane(pwicp_ctx* ctx, const float* tgt_xyz, const float* tgt_nrm, int n1,

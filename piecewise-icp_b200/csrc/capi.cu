@@ -125,7 +125,7 @@ void pwicp_ctx_destroy(pwicp_ctx* p) {
     c->tgt.release(); c->c1.release();
     DevBuf* bufs[] = {&c->tgt_aux, &c->tgt_ok, &c->ct2, &c->bp2, &c->bpstd2, &c->patch_xyz, &c->patch_id,
                       &c->patch_off, &c->cloud2, &c->icp_src, &c->icp_work, &c->icp_partials, &c->icp_out,
-                      &c->icp_idx, &c->tgt_xyz, &c->tgt_nrm_raw, &c->tgt_std_raw, &c->tgt_ok_raw, &c->keys, &c->vals, &c->keys2, &c->vals2, &c->cub_tmp, &c->scratch_a,
+                      &c->icp_idx, &c->icp_sorted, &c->icp_perm, &c->icp_seed, &c->icp_match, &c->ct_seed, &c->bp_seed, &c->pp_seed, &c->ct_order, &c->tgt_xyz, &c->tgt_nrm_raw, &c->tgt_std_raw, &c->tgt_ok_raw, &c->keys, &c->vals, &c->keys2, &c->vals2, &c->cub_tmp, &c->scratch_a,
                       &c->scratch_b, &c->scratch_c, &c->scratch_d, &c->flags, &c->pos, &c->l2flush};
     for (DevBuf* b : bufs) b->release();
     if (c->pinned) cudaFreeHost(c->pinned);
@@ -170,8 +170,25 @@ void pwicp_icp_default_params(pwicp_icp_params* p) {
 }
 
 // ---- uploads -------------------------------------------------------------------------------
+static int reset_seeds(Ctx* ctx) {
+    ctx->icp_seed_valid = false;
+    ctx->ct_order_valid = false;
+    if (ctx->n2 > 0) {
+        PW_TRY(ctx->ct_seed.reserve(ctx, (size_t)ctx->n2 * 4));
+        PW_TRY(ctx->bp_seed.reserve(ctx, (size_t)ctx->n2 * 24));
+        PW_CUDA(cudaMemsetAsync(ctx->ct_seed.p, 0xff, (size_t)ctx->n2 * 4, ctx->stream));
+        PW_CUDA(cudaMemsetAsync(ctx->bp_seed.p, 0xff, (size_t)ctx->n2 * 24, ctx->stream));
+    }
+    if (ctx->mp2 > 0) {
+        PW_TRY(ctx->pp_seed.reserve(ctx, (size_t)ctx->mp2 * 4));
+        PW_CUDA(cudaMemsetAsync(ctx->pp_seed.p, 0xff, (size_t)ctx->mp2 * 4, ctx->stream));
+    }
+    return PWICP_OK;
+}
+
 static int target_build_resident(Ctx* ctx, int n1) {
     PW_TRY(grid_build(ctx, ctx->tgt, ctx->tgt_xyz.as<float>(), n1));
+    PW_TRY(reset_seeds(ctx));
     // normals / sigma / ok flags into level-0 order
     PW_TRY(ctx->tgt_aux.reserve(ctx, (size_t)n1 * sizeof(float4)));
     PW_TRY(ctx->tgt_ok.reserve(ctx, (size_t)n1));
@@ -258,8 +275,9 @@ int pwicp_source_upload(pwicp_ctx* p, const float* ct_xyz, const float* bp_xyz, 
         patch_id_kernel<<<(mp + 255) / 256, 256, 0, ctx->stream>>>(ctx->patch_off.as<int>(), n2, mp, ctx->patch_id.as<int>());
         ctx->launches++;
     }
-    PW_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->n2 = n2;
+    PW_TRY(reset_seeds(ctx));
+    PW_CUDA(cudaStreamSynchronize(ctx->stream));
     return PWICP_OK;
 }
 
@@ -270,6 +288,7 @@ int pwicp_clouds_upload(pwicp_ctx* p, const float* cloud1, int m1, const float* 
     ctx->m1 = ctx->m2 = 0;
     PW_TRY(upload_checked(ctx, ctx->scratch_a, cloud1, (size_t)3 * m1, "cloud1"));
     PW_TRY(grid_build(ctx, ctx->c1, ctx->scratch_a.as<float>(), m1));
+    PW_TRY(reset_seeds(ctx));
     PW_TRY(upload_checked(ctx, ctx->cloud2, cloud2, (size_t)3 * m2, "cloud2"));
     ctx->m1 = m1; ctx->m2 = m2;
     return PWICP_OK;
@@ -327,6 +346,7 @@ int pwicp_icp_source_upload(pwicp_ctx* p, const float* src, int n) {
     if (!ctx || n < 1 || !src) { set_error(ctx, "icp_source_upload: bad arguments"); return PWICP_ERR_ARG; }
     PW_CUDA(cudaSetDevice(ctx->device));
     PW_TRY(upload_checked(ctx, ctx->scratch_a, src, (size_t)3 * n, "icp source"));
+    ctx->icp_seed_valid = false;
     PW_TRY(icp_expand_source(ctx, ctx->scratch_a.as<float>(), n));
     PW_CUDA(cudaStreamSynchronize(ctx->stream));
     return PWICP_OK;
@@ -339,6 +359,7 @@ int pwicp_icp_source_all(pwicp_ctx* p) {
     PW_TRY(ctx->icp_src.reserve(ctx, (size_t)ctx->n2 * sizeof(float4)));
     PW_CUDA(cudaMemcpyAsync(ctx->icp_src.p, ctx->ct2.p, (size_t)ctx->n2 * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
     ctx->n_icp = ctx->n2;
+    ctx->icp_seed_valid = false;
     PW_CUDA(cudaStreamSynchronize(ctx->stream));
     return PWICP_OK;
 }
@@ -350,6 +371,14 @@ int pwicp_icp_run(pwicp_ctx* p, const pwicp_icp_params* prm, float* T16, pwicp_i
     PW_CUDA(cudaSetDevice(ctx->device));
     pwicp_icp_params d; pwicp_icp_default_params(&d);
     return icp_run_device(ctx, prm ? *prm : d, T16, res, mse_trace, T_trace, idx_trace);
+}
+
+int pwicp_icp_order(pwicp_ctx* p, int* perm) {
+    Ctx* ctx = reinterpret_cast<Ctx*>(p);
+    if (!ctx || !perm || ctx->n_icp < 1 || !ctx->icp_perm.p) { set_error(ctx, "icp_order: no inner loop has run"); return PWICP_ERR_ARG; }
+    PW_CUDA(cudaSetDevice(ctx->device));
+    PW_CUDA(cudaMemcpy(perm, ctx->icp_perm.p, (size_t)ctx->n_icp * 4, cudaMemcpyDeviceToHost));
+    return PWICP_OK;
 }
 
 int pwicp_icp_p2plane(pwicp_ctx* p, const float* tgt_xyz, const float* tgt_nrm, int n1, const float* src_xyz,
@@ -381,7 +410,7 @@ int pwicp_piecewise_icp(pwicp_ctx* p, const pwicp_pair_params* pp, int is_manual
     if (!is_manual) {
         if (!ctx->c1.dev.nlevels || ctx->m2 < 1) { set_error(ctx, "piecewise_icp: clouds not uploaded"); return PWICP_ERR_ARG; }
         double Dist75 = 0;
-        PW_TRY(percentile_dev(ctx, ctx->c1.dev, ctx->cloud2.as<float>(), ctx->m2, nullptr, nullptr, ctx->m2, 0.75f, &Dist75));
+        PW_TRY(percentile_dev(ctx, ctx->c1.dev, ctx->cloud2.as<float>(), ctx->m2, nullptr, nullptr, ctx->m2, 0.75f, &Dist75, nullptr));
         DTinit = Dist75 * 3.0;                                              // :627-630
     }
     st.currDT = DTinit; st.BBchange_1 = 0.f; st.BBchange_2 = 0.f;
@@ -420,7 +449,7 @@ int pwicp_percentile_nn(pwicp_ctx* p, const float* cloud1, int m1, const float* 
     PW_TRY(upload_checked(ctx, ctx->scratch_a, cloud1, (size_t)3 * m1, "cloud1"));
     int rc = grid_build(ctx, g, ctx->scratch_a.as<float>(), m1);
     if (rc == PWICP_OK) rc = upload_checked(ctx, ctx->scratch_c, cloud2, (size_t)3 * m2, "cloud2");
-    if (rc == PWICP_OK) rc = percentile_dev(ctx, g.dev, ctx->scratch_c.as<float>(), m2, nullptr, nullptr, m2, pct, out);
+    if (rc == PWICP_OK) rc = percentile_dev(ctx, g.dev, ctx->scratch_c.as<float>(), m2, nullptr, nullptr, m2, pct, out, nullptr);
     g.release();
     return rc;
 }
@@ -462,7 +491,7 @@ int pwicp_vcm(pwicp_ctx* p, const float* src, int n, double* vcm36, int* singula
     PW_TRY(ctx->scratch_b.reserve(ctx, (size_t)n * sizeof(float4)));
     expand_f4_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->scratch_a.as<float>(), n, ctx->scratch_b.as<float4>());
     ctx->launches++;
-    return vcm_dev(ctx, ctx->scratch_b.as<float4>(), n, vcm36, singular);
+    return vcm_dev(ctx, ctx->scratch_b.as<float4>(), n, vcm36, singular, nullptr);
 }
 
 int pwicp_transform(pwicp_ctx* p, float* xyz, int n, const float* T16) {

@@ -96,7 +96,12 @@ struct Ctx {
     DevBuf ct2, bp2, bpstd2, patch_xyz, patch_id, patch_off, cloud2;
     int n2 = 0, m2 = 0, mp2 = 0;
     // inner loop
-    DevBuf icp_src, icp_work, icp_partials, icp_out, icp_idx;
+    DevBuf icp_src, icp_sorted, icp_perm, icp_work, icp_partials, icp_out, icp_idx;
+    DevBuf icp_seed, icp_match;   // seeds in icp_src order / matches in processing order
+    bool icp_seed_valid = false;
+    // temporal-coherence seeds of the outer iteration (level-0 positions, -1 = none)
+    DevBuf ct_seed, bp_seed, pp_seed, ct_order;
+    bool ct_order_valid = false;
     int n_icp = 0;
     // scratch
     DevBuf keys, vals, keys2, vals2, cub_tmp, scratch_a, scratch_b, scratch_c, scratch_d, flags, pos;
@@ -122,10 +127,10 @@ int outer_single_iteration(Ctx* ctx, const pwicp_pair_params& pp, pwicp_state* s
                            unsigned char* stable_flags, pwicp_iter_stats* stats);
 int percentile_dev(Ctx* ctx, const GridDev& g, const float* q_packed_dev, int nq,
                    const int* patch_id_dev, const int* flags_dev, long long n_valid,
-                   float pct, double* out);
+                   float pct, double* out, int* seeds_dev);
 float bbox_corner_change_host(const double* bb6, const float* T16);
 int icp_expand_source(Ctx* ctx, const float* packed_dev, int n);
-int vcm_dev(Ctx* ctx, const float4* src_dev, int n, double* vcm36, int* singular);
+int vcm_dev(Ctx* ctx, const float4* src_dev, int n, double* vcm36, int* singular, int* seeds_dev);
 int transform_packed_dev(Ctx* ctx, float* xyz_dev, size_t n, const float* T16);
 int bbox_packed_dev(Ctx* ctx, const float* xyz_dev, size_t n, float* mn3, float* mx3);
 void octree_cube(const float* mn, const float* mx, double res, double* bb6);

@@ -271,18 +271,22 @@ int grid_build(Ctx* ctx, GridOwner& g, const float* xyz, int n) {
 // ---- batched query -------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 nn_kernel(GridDev g, const float* __restrict__ q, int nq, int* __restrict__ idx, float* __restrict__ d2) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nq) return;
-    float px = q[3 * (size_t)i], py = q[3 * (size_t)i + 1], pz = q[3 * (size_t)i + 2];
-    Best b = nn_search(g, px, py, pz);
-    if (idx) idx[i] = b.idx;
-    if (d2) d2[i] = b.d2;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < nq;
+    float px = 0.f, py = 0.f, pz = 0.f;
+    if (active) { px = q[3 * (size_t)i]; py = q[3 * (size_t)i + 1]; pz = q[3 * (size_t)i + 2]; }
+    if (active) {
+        const Best b = nn_search_seeded(g, px, py, pz, -1);
+        if (idx) idx[i] = b.idx;
+        if (d2) d2[i] = b.d2;
+    }
 }
 
 int nn_query_packed(Ctx* ctx, const GridDev& g, const float* q_dev, int nq, int* idx_dev, float* d2_dev) {
     if (nq <= 0) return PWICP_OK;
+    const size_t smem = 0;
     int blocks = (nq + 255) / 256;
-    nn_kernel<<<blocks, 256, 0, ctx->stream>>>(g, q_dev, nq, idx_dev, d2_dev);
+    nn_kernel<<<blocks, 256, smem, ctx->stream>>>(g, q_dev, nq, idx_dev, d2_dev);
     ctx->launches++;
     PW_CUDA(cudaGetLastError());
     return PWICP_OK;

@@ -18,6 +18,8 @@
 #include <cooperative_groups.h>
 
 #include "common.cuh"
+#include <cub/cub.cuh>
+
 #include "nn_search.cuh"
 #include "small_algebra.cuh"
 
@@ -30,6 +32,8 @@ struct IcpArgs {
     const float4* aux;        // level-0 order: nx, ny, nz, ctstd
     const float4* src;        // source set (read only)
     float4* work;             // transformed copy, updated in place every iteration
+    int* match;               // per source point: level-0 position of its last match (seed of the next search)
+    int use_seed0;            // match[] already holds seeds for the first iteration
     int n;
     int max_iter;
     int force_iters;
@@ -117,16 +121,23 @@ __global__ void __launch_bounds__(kIcpThreads, 3) icp_persistent_kernel(const Ic
 
         for (long b = gw; b < nb; b += NW) {
             const long i = b * 32 + lane;
+            const bool active = i < a.n;
             float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
-            if (i < a.n) {
-                float4 p = (it == 0) ? __ldg(a.src + i) : a.work[i];
+            float4 p = lo;
+            if (active) {
+                p = (it == 0) ? __ldg(a.src + i) : a.work[i];
                 if (it > 0) {
                     float x, y, z;
                     xform_point(T, p.x, p.y, p.z, x, y, z);
                     p.x = x; p.y = y; p.z = z;
                 }
                 a.work[i] = p;
-                Best bb = nn_search(a.g, p.x, p.y, p.z);
+            }
+            int seed = -1;
+            if (active && (it > 0 || a.use_seed0)) seed = a.match[i];
+            if (active) {
+                const Best bb = nn_search_seeded<true>(a.g, p.x, p.y, p.z, seed);
+                a.match[i] = bb.pos;
                 const float4 nq = __ldg(a.aux + bb.pos);
                 const float sx = p.x, sy = p.y, sz = p.z;
                 const float dx = bb.qx, dy = bb.qy, dz = bb.qz;
@@ -140,7 +151,8 @@ __global__ void __launch_bounds__(kIcpThreads, 3) icp_persistent_kernel(const Ic
                 hi.y = nz;
                 hi.z = nx * dx + ny * dy + nz * dz - nx * sx - ny * sy - nz * sz;
                 hi.w = bb.d2;
-                if (a.idx_trace) a.idx_trace[(size_t)it * a.n + i] = bb.idx;
+                // traces are reported in the caller's order (p.w = original source index)
+                if (a.idx_trace) a.idx_trace[(size_t)it * a.n + __float_as_int(p.w)] = bb.idx;
             }
             float4* row = reinterpret_cast<float4*>(&s_rows[warp][lane][0]);
             row[0] = lo; row[1] = hi;
@@ -195,6 +207,75 @@ int icp_expand_source(Ctx* ctx, const float* packed_dev, int n) {
     return PWICP_OK;
 }
 
+// key = Morton code of the finest-level cell of the source point (same cell expression as the
+// grid build), so that consecutive points of the sorted order sit in a compact 3-D neighbourhood
+__device__ __forceinline__ unsigned long long spread21(unsigned int v) {
+    unsigned long long x = v & 0x1fffffu;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+
+__global__ void src_key_kernel(const float4* __restrict__ src, int n, float ox, float oy, float oz, float inv_h,
+                               int dx, int dy, int dz, unsigned long long* keys, uint32_t* vals) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = src[i];
+    float fx = (p.x - ox) * inv_h, fy = (p.y - oy) * inv_h, fz = (p.z - oz) * inv_h;
+    int cx = min(max((int)floorf(fx), 0), dx - 1);
+    int cy = min(max((int)floorf(fy), 0), dy - 1);
+    int cz = min(max((int)floorf(fz), 0), dz - 1);
+    keys[i] = spread21(cx) | (spread21(cy) << 1) | (spread21(cz) << 2);
+    vals[i] = (uint32_t)i;
+}
+
+__global__ void src_gather_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ order, int n, float4* out,
+                                  const int* __restrict__ seed_in, int* __restrict__ seed_out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t o = order[i];
+    float4 p = src[o];
+    p.w = __int_as_float((int)o);
+    out[i] = p;
+    if (seed_in) seed_out[i] = seed_in[o];
+}
+
+// Sorts the source set by the target-grid cell it starts in (stable: ties keep the caller's
+// order), so that the 8 queries of a tile group share a small candidate block.  The processing
+// order only affects the order of the double sums (DESIGN.md "reduction geometry").
+static int icp_sort_source(Ctx* ctx, int n, bool have_seed) {
+    const GridLevel& L = ctx->tgt.dev.lv[0];
+    PW_TRY(ctx->keys.reserve(ctx, (size_t)n * 8));
+    PW_TRY(ctx->vals.reserve(ctx, (size_t)n * 4));
+    PW_TRY(ctx->keys2.reserve(ctx, (size_t)n * 8));
+    PW_TRY(ctx->icp_perm.reserve(ctx, (size_t)n * 4));
+    PW_TRY(ctx->icp_sorted.reserve(ctx, (size_t)n * sizeof(float4)));
+    PW_TRY(ctx->icp_match.reserve(ctx, (size_t)n * sizeof(int)));
+    const int blocks = (n + 255) / 256;
+    src_key_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->icp_src.as<float4>(), n, ctx->tgt.dev.ox, ctx->tgt.dev.oy,
+                                                    ctx->tgt.dev.oz, L.inv_h, L.dx, L.dy, L.dz,
+                                                    ctx->keys.as<unsigned long long>(), ctx->vals.as<uint32_t>());
+    int maxd = std::max(L.dx, std::max(L.dy, L.dz));
+    int b1 = 1; while ((1 << b1) < maxd && b1 < 21) ++b1;
+    const int bits = 3 * b1;
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, ctx->keys.as<unsigned long long>(), ctx->keys2.as<unsigned long long>(),
+                                    ctx->vals.as<uint32_t>(), ctx->icp_perm.as<uint32_t>(), n, 0, bits, ctx->stream);
+    PW_TRY(ctx->cub_tmp.reserve(ctx, tmp));
+    size_t cap = ctx->cub_tmp.cap;
+    PW_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, cap, ctx->keys.as<unsigned long long>(), ctx->keys2.as<unsigned long long>(),
+                                            ctx->vals.as<uint32_t>(), ctx->icp_perm.as<uint32_t>(), n, 0, bits, ctx->stream));
+    src_gather_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->icp_src.as<float4>(), ctx->icp_perm.as<uint32_t>(), n,
+                                                       ctx->icp_sorted.as<float4>(),
+                                                       have_seed ? ctx->icp_seed.as<int>() : nullptr, ctx->icp_match.as<int>());
+    ctx->launches += 5;
+    PW_CUDA(cudaGetLastError());
+    return PWICP_OK;
+}
+
 int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_result* res,
                    double* mse_trace, float* T_trace, int* idx_trace) {
     const int n = ctx->n_icp;
@@ -202,8 +283,9 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     if (n < 3) { set_error(ctx, "icp: fewer than 3 correspondences"); return PWICP_ERR_TOO_FEW_CORR; }
     if (prm.max_iter < 1 || prm.max_iter > kMaxIcpIter) { set_error(ctx, "icp: max_iter out of range"); return PWICP_ERR_ARG; }
 
+    const size_t smem = 0;
     int occ = 0;
-    PW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, icp_persistent_kernel, kIcpThreads, 0));
+    PW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, icp_persistent_kernel, kIcpThreads, smem));
     if (occ < 1) { set_error(ctx, "icp: kernel does not fit on an SM"); return PWICP_ERR_CUDA; }
     const long nb = ((long)n + 31) / 32;
     long want = (nb + kIcpWarps - 1) / kIcpWarps;
@@ -217,11 +299,18 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     PW_CUDA(cudaMemsetAsync(ob, 0, out_bytes, ctx->stream));
     if (idx_trace) PW_TRY(ctx->icp_idx.reserve(ctx, (size_t)prm.max_iter * n * sizeof(int)));
 
+    PW_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    const bool have_seed = ctx->icp_seed_valid && ctx->icp_seed.p != nullptr;
+    PW_TRY(icp_sort_source(ctx, n, have_seed));
+    ctx->icp_seed_valid = false;                       // seeds belong to one source set
+
     IcpArgs a;
     a.g = ctx->tgt.dev;
     a.aux = ctx->tgt_aux.as<float4>();
-    a.src = ctx->icp_src.as<float4>();
+    a.src = ctx->icp_sorted.as<float4>();
     a.work = ctx->icp_work.as<float4>();
+    a.match = ctx->icp_match.as<int>();
+    a.use_seed0 = have_seed ? 1 : 0;
     a.n = n;
     a.max_iter = prm.max_iter;
     a.force_iters = prm.force_iters;
@@ -237,8 +326,7 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     a.idx_trace = idx_trace ? ctx->icp_idx.as<int>() : nullptr;
 
     void* kargs[] = {(void*)&a};
-    PW_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-    PW_CUDA(cudaLaunchCooperativeKernel((void*)icp_persistent_kernel, dim3(grid), dim3(kIcpThreads), kargs, 0, ctx->stream));
+    PW_CUDA(cudaLaunchCooperativeKernel((void*)icp_persistent_kernel, dim3(grid), dim3(kIcpThreads), kargs, smem, ctx->stream));
     ctx->launches++;
     PW_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
 

@@ -1,44 +1,46 @@
-// nn_search.cuh -- exact 1-NN over the cell-sorted grid pyramid (device code).
+// nn_search.cuh -- exact 1-NN over the cell-sorted grid pyramid: "seed + ball" search (device code).
 //
 // Replaces pcl::KdTreeFLANN<PointXYZ, flann::L2_Simple<float>>::nearestKSearch(p, 1) as reached
 // from pcl::registration::CorrespondenceEstimation::determineCorrespondences
 // (reference call sites: src/Registration.cpp:737-747, :1293-1297, :597-601,
 // src/CommonFunc.cpp:269-273 and the inner loop of src/Registration.cpp:1266).
 //
+// Idea: any target point s gives an upper bound d(p, s) of the NN distance, so the exact answer
+// lies in the cells the closed ball B(p, d) touches.  ICP is temporally coherent -- the match of
+// the previous iteration is almost always still (nearly) the nearest -- so with that match as the
+// seed the ball covers one to three cells and every lane of a warp does the same small amount of
+// work.  Without a seed the best point of the query's home cell (or of the first non-empty home
+// cell on a coarser level) is taken.  When the ball spans many fine cells the scan runs on the
+// pyramid level whose cells are about as large as the ball.
+//
 // Parity rules:
 //   * distance = ((dx*dx) + dy*dy) + dz*dz in float32 with separately rounded operations
 //     (__fmul_rn/__fadd_rn never contract into FMA);
-//   * the search is exact: a cell is skipped only when a conservative lower bound of the
-//     distance to anything inside it exceeds the current best;
+//   * exact: the scanned box covers the ball with a conservative margin for the float rounding of
+//     the cell assignment; a row is skipped only when its lower bound exceeds the current best;
 //   * exact float ties resolve to the lowest original target index.
+//
+// History (profiles/r01a-c): a ring search with per-lane pruning was exact but ran 8 of 32 lanes;
+// warp-cooperative group tiles (TMA-staged or read through L1) lost to load imbalance at the grid
+// barrier.  The seeded ball is both simpler and faster.
 #pragma once
 #include "common.cuh"
 
 namespace pwicp {
 
+constexpr float kBallMaxCells = 6.0f;   // scan on the finest level whose ball radius is <= this many cells
+                                        // (finer is cheaper unless the ball is mostly empty space: rows ~ (2r+1)^2)
+
 struct Best {
-    float d2;      // best squared distance so far (float, reference arithmetic)
+    float d2;      // squared distance of the match (float, reference arithmetic)
     int idx;       // original target index
-    int pos;       // position in the level-0 sorted array, -1 when found on a coarser level
+    int pos;       // position in the level-0 sorted array
     float qx, qy, qz;  // the matched target point (bit-identical to the caller's array)
 };
 
 __device__ __forceinline__ float l2_simple(float px, float py, float pz, float qx, float qy, float qz) {
     float dx = __fsub_rn(px, qx), dy = __fsub_rn(py, qy), dz = __fsub_rn(pz, qz);
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-}
-
-__device__ __forceinline__ void scan_range(const float4* __restrict__ pts, uint32_t s, uint32_t e,
-                                           float px, float py, float pz, bool level0, Best& b) {
-    for (uint32_t i = s; i < e; ++i) {
-        float4 q = __ldg(pts + i);
-        float d = l2_simple(px, py, pz, q.x, q.y, q.z);
-        int id = __float_as_int(q.w);
-        if (d < b.d2 || (d == b.d2 && id < b.idx)) {
-            b.d2 = d; b.idx = id; b.pos = level0 ? (int)i : -1;
-            b.qx = q.x; b.qy = q.y; b.qz = q.z;
-        }
-    }
 }
 
 // lower bound (in cell units) of |p - q| along one axis for any q stored in cell k.
@@ -50,80 +52,182 @@ __device__ __forceinline__ float axis_gap(float f, int k, float m) {
     return fmaxf(g, 0.0f);
 }
 
-// Searches rings 0..rmax (Chebyshev distance in cells around the home cell) of one level.
-// Returns true when the result is proven exact.
-__device__ __forceinline__ bool search_level(const GridLevel& L, float ox, float oy, float oz,
-                                             float px, float py, float pz, int rmax, bool level0,
-                                             Best& b) {
-    const float fx = (px - ox) * L.inv_h, fy = (py - oy) * L.inv_h, fz = (pz - oz) * L.inv_h;
-    const int cx = min(max((int)floorf(fx), 0), L.dx - 1);
-    const int cy = min(max((int)floorf(fy), 0), L.dy - 1);
-    const int cz = min(max((int)floorf(fz), 0), L.dz - 1);
-    const float mx = 0.01f + fabsf(fx) * 4e-6f, my = 0.01f + fabsf(fy) * 4e-6f,
-                mz = 0.01f + fabsf(fz) * 4e-6f;
-    const uint32_t* __restrict__ cs = L.cell_start;
+// One cell row (ky, kz) of the ball: chord test against the CURRENT best, then a range scan.
+__device__ __forceinline__ void ball_row(const GridLevel& L, int ky, int kz, float fx, float fy, float fz,
+                                         float mx, float my, float mz, int lx, int hx,
+                                         float px, float py, float pz, bool level0,
+                                         float& bd, int& bi, int& bpos) {
+    const float gy = axis_gap(fy, ky, my), gz = axis_gap(fz, kz, mz);
+    const float gyz = gy * gy + gz * gz, bc = bd * L.inv_h2;
+    if (gyz > bc) return;                                        // row entirely outside the ball
+    const float w = sqrtf(bc - gyz) * 1.00001f;                  // half chord of the ball along x
+    const int lxr = max(lx, (int)floorf(fx - w - mx)), hxr = min(hx, (int)floorf(fx + w + mx));
+    if (lxr > hxr) return;
+    const uint32_t row = ((uint32_t)kz * (uint32_t)L.dy + (uint32_t)ky) * (uint32_t)L.dx;
+    const uint32_t s = __ldg(L.cell_start + row + lxr), e = __ldg(L.cell_start + row + hxr + 1);
+    const float4* __restrict__ pts = L.pts;
+    for (uint32_t i = s; i < e; ++i) {
+        const float4 q = __ldg(pts + i);
+        const float d = l2_simple(px, py, pz, q.x, q.y, q.z);
+        const int id = __float_as_int(q.w);
+        if (d < bd || (d == bd && id < bi)) { bd = d; bi = id; bpos = level0 ? (int)i : -1; }
+    }
+}
 
-    for (int r = 0; r <= rmax; ++r) {
-        const int z0 = max(cz - r, 0), z1 = min(cz + r, L.dz - 1);
-        const int y0 = max(cy - r, 0), y1 = min(cy + r, L.dy - 1);
-        const int x0 = max(cx - r, 0), x1 = min(cx + r, L.dx - 1);
+// Large balls (more than 3x3 rows): rows nearest-first, as square rings in y/z around the home
+// row.  As soon as a closer target is met the ball shrinks and the remaining rings fall outside
+// it, so a query far from the surface does not pay for the whole initial ball.  Out of line: this
+// is the rare path and must not cost the common one registers.
+__device__ __forceinline__ void ball_scan_rings(const GridLevel& L, float fx, float fy, float fz,
+                                                    float mx, float my, float mz,
+                                                    int lx, int hx, int ly, int hy, int lz, int hz,
+                                                    float px, float py, float pz, bool level0,
+                                                    float& bd, int& bi, int& bpos) {
+    const int cy = min(max((int)floorf(fy), ly), hy), cz = min(max((int)floorf(fz), lz), hz);
+    const int R = max(max(cy - ly, hy - cy), max(cz - lz, hz - cz));
+    ball_row(L, cy, cz, fx, fy, fz, mx, my, mz, lx, hx, px, py, pz, level0, bd, bi, bpos);
+    for (int t = 1; t <= R; ++t) {
+        // every row of ring t (and of all later rings) is at least this far away in y or z
+        const float g = fminf(fminf(axis_gap(fy, cy - t, my), axis_gap(fy, cy + t, my)),
+                              fminf(axis_gap(fz, cz - t, mz), axis_gap(fz, cz + t, mz)));
+        if (g * g > bd * L.inv_h2) break;
+        const int z0 = max(cz - t, lz), z1 = min(cz + t, hz), y0 = max(cy - t, ly), y1 = min(cy + t, hy);
         for (int kz = z0; kz <= z1; ++kz) {
-            const float gz = axis_gap(fz, kz, mz);
-            const bool zshell = (kz - cz == r) || (cz - kz == r);
+            const bool full = (kz == cz - t || kz == cz + t);
             for (int ky = y0; ky <= y1; ++ky) {
-                const float gy = axis_gap(fy, ky, my);
-                const float gyz = gy * gy + gz * gz;
-                float bc = b.d2 * L.inv_h2;          // best in cell units^2
-                if (gyz > bc) continue;
-                const uint32_t row = ((uint32_t)kz * (uint32_t)L.dy + (uint32_t)ky) * (uint32_t)L.dx;
-                const bool shell_row = zshell || (ky - cy == r) || (cy - ky == r);
-                if (shell_row) {
-                    int xl = x0, xh = x1;
-                    while (xl <= xh) { float g = axis_gap(fx, xl, mx); if (g * g + gyz > bc) ++xl; else break; }
-                    while (xh >= xl) { float g = axis_gap(fx, xh, mx); if (g * g + gyz > bc) --xh; else break; }
-                    if (xl <= xh) scan_range(L.pts, __ldg(cs + row + xl), __ldg(cs + row + xh + 1), px, py, pz, level0, b);
-                } else {
-                    // interior row of the shell: only the two end cells are new
-                    if (cx - r >= 0) {
-                        float g = axis_gap(fx, cx - r, mx);
-                        if (g * g + gyz <= bc)
-                            scan_range(L.pts, __ldg(cs + row + cx - r), __ldg(cs + row + cx - r + 1), px, py, pz, level0, b);
-                    }
-                    if (cx + r <= L.dx - 1) {
-                        bc = b.d2 * L.inv_h2;
-                        float g = axis_gap(fx, cx + r, mx);
-                        if (g * g + gyz <= bc)
-                            scan_range(L.pts, __ldg(cs + row + cx + r), __ldg(cs + row + cx + r + 1), px, py, pz, level0, b);
-                    }
-                }
+                if (!full && ky != cy - t && ky != cy + t) continue;
+                ball_row(L, ky, kz, fx, fy, fz, mx, my, mz, lx, hx, px, py, pz, level0, bd, bi, bpos);
             }
         }
-        // exactness test: everything not yet visited lies outside the block of radius r
-        float bound = 3.0e38f;
-        bool any = false;
-        if (cx - r - 1 >= 0)    { bound = fminf(bound, axis_gap(fx, cx - r - 1, mx)); any = true; }
-        if (cx + r + 1 < L.dx)  { bound = fminf(bound, axis_gap(fx, cx + r + 1, mx)); any = true; }
-        if (cy - r - 1 >= 0)    { bound = fminf(bound, axis_gap(fy, cy - r - 1, my)); any = true; }
-        if (cy + r + 1 < L.dy)  { bound = fminf(bound, axis_gap(fy, cy + r + 1, my)); any = true; }
-        if (cz - r - 1 >= 0)    { bound = fminf(bound, axis_gap(fz, cz - r - 1, mz)); any = true; }
-        if (cz + r + 1 < L.dz)  { bound = fminf(bound, axis_gap(fz, cz + r + 1, mz)); any = true; }
-        if (!any) return true;                        // the whole level has been covered
-        if (b.d2 * L.inv_h2 < bound * bound) return true;
     }
-    return false;
+}
+
+static __device__ __noinline__ void ball_scan_rings_ool(const GridLevel& L, float fx, float fy, float fz,
+                                                        float mx, float my, float mz,
+                                                        int lx, int hx, int ly, int hy, int lz, int hz,
+                                                        float px, float py, float pz, bool level0,
+                                                        float& bd, int& bi, int& bpos) {
+    ball_scan_rings(L, fx, fy, fz, mx, my, mz, lx, hx, ly, hy, lz, hz, px, py, pz, level0, bd, bi, bpos);
+}
+
+// Scans every cell of level L that the closed ball of radius sqrt(bd) around p touches.
+// bd / bi / bpos are updated in place (bpos only on level 0, else -1 on improvement).
+// kLean: the caller is register-bound (persistent ICP kernel); the rare large-ball path goes
+// through an out-of-line copy.
+template <bool kLean>
+__device__ __forceinline__ void ball_scan(const GridLevel& L, float ox, float oy, float oz,
+                                          float px, float py, float pz, bool level0,
+                                          float& bd, int& bi, int& bpos) {
+    const float fx = (px - ox) * L.inv_h, fy = (py - oy) * L.inv_h, fz = (pz - oz) * L.inv_h;
+    const float mx = 0.01f + fabsf(fx) * 4e-6f, my = 0.01f + fabsf(fy) * 4e-6f, mz = 0.01f + fabsf(fz) * 4e-6f;
+    // radius in cell units, rounded up generously (float sqrt/mul errors are ~1e-7 relative)
+    const float r = sqrtf(bd) * L.inv_h * 1.00001f;
+    const int lx = min(max((int)floorf(fx - r - mx), 0), L.dx - 1), hx = min(max((int)floorf(fx + r + mx), 0), L.dx - 1);
+    const int ly = min(max((int)floorf(fy - r - my), 0), L.dy - 1), hy = min(max((int)floorf(fy + r + my), 0), L.dy - 1);
+    const int lz = min(max((int)floorf(fz - r - mz), 0), L.dz - 1), hz = min(max((int)floorf(fz + r + mz), 0), L.dz - 1);
+    if (hy - ly <= 2 && hz - lz <= 2) {
+        // the common case (seeded ICP iteration): one to nine rows, plain nested loops
+        for (int kz = lz; kz <= hz; ++kz)
+            for (int ky = ly; ky <= hy; ++ky)
+                ball_row(L, ky, kz, fx, fy, fz, mx, my, mz, lx, hx, px, py, pz, level0, bd, bi, bpos);
+    } else if (kLean) {
+        ball_scan_rings_ool(L, fx, fy, fz, mx, my, mz, lx, hx, ly, hy, lz, hz, px, py, pz, level0, bd, bi, bpos);
+    } else {
+        ball_scan_rings(L, fx, fy, fz, mx, my, mz, lx, hx, ly, hy, lz, hz, px, py, pz, level0, bd, bi, bpos);
+    }
+}
+
+// Best of (a sample of) the points in [s, e): candidate seed.
+__device__ __forceinline__ void seed_range(const float4* __restrict__ pts, uint32_t s, uint32_t e, uint32_t step,
+                                           float px, float py, float pz, bool level0, float& bd, int& bi, int& bpos) {
+    for (uint32_t i = s; i < e; i += step) {
+        const float4 q = __ldg(pts + i);
+        const float d = l2_simple(px, py, pz, q.x, q.y, q.z);
+        const int id = __float_as_int(q.w);
+        if (d < bd || (d == bd && id < bi)) { bd = d; bi = id; bpos = level0 ? (int)i : -1; }
+    }
+}
+
+// A candidate for a query without (usable) history.  Any target point is a valid seed; a close
+// one keeps the ball small.  Per level, finest first: the home cell, then its 3x3x3 block; the
+// first level that yields a candidate wins.  Coarse cells are sampled, not scanned.
+__device__ __forceinline__ void find_seed(const GridDev& g, float px, float py, float pz,
+                                          float& bd, int& bi, int& bpos) {
+    for (int l = 0; l < g.nlevels; ++l) {
+        const GridLevel& L = g.lv[l];
+        const int cx = min(max((int)floorf((px - g.ox) * L.inv_h), 0), L.dx - 1);
+        const int cy = min(max((int)floorf((py - g.oy) * L.inv_h), 0), L.dy - 1);
+        const int cz = min(max((int)floorf((pz - g.oz) * L.inv_h), 0), L.dz - 1);
+        const uint32_t c = ((uint32_t)cz * (uint32_t)L.dy + (uint32_t)cy) * (uint32_t)L.dx + (uint32_t)cx;
+        const uint32_t s = __ldg(L.cell_start + c), e = __ldg(L.cell_start + c + 1);
+        if (e > s) {
+            const uint32_t step = (l == 0 || e - s <= 16u) ? 1u : (e - s) / 16u;
+            seed_range(L.pts, s, e, step, px, py, pz, l == 0, bd, bi, bpos);
+            return;
+        }
+        bool found = false;
+        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, L.dx - 1);
+        for (int kz = max(cz - 1, 0); kz <= min(cz + 1, L.dz - 1); ++kz)
+            for (int ky = max(cy - 1, 0); ky <= min(cy + 1, L.dy - 1); ++ky) {
+                const uint32_t row = ((uint32_t)kz * (uint32_t)L.dy + (uint32_t)ky) * (uint32_t)L.dx;
+                const uint32_t rs = __ldg(L.cell_start + row + x0), re = __ldg(L.cell_start + row + x1 + 1);
+                if (re > rs) {
+                    const uint32_t step = (l == 0 || re - rs <= 8u) ? 1u : (re - rs) / 8u;
+                    seed_range(L.pts, rs, re, step, px, py, pz, l == 0, bd, bi, bpos);
+                    found = true;
+                }
+            }
+        if (found) return;
+    }
+    // nothing near on any level (query far outside the target): take the first sorted target
+    const float4 q = __ldg(g.lv[0].pts);
+    const float d = l2_simple(px, py, pz, q.x, q.y, q.z);
+    if (d < bd) { bd = d; bi = __float_as_int(q.w); bpos = 0; }
+}
+
+static __device__ __noinline__ void find_seed_ool(const GridDev& g, float px, float py, float pz,
+                                                  float& bd, int& bi, int& bpos) {
+    find_seed(g, px, py, pz, bd, bi, bpos);
+}
+
+// Exact nearest neighbour.  seed_pos >= 0: level-0 position of a target known to be close
+// (normally the previous match); -1: none.
+// kLean = true (inner ICP loop): seeds come from the previous inner iteration and are never stale,
+// so the stale-seed test is dropped and the rare paths are kept out of line.
+template <bool kLean = false>
+__device__ __forceinline__ Best nn_search_seeded(const GridDev& g, float px, float py, float pz, int seed_pos) {
+    float bd = __int_as_float(0x7f800000);
+    int bi = 0x7fffffff, bpos = -1;
+    if (seed_pos >= 0) {
+        const float4 q = __ldg(g.lv[0].pts + seed_pos);
+        bd = l2_simple(px, py, pz, q.x, q.y, q.z);
+        bi = __float_as_int(q.w);
+        bpos = seed_pos;
+        // a stale seed (the cloud moved by a good part of a cell since it was recorded) would make
+        // the ball large: the home cell usually holds a better candidate
+        if (!kLean && bd * g.lv[0].inv_h2 > 0.25f) find_seed(g, px, py, pz, bd, bi, bpos);
+    } else if (kLean) {
+        find_seed_ool(g, px, py, pz, bd, bi, bpos);
+    } else {
+        find_seed(g, px, py, pz, bd, bi, bpos);
+    }
+    // finest level on which the ball spans only a few cells
+    int l = 0;
+    float r = sqrtf(bd) * g.lv[0].inv_h;
+    while (l < g.nlevels - 1 && r > kBallMaxCells) { ++l; r *= (1.0f / kLevelFactor); }
+    ball_scan<kLean>(g.lv[l], g.ox, g.oy, g.oz, px, py, pz, l == 0, bd, bi, bpos);
+
+    Best b;
+    b.d2 = bd; b.idx = bi;
+    if (bpos < 0) bpos = (int)__ldg(g.inv_perm + bi);
+    b.pos = bpos;
+    const float4 q = __ldg(g.lv[0].pts + bpos);
+    b.qx = q.x; b.qy = q.y; b.qz = q.z;
+    return b;
 }
 
 __device__ __forceinline__ Best nn_search(const GridDev& g, float px, float py, float pz) {
-    Best b;
-    b.d2 = __int_as_float(0x7f800000); b.idx = 0x7fffffff; b.pos = -1;
-    b.qx = b.qy = b.qz = 0.f;
-    const int last = g.nlevels - 1;
-    for (int l = 0; l <= last; ++l) {
-        const int rmax = (l == last) ? 0x3fffffff : kRingsPerLevel;
-        if (search_level(g.lv[l], g.ox, g.oy, g.oz, px, py, pz, rmax, l == 0, b)) break;
-    }
-    if (b.pos < 0 && b.idx != 0x7fffffff) b.pos = (int)__ldg(g.inv_perm + b.idx);
-    return b;
+    return nn_search_seeded(g, px, py, pz, -1);
 }
 
 }  // namespace pwicp

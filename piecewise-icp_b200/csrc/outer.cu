@@ -27,11 +27,24 @@ classify_dist_kernel(GridDev g, const float4* __restrict__ aux, const unsigned c
                      const float4* __restrict__ ct2, const float4* __restrict__ bp2,
                      const float* __restrict__ bpstd2, int n2, float minLoD, float maxLoD,
                      float* __restrict__ pl, float* __restrict__ pt2pt, float* __restrict__ lod,
-                     int* __restrict__ lod_minmax) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 7 * n2) return;
-    const float4 p = (t < n2) ? __ldg(ct2 + t) : __ldg(bp2 + (t - n2));
-    const Best b = nn_search(g, p.x, p.y, p.z);
+                     int* __restrict__ lod_minmax, const uint32_t* __restrict__ order,
+                     int* __restrict__ ct_seed, int* __restrict__ bp_seed) {
+    // thread u handles the u-th query of the Morton-ordered patch list (spatially compact groups);
+    // t is the query's slot in the caller's order: centroid t < n2, boundary point t - n2
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = u < 7 * n2;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    int t = 0, seed = -1;
+    if (active) {
+        if (u < n2) { t = (int)order[u]; p = __ldg(ct2 + t); seed = ct_seed[t]; }
+        else {
+            const int v = u - n2, bpi = 6 * (int)order[v / 6] + v % 6;
+            t = n2 + bpi; p = __ldg(bp2 + bpi); seed = bp_seed[bpi];
+        }
+    }
+    if (!active) return;
+    const Best b = nn_search_seeded(g, p.x, p.y, p.z, seed);
+    if (t < n2) ct_seed[t] = b.pos; else bp_seed[t - n2] = b.pos;
     const float4 a = __ldg(aux + b.pos);
     float resDis;
     if (__ldg(ok + b.pos)) {
@@ -59,7 +72,7 @@ __global__ void classify_flag_kernel(const float* __restrict__ pl, const float* 
                                      int n2, float currDT, float DTctct, int* __restrict__ flags,
                                      unsigned long long* __restrict__ n_pts) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n2) return;
+    if (i >= n2) return;      // n2 tail: the remaining lanes of the warp stay converged below
     const float L = lod[i];
     const float thr = (currDT <= L) ? L : currDT;
     bool pass = true;
@@ -69,16 +82,20 @@ __global__ void classify_flag_kernel(const float* __restrict__ pl, const float* 
     if (thr < pl[i]) pass = false;
     const bool stable = pass && (pt2pt[i] < DTctct);
     flags[i] = stable ? 1 : 0;
-    if (stable) atomicAdd(n_pts, (unsigned long long)(patch_off[i + 1] - patch_off[i]));
+    // points of the stable patches: warp-aggregated (one atomic per warp, integer -> deterministic)
+    unsigned int np = stable ? (unsigned int)(patch_off[i + 1] - patch_off[i]) : 0u;
+    np = __reduce_add_sync(__activemask(), np);
+    if ((threadIdx.x & 31) == 0 && np) atomicAdd(n_pts, (unsigned long long)np);
 }
 
 __global__ void compact_kernel(const float4* __restrict__ ct2, const int* __restrict__ flags,
                                const int* __restrict__ pos, int n2, float4* __restrict__ out,
-                               unsigned char* __restrict__ flags_u8) {
+                               unsigned char* __restrict__ flags_u8, const int* __restrict__ ct_seed,
+                               int* __restrict__ seed_out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n2) return;
     const int f = flags[i];
-    if (f) out[pos[i]] = ct2[i];
+    if (f) { out[pos[i]] = ct2[i]; seed_out[pos[i]] = ct_seed[i]; }
     if (flags_u8) flags_u8[i] = (unsigned char)f;
 }
 
@@ -87,22 +104,31 @@ __global__ void compact_kernel(const float4* __restrict__ ct2, const int* __rest
 // they sort behind every valid distance.
 __global__ void __launch_bounds__(256)
 percentile_d2_kernel(GridDev g, const float* __restrict__ q, int nq, const int* __restrict__ patch_id,
-                     const int* __restrict__ flags, float* __restrict__ d2) {
+                     const int* __restrict__ flags, float* __restrict__ d2, int* __restrict__ seeds) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nq) return;
-    if (flags && !flags[patch_id[i]]) { d2[i] = __int_as_float(0x7f800000); return; }
-    const Best b = nn_search(g, q[3 * (size_t)i], q[3 * (size_t)i + 1], q[3 * (size_t)i + 2]);
-    d2[i] = b.d2;
+    const bool inrange = i < nq;
+    const bool active = inrange && !(flags && !flags[patch_id[i]]);
+    float px = 0.f, py = 0.f, pz = 0.f;
+    if (active) { px = q[3 * (size_t)i]; py = q[3 * (size_t)i + 1]; pz = q[3 * (size_t)i + 2]; }
+    const int seed = (active && seeds) ? seeds[i] : -1;
+    float dist2 = __int_as_float(0x7f800000);
+    if (active) {
+        const Best b = nn_search_seeded(g, px, py, pz, seed);
+        if (seeds) seeds[i] = b.pos;
+        dist2 = b.d2;
+    }
+    if (inrange) d2[i] = dist2;
 }
 
 int percentile_dev(Ctx* ctx, const GridDev& g, const float* q, int nq, const int* patch_id,
-                   const int* flags, long long n_valid, float pct, double* out) {
+                   const int* flags, long long n_valid, float pct, double* out, int* seeds) {
     if (nq < 1 || n_valid < 1) { set_error(ctx, "percentile: empty query set"); return PWICP_ERR_ARG; }
     PW_TRY(ctx->scratch_a.reserve(ctx, (size_t)nq * 4));
     PW_TRY(ctx->scratch_b.reserve(ctx, (size_t)nq * 4));
     float* d2 = ctx->scratch_a.as<float>();
     float* d2s = ctx->scratch_b.as<float>();
-    percentile_d2_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(g, q, nq, patch_id, flags, d2);
+    const size_t smem = 0;
+    percentile_d2_kernel<<<(nq + 255) / 256, 256, smem, ctx->stream>>>(g, q, nq, patch_id, flags, d2, seeds);
     size_t tmp = 0;
     cub::DeviceRadixSort::SortKeys(nullptr, tmp, d2, d2s, nq, 0, 32, ctx->stream);
     PW_TRY(ctx->cub_tmp.reserve(ctx, tmp));
@@ -198,8 +224,7 @@ void octree_cube(const float* mn, const float* mx, double res, double* bb) {
 // ---- (9) VCM, src/Registration.cpp:1273-1343 ------------------------------------------------
 constexpr int kVcmBlocks = 296;
 
-__device__ __forceinline__ void vcm_row(const GridDev& g, const float4* aux, const float4 q, double* a, double& L) {
-    const Best b = nn_search(g, q.x, q.y, q.z);
+__device__ __forceinline__ void vcm_row(const float4* aux, const Best& b, const float4 q, double* a, double& L) {
     const float4 nq = __ldg(aux + b.pos);
     const double Qx = q.x, Qy = q.y, Qz = q.z, Px = b.qx, Py = b.qy, Pz = b.qz;
     const double Nx = nq.x, Ny = nq.y, Nz = nq.z;
@@ -212,14 +237,21 @@ __device__ __forceinline__ void vcm_row(const GridDev& g, const float4* aux, con
 // pass 1: per-block partial sums of v^T v with v = A x - L
 __global__ void __launch_bounds__(256)
 vcm_kernel(GridDev g, const float4* __restrict__ aux, const float4* __restrict__ src, int n, int pass,
-           const double* __restrict__ X, double* __restrict__ partials) {
+           const double* __restrict__ X, double* __restrict__ partials, int* __restrict__ seeds) {
     __shared__ double sm[8][27];
     double acc[27];
 #pragma unroll
     for (int v = 0; v < 27; ++v) acc[v] = 0.0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const int i = base + threadIdx.x;
+        const bool active = i < n;
+        const float4 q = active ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int seed = (active && seeds) ? seeds[i] : -1;
+        if (!active) continue;
+        const Best b = nn_search_seeded(g, q.x, q.y, q.z, seed);
+        if (seeds) seeds[i] = b.pos;
         double a[6], L;
-        vcm_row(g, aux, src[i], a, L);
+        vcm_row(aux, b, q, a, L);
         if (pass == 0) {
             int v = 0;
 #pragma unroll
@@ -251,14 +283,15 @@ vcm_kernel(GridDev g, const float4* __restrict__ aux, const float4* __restrict__
     }
 }
 
-int vcm_dev(Ctx* ctx, const float4* src, int n, double* vcm36, int* singular) {
+int vcm_dev(Ctx* ctx, const float4* src, int n, double* vcm36, int* singular, int* seeds) {
     if (n < 7) { set_error(ctx, "vcm: needs more than 6 stable patches"); return PWICP_ERR_TOO_FEW_STABLE; }
     const int blocks = std::min(kVcmBlocks, (n + 255) / 256);
     PW_TRY(ctx->scratch_c.reserve(ctx, (size_t)kVcmBlocks * 27 * 8 + 64));
     double* part = ctx->scratch_c.as<double>();
     double* Xd = part + (size_t)kVcmBlocks * 27;
     std::vector<double> hp((size_t)blocks * 27);
-    vcm_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->tgt.dev, ctx->tgt_aux.as<float4>(), src, n, 0, nullptr, part);
+    const size_t smem = 0;
+    vcm_kernel<<<blocks, 256, smem, ctx->stream>>>(ctx->tgt.dev, ctx->tgt_aux.as<float4>(), src, n, 0, nullptr, part, seeds);
     ctx->launches++;
     PW_CUDA(cudaMemcpyAsync(hp.data(), part, hp.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
     PW_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -272,7 +305,7 @@ int vcm_dev(Ctx* ctx, const float4* src, int n, double* vcm36, int* singular) {
     if (singular) *singular = (std::fabs(det) < 1e-9) ? 1 : 0;      // :1324-1325 (reported only)
     for (int r = 0; r < 6; ++r) { double s = 0; for (int c = 0; c < 6; ++c) s += Q[r * 6 + c] * ATL[c]; X[r] = s; }
     PW_CUDA(cudaMemcpyAsync(Xd, X, sizeof(X), cudaMemcpyHostToDevice, ctx->stream));
-    vcm_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->tgt.dev, ctx->tgt_aux.as<float4>(), src, n, 1, Xd, part);
+    vcm_kernel<<<blocks, 256, smem, ctx->stream>>>(ctx->tgt.dev, ctx->tgt_aux.as<float4>(), src, n, 1, Xd, part, seeds);
     ctx->launches++;
     PW_CUDA(cudaMemcpyAsync(hp.data(), part, hp.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
     PW_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -280,6 +313,57 @@ int vcm_dev(Ctx* ctx, const float4* src, int n, double* vcm36, int* singular) {
     for (int b = 0; b < blocks; ++b) vtpv += hp[(size_t)b * 27];
     const double STD0 = 1 * std::sqrt(vtpv / double(n - 6));
     for (int k = 0; k < 36; ++k) vcm36[k] = STD0 * STD0 * Q[k];
+    return PWICP_OK;
+}
+
+// ---- Morton order of the source patches (once per pair) ------------------------------------
+__device__ __forceinline__ unsigned long long spread21_o(unsigned int v) {
+    unsigned long long x = v & 0x1fffffu;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+
+__global__ void patch_key_kernel(const float4* __restrict__ ct2, int n, float ox, float oy, float oz, float inv_h,
+                                 int dx, int dy, int dz, unsigned long long* keys, uint32_t* vals) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = ct2[i];
+    int cx = min(max((int)floorf((p.x - ox) * inv_h), 0), dx - 1);
+    int cy = min(max((int)floorf((p.y - oy) * inv_h), 0), dy - 1);
+    int cz = min(max((int)floorf((p.z - oz) * inv_h), 0), dz - 1);
+    keys[i] = spread21_o(cx) | (spread21_o(cy) << 1) | (spread21_o(cz) << 2);
+    vals[i] = (uint32_t)i;
+}
+
+// Processing order of the classification queries: patches sorted by the Morton code of the
+// target-grid cell of their centroid.  Results are written back in the caller's order, so the
+// order only shapes the query groups of the tile search.
+static int ensure_patch_order(Ctx* ctx) {
+    if (ctx->ct_order_valid) return PWICP_OK;
+    const int n = ctx->n2;
+    const GridLevel& L = ctx->tgt.dev.lv[0];
+    PW_TRY(ctx->keys.reserve(ctx, (size_t)n * 8));
+    PW_TRY(ctx->vals.reserve(ctx, (size_t)n * 4));
+    PW_TRY(ctx->keys2.reserve(ctx, (size_t)n * 8));
+    PW_TRY(ctx->ct_order.reserve(ctx, (size_t)n * 4));
+    patch_key_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->ct2.as<float4>(), n, ctx->tgt.dev.ox, ctx->tgt.dev.oy,
+                                                             ctx->tgt.dev.oz, L.inv_h, L.dx, L.dy, L.dz,
+                                                             ctx->keys.as<unsigned long long>(), ctx->vals.as<uint32_t>());
+    int maxd = std::max(L.dx, std::max(L.dy, L.dz));
+    int b1 = 1; while ((1 << b1) < maxd && b1 < 21) ++b1;
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, ctx->keys.as<unsigned long long>(), ctx->keys2.as<unsigned long long>(),
+                                    ctx->vals.as<uint32_t>(), ctx->ct_order.as<uint32_t>(), n, 0, 3 * b1, ctx->stream);
+    PW_TRY(ctx->cub_tmp.reserve(ctx, tmp));
+    size_t cap = ctx->cub_tmp.cap;
+    PW_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, cap, ctx->keys.as<unsigned long long>(), ctx->keys2.as<unsigned long long>(),
+                                            ctx->vals.as<uint32_t>(), ctx->ct_order.as<uint32_t>(), n, 0, 3 * b1, ctx->stream));
+    ctx->launches += 4;
+    ctx->ct_order_valid = true;
     return PWICP_OK;
 }
 
@@ -337,9 +421,12 @@ int outer_single_iteration(Ctx* ctx, const pwicp_pair_params& pp, pwicp_state* s
     struct { int mn, mx; unsigned long long np; } init = {0x7fffffff, (int)0x80000000, 0ull};
     PW_CUDA(cudaMemcpyAsync(minmax, &init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
 
-    classify_dist_kernel<<<(7 * n2 + 255) / 256, 256, 0, ctx->stream>>>(
+    const size_t tsmem = 0;
+    PW_TRY(ensure_patch_order(ctx));
+    classify_dist_kernel<<<(7 * n2 + 255) / 256, 256, tsmem, ctx->stream>>>(
         ctx->tgt.dev, ctx->tgt_aux.as<float4>(), ctx->tgt_ok.as<unsigned char>(), ctx->ct2.as<float4>(),
-        ctx->bp2.as<float4>(), ctx->bpstd2.as<float>(), n2, minLoD, maxLoD, pl, pt2pt, lod, minmax);
+        ctx->bp2.as<float4>(), ctx->bpstd2.as<float>(), n2, minLoD, maxLoD, pl, pt2pt, lod, minmax,
+        ctx->ct_order.as<uint32_t>(), ctx->ct_seed.as<int>(), ctx->bp_seed.as<int>());
     const float DTctct = currDT + 1 * (pp.SVRes1 + pp.SVRes2);             // :817
     classify_flag_kernel<<<(n2 + 255) / 256, 256, 0, ctx->stream>>>(
         pl, pt2pt, lod, ctx->patch_off.as<int>(), n2, currDT, DTctct, flags, npts);
@@ -349,8 +436,10 @@ int outer_single_iteration(Ctx* ctx, const pwicp_pair_params& pp, pwicp_state* s
     size_t cap = ctx->cub_tmp.cap;
     PW_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, cap, flags, pos, n2, ctx->stream));
     PW_TRY(ctx->icp_src.reserve(ctx, (size_t)n2 * sizeof(float4)));
+    PW_TRY(ctx->icp_seed.reserve(ctx, (size_t)n2 * sizeof(int)));
     compact_kernel<<<(n2 + 255) / 256, 256, 0, ctx->stream>>>(ctx->ct2.as<float4>(), flags, pos, n2,
-                                                              ctx->icp_src.as<float4>(), flags_u8);
+                                                              ctx->icp_src.as<float4>(), flags_u8,
+                                                              ctx->ct_seed.as<int>(), ctx->icp_seed.as<int>());
     ctx->launches += 5;
     struct { int mn, mx; unsigned long long np; int lastpos, lastflag; } h;
     PW_CUDA(cudaMemcpyAsync(&h, minmax, 16, cudaMemcpyDeviceToHost, ctx->stream));
@@ -375,6 +464,7 @@ int outer_single_iteration(Ctx* ctx, const pwicp_pair_params& pp, pwicp_state* s
 
     // (5) inner ICP on the stable centroids against ALL target centroids, :877
     ctx->n_icp = nStable;
+    ctx->icp_seed_valid = true;          // the classification matches are the exact NN of ICP iteration 0
     float transMatICP[16];
     pwicp_icp_result ir;
     PW_TRY(icp_run_device(ctx, icp, transMatICP, &ir, nullptr, nullptr, nullptr));
@@ -397,7 +487,7 @@ int outer_single_iteration(Ctx* ctx, const pwicp_pair_params& pp, pwicp_state* s
     if (!st->toStage2) {
         double Dist75 = 0;
         PW_TRY(percentile_dev(ctx, ctx->c1.dev, ctx->patch_xyz.as<float>(), ctx->mp2, ctx->patch_id.as<int>(),
-                              flags, nStablePts, 0.75f, &Dist75));           // :905
+                              flags, nStablePts, 0.75f, &Dist75, ctx->pp_seed.as<int>()));   // :905
         if (stats) stats->P75 = Dist75;
         if (currDT > Dist75) currDT = Dist75;
         else st->toStage2 = 1;
@@ -426,7 +516,7 @@ int outer_single_iteration(Ctx* ctx, const pwicp_pair_params& pp, pwicp_state* s
     // (9) VCM from the pre-update stable centroids (icp_src is never modified by the loop), :957-961
     if (st->toStage3 && vcm36) {
         int sing = 0;
-        PW_TRY(vcm_dev(ctx, ctx->icp_src.as<float4>(), nStable, vcm36, &sing));
+        PW_TRY(vcm_dev(ctx, ctx->icp_src.as<float4>(), nStable, vcm36, &sing, ctx->icp_seed.as<int>()));
         if (stats) { stats->vcm_written = 1; stats->vcm_singular = sing; }
     }
     PW_CUDA(cudaEventRecord(e1, ctx->stream));

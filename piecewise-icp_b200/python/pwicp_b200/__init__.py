@@ -59,7 +59,7 @@ EXPORTS = [
     "pwicp_last_error", "pwicp_last_device_ms", "pwicp_launch_count", "pwicp_flush_l2",
     "pwicp_sync", "pwicp_set_cells_per_point", "pwicp_target_upload", "pwicp_target_rebuild", "pwicp_source_upload",
     "pwicp_clouds_upload", "pwicp_source_download", "pwicp_nn", "pwicp_icp_default_params",
-    "pwicp_icp_source_upload", "pwicp_icp_source_all", "pwicp_icp_run", "pwicp_icp_p2plane",
+    "pwicp_icp_source_upload", "pwicp_icp_source_all", "pwicp_icp_run", "pwicp_icp_order", "pwicp_icp_p2plane",
     "pwicp_single_iteration", "pwicp_piecewise_icp", "pwicp_percentile_nn", "pwicp_overlap_ratio",
     "pwicp_vcm", "pwicp_transform", "pwicp_octree_bbox", "pwicp_bbox_corner_change",
     "pwicp_matrix2angle", "pwicp_mat4_mul",
@@ -102,6 +102,7 @@ def load_library(path=None):
     L.pwicp_icp_source_upload.argtypes = [vp, vp, C.c_int]
     L.pwicp_icp_source_all.argtypes = [vp]
     L.pwicp_icp_run.argtypes = [vp, C.POINTER(IcpParams), vp, C.POINTER(IcpResult), vp, vp, vp]
+    L.pwicp_icp_order.argtypes = [vp, vp]
     L.pwicp_icp_p2plane.argtypes = [vp, vp, vp, C.c_int, vp, C.c_int, C.POINTER(IcpParams), vp,
                                     C.POINTER(IcpResult)]
     L.pwicp_single_iteration.argtypes = [vp, C.POINTER(PairParams), C.POINTER(State),
@@ -279,6 +280,11 @@ class Context:
             out.update(mse=mse[:res.n_iter], T_trace=Ttr[:res.n_iter].reshape(-1, 4, 4),
                        idx_trace=itr[:res.n_iter])
         return out
+
+    def icp_order(self):
+        perm = np.zeros(self._n_icp, np.int32)
+        self._chk(self.L.pwicp_icp_order(self.h, _ptr(perm)))
+        return perm
 
     def icp_p2plane(self, tgt, nrm, src, prm=None):
         """Host buffers in, transformation out: P2PICPwithPatchNormal(target, source, eps)."""

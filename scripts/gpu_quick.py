@@ -32,9 +32,10 @@ def main():
     r = ctx.icp_run(P.icp_params(max_iter=20, force_iters=1), trace=True)
     print("icp ms", r["device_ms"], "iters", r["n_iter"], "geom", r["grid_blocks"], r["warps_per_block"],
           "Gcorr/s", r["correspondences"] / r["device_ms"] / 1e6)
-    o = O.icp(d["ct1"], d["nrm1"], d["ct2"], O.icp_params(max_iter=20, force_iters=1, reduce_mode=1,
+    perm = ctx.icp_order()
+    o = O.icp(d["ct1"], d["nrm1"], d["ct2"][perm], O.icp_params(max_iter=20, force_iters=1, reduce_mode=1,
               grid_blocks=r["grid_blocks"], warps_per_block=r["warps_per_block"]), trace=True)
-    print("ICP T bit-equal", np.array_equal(r["T"], o["T"]), "idx trace equal", np.array_equal(r["idx_trace"], o["idx_trace"]),
+    print("ICP T bit-equal", np.array_equal(r["T"], o["T"]), "idx trace equal", np.array_equal(r["idx_trace"][:, perm], o["idx_trace"]),
           "T_trace equal", np.array_equal(r["T_trace"], o["T_trace"]), "mse equal", np.array_equal(r["mse"], o["mse"]))
     if not np.array_equal(r["T_trace"], o["T_trace"]):
         bad = [k for k in range(len(o["T_trace"])) if not np.array_equal(r["T_trace"][k], o["T_trace"][k])]
