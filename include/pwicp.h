@@ -171,6 +171,9 @@ int pwicp_percentile_nn(pwicp_ctx* ctx, const float* cloud1, int m1, const float
 /* calOverlapRatioByC2Cdist (src/Registration.cpp:593-614) */
 int pwicp_overlap_ratio(pwicp_ctx* ctx, const float* cloud1, int m1, const float* cloud2, int m2,
                         float DTinit, float* out);
+/* squared distance of every point to its nearest OTHER point of the same cloud: the second
+ * neighbour of KdTreeFLANN::nearestKSearch(i, 2) in calPCresolution (src/CommonFunc.cpp:239-263) */
+int pwicp_self_nn(pwicp_ctx* ctx, const float* xyz, int n, float* d2);
 /* calTransParaVCM (src/Registration.cpp:1273-1343) on the resident centroid target */
 int pwicp_vcm(pwicp_ctx* ctx, const float* src_stable_xyz, int n, double* vcm36, int* singular);
 /* pcl::transformPointCloud (src/Registration.cpp:943-954), in place on a host array */

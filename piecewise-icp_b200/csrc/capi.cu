@@ -482,6 +482,23 @@ int pwicp_overlap_ratio(pwicp_ctx* p, const float* cloud1, int m1, const float* 
     return rc;
 }
 
+int pwicp_self_nn(pwicp_ctx* p, const float* xyz, int n, float* d2) {
+    Ctx* ctx = reinterpret_cast<Ctx*>(p);
+    if (!ctx || !xyz || !d2 || n < 2) { set_error(ctx, "self_nn: bad arguments"); return PWICP_ERR_ARG; }
+    PW_CUDA(cudaSetDevice(ctx->device));
+    GridOwner g;
+    PW_TRY(upload_checked(ctx, ctx->scratch_a, xyz, (size_t)3 * n, "cloud"));
+    int rc = grid_build(ctx, g, ctx->scratch_a.as<float>(), n);
+    if (rc == PWICP_OK) rc = ctx->scratch_b.reserve(ctx, (size_t)n * 4);
+    if (rc == PWICP_OK) rc = self_nn_dev(ctx, g.dev, ctx->scratch_b.as<float>());
+    if (rc == PWICP_OK) {
+        if (cudaMemcpyAsync(d2, ctx->scratch_b.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) { set_error(ctx, "self_nn: copy failed"); rc = PWICP_ERR_CUDA; }
+    }
+    g.release();
+    return rc;
+}
+
 int pwicp_vcm(pwicp_ctx* p, const float* src, int n, double* vcm36, int* singular) {
     Ctx* ctx = reinterpret_cast<Ctx*>(p);
     if (!ctx || !src || !vcm36 || n < 1) { set_error(ctx, "vcm: bad arguments"); return PWICP_ERR_ARG; }

@@ -114,6 +114,7 @@ struct Ctx {
 int grid_build(Ctx* ctx, GridOwner& g, const float* xyz_dev_packed, int n);
 int nn_query_packed(Ctx* ctx, const GridDev& g, const float* q_dev_packed, int nq, int* idx_dev,
                     float* d2_dev);
+int self_nn_dev(Ctx* ctx, const GridDev& g, float* d2_dev);
 int upload_packed(Ctx* ctx, DevBuf& buf, const float* host_xyz, size_t n_floats);
 int check_finite_dev(Ctx* ctx, const float* dev, size_t n_floats, bool* ok);
 

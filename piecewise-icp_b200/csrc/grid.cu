@@ -282,6 +282,50 @@ nn_kernel(GridDev g, const float* __restrict__ q, int nq, int* __restrict__ idx,
     }
 }
 
+// ---- self NN: distance of every target point to its nearest OTHER point ---------------------
+// Serves calPCresolution (reference src/CommonFunc.cpp:239-263: KdTreeFLANN::nearestKSearch(i, 2),
+// second neighbour).  One thread per sorted position; the sorted-array neighbour is the seed, the
+// ball through it is scanned with the thread's own index excluded.  d2 is written in the
+// caller's (original) order.
+__global__ void __launch_bounds__(256)
+self_nn_kernel(GridDev g, float* __restrict__ d2_out) {
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= g.n) return;
+    const GridLevel& L = g.lv[0];
+    const float4 p = __ldg(L.pts + pos);
+    const int self = __float_as_int(p.w);
+    const float4 s = __ldg(L.pts + (pos + 1 < g.n ? pos + 1 : pos - 1));
+    float bd = l2_simple(p.x, p.y, p.z, s.x, s.y, s.z);
+    const float fx = (p.x - g.ox) * L.inv_h, fy = (p.y - g.oy) * L.inv_h, fz = (p.z - g.oz) * L.inv_h;
+    const float mx = 0.01f + fabsf(fx) * 4e-6f, my = 0.01f + fabsf(fy) * 4e-6f, mz = 0.01f + fabsf(fz) * 4e-6f;
+    const float r = sqrtf(bd) * L.inv_h * 1.00001f;
+    const int lx = min(max((int)floorf(fx - r - mx), 0), L.dx - 1), hx = min(max((int)floorf(fx + r + mx), 0), L.dx - 1);
+    const int ly = min(max((int)floorf(fy - r - my), 0), L.dy - 1), hy = min(max((int)floorf(fy + r + my), 0), L.dy - 1);
+    const int lz = min(max((int)floorf(fz - r - mz), 0), L.dz - 1), hz = min(max((int)floorf(fz + r + mz), 0), L.dz - 1);
+    for (int kz = lz; kz <= hz; ++kz)
+        for (int ky = ly; ky <= hy; ++ky) {
+            const float gy = axis_gap(fy, ky, my), gz = axis_gap(fz, kz, mz);
+            if (gy * gy + gz * gz > bd * L.inv_h2) continue;
+            const uint32_t row = ((uint32_t)kz * (uint32_t)L.dy + (uint32_t)ky) * (uint32_t)L.dx;
+            const uint32_t b = __ldg(L.cell_start + row + lx), e = __ldg(L.cell_start + row + hx + 1);
+            for (uint32_t i = b; i < e; ++i) {
+                const float4 q = __ldg(L.pts + i);
+                if (__float_as_int(q.w) == self) continue;
+                const float d = l2_simple(p.x, p.y, p.z, q.x, q.y, q.z);
+                if (d < bd) bd = d;
+            }
+        }
+    d2_out[self] = bd;
+}
+
+int self_nn_dev(Ctx* ctx, const GridDev& g, float* d2_dev) {
+    if (g.n < 2) { set_error(ctx, "self_nn: needs at least 2 points"); return PWICP_ERR_ARG; }
+    self_nn_kernel<<<(g.n + 255) / 256, 256, 0, ctx->stream>>>(g, d2_dev);
+    ctx->launches++;
+    PW_CUDA(cudaGetLastError());
+    return PWICP_OK;
+}
+
 int nn_query_packed(Ctx* ctx, const GridDev& g, const float* q_dev, int nq, int* idx_dev, float* d2_dev) {
     if (nq <= 0) return PWICP_OK;
     const size_t smem = 0;

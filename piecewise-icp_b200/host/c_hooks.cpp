@@ -1,0 +1,126 @@
+// c_hooks.cpp -- small C-linkage views of host-side mirror functions (used by the Python binding
+// and by the CPU tests; none of them needs a CUDA device).
+#include <cstring>
+
+#include "Registration.h"
+
+extern "C" {
+
+struct pwicp_config_c {
+    char path1[1024], path2[1024];
+    int isSetResSVsize; float PCres1, PCres2, SVsize1, SVsize2;
+    int isSetDTinit; float DTinit, DTmin; int isVisual;
+};
+
+int pwicp_host_read_config(const char* path, pwicp_config_c* out) {
+    ConfigPara c;
+    if (!readConfigFile(path, c)) return 0;
+    std::memset(out, 0, sizeof(*out));
+    std::strncpy(out->path1, c.FolderFilePath1.c_str(), sizeof(out->path1) - 1);
+    std::strncpy(out->path2, c.FolderFilePath2.c_str(), sizeof(out->path2) - 1);
+    out->isSetResSVsize = c.isSetResSVsize; out->PCres1 = c.PCres1; out->PCres2 = c.PCres2;
+    out->SVsize1 = c.SVsize1; out->SVsize2 = c.SVsize2; out->isSetDTinit = c.isSetDTinit;
+    out->DTinit = c.DTinit; out->DTmin = c.DTmin; out->isVisual = c.isVisual;
+    return 1;
+}
+
+int pwicp_host_patch_normal(const float* xyz, int n, float* n3) {
+    pcl::PointCloud<pcl::PointXYZ> c;
+    c.resize(n);
+    for (int i = 0; i < n; ++i) { c.points[i].x = xyz[3 * i]; c.points[i].y = xyz[3 * i + 1]; c.points[i].z = xyz[3 * i + 2]; }
+    return calPatchNormal(c, n3[0], n3[1], n3[2]) ? 1 : 0;
+}
+
+// number of points, or -1; xyz may be NULL to query the size only
+int pwicp_host_load_pcd(const char* path, float* xyz, int cap) {
+    pcl::PointCloud<pcl::PointXYZ> c;
+    if (pcl::io::loadPCDFile(path, c) != 0) return -1;
+    if (xyz) for (int i = 0; i < (int)c.size() && i < cap; ++i) { xyz[3 * i] = c.points[i].x; xyz[3 * i + 1] = c.points[i].y; xyz[3 * i + 2] = c.points[i].z; }
+    return (int)c.size();
+}
+
+int pwicp_host_save_pcd(const char* path, const float* xyz, int n) {
+    pcl::PointCloud<pcl::PointXYZ> c;
+    c.resize(n);
+    for (int i = 0; i < n; ++i) { c.points[i].x = xyz[3 * i]; c.points[i].y = xyz[3 * i + 1]; c.points[i].z = xyz[3 * i + 2]; }
+    return pcl::io::savePCDFileBinary(path, c);
+}
+
+// time stamps of the listed scan files in processing order; returns the count
+int pwicp_host_list_epochs(const char* folder, long* times, int cap) {
+    std::vector<std::string> files; std::vector<long> t;
+    const int n = extractAllFilesFromFolder(folder, files, t);
+    for (int i = 0; i < n && i < cap; ++i) times[i] = t[i];
+    return n;
+}
+
+// patch generation stand-in + per-patch statistics on a host cloud: returns the number of patches,
+// fills centroids (3 floats each), boundary points (18), sigmas (BPstd, CTstd), up to cap patches
+int pwicp_host_patches(const float* xyz, int n, float svRes, float* ct, float* bp, float* bpstd, float* ctstd, int cap) {
+    pcl::PointCloud<pcl::PointXYZ>::Ptr c(new pcl::PointCloud<pcl::PointXYZ>), CT(new pcl::PointCloud<pcl::PointXYZ>), BP(new pcl::PointCloud<pcl::PointXYZ>);
+    c->resize(n);
+    for (int i = 0; i < n; ++i) { c->points[i].x = xyz[3 * i]; c->points[i].y = xyz[3 * i + 1]; c->points[i].z = xyz[3 * i + 2]; }
+    pcl::PointCloud<pcl::PointXYZ>* patches = nullptr;
+    const int np = PatchGenerationAndRefinement(c, svRes, CT, BP, patches, false);
+    std::vector<float> sb, sc;
+    calBPandCTSTD(patches, np, sb, sc);
+    for (int i = 0; i < np && i < cap; ++i) {
+        ct[3 * i] = CT->points[i].x; ct[3 * i + 1] = CT->points[i].y; ct[3 * i + 2] = CT->points[i].z;
+        for (int k = 0; k < 6; ++k) { bp[18 * i + 3 * k] = BP->points[6 * i + k].x; bp[18 * i + 3 * k + 1] = BP->points[6 * i + k].y; bp[18 * i + 3 * k + 2] = BP->points[6 * i + k].z; }
+        bpstd[i] = sb[i]; ctstd[i] = sc[i];
+    }
+    delete[] patches;
+    return np;
+}
+
+// calTransToReferenceEpoch as a file-to-file operation (F2)
+void pwicp_host_chain_to_reference(const char* transMatFile, int pairMode, const char* pairFile, int epochNum,
+                                   const char* outTM, const char* outTP) {
+    std::vector<int> ts; std::vector<Eigen::Matrix4f> T; std::vector<Eigen::MatrixXd> V;
+    calTransToReferenceEpoch(transMatFile, pairMode, pairFile, epochNum, outTM, outTP, ts, T, V);
+}
+
+}  // extern "C"
+
+// ---- the reference's outer loop written with the mirror's per-iteration function ---------------
+// mode 0: Piecewise_ICP (one upload, device loop); mode 1: the reference's own loop shape
+// (src/Registration.cpp:680-694): while(!g_toStage3) PwICP_singleIteration(...), composing
+// transMat = cur * transMat on the host.  Both must give the same answer.
+extern bool g_toStage2, g_toStage3;
+
+extern "C" int pwicp_host_register_clouds(const float* xyz1, int n1, const float* xyz2, int n2, float Res, float SVsize,
+                                          float DTinit, float DTmin, int mode, float* T16, double* vcm36, float* dtseries, int cap) {
+    pcl::PointCloud<pcl::PointXYZ>::Ptr c1(new pcl::PointCloud<pcl::PointXYZ>), c2(new pcl::PointCloud<pcl::PointXYZ>);
+    c1->resize(n1); c2->resize(n2);
+    for (int i = 0; i < n1; ++i) { c1->points[i].x = xyz1[3 * i]; c1->points[i].y = xyz1[3 * i + 1]; c1->points[i].z = xyz1[3 * i + 2]; }
+    for (int i = 0; i < n2; ++i) { c2->points[i].x = xyz2[3 * i]; c2->points[i].y = xyz2[3 * i + 1]; c2->points[i].z = xyz2[3 * i + 2]; }
+    std::vector<float> series;
+    Eigen::Matrix4f T = Eigen::Matrix4f::Identity();
+    Eigen::MatrixXd VCM;
+    if (mode == 0) {
+        Piecewise_ICP(c1, c2, true, Res, Res, SVsize, SVsize, true, DTinit, DTmin, series, T, VCM);
+    } else {
+        g_toStage2 = false; g_toStage3 = false;
+        pcl::PointCloud<pcl::PointXYZ>* SV1 = nullptr; pcl::PointCloud<pcl::PointXYZ>* SV2 = nullptr;
+        pcl::PointCloud<pcl::PointXYZ>::Ptr CT1(new pcl::PointCloud<pcl::PointXYZ>), CT2(new pcl::PointCloud<pcl::PointXYZ>);
+        pcl::PointCloud<pcl::PointXYZ>::Ptr BP1(new pcl::PointCloud<pcl::PointXYZ>), BP2(new pcl::PointCloud<pcl::PointXYZ>);
+        const int m1 = PatchGenerationAndRefinement(c1, SVsize, CT1, BP1, SV1, false);
+        const int m2 = PatchGenerationAndRefinement(c2, SVsize, CT2, BP2, SV2, false);
+        std::vector<float> BPstd1, BPstd2, CTstd1, CTstd2;
+        calBPandCTSTD(SV1, m1, BPstd1, CTstd1);
+        calBPandCTSTD(SV2, m2, BPstd2, CTstd2);
+        float currDT = DTinit, BB1 = 0.0f, BB2 = 0.0f;
+        series.push_back(currDT);
+        while (!g_toStage3) {
+            Eigen::Matrix4f cur = PwICP_singleIteration(c1, c2, Res, Res, SVsize, SVsize, SV1, SV2, CT1, CT2, BP1, BP2,
+                                                        CTstd1, BPstd2, DTmin, currDT, BB1, BB2, VCM);
+            T = cur * T;
+            series.push_back(currDT);
+        }
+        delete[] SV1; delete[] SV2;
+    }
+    std::memcpy(T16, T.m, sizeof(T.m));
+    for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) vcm36[r * 6 + c] = VCM(r, c);
+    for (int k = 0; k < (int)series.size() && k < cap; ++k) dtseries[k] = series[k];
+    return (int)series.size();
+}

@@ -61,7 +61,7 @@ EXPORTS = [
     "pwicp_clouds_upload", "pwicp_source_download", "pwicp_nn", "pwicp_icp_default_params",
     "pwicp_icp_source_upload", "pwicp_icp_source_all", "pwicp_icp_run", "pwicp_icp_order", "pwicp_icp_p2plane",
     "pwicp_single_iteration", "pwicp_piecewise_icp", "pwicp_percentile_nn", "pwicp_overlap_ratio",
-    "pwicp_vcm", "pwicp_transform", "pwicp_octree_bbox", "pwicp_bbox_corner_change",
+    "pwicp_self_nn", "pwicp_vcm", "pwicp_transform", "pwicp_octree_bbox", "pwicp_bbox_corner_change",
     "pwicp_matrix2angle", "pwicp_mat4_mul",
 ]
 
@@ -112,6 +112,7 @@ def load_library(path=None):
                                       C.POINTER(C.c_int), vp]
     L.pwicp_percentile_nn.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_float, C.POINTER(C.c_double)]
     L.pwicp_overlap_ratio.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_float, C.POINTER(C.c_float)]
+    L.pwicp_self_nn.argtypes = [vp, vp, C.c_int, vp]
     L.pwicp_vcm.argtypes = [vp, vp, C.c_int, vp, C.POINTER(C.c_int)]
     L.pwicp_transform.argtypes = [vp, vp, C.c_int, vp]
     L.pwicp_octree_bbox.argtypes = [vp, vp, C.c_int, C.c_double, vp]
@@ -334,6 +335,12 @@ class Context:
         out = C.c_float(0)
         self._chk(self.L.pwicp_overlap_ratio(self.h, _ptr(c1), len(c1), _ptr(c2), len(c2), DTinit, C.byref(out)))
         return out.value
+
+    def self_nn(self, pts):
+        p = _f32(pts)
+        d2 = np.zeros(len(p), np.float32)
+        self._chk(self.L.pwicp_self_nn(self.h, _ptr(p), len(p), _ptr(d2)))
+        return d2
 
     def vcm(self, src):
         s = _f32(src)

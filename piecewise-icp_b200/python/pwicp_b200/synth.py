@@ -158,3 +158,68 @@ def make_pair(n, seed=SEED_TARGET, s=0.05, motion=DEFAULT_MOTION, changed=0.2, p
     out["DTmin"] = float(DTmin)
     out["T_true"] = np.linalg.inv(T_mov)
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Dense synthetic scans (PCD files) for the file-level drivers PiecewiseICP_pair_call / _4D_call
+# ---------------------------------------------------------------------------------------------
+def make_scan(extent=4.0, spacing=0.01, seed=1, motion=None, bump=None, noise=3e-4):
+    """Dense scan of the synthetic terrain: jittered grid of `spacing` over a square of side
+    `extent` [m], range noise along the normal; optional local change `bump` = (cx, cy, radius,
+    height) and rigid `motion` (rx, ry, rz, tx, ty, tz) applied to the whole scan."""
+    rng = np.random.default_rng(np.random.PCG64(seed))
+    n = int(round(extent / spacing))
+    ix, iy = np.meshgrid(np.arange(n), np.arange(n), indexing="xy")
+    x = (ix.ravel() - n / 2) * spacing + rng.uniform(-0.3 * spacing, 0.3 * spacing, n * n)
+    y = (iy.ravel() - n / 2) * spacing + rng.uniform(-0.3 * spacing, 0.3 * spacing, n * n)
+    z, zx, zy = _terrain(3.0 * x, 3.0 * y)            # a steeper, smaller-scale version of the terrain
+    z = z / 6.0
+    nrm = np.stack([-zx / 2.0, -zy / 2.0, np.ones_like(z)], 1)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    pts = np.stack([x, y, z], 1) + rng.normal(0, noise, (n * n, 1)) * nrm
+    if bump is not None:
+        cx, cy, rad, hgt = bump
+        d2 = (x - cx) ** 2 + (y - cy) ** 2
+        pts[:, 2] += hgt * np.exp(-d2 / (2 * (rad / 2.5) ** 2)) * (d2 < rad * rad)
+    if motion is not None:
+        T = rigid_matrix(*motion)
+        pts = pts @ T[:3, :3].T + T[:3, 3]
+    return pts.astype(np.float32)
+
+
+def write_pcd(path, xyz):
+    xyz = np.ascontiguousarray(xyz, np.float32)
+    with open(path, "wb") as f:
+        f.write(("# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\n"
+                 "COUNT 1 1 1\nWIDTH %d\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS %d\nDATA binary\n" % (len(xyz), len(xyz))).encode())
+        f.write(xyz.tobytes())
+
+
+def write_config(path, p1, p2, res=0.01, sv=0.1, dtinit=0.05, dtmin=0.004, manual_res=1, manual_dt=1, crlf=True):
+    """The 11-line positional configuration file of the reference (configuration_files/*.txt)."""
+    lines = [f"FolderFilePath1: {p1}", f"FolderFilePath2: {p2}", f"isSetResSVsize:{manual_res}", f"PCres1:{res}",
+             f"PCres2:{res}", f"SVsize1:{sv}", f"SVsize2:{sv}", f"isSetDTinit:{manual_dt}", f"DTinit:{dtinit}",
+             f"DisThrhdmin:{dtmin}", "isVisual:0"]
+    with open(path, "w", newline="") as f:
+        f.write(("\r\n" if crlf else "\n").join(lines))      # no trailing newline, like the shipped files
+
+
+def make_series(folder, n_epochs=4, extent=3.0, spacing=0.01, seed=100):
+    """Writes Epoch_001.pcd .. Epoch_00N.pcd (each with its own rigid motion and a growing local
+    change) and defined_transformations.txt (ground truth: epoch -> reference)."""
+    import os
+    os.makedirs(folder, exist_ok=True)
+    rng = np.random.default_rng(seed)
+    gt = []
+    for e in range(n_epochs):
+        motion = None if e == 0 else tuple(np.concatenate([rng.uniform(-0.004, 0.004, 3), rng.uniform(-0.01, 0.01, 3)]))
+        bump = None if e == 0 else (0.4, -0.3, 0.35, 0.02 * e)
+        pts = make_scan(extent, spacing, seed + e, motion, bump)
+        write_pcd(os.path.join(folder, "Epoch_%03d.pcd" % (e + 1)), pts)
+        gt.append(np.eye(4) if motion is None else np.linalg.inv(rigid_matrix(*motion)))
+    with open(os.path.join(folder, "..", "defined_transformations.txt") if False else os.path.join(os.path.dirname(folder.rstrip("/")), "defined_transformations.txt"), "w") as f:
+        for e, T in enumerate(gt):
+            f.write("%d\n" % (e + 1))
+            for r in range(4):
+                f.write(" ".join("%.12f" % v for v in T[r]) + "\n")
+    return gt

@@ -1,0 +1,309 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI (ctypes -> libpwicp.so),
+against the CPU oracle on the same seeded inputs, against the committed golden vectors, and --
+at BASELINE.json's full sizes -- through size-independent properties.
+
+Bars (BASELINE.json north_star): correspondence indices and float squared distances bit-exact;
+rotation / translation within 1e-6 rad / 1e-6 m of the reference-order oracle; the whole inner
+loop bit-exact against the oracle run in the device's summation order.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import pwicp_b200 as P
+from pwicp_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pair2k.npz")
+POSE_TOL_RAD = 1e-6     # north_star: rotation within 1e-6 rad
+POSE_TOL_M = 1e-6       # north_star: translation within 1e-6 m
+
+
+def pose_diff(Ta, Tb):
+    a, b = P.matrix2angle(Ta), P.matrix2angle(Tb)
+    return float(np.abs(a - b).max()), float(np.abs(np.asarray(Ta)[:3, 3] - np.asarray(Tb)[:3, 3]).max())
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD)
+
+
+@pytest.fixture(scope="module")
+def pair2k():
+    return synth.make_pair(2000, seed=20250606)
+
+
+@pytest.fixture(scope="module")
+def pair60k():
+    return synth.make_pair(60000, seed=777)
+
+
+# ------------------------------------------------------------------------------------------ A1
+def test_nn_matches_oracle_bit_exact(gpu_ctx, oracle, pair60k):
+    d = pair60k
+    gpu_ctx.target_upload(d["ct1"], d["nrm1"], d["ctstd1"])
+    q = np.concatenate([d["ct2"], d["bp2"]])
+    idx, d2 = gpu_ctx.nn(q)
+    oi, od = oracle.nn(d["ct1"], q)
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(d2, od)
+
+
+def test_nn_golden_vectors(gpu_ctx, gold, pair2k):
+    d = pair2k
+    gpu_ctx.target_upload(d["ct1"], d["nrm1"], d["ctstd1"])
+    idx, d2 = gpu_ctx.nn(np.concatenate([d["ct2"], d["bp2"]]))
+    assert np.array_equal(idx, gold["nn_pair_idx"]) and np.array_equal(d2, gold["nn_pair_d2"])
+    rng = np.random.default_rng(7)
+    tgt = rng.uniform(-5, 5, (100000, 3)).astype(np.float32)
+    qry = rng.uniform(-6, 6, (20000, 3)).astype(np.float32)
+    gpu_ctx.target_upload(tgt)
+    idx, d2 = gpu_ctx.nn(qry)
+    assert np.array_equal(idx, gold["nn_rand_idx"]) and np.array_equal(d2, gold["nn_rand_d2"])
+
+
+@pytest.mark.parametrize("n1", [1, 2, 3, 5, 17, 300])
+def test_nn_tiny_targets(gpu_ctx, oracle, n1):
+    rng = np.random.default_rng(n1)
+    tgt = rng.normal(0, 1, (n1, 3)).astype(np.float32)
+    qry = rng.normal(0, 2, (257, 3)).astype(np.float32)
+    gpu_ctx.target_upload(tgt)
+    idx, d2 = gpu_ctx.nn(qry)
+    oi, od = oracle.nn(tgt, qry, brute=True)
+    assert np.array_equal(idx, oi) and np.array_equal(d2, od)
+
+
+def test_nn_edge_cases(gpu_ctx, oracle):
+    rng = np.random.default_rng(11)
+    # exact ties and duplicates -> lowest original index
+    base = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [1, 0, 0], [0, 0, 1]], np.float32)
+    tgt = np.tile(base, (50, 1))
+    gpu_ctx.target_upload(tgt)
+    idx, d2 = gpu_ctx.nn(np.zeros((40, 3), np.float32))
+    assert (idx == 0).all() and (d2 == 1.0).all()
+    qry = (base[rng.integers(0, 6, 300)] * np.float32(0.75)).astype(np.float32)
+    idx, d2 = gpu_ctx.nn(qry)
+    oi, od = oracle.nn(tgt, qry, brute=True)
+    assert np.array_equal(idx, oi) and np.array_equal(d2, od)
+    # queries exactly on targets, degenerate (planar / collinear) targets, far-away queries
+    flat = rng.uniform(-3, 3, (5000, 3)).astype(np.float32); flat[:, 2] = 0.25
+    line = np.zeros((2000, 3), np.float32); line[:, 0] = np.linspace(-4, 4, 2000, dtype=np.float32)
+    for tgt in (flat, line):
+        gpu_ctx.target_upload(tgt)
+        qry = np.concatenate([tgt[::7], rng.normal(0, 3, (2000, 3)).astype(np.float32),
+                              (rng.normal(0, 1, (500, 3)) * 500).astype(np.float32)])
+        idx, d2 = gpu_ctx.nn(qry)
+        oi, od = oracle.nn(tgt, qry)
+        assert np.array_equal(idx, oi) and np.array_equal(d2, od)
+        assert (d2[: len(tgt[::7])] == 0).all()
+    # empty query batch
+    idx, d2 = gpu_ctx.nn(np.zeros((0, 3), np.float32))
+    assert len(idx) == 0
+
+
+def test_nn_partial_overlap_far_queries(gpu_ctx, oracle, pair60k):
+    """Queries far from a dense surface (non-overlapping scan parts) stay exact."""
+    d = pair60k
+    gpu_ctx.target_upload(d["ct1"])
+    rng = np.random.default_rng(5)
+    q = d["ct2"][::5].copy()
+    q[:, 2] += rng.uniform(0.3, 3.0, len(q)).astype(np.float32)
+    q[::3, 0] += np.float32(20.0)
+    idx, d2 = gpu_ctx.nn(q)
+    oi, od = oracle.nn(d["ct1"], q)
+    assert np.array_equal(idx, oi) and np.array_equal(d2, od)
+
+
+def test_nonfinite_input_is_rejected(gpu_ctx):
+    tgt = np.zeros((10, 3), np.float32); tgt[3, 1] = np.nan
+    with pytest.raises(P.PwicpError) as e:
+        gpu_ctx.target_upload(tgt)
+    assert e.value.status == -3
+    gpu_ctx.target_upload(np.eye(3, dtype=np.float32))
+    q = np.zeros((5, 3), np.float32); q[0, 0] = np.inf
+    with pytest.raises(P.PwicpError) as e:
+        gpu_ctx.nn(q)
+    assert e.value.status == -3
+
+
+# ------------------------------------------------------------------------------------- A3 - A6
+def test_inner_loop_bit_exact_in_device_order(gpu_ctx, oracle, pair60k):
+    d = pair60k
+    gpu_ctx.target_upload(d["ct1"], d["nrm1"], d["ctstd1"])
+    gpu_ctx.icp_source_upload(d["ct2"])
+    r = gpu_ctx.icp_run(P.icp_params(max_iter=12, force_iters=1), trace=True)
+    perm = gpu_ctx.icp_order()
+    assert sorted(perm.tolist()) == list(range(len(d["ct2"])))
+    o = oracle.icp(d["ct1"], d["nrm1"], d["ct2"][perm],
+                   oracle.icp_params(max_iter=12, force_iters=1, reduce_mode=1,
+                                     grid_blocks=r["grid_blocks"], warps_per_block=r["warps_per_block"]),
+                   trace=True)
+    assert r["n_iter"] == o["n_iter"] == 12
+    assert np.array_equal(r["idx_trace"][:, perm], o["idx_trace"])    # indices of every inner iteration
+    assert np.array_equal(r["T_trace"], o["T_trace"])                 # every incremental transform
+    assert np.array_equal(r["mse"], o["mse"])
+    assert np.array_equal(r["T"], o["T"])
+
+
+def test_inner_loop_pose_vs_reference_order(gpu_ctx, oracle, pair60k, gold, pair2k):
+    for d in (pair60k, pair2k):
+        gpu_ctx.target_upload(d["ct1"], d["nrm1"], d["ctstd1"])
+        gpu_ctx.icp_source_upload(d["ct2"])
+        for prm_g, prm_o in ((P.icp_params(), oracle.icp_params()),
+                             (P.icp_params(max_iter=10, force_iters=1), oracle.icp_params(max_iter=10, force_iters=1))):
+            r = gpu_ctx.icp_run(prm_g)
+            o = oracle.icp(d["ct1"], d["nrm1"], d["ct2"], prm_o)      # sequential sums, what PCL does
+            assert r["n_iter"] == o["n_iter"] and r["state"] == o["state"]
+            da, dt = pose_diff(r["T"], o["T"])
+            assert da <= POSE_TOL_RAD and dt <= POSE_TOL_M
+    r = gpu_ctx.icp_run(P.icp_params(max_iter=10, force_iters=1), trace=True)
+    da, dt = pose_diff(r["T"], gold["icp_T"])
+    assert da <= POSE_TOL_RAD and dt <= POSE_TOL_M
+    assert np.allclose(r["mse"], gold["icp_mse"], rtol=1e-9)
+    r = gpu_ctx.icp_run()
+    assert r["n_iter"] == int(gold["icp_default_iters"]) and r["state"] == int(gold["icp_default_state"])
+
+
+def test_inner_loop_host_buffer_call_and_errors(gpu_ctx, oracle, pair2k):
+    d = pair2k
+    r = gpu_ctx.icp_p2plane(d["ct1"], d["nrm1"], d["ct2"])
+    o = oracle.icp(d["ct1"], d["nrm1"], d["ct2"])
+    da, dt = pose_diff(r["T"], o["T"])
+    assert da <= POSE_TOL_RAD and dt <= POSE_TOL_M and r["n_iter"] == o["n_iter"]
+    with pytest.raises(P.PwicpError) as e:                            # < 3 correspondences
+        gpu_ctx.icp_p2plane(d["ct1"], d["nrm1"], d["ct2"][:2])
+    assert e.value.status == -6
+    r1 = gpu_ctx.icp_p2plane(d["ct1"], d["nrm1"], d["ct2"][:3], P.icp_params(max_iter=1))
+    assert r1["n_iter"] == 1 and r1["state"] == 1
+
+
+# ------------------------------------------------------------------------------- A2, A7, A8, A10
+def test_single_iteration_matches_oracle(gpu_ctx, oracle, pair60k):
+    d = pair60k
+    gpu_ctx.upload_pair(d)
+    pd = oracle.PairData(d)
+    pp = P.PairParams(d["Res1"], d["Res2"], d["SVRes1"], d["SVRes2"], d["DTmin"])
+    gs, os_ = P.State(0.05, 0, 0, 0, 0), oracle.State(0.05, 0, 0, 0, 0)
+    for k in range(3):
+        T, V, flags, st = gpu_ctx.single_iteration(pp, gs)
+        rc, To, Vo, fo, so = oracle.single_iteration(pd, os_)
+        assert rc == 0
+        assert np.array_equal(flags, fo)                              # classification, patch by patch
+        assert st.n_stable == so.n_stable and st.n_stable_pts == so.n_stable_pts
+        assert st.LoDet_min == so.LoDet_min and st.LoDet_max == so.LoDet_max
+        assert st.icp_iters == so.icp_iters and st.icp_state == so.icp_state
+        da, dt = pose_diff(T, To)
+        assert da <= POSE_TOL_RAD and dt <= POSE_TOL_M
+        assert np.allclose(list(st.bb6), list(so.bb6), rtol=0, atol=1e-6)
+        assert abs(st.maxBBchange - so.maxBBchange) <= 1e-6
+        if not np.isnan(so.P75):
+            assert abs(st.P75 - so.P75) <= 1e-6
+        assert abs(gs.currDT - os_.currDT) <= 1e-7
+        assert (gs.toStage2, gs.toStage3) == (os_.toStage2, os_.toStage3)
+    dl = gpu_ctx.source_download()
+    for k, ref in (("cloud2", pd.cloud2), ("ct2", pd.ct2), ("bp2", pd.bp2), ("patch_pts2", pd.patch_pts2)):
+        assert np.abs(dl[k] - ref).max() <= 2e-6
+
+
+def test_outer_loop_matches_oracle_and_golden(gpu_ctx, oracle, gold, pair2k):
+    d = pair2k
+    pp = P.PairParams(d["Res1"], d["Res2"], d["SVRes1"], d["SVRes2"], d["DTmin"])
+    for manual, dtinit, key in ((1, 0.05, "outer"), (0, 0.0, "outer_auto")):
+        gpu_ctx.upload_pair(d)
+        g = gpu_ctx.piecewise_icp(pp, manual, dtinit)
+        o = oracle.piecewise_icp(oracle.PairData(d), manual, dtinit)
+        assert g["n_outer"] == o["rc"]
+        assert np.allclose(g["DTseries"], o["DTseries"], rtol=1e-6, atol=0)
+        assert np.allclose(g["DTseries"], gold[key + "_DTseries"], rtol=1e-6, atol=0)
+        assert (np.diff(g["DTseries"]) <= 0).all()
+        da, dt = pose_diff(g["T"], o["T"])
+        assert da <= POSE_TOL_RAD and dt <= POSE_TOL_M
+        da, dt = pose_diff(g["T"], gold[key + "_T"])
+        assert da <= POSE_TOL_RAD and dt <= POSE_TOL_M
+        assert [s.n_stable for s in g["stats"]] == [s.n_stable for s in o["stats"]]
+        assert [s.icp_iters for s in g["stats"]] == [s.icp_iters for s in o["stats"]]
+        assert np.allclose(g["VCM"], o["VCM"], rtol=1e-6, atol=0)      # relative 1e-6
+    assert np.allclose(g["VCM"], g["VCM"].T, rtol=1e-9)
+
+
+def test_outer_loop_error_codes(gpu_ctx, pair2k):
+    d = dict(pair2k)
+    pp = P.PairParams(d["Res1"], d["Res2"], d["SVRes1"], d["SVRes2"], d["DTmin"])
+    gpu_ctx.upload_pair(d)
+    gpu_ctx.source_upload(d["ct2"][:3], d["bp2"][:18], d["bpstd2"][:3], d["patch_off2"][:4], d["patch_pts2"][: d["patch_off2"][3]])
+    with pytest.raises(P.PwicpError) as e:
+        gpu_ctx.single_iteration(pp, P.State(0.05, 0, 0, 0, 0))
+    assert e.value.status == -4                                        # src/Registration.cpp:728-731
+    gpu_ctx.source_upload(d["ct2"] + np.float32(5), d["bp2"] + np.float32(5), d["bpstd2"], d["patch_off2"], d["patch_pts2"])
+    with pytest.raises(P.PwicpError) as e:
+        gpu_ctx.single_iteration(pp, P.State(0.05, 0, 0, 0, 0))
+    assert e.value.status == -5                                        # src/Registration.cpp:864-867
+
+
+def test_standalone_pieces(gpu_ctx, oracle, gold, pair2k):
+    d = pair2k
+    # percentile (A7), bit-identical value
+    assert gpu_ctx.percentile_nn(d["cloud1"], d["cloud2"], 0.75) == oracle.percentile_nn(d["cloud1"], d["cloud2"], 0.75) == gold["p75"][0]
+    for pct in (0.0, 0.5, 0.999):
+        assert gpu_ctx.percentile_nn(d["cloud1"], d["cloud2"], pct) == oracle.percentile_nn(d["cloud1"], d["cloud2"], pct)
+    # overlap ratio (F1)
+    _, d2 = oracle.nn(d["cloud1"], d["cloud2"])
+    ratio = np.float32(np.float32((np.sqrt(d2) < np.float32(0.05)).sum()) / np.float32(len(d2)))
+    assert gpu_ctx.overlap_ratio(d["cloud1"], d["cloud2"], 0.05) == ratio
+    # transform (A5) bit-exact, odd sizes exercise the vector tail
+    T = synth.rigid_matrix(0.01, -0.02, 0.03, 0.1, 0.2, -0.3).astype(np.float32)
+    for n in (1, 2, 3, 4, 5, 1023, 4099):
+        p = d["cloud2"][:n]
+        assert np.array_equal(gpu_ctx.transform(p, T), oracle.transform(p, T))
+    # octree bounding cube (A7)
+    for res in (0.01, 0.3):
+        assert np.array_equal(gpu_ctx.octree_bbox(d["cloud2"], res), oracle.octree_bbox(d["cloud2"], res))
+    assert np.array_equal(gpu_ctx.octree_bbox(d["cloud2"], 0.01), gold["octree_bb"])
+    # VCM (A8)
+    gpu_ctx.target_upload(d["ct1"], d["nrm1"], d["ctstd1"])
+    src = d["ct2"][~d["changed"]][:500]
+    V, sing = gpu_ctx.vcm(src)
+    Vo, so = oracle.vcm(d["ct1"], d["nrm1"], src)
+    assert np.allclose(V, Vo, rtol=1e-6, atol=0) and sing == so
+    assert np.allclose(V, gold["vcm"], rtol=1e-6, atol=0)
+
+
+# --------------------------------------------------------------------- full size (BASELINE configs)
+def test_full_size_properties_1m(gpu_ctx, oracle):
+    """configs[1]: 1M-centroid pair.  Size-independent properties + an oracle-checked sample."""
+    d = synth.make_pair(1_000_000, with_clouds=False)
+    n = len(d["ct1"])
+    gpu_ctx.target_upload(d["ct1"], d["nrm1"], d["ctstd1"])
+    # (a) every target point is its own nearest neighbour at distance 0 (the generator is tie-free)
+    idx, d2 = gpu_ctx.nn(d["ct1"])
+    assert np.array_equal(idx, np.arange(n, dtype=np.int32)) and not d2.any()
+    # (b) the reported distance is the reference float expression of the reported pair
+    idx, d2 = gpu_ctx.nn(d["ct2"])
+    df = d["ct2"] - d["ct1"][idx]
+    assert np.array_equal(d2, ((df[:, 0] * df[:, 0] + df[:, 1] * df[:, 1]) + df[:, 2] * df[:, 2]).astype(np.float32))
+    # (c) a random sample against brute force over all 1M targets
+    rng = np.random.default_rng(1)
+    pick = rng.choice(len(d["ct2"]), 300, replace=False)
+    oi, od = oracle.nn(d["ct1"], d["ct2"][pick], brute=True)
+    assert np.array_equal(idx[pick], oi) and np.array_equal(d2[pick], od)
+    # (d) whole set against the oracle KD-tree
+    oi, od = oracle.nn(d["ct1"], d["ct2"])
+    assert np.array_equal(idx, oi) and np.array_equal(d2, od)
+    # (e) three inner iterations, bit-exact in device order, pose within tolerance in reference order
+    gpu_ctx.icp_source_upload(d["ct2"])
+    r = gpu_ctx.icp_run(P.icp_params(max_iter=3, force_iters=1), trace=True)
+    perm = gpu_ctx.icp_order()
+    o1 = oracle.icp(d["ct1"], d["nrm1"], d["ct2"][perm],
+                    oracle.icp_params(max_iter=3, force_iters=1, reduce_mode=1, grid_blocks=r["grid_blocks"],
+                                      warps_per_block=r["warps_per_block"]), trace=True)
+    assert np.array_equal(r["T_trace"], o1["T_trace"]) and np.array_equal(r["idx_trace"][:, perm], o1["idx_trace"])
+    o0 = oracle.icp(d["ct1"], d["nrm1"], d["ct2"], oracle.icp_params(max_iter=3, force_iters=1))
+    da, dt = pose_diff(r["T"], o0["T"])
+    assert da <= POSE_TOL_RAD and dt <= POSE_TOL_M
+    # (f) 50 forced iterations are deterministic run to run
+    a = gpu_ctx.icp_run(P.icp_params(max_iter=50, force_iters=1))
+    b = gpu_ctx.icp_run(P.icp_params(max_iter=50, force_iters=1))
+    assert np.array_equal(a["T"], b["T"]) and a["correspondences"] == 50 * len(d["ct2"])

@@ -1,0 +1,137 @@
+"""GPU tests of the file-level drivers of libpwicp_host.so: the reference's two public entry
+points on synthetic PCD scans, the three 4D pair modes and the epoch-sharded form."""
+import os
+
+import numpy as np
+import pytest
+
+import pwicp_b200 as P
+from pwicp_b200 import host, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def read_transmatrix_file(path):
+    lines = open(path).read().splitlines()
+    assert lines[0] == "4x4 Transformation Matrix:"
+    T = np.array([[float(v) for v in lines[1 + r].split()] for r in range(4)])
+    assert lines[6] == "Rotation Angles (unit: gon):" and lines[7].startswith("Rx = ")
+    assert lines[10] == "Translation (unit: m):" and lines[11].startswith("tx = ")
+    assert lines[15] == "6x6 Variance-Covariance Matrix of transformation parameters:"
+    V = np.array([[float(v) for v in lines[16 + r].split()] for r in range(6)])
+    assert lines[23] == "Standard Deviations of estimated transformation parameters:"
+    assert lines[24].startswith("Std_Rx = ") and lines[24].endswith(" mgon") and lines[29].endswith(" mm")
+    return T, V
+
+
+def read_blocks(path, n):
+    vals = open(path).read().split()
+    out, p = [], 0
+    for _ in range(n):
+        t = int(vals[p]); p += 1
+        T = np.array(vals[p:p + 16], float).reshape(4, 4); p += 16
+        V = np.array(vals[p:p + 36], float).reshape(6, 6); p += 36
+        out.append((t, T, V))
+    assert p == len(vals)
+    return out
+
+
+@pytest.fixture(scope="module")
+def series(tmp_path_factory):
+    root = tmp_path_factory.mktemp("series")
+    folder = str(root / "scans")
+    gt = synth.make_series(folder, n_epochs=4, extent=3.0, spacing=0.01, seed=100)
+    return str(root), folder, gt
+
+
+def pose_err(T, Tgt):
+    da = np.abs(P.matrix2angle(T.astype(np.float32)) - P.matrix2angle(Tgt.astype(np.float32))).max()
+    dt = np.abs(T[:3, 3] - Tgt[:3, 3]).max()
+    return da, dt
+
+
+def test_pair_call_end_to_end(series, tmp_path):
+    root, folder, gt = series
+    cfg = str(tmp_path / "configuration_pair.txt")
+    synth.write_config(cfg, os.path.join(folder, "Epoch_001.pcd"), os.path.join(folder, "Epoch_002.pcd"))
+    prefix = str(tmp_path) + "/"
+    assert host.pair_call(cfg, prefix)
+    T, V = read_transmatrix_file(prefix + "TransMatrix.txt")
+    da, dt = pose_err(T, gt[1])
+    assert da < 3e-4 and dt < 1.5e-3, (da, dt)               # the authors' error level (<= 57 mgon, ~1 mm)
+    assert np.allclose(V, V.T, rtol=1e-6, atol=1e-18) and (np.diag(V) > 0).all()
+    src = host.load_pcd(os.path.join(folder, "Epoch_002.pcd"))
+    reg = host.load_pcd(prefix + "RegisteredSourceCloud.pcd")
+    assert reg.shape == src.shape
+    exp = src @ T[:3, :3].T.astype(np.float32) + T[:3, 3].astype(np.float32)
+    assert np.abs(reg - exp).max() < 1e-5
+    # error behaviour: missing config / missing clouds -> false, no exception
+    assert not host.pair_call(str(tmp_path / "nope.txt"), prefix)
+    synth.write_config(cfg, "/nonexistent/a.pcd", "/nonexistent/b.pcd")
+    assert not host.pair_call(cfg, prefix)
+
+
+def test_device_loop_equals_reference_shaped_loop(series):
+    """Piecewise_ICP (device loop) == while(!stage3) PwICP_singleIteration (mirror function)."""
+    root, folder, gt = series
+    a = host.load_pcd(os.path.join(folder, "Epoch_001.pcd"))[::2]
+    b = host.load_pcd(os.path.join(folder, "Epoch_003.pcd"))[::2]
+    r0 = host.register_clouds(a, b, 0.01, 0.1, 0.05, 0.004, mode=0)
+    r1 = host.register_clouds(a, b, 0.01, 0.1, 0.05, 0.004, mode=1)
+    assert np.array_equal(r0["DTseries"], r1["DTseries"]) and len(r0["DTseries"]) >= 3
+    assert np.array_equal(r0["T"], r1["T"])
+    assert np.allclose(r0["VCM"], r1["VCM"], rtol=1e-9)
+    da, dt = pose_err(r0["T"].astype(np.float64), gt[2])
+    assert da < 3e-4 and dt < 1.5e-3
+
+
+@pytest.mark.parametrize("mode,tag", [(0, "Direct2Ref"), (2, "Fixed"), (-1, "Adaptive")])
+def test_4d_call_modes(series, tmp_path, monkeypatch, mode, tag):
+    root, folder, gt = series
+    out = str(tmp_path) + "/"
+    cfg = str(tmp_path / "configuration_4d.txt")
+    synth.write_config(cfg, folder, out)
+    monkeypatch.chdir(tmp_path)                                # RegPairFile.txt goes to the CWD
+    monkeypatch.setenv("PWICP_GROUND_TRUTH", os.path.join(root, "defined_transformations.txt"))
+    assert host.call_4d(cfg, 0, 4, mode, 0.75)
+    for e in (2, 3, 4):
+        assert os.path.exists(out + f"{e}_{tag}_TransMatrix.txt")
+    blocks = read_blocks(out + "TransMatrices.txt", 3)
+    assert [b[0] for b in blocks] == [2, 3, 4]
+    toref = read_blocks(out + "TransMatrices_toRef.txt", 3)
+    for k, (t, T, V) in enumerate(toref):
+        da, dt = pose_err(T, gt[k + 1])
+        assert da < 6e-4 and dt < 3e-3, (mode, k, da, dt)
+    hdr = open(out + "TransParameters.txt").readline()
+    assert hdr.startswith("Epoch  Rx[gon]") and len(open(out + "TransParameters.txt").read().splitlines()) == 4
+    err = open(out + "TransPara_AbsError.txt").read().splitlines()
+    assert err[0].startswith("Err_Rx[mgon]") and len(err) == 4
+    if mode < 0:
+        pairs = [tuple(map(int, l.split())) for l in open(tmp_path / "RegPairFile.txt").read().splitlines()]
+        assert [p[0] for p in pairs] == [1, 2, 3] and all(0 <= p[1] < p[0] for p in pairs)
+
+
+def test_4d_epoch_sharding_matches_single_process(series, tmp_path, monkeypatch):
+    root, folder, gt = series
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setenv("PWICP_GROUND_TRUTH", "/nonexistent")
+    outs = {}
+    for name in ("single", "sharded"):
+        out = str(tmp_path / name) + "/"
+        os.makedirs(out)
+        cfg = str(tmp_path / f"cfg_{name}.txt")
+        synth.write_config(cfg, folder, out)
+        if name == "single":
+            assert host.call_4d(cfg, 0, 4, 0, 0.75)
+        else:
+            arrays = []
+            for rank in range(2):                               # the two ranks, one after the other
+                done, recs = host.shard_4d(cfg, 0, 4, 0, 0.75, rank, 2, 0)
+                assert done == (2 if rank == 0 else 1)
+                arrays.append(host.records_to_array(recs))
+            merged = host.array_to_records(host.merge_records(arrays))
+            assert all(merged[k].status == 1 for k in range(3))
+            assert host.finalize_4d(cfg, 0, 4, 0, merged)
+        outs[name] = out
+    for f in ("TransMatrices.txt", "TransParameters.txt", "TransMatrices_toRef.txt", "TransParameters_toRef.txt"):
+        assert open(outs["single"] + f).read() == open(outs["sharded"] + f).read(), f
