@@ -100,8 +100,9 @@ void pwicp_icp_default_params(pwicp_icp_params* p);
 typedef struct {
     int   n_iter;           /* inner iterations done */
     int   conv_state;       /* PWICP_CONV_* */
-    int   grid_blocks;      /* reduction geometry used: blocks x warps_per_block */
+    int   grid_blocks;      /* launch geometry (informational): CTAs x warps_per_block */
     int   warps_per_block;
+    int   group_batches;    /* reduction geometry: 32-point batches per group */
     float device_ms;        /* whole inner loop, CUDA events */
     long long correspondences;  /* n_iter * n_source */
 } pwicp_icp_result;

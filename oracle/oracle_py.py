@@ -20,8 +20,8 @@ u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
 
 class IcpParams(C.Structure):
     _fields_ = [("max_iter", C.c_int), ("tf_eps", C.c_double), ("fit_eps", C.c_double),
-                ("force_iters", C.c_int), ("reduce_mode", C.c_int), ("grid_blocks", C.c_int),
-                ("warps_per_block", C.c_int), ("rot_thr_default", C.c_int)]
+                ("force_iters", C.c_int), ("reduce_mode", C.c_int), ("group_batches", C.c_int),
+                ("reserved", C.c_int), ("rot_thr_default", C.c_int)]
 
 
 class Pair(C.Structure):
@@ -97,9 +97,8 @@ def _f32(a):
 
 
 def icp_params(max_iter=100, tf_eps=1e-8, fit_eps=1e-6, force_iters=0, reduce_mode=0,
-               grid_blocks=0, warps_per_block=0, rot_thr_default=0):
-    return IcpParams(max_iter, tf_eps, fit_eps, force_iters, reduce_mode, grid_blocks,
-                     warps_per_block, rot_thr_default)
+               group_batches=0, rot_thr_default=0):
+    return IcpParams(max_iter, tf_eps, fit_eps, force_iters, reduce_mode, group_batches, 0, rot_thr_default)
 
 
 def nn(tgt, qry, brute=False):
@@ -116,10 +115,10 @@ def transform(pts, T):
     return out
 
 
-def lls_step(src, match, tgt, nrm, reduce_mode=0, grid_blocks=0, warps_per_block=0):
+def lls_step(src, match, tgt, nrm, reduce_mode=0, group_batches=0):
     ATA = np.zeros(36); ATb = np.zeros(6); x = np.zeros(6); T = np.zeros(16, np.float32)
     lib().orc_lls_step(_f32(src), np.ascontiguousarray(match, np.int32), len(src), _f32(tgt),
-                       _f32(nrm), reduce_mode, grid_blocks, warps_per_block, ATA, ATb, x, T)
+                       _f32(nrm), reduce_mode, group_batches, 0, ATA, ATb, x, T)
     return ATA.reshape(6, 6), ATb, x, T.reshape(4, 4)
 
 

@@ -264,7 +264,7 @@ const ValTab g_vt;
 
 /* Accumulate the 28 values over all rows.  u7: n x 7 floats, d2: n floats, valid: n flags. */
 void accumulate28(const float* u7, const float* d2, const unsigned char* valid, int n,
-                  int reduce_mode, int grid_blocks, int wpb, double* out28) {
+                  int reduce_mode, int group_batches, int /*unused*/, double* out28) {
     if (reduce_mode == 0) {
         /* [PCL] one sequential loop in correspondence order */
         for (int v = 0; v < 28; ++v) out28[v] = 0.0;
@@ -276,37 +276,47 @@ void accumulate28(const float* u7, const float* d2, const unsigned char* valid, 
         }
         return;
     }
-    /* Summation order of the CUDA kernel (DESIGN.md "reduction geometry"): global warp W of NW =
-     * grid_blocks*wpb handles 32-point batches W, W+NW, ... sequentially; block partial = warps in
-     * order; grid total = lane l sums blocks l, l+32, ... then an xor butterfly 16,8,4,2,1. */
-    const int NW = grid_blocks * wpb;
+    /* Summation order of the CUDA kernel (DESIGN.md "reduction geometry"): per 32-point batch the
+     * rows in order starting from 0; per group of `group_batches` consecutive batches: lane l sums the
+     * batch sums l, l+32, ... in order, then an xor butterfly 16,8,4,2,1 over the 32 lanes; the
+     * grand total applies the same lane-strided sum + butterfly to the group sums. */
     const long nb = ((long)n + 31) / 32;
-    std::vector<double> wacc((size_t)NW * 28, 0.0);
-    for (int W = 0; W < NW; ++W) {
-        double* acc = &wacc[(size_t)W * 28];
-        for (long g = W; g < nb; g += NW) {
-            for (int r = 0; r < 32; ++r) {
-                long i = g * 32 + r;
-                if (i >= n) break;
-                const float* u = u7 + 7 * (size_t)i;
-                if (valid[i])
-                    for (int v = 0; v < 27; ++v) acc[v] += (double)u[g_vt.a[v]] * (double)u[g_vt.b[v]];
-                acc[27] += (double)d2[i];
-            }
+    const int gb = group_batches > 0 ? group_batches : 512;
+    const long ng = (nb + gb - 1) / gb;
+    std::vector<double> bsum((size_t)nb * 28, 0.0), gsum((size_t)ng * 28, 0.0);
+    for (long b = 0; b < nb; ++b) {
+        double* acc = &bsum[(size_t)b * 28];
+        for (int r = 0; r < 32; ++r) {
+            long i = b * 32 + r;
+            if (i >= n) break;
+            const float* u = u7 + 7 * (size_t)i;
+            if (valid[i])
+                for (int v = 0; v < 27; ++v) acc[v] += (double)u[g_vt.a[v]] * (double)u[g_vt.b[v]];
+            acc[27] += (double)d2[i];
         }
     }
-    std::vector<double> bacc((size_t)grid_blocks * 28);
-    for (int b = 0; b < grid_blocks; ++b)
+    for (long g = 0; g < ng; ++g) {
+        const long gsize = std::min((long)gb, nb - g * gb);
         for (int v = 0; v < 28; ++v) {
-            double s = wacc[((size_t)b * wpb) * 28 + v];
-            for (int w = 1; w < wpb; ++w) s += wacc[((size_t)b * wpb + w) * 28 + v];
-            bacc[(size_t)b * 28 + v] = s;
+            double lane[32];
+            for (int l = 0; l < 32; ++l) {
+                double s = 0.0;
+                for (long k = l; k < gsize; k += 32) s += bsum[(size_t)(g * gb + k) * 28 + v];
+                lane[l] = s;
+            }
+            for (int off = 16; off >= 1; off >>= 1) {
+                double nxt[32];
+                for (int l = 0; l < 32; ++l) nxt[l] = lane[l] + lane[l ^ off];
+                std::memcpy(lane, nxt, sizeof(lane));
+            }
+            gsum[(size_t)g * 28 + v] = lane[0];
         }
+    }
     for (int v = 0; v < 28; ++v) {
         double lane[32];
         for (int l = 0; l < 32; ++l) {
             double s = 0.0;
-            for (int b = l; b < grid_blocks; b += 32) s += bacc[(size_t)b * 28 + v];
+            for (long g = l; g < ng; g += 32) s += gsum[(size_t)g * 28 + v];
             lane[l] = s;
         }
         for (int off = 16; off >= 1; off >>= 1) {
@@ -353,7 +363,7 @@ void set_identity(float* T) { for (int i = 0; i < 16; ++i) T[i] = (i % 5 == 0) ?
 orc_icp_params default_icp() {
     orc_icp_params p;
     p.max_iter = 100; p.tf_eps = 1e-8; p.fit_eps = 1e-6; p.force_iters = 0;
-    p.reduce_mode = 0; p.grid_blocks = 0; p.warps_per_block = 0; p.rot_thr_default = 0;
+    p.reduce_mode = 0; p.group_batches = 0; p.reserved = 0; p.rot_thr_default = 0;
     return p;
 }
 
@@ -385,8 +395,8 @@ int icp_run(const KdTree& tree, const float* tgt, const float* nrm, const float*
         }
         double s28[28], ATA[36], ATb[6], x[6];
         float T[16];
-        accumulate28(u7.data(), d2.data(), valid.data(), n2s, prm.reduce_mode, prm.grid_blocks,
-                     prm.warps_per_block, s28);
+        accumulate28(u7.data(), d2.data(), valid.data(), n2s, prm.reduce_mode, prm.group_batches,
+                     prm.reserved, s28);
         solve_from28(s28, ATA, ATb, x, T);
         orc_transform(cur.data(), n2s, T);            /* transformCloud(input_transformed, ..) */
         mat4_mul(T, Tfinal, Tfinal);                  /* final = T * final */
@@ -556,7 +566,7 @@ void orc_transform(float* pts, int n, const float* T) {
 void orc_mat4_mul(const float* A, const float* B, float* C) { mat4_mul(A, B, C); }
 
 int orc_lls_step(const float* src, const int* match, int n, const float* tgt, const float* nrm,
-                 int reduce_mode, int grid_blocks, int warps_per_block,
+                 int reduce_mode, int group_batches, int reserved,
                  double* ATA36, double* ATb6, double* x6, float* T16) {
     std::vector<float> u7(7 * (size_t)n), d2(n);
     std::vector<unsigned char> valid(n);
@@ -569,7 +579,7 @@ int orc_lls_step(const float* src, const int* match, int n, const float* tgt, co
         d2[i] = l2_simple(s, d);
     }
     double s28[28];
-    accumulate28(u7.data(), d2.data(), valid.data(), n, reduce_mode, grid_blocks, warps_per_block, s28);
+    accumulate28(u7.data(), d2.data(), valid.data(), n, reduce_mode, group_batches, reserved, s28);
     solve_from28(s28, ATA36, ATb6, x6, T16);
     return 0;
 }

@@ -41,10 +41,10 @@ void orc_transform(float* pts, int n, const float* T16);
 /* ---- A4: TransformationEstimationPointToPlaneLLS::estimateRigidTransformation
  * (reached from src/Registration.cpp:1266).  reduce_mode 0 = sequential double sums in
  * correspondence order (what PCL does); reduce_mode 1 = the summation order of the CUDA kernel
- * (grid_blocks x warps_per_block warps, 32-point batches; see DESIGN.md "reduction geometry"),
+ * (32-point batches, groups of group_batches batches; see DESIGN.md "reduction geometry"),
  * used to prove the GPU loop bit-exactly. Outputs: ATA (36), ATb (6), x (6), T (16 f32). */
 int orc_lls_step(const float* src, const int* match, int n, const float* tgt, const float* nrm,
-                 int reduce_mode, int grid_blocks, int warps_per_block,
+                 int reduce_mode, int group_batches, int reserved,
                  double* ATA36, double* ATb6, double* x6, float* T16);
 
 /* ---- A3 + A6: P2PICPwithPatchNormal (src/Registration.cpp:1255-1269) =
@@ -55,8 +55,8 @@ typedef struct {
     double fit_eps;         /* 1e-6 (src/Registration.cpp:877, :1263) */
     int    force_iters;     /* !=0: benchmark mode, run exactly max_iter iterations */
     int    reduce_mode;     /* see orc_lls_step */
-    int    grid_blocks;
-    int    warps_per_block;
+    int    group_batches;   /* reduce_mode 1: 32-point batches per reduction group (device: 64) */
+    int    reserved;
     int    rot_thr_default; /* !=0: leave the rotation threshold at PCL's default 0.99999 */
 } orc_icp_params;
 

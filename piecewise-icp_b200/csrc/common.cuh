@@ -16,6 +16,8 @@ constexpr int kRingsPerLevel = 2;  // rings searched on a level before moving to
 constexpr int kIcpThreads = 256;   // 8 warps per CTA (reduction geometry)
 constexpr int kIcpWarps = kIcpThreads / 32;
 constexpr int kNumVals = 28;       // 21 ATA + 6 ATb + sum d2
+constexpr int kGroupBatches = 512; // batches (of 32 points) per reduction group
+constexpr int kGrab = 1;           // batches a warp takes per atomic hand-out
 constexpr int kMaxIcpIter = 1024;
 
 struct GridLevel {
@@ -33,13 +35,24 @@ struct GridDev {
     const uint32_t* inv_perm;    // original index -> position in level 0
 };
 
+// simple device buffer that grows on demand (never shrinks: rebuilding a grid of the same size
+// does not touch the allocator -- cudaMalloc/cudaFree serialise across processes and cost ms)
+struct Ctx;
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(Ctx* ctx, size_t bytes);
+    void release();
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
 // Owns the device memory of one grid pyramid.
 struct GridOwner {
     GridDev dev{};
-    void* pts[kMaxLevels] = {nullptr, nullptr, nullptr};
-    void* cells[kMaxLevels] = {nullptr, nullptr, nullptr};
-    void* inv_perm = nullptr;
-    uint32_t* perm0 = nullptr;   // level-0 order: position -> original index
+    DevBuf pts[kMaxLevels], cells[kMaxLevels];
+    DevBuf inv_perm;
+    DevBuf perm0_buf;            // level-0 order: position -> original index
+    uint32_t* perm0 = nullptr;
     float h0 = 0.f;
     int n = 0;
     void release();
@@ -62,15 +75,6 @@ void set_error(Ctx* c, const std::string& msg);
         int s__ = (call);                                                                    \
         if (s__ != PWICP_OK) return s__;                                                     \
     } while (0)
-
-// simple device buffer that grows on demand
-struct DevBuf {
-    void* p = nullptr;
-    size_t cap = 0;
-    int reserve(Ctx* ctx, size_t bytes);
-    void release();
-    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
-};
 
 struct Ctx {
     int device = 0;

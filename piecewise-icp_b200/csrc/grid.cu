@@ -15,14 +15,9 @@ namespace pwicp {
 
 // ---- small utilities ----------------------------------------------------------------------
 void GridOwner::release() {
-    for (int l = 0; l < kMaxLevels; ++l) {
-        if (pts[l]) cudaFree(pts[l]);
-        if (cells[l]) cudaFree(cells[l]);
-        pts[l] = cells[l] = nullptr;
-    }
-    if (inv_perm) cudaFree(inv_perm);
-    if (perm0) cudaFree(perm0);
-    inv_perm = nullptr; perm0 = nullptr; n = 0;
+    for (int l = 0; l < kMaxLevels; ++l) { pts[l].release(); cells[l].release(); }
+    inv_perm.release(); perm0_buf.release();
+    perm0 = nullptr; n = 0;
     dev = GridDev{};
 }
 
@@ -174,7 +169,8 @@ __global__ void gather_sorted_kernel(const float* __restrict__ xyz, const uint32
 static int bits_for(uint64_t v) { int b = 1; while ((1ull << b) < v && b < 32) ++b; return b; }
 
 int grid_build(Ctx* ctx, GridOwner& g, const float* xyz, int n) {
-    g.release();
+    g.dev = GridDev{};                 // invalid until the build completes; buffers are reused
+    g.n = 0;
     if (n < 1) { set_error(ctx, "grid_build: empty target"); return PWICP_ERR_ARG; }
     float mn[3], mx[3];
     PW_TRY(bbox_packed_dev(ctx, xyz, (size_t)n, mn, mx));
@@ -217,9 +213,8 @@ int grid_build(Ctx* ctx, GridOwner& g, const float* xyz, int n) {
         PW_TRY(ctx->vals.reserve(ctx, (size_t)n * 4));
         PW_TRY(ctx->keys2.reserve(ctx, (size_t)n * 4));
         PW_TRY(ctx->vals2.reserve(ctx, (size_t)n * 4));
-        uint32_t* cells = nullptr;
-        PW_CUDA(cudaMalloc(&cells, (ncells + 1) * sizeof(uint32_t)));
-        g.cells[l] = cells;
+        PW_TRY(g.cells[l].reserve(ctx, (ncells + 1) * sizeof(uint32_t)));
+        uint32_t* cells = g.cells[l].as<uint32_t>();
         PW_CUDA(cudaMemsetAsync(cells, 0, (ncells + 1) * sizeof(uint32_t), ctx->stream));
         int blocks = (n + 255) / 256;
         cell_key_kernel<<<blocks, 256, 0, ctx->stream>>>(xyz, n, mn[0], mn[1], mn[2], inv_h, d[0], d[1], d[2],
@@ -241,14 +236,14 @@ int grid_build(Ctx* ctx, GridOwner& g, const float* xyz, int n) {
                                                 ctx->keys2.as<uint32_t>(), ctx->vals.as<uint32_t>(),
                                                 ctx->vals2.as<uint32_t>(), n, 0, bits_for(ncells), ctx->stream));
         ctx->launches += 6;
-        float4* pts = nullptr;
-        PW_CUDA(cudaMalloc(&pts, (size_t)n * sizeof(float4)));
-        g.pts[l] = pts;
+        PW_TRY(g.pts[l].reserve(ctx, (size_t)n * sizeof(float4)));
+        float4* pts = g.pts[l].as<float4>();
         uint32_t* invp = nullptr;
         if (l == 0) {
-            PW_CUDA(cudaMalloc(&g.inv_perm, (size_t)n * sizeof(uint32_t)));
-            PW_CUDA(cudaMalloc(&g.perm0, (size_t)n * sizeof(uint32_t)));
-            invp = (uint32_t*)g.inv_perm;
+            PW_TRY(g.inv_perm.reserve(ctx, (size_t)n * sizeof(uint32_t)));
+            PW_TRY(g.perm0_buf.reserve(ctx, (size_t)n * sizeof(uint32_t)));
+            g.perm0 = g.perm0_buf.as<uint32_t>();
+            invp = g.inv_perm.as<uint32_t>();
             PW_CUDA(cudaMemcpyAsync(g.perm0, ctx->vals2.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
         }
         gather_sorted_kernel<<<blocks, 256, 0, ctx->stream>>>(xyz, ctx->vals2.as<uint32_t>(), n, pts, invp);
@@ -263,7 +258,7 @@ int grid_build(Ctx* ctx, GridOwner& g, const float* xyz, int n) {
         hl *= kLevelFactor;
     }
     g.dev.nlevels = nlev;
-    g.dev.inv_perm = (const uint32_t*)g.inv_perm;
+    g.dev.inv_perm = g.inv_perm.as<uint32_t>();
     PW_CUDA(cudaStreamSynchronize(ctx->stream));
     return PWICP_OK;
 }

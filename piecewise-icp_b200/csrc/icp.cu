@@ -13,8 +13,11 @@
 // transform and evaluates the convergence criteria -- identical instructions on identical
 // inputs, so all CTAs take the same decision without a second barrier or a host round trip.
 //
-// The summation order ("reduction geometry") is deterministic and is reproduced by the
-// oracle's reduce_mode=1 for the bit-exact whole-loop parity test.
+// Batches of 32 points are handed out dynamically (their cost is data dependent; a static split
+// left half of the SM time waiting at the grid barrier, profiles/r01c_*), yet the summation order
+// ("reduction geometry") is fixed: rows of a batch in order, batches of a 64-batch group
+// in order (a second, cheap grid-wide pass), groups by a lane-strided sum + butterfly.
+// The oracle's reduce_mode=1 reproduces it for the bit-exact whole-loop parity test.
 #include <cooperative_groups.h>
 
 #include "common.cuh"
@@ -23,6 +26,9 @@
 #include "nn_search.cuh"
 #include "small_algebra.cuh"
 
+#ifndef PWICP_ICP_MINBLOCKS
+#define PWICP_ICP_MINBLOCKS 3
+#endif
 namespace cg = cooperative_groups;
 
 namespace pwicp {
@@ -38,65 +44,157 @@ struct IcpArgs {
     int max_iter;
     int force_iters;
     double rot_thr, transl_thr, mse_rel, mse_abs;
-    double* partials;         // [2][gridDim.x][28]
+    double* batch_part;       // [nb][28]: sums of one 32-point batch
+    double* group_part;       // [ng][28]: sums of kGroupBatches consecutive batches
+    int* batch_counter;       // [max_iter], zeroed before the launch: dynamic batch hand-out
     float* out_T;             // 16: final transformation
     int* out_state;           // [0] n_iter, [1] conv_state
     double* mse_trace;        // nullable
     float* T_trace;           // nullable
     int* idx_trace;           // nullable, [iter][n]
+    long long* timing;        // debug build only
 };
 
-// Thread 0 of every CTA: totals -> 6x6 solve -> float transform -> convergence decision.
-// Kept out of line so its local arrays do not inflate the register budget of the search loop.
-__device__ __noinline__ int icp_finish(const IcpArgs& a, int it, const double* s_tot, float* s_T,
-                                       float* s_Tfinal, double& prev_mse) {
-    double tot[kNumVals], x[6];
-    for (int v = 0; v < kNumVals; ++v) tot[v] = s_tot[v];
+// Shared scratch of the per-iteration solve.
+struct FinishSmem {
+    double A[6][6];      // ATA, then its LU factors in place
+    double inv[6][6];
+    double b[6], x[6];
+    double sc[3][2];     // sin / cos of alpha, beta, gamma
+    int piv[6];
     float Tn[16];
-    solve_from28(tot, x, Tn);
-    for (int k = 0; k < 16; ++k) s_T[k] = Tn[k];
-    float Tf[16];
-    mat4_mul(Tn, s_Tfinal, Tf);                       // final = T * final
-    for (int k = 0; k < 16; ++k) s_Tfinal[k] = Tf[k];
-    const double mse = tot[27] / (double)a.n;
-    const int iters = it + 1;
-    int state = 0;
-    // DefaultConvergenceCriteria<float>::hasConverged(), in PCL's order
-    if (iters >= a.max_iter) state = PWICP_CONV_ITERATIONS;
-    else if (!a.force_iters) {
-        const double cos_angle = 0.5 * (double)(Tn[0] + Tn[5] + Tn[10] - 1.0f);
-        const double transl_sq = (double)(Tn[3] * Tn[3] + Tn[7] * Tn[7] + Tn[11] * Tn[11]);
-        if (cos_angle >= a.rot_thr && transl_sq <= a.transl_thr) state = PWICP_CONV_TRANSFORM;
-        else if (fabs(mse - prev_mse) < a.mse_abs) state = PWICP_CONV_ABS_MSE;
-        else if (fabs(mse - prev_mse) / prev_mse < a.mse_rel) state = PWICP_CONV_REL_MSE;
+};
+
+// Warp 0 of every CTA: totals -> 6x6 solve -> float transform -> convergence decision.
+// Every scalar operation is the one small_algebra.cuh's sequential inverse6()/solve_from28()
+// performs (same operands, same order per element), so the result is bit-identical to the
+// single-thread version and to the oracle; the lanes only shorten the critical path (the
+// single-thread solve cost ~25 us per inner iteration, profiles/r01d_*).
+__device__ __forceinline__ int icp_finish_warp(const IcpArgs& a, int it, const double* s_tot, float* s_T,
+                                               float* s_Tfinal, double& prev_mse, FinishSmem& F, int lane) {
+    // ATA (mirrored) and ATb from the 28 totals
+    for (int idx = lane; idx < 36; idx += 32) {
+        const int r = idx / 6, c = idx % 6, lo = min(r, c), hi = max(r, c);
+        F.A[r][c] = s_tot[lo * 6 - lo * (lo - 1) / 2 + (hi - lo)];
     }
-    prev_mse = mse;
-    if (blockIdx.x == 0) {
-        if (a.mse_trace) a.mse_trace[it] = mse;
-        if (a.T_trace) for (int k = 0; k < 16; ++k) a.T_trace[(size_t)it * 16 + k] = Tn[k];
-        if (state) {
-            for (int k = 0; k < 16; ++k) a.out_T[k] = Tf[k];
-            a.out_state[0] = iters;
-            a.out_state[1] = state;
+    if (lane < 6) { F.b[lane] = s_tot[21 + lane]; F.piv[lane] = lane; }
+    __syncwarp();
+    // LU with partial pivoting (inverse6)
+    for (int k = 0; k < 6; ++k) {
+        int p = k;
+        if (lane == 0) {
+            double big = fabs(F.A[k][k]);
+            for (int r = k + 1; r < 6; ++r) { const double v = fabs(F.A[r][k]); if (v > big) { big = v; p = r; } }
+        }
+        p = __shfl_sync(0xffffffffu, p, 0);
+        if (p != k) {
+            if (lane < 6) { const double t = F.A[k][lane]; F.A[k][lane] = F.A[p][lane]; F.A[p][lane] = t; }
+            if (lane == 0) { const int t = F.piv[k]; F.piv[k] = F.piv[p]; F.piv[p] = t; }
+        }
+        __syncwarp();
+        const double d = F.A[k][k];
+        if (d == 0.0) continue;
+        const int m = 5 - k;                                    // trailing block is m x m
+        double f = 0.0, upd = 0.0;
+        int r = 0, c = 0;
+        const bool on = lane < m * m;
+        if (on) {
+            r = k + 1 + lane / m; c = k + 1 + lane % m;
+            f = F.A[r][k] / d;
+            upd = F.A[r][c] - f * F.A[k][c];
+        }
+        __syncwarp();
+        if (on) { F.A[r][c] = upd; if (c == k + 1) F.A[r][k] = f; }
+        __syncwarp();
+    }
+    // inverse: lane j solves L U x = P e_j
+    if (lane < 6) {
+        double y[6], xs[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            double sacc = (F.piv[r] == lane) ? 1.0 : 0.0;
+#pragma unroll
+            for (int c = 0; c < r; ++c) sacc -= F.A[r][c] * y[c];
+            y[r] = sacc;
+        }
+#pragma unroll
+        for (int r = 5; r >= 0; --r) {
+            double sacc = y[r];
+#pragma unroll
+            for (int c = r + 1; c < 6; ++c) sacc -= F.A[r][c] * xs[c];
+            xs[r] = sacc / F.A[r][r];
+        }
+#pragma unroll
+        for (int r = 0; r < 6; ++r) F.inv[r][lane] = xs[r];
+    }
+    __syncwarp();
+    if (lane < 6) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) sacc += F.inv[lane][c] * F.b[c];
+        F.x[lane] = sacc;
+    }
+    __syncwarp();
+    if (lane < 3) { F.sc[lane][0] = sin(F.x[lane]); F.sc[lane][1] = cos(F.x[lane]); }
+    __syncwarp();
+    if (lane == 0) {
+        float Tn[16];
+        construct_T_sc(F.sc[0][0], F.sc[0][1], F.sc[1][0], F.sc[1][1], F.sc[2][0], F.sc[2][1], F.x, Tn);
+        for (int k = 0; k < 16; ++k) F.Tn[k] = Tn[k];
+    }
+    __syncwarp();
+    // final = T * final, one entry per lane (mat4_mul's order: sum over k = 0..3)
+    float tf = 0.f;
+    if (lane < 16) {
+        const int i = lane / 4, j = lane % 4;
+        tf = F.Tn[i * 4 + 0] * s_Tfinal[0 * 4 + j];
+        tf += F.Tn[i * 4 + 1] * s_Tfinal[1 * 4 + j];
+        tf += F.Tn[i * 4 + 2] * s_Tfinal[2 * 4 + j];
+        tf += F.Tn[i * 4 + 3] * s_Tfinal[3 * 4 + j];
+    }
+    __syncwarp();
+    if (lane < 16) { s_Tfinal[lane] = tf; s_T[lane] = F.Tn[lane]; }
+    __syncwarp();
+    int state = 0;
+    if (lane == 0) {
+        const float* Tn = F.Tn;
+        const double mse = s_tot[27] / (double)a.n;
+        const int iters = it + 1;
+        // DefaultConvergenceCriteria<float>::hasConverged(), in PCL's order
+        if (iters >= a.max_iter) state = PWICP_CONV_ITERATIONS;
+        else if (!a.force_iters) {
+            const double cos_angle = 0.5 * (double)(Tn[0] + Tn[5] + Tn[10] - 1.0f);
+            const double transl_sq = (double)(Tn[3] * Tn[3] + Tn[7] * Tn[7] + Tn[11] * Tn[11]);
+            if (cos_angle >= a.rot_thr && transl_sq <= a.transl_thr) state = PWICP_CONV_TRANSFORM;
+            else if (fabs(mse - prev_mse) < a.mse_abs) state = PWICP_CONV_ABS_MSE;
+            else if (fabs(mse - prev_mse) / prev_mse < a.mse_rel) state = PWICP_CONV_REL_MSE;
+        }
+        prev_mse = mse;
+        if (blockIdx.x == 0) {
+            if (a.mse_trace) a.mse_trace[it] = mse;
+            if (a.T_trace) for (int k = 0; k < 16; ++k) a.T_trace[(size_t)it * 16 + k] = Tn[k];
+            if (state) {
+                for (int k = 0; k < 16; ++k) a.out_T[k] = s_Tfinal[k];
+                a.out_state[0] = iters;
+                a.out_state[1] = state;
+            }
         }
     }
-    return state;
+    return __shfl_sync(0xffffffffu, state, 0);
 }
 
-__global__ void __launch_bounds__(kIcpThreads, 3) icp_persistent_kernel(const IcpArgs a) {
+__global__ void __launch_bounds__(kIcpThreads, PWICP_ICP_MINBLOCKS) icp_persistent_kernel(const IcpArgs a) {
     cg::grid_group grid = cg::this_grid();
     __shared__ __align__(16) float s_rows[kIcpWarps][32][8];
-    __shared__ double s_wacc[kIcpWarps][kNumVals];
     __shared__ double s_tot[kNumVals];
     __shared__ float s_T[16];
     __shared__ float s_Tfinal[16];
     __shared__ int s_stop;
+    __shared__ FinishSmem s_fin;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int G = gridDim.x;
-    const long NW = (long)G * kIcpWarps;
-    const long gw = (long)blockIdx.x * kIcpWarps + warp;
-    const long nb = ((long)a.n + 31) / 32;
+    const int nb = (a.n + 31) / 32;                              // 32-point batches
+    const int ng = (nb + kGroupBatches - 1) / kGroupBatches;     // groups of kGroupBatches batches
 
     // which pair of row terms this lane accumulates: 21 upper-triangle ATA entries (row-major),
     // 6 ATb entries (u_r * u_6), lane 27 = sum of squared NN distances
@@ -113,83 +211,114 @@ __global__ void __launch_bounds__(kIcpThreads, 3) icp_persistent_kernel(const Ic
     double prev_mse = 1.7976931348623157e308;   // DBL_MAX
     __syncthreads();
 
+#ifdef PWICP_TIMING
+#define PW_TS(k) do { if (tid == 0 && it == 10 && a.timing) a.timing[blockIdx.x * 8 + (k)] = clock64(); } while (0)
+#else
+#define PW_TS(k)
+#endif
     for (int it = 0;; ++it) {
-        double acc = 0.0;
+        PW_TS(0);
         float T[12];
 #pragma unroll
         for (int k = 0; k < 12; ++k) T[k] = s_T[k];
 
-        for (long b = gw; b < nb; b += NW) {
-            const long i = b * 32 + lane;
-            const bool active = i < a.n;
-            float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
-            float4 p = lo;
-            if (active) {
-                p = (it == 0) ? __ldg(a.src + i) : a.work[i];
-                if (it > 0) {
-                    float x, y, z;
-                    xform_point(T, p.x, p.y, p.z, x, y, z);
-                    p.x = x; p.y = y; p.z = z;
+        // ---- phase A: batches are handed out dynamically, kGrab at a time (the cost of a batch
+        // depends on the data), but every sum below is formed in an order that does not depend on
+        // which warp does it
+        for (;;) {
+            int b0 = 0;
+            if (lane == 0) b0 = atomicAdd(a.batch_counter + it, kGrab);
+            b0 = __shfl_sync(0xffffffffu, b0, 0);
+            if (b0 >= nb) break;
+            const int b1 = min(b0 + kGrab, nb);
+            for (int b = b0; b < b1; ++b) {
+                const int i = b * 32 + lane;
+                const bool active = i < a.n;
+                float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+                if (active) {
+                    float4 p = (it == 0) ? __ldg(a.src + i) : a.work[i];
+                    if (it > 0) {
+                        float x, y, z;
+                        xform_point(T, p.x, p.y, p.z, x, y, z);
+                        p.x = x; p.y = y; p.z = z;
+                    }
+                    a.work[i] = p;
+                    const int seed = (it > 0 || a.use_seed0) ? a.match[i] : -1;
+                    const Best bb = nn_search_seeded<true>(a.g, p.x, p.y, p.z, seed);
+                    a.match[i] = bb.pos;
+                    const float4 nq = __ldg(a.aux + bb.pos);
+                    const float sx = p.x, sy = p.y, sz = p.z;
+                    const float dx = bb.qx, dy = bb.qy, dz = bb.qz;
+                    const float nx = nq.x, ny = nq.y, nz = nq.z;
+                    // float expressions of TransformationEstimationPointToPlaneLLS (no FMA)
+                    lo.x = nz * sy - ny * sz;
+                    lo.y = nx * sz - nz * sx;
+                    lo.z = ny * sx - nx * sy;
+                    lo.w = nx;
+                    hi.x = ny;
+                    hi.y = nz;
+                    hi.z = nx * dx + ny * dy + nz * dz - nx * sx - ny * sy - nz * sz;
+                    hi.w = bb.d2;
+                    // traces are reported in the caller's order (p.w = original source index)
+                    if (a.idx_trace) a.idx_trace[(size_t)it * a.n + __float_as_int(p.w)] = bb.idx;
                 }
-                a.work[i] = p;
-            }
-            int seed = -1;
-            if (active && (it > 0 || a.use_seed0)) seed = a.match[i];
-            if (active) {
-                const Best bb = nn_search_seeded<true>(a.g, p.x, p.y, p.z, seed);
-                a.match[i] = bb.pos;
-                const float4 nq = __ldg(a.aux + bb.pos);
-                const float sx = p.x, sy = p.y, sz = p.z;
-                const float dx = bb.qx, dy = bb.qy, dz = bb.qz;
-                const float nx = nq.x, ny = nq.y, nz = nq.z;
-                // float expressions of TransformationEstimationPointToPlaneLLS (no FMA)
-                lo.x = nz * sy - ny * sz;
-                lo.y = nx * sz - nz * sx;
-                lo.z = ny * sx - nx * sy;
-                lo.w = nx;
-                hi.x = ny;
-                hi.y = nz;
-                hi.z = nx * dx + ny * dy + nz * dz - nx * sx - ny * sy - nz * sz;
-                hi.w = bb.d2;
-                // traces are reported in the caller's order (p.w = original source index)
-                if (a.idx_trace) a.idx_trace[(size_t)it * a.n + __float_as_int(p.w)] = bb.idx;
-            }
-            float4* row = reinterpret_cast<float4*>(&s_rows[warp][lane][0]);
-            row[0] = lo; row[1] = hi;
-            __syncwarp();
-            if (lane < kNumVals) {
+                float4* row = reinterpret_cast<float4*>(&s_rows[warp][lane][0]);
+                row[0] = lo; row[1] = hi;
+                __syncwarp();
+                // batch sums: lane v adds its product over rows 0..31 in order, starting from 0
+                if (lane < kNumVals) {
+                    double acc = 0.0;
 #pragma unroll 8
-                for (int r = 0; r < 32; ++r) {
-                    const double x = (double)s_rows[warp][r][va];
-                    const double y = (lane == 27) ? 1.0 : (double)s_rows[warp][r][vb];
-                    acc += x * y;      // exact product of two float values, then one rounding
+                    for (int r = 0; r < 32; ++r) {
+                        const double x = (double)s_rows[warp][r][va];
+                        const double y = (lane == 27) ? 1.0 : (double)s_rows[warp][r][vb];
+                        acc += x * y;      // exact product of two float values, then one rounding
+                    }
+                    __stcg(a.batch_part + (size_t)b * kNumVals + lane, acc);
                 }
+                __syncwarp();
             }
-            __syncwarp();
         }
-        if (lane < kNumVals) s_wacc[warp][lane] = acc;
-        __syncthreads();
-        if (tid < kNumVals) {
-            double s = s_wacc[0][tid];
-#pragma unroll
-            for (int w = 1; w < kIcpWarps; ++w) s += s_wacc[w][tid];
-            a.partials[((size_t)(it & 1) * G + blockIdx.x) * kNumVals + tid] = s;
-        }
+        PW_TS(1);
         grid.sync();
+        PW_TS(2);
 
-        // fixed-order reduction of the CTA partials (every CTA computes the same totals)
-        const double* P = a.partials + (size_t)(it & 1) * G * kNumVals;
-        for (int v = warp; v < kNumVals; v += kIcpWarps) {
-            double s = 0.0;
-            for (int b = lane; b < G; b += 32) s += __ldcg(P + (size_t)b * kNumVals + v);
+        // ---- phase B1: one warp per (group, value): lane l adds the group's batch sums l, l+32, ...
+        // in ascending order, then an xor butterfly 16,8,4,2,1 -- a fixed order, 16 independent loads
+        {
+            const int gwarp = blockIdx.x * kIcpWarps + warp, nwarps = gridDim.x * kIcpWarps;
+            for (int w = gwarp; w < ng * kNumVals; w += nwarps) {
+                const int g = w / kNumVals, v = w % kNumVals;
+                const int gsize = min(kGroupBatches, nb - g * kGroupBatches);
+                const double* bp = a.batch_part + (size_t)g * kGroupBatches * kNumVals + v;
+                double sg = 0.0;
+                for (int k = lane; k < gsize; k += 32) sg += __ldcg(bp + (size_t)k * kNumVals);
 #pragma unroll
-            for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == 0) s_tot[v] = s;
+                for (int o = 16; o; o >>= 1) sg += __shfl_xor_sync(0xffffffffu, sg, o);
+                if (lane == 0) __stcg(a.group_part + (size_t)g * kNumVals + v, sg);
+            }
+        }
+        PW_TS(3);
+        grid.sync();
+        PW_TS(4);
+
+        // ---- phase B2: the same pattern over the group sums (every CTA computes the same totals)
+        const double* P = a.group_part;
+        for (int v = warp; v < kNumVals; v += kIcpWarps) {
+            double sv = 0.0;
+            for (int g = lane; g < ng; g += 32) sv += __ldcg(P + (size_t)g * kNumVals + v);
+#pragma unroll
+            for (int o = 16; o; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
+            if (lane == 0) s_tot[v] = sv;
         }
         __syncthreads();
 
-        if (tid == 0) s_stop = icp_finish(a, it, s_tot, s_T, s_Tfinal, prev_mse);
+        if (warp == 0) {
+            const int st = icp_finish_warp(a, it, s_tot, s_T, s_Tfinal, prev_mse, s_fin, lane);
+            if (lane == 0) s_stop = st;
+        }
         __syncthreads();
+        PW_TS(5);
         if (s_stop) break;
     }
 }
@@ -288,11 +417,16 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     PW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, icp_persistent_kernel, kIcpThreads, smem));
     if (occ < 1) { set_error(ctx, "icp: kernel does not fit on an SM"); return PWICP_ERR_CUDA; }
     const long nb = ((long)n + 31) / 32;
+    // enough CTAs that every warp can own a batch, never more than can be co-resident
     long want = (nb + kIcpWarps - 1) / kIcpWarps;
     int grid = (int)std::min<long>((long)occ * ctx->num_sms, std::max<long>(1, want));
 
     PW_TRY(ctx->icp_work.reserve(ctx, (size_t)n * sizeof(float4)));
-    PW_TRY(ctx->icp_partials.reserve(ctx, (size_t)2 * grid * kNumVals * sizeof(double)));
+    const int ngroups = (int)((nb + kGroupBatches - 1) / kGroupBatches);
+    const size_t bytes_batch = (size_t)nb * kNumVals * sizeof(double);
+    const size_t bytes_group = (size_t)2 * ngroups * kNumVals * sizeof(double);
+    const size_t bytes_cnt = ((size_t)prm.max_iter + ngroups) * sizeof(int);
+    PW_TRY(ctx->icp_partials.reserve(ctx, bytes_batch + bytes_group + bytes_cnt + 64));
     const size_t out_bytes = 64 + 16 + (size_t)prm.max_iter * (8 + 64);
     PW_TRY(ctx->icp_out.reserve(ctx, out_bytes));
     char* ob = ctx->icp_out.as<char>();
@@ -311,6 +445,7 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     a.work = ctx->icp_work.as<float4>();
     a.match = ctx->icp_match.as<int>();
     a.use_seed0 = have_seed ? 1 : 0;
+
     a.n = n;
     a.max_iter = prm.max_iter;
     a.force_iters = prm.force_iters;
@@ -318,12 +453,22 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     a.transl_thr = prm.tf_eps;
     a.mse_rel = prm.fit_eps;
     a.mse_abs = 1e-12;
-    a.partials = ctx->icp_partials.as<double>();
+    a.batch_part = ctx->icp_partials.as<double>();
+    a.group_part = a.batch_part + (size_t)nb * kNumVals;
+    a.batch_counter = reinterpret_cast<int*>(ctx->icp_partials.as<char>() + bytes_batch + bytes_group);
+    PW_CUDA(cudaMemsetAsync(a.batch_counter, 0, bytes_cnt, ctx->stream));
     a.out_T = reinterpret_cast<float*>(ob);
     a.out_state = reinterpret_cast<int*>(ob + 64);
     a.mse_trace = mse_trace ? reinterpret_cast<double*>(ob + 80) : nullptr;
     a.T_trace = T_trace ? reinterpret_cast<float*>(ob + 80 + (size_t)prm.max_iter * 8) : nullptr;
     a.idx_trace = idx_trace ? ctx->icp_idx.as<int>() : nullptr;
+    a.timing = nullptr;
+#ifdef PWICP_TIMING
+    static long long* d_timing = nullptr;
+    if (!d_timing) cudaMalloc(&d_timing, 1024 * 8 * sizeof(long long));
+    cudaMemsetAsync(d_timing, 0, 1024 * 8 * sizeof(long long), ctx->stream);
+    a.timing = d_timing;
+#endif
 
     void* kargs[] = {(void*)&a};
     PW_CUDA(cudaLaunchCooperativeKernel((void*)icp_persistent_kernel, dim3(grid), dim3(kIcpThreads), kargs, smem, ctx->stream));
@@ -336,11 +481,22 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     float ms = 0.f;
     PW_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->last_ms = ms;
+#ifdef PWICP_TIMING
+    {
+        std::vector<long long> ht(1024 * 8);
+        cudaMemcpy(ht.data(), d_timing, ht.size() * 8, cudaMemcpyDeviceToHost);
+        long long t0min = -1;
+        for (int b = 0; b < grid; ++b) if (ht[b * 8]) t0min = (t0min < 0 || ht[b * 8] < t0min) ? ht[b * 8] : t0min;
+        double sum[6] = {0}, mx[6] = {0}, mn[6] = {1e30, 1e30, 1e30, 1e30, 1e30, 1e30};
+        for (int b = 0; b < grid; ++b) for (int k = 0; k < 6; ++k) { double v = (double)(ht[b * 8 + k] - t0min); sum[k] += v; mx[k] = std::max(mx[k], v); mn[k] = std::min(mn[k], v); }
+        if (t0min > 0) { printf("TIMING it=10 cycles (min/avg/max over %d CTAs):", grid); for (int k = 0; k < 6; ++k) printf(" [%d] %.0f/%.0f/%.0f", k, mn[k], sum[k] / grid, mx[k]); printf("\n"); }
+    }
+#endif
     const int n_iter = host.st[0];
     if (T16) for (int k = 0; k < 16; ++k) T16[k] = host.T[k];
     if (res) {
         res->n_iter = n_iter; res->conv_state = host.st[1];
-        res->grid_blocks = grid; res->warps_per_block = kIcpWarps;
+        res->grid_blocks = grid; res->warps_per_block = kIcpWarps; res->group_batches = kGroupBatches;
         res->device_ms = ms; res->correspondences = (long long)n_iter * n;
     }
     if (mse_trace) PW_CUDA(cudaMemcpy(mse_trace, ob + 80, (size_t)n_iter * 8, cudaMemcpyDeviceToHost));

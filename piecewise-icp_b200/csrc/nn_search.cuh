@@ -126,7 +126,9 @@ __device__ __forceinline__ void ball_scan(const GridLevel& L, float ox, float oy
     const int ly = min(max((int)floorf(fy - r - my), 0), L.dy - 1), hy = min(max((int)floorf(fy + r + my), 0), L.dy - 1);
     const int lz = min(max((int)floorf(fz - r - mz), 0), L.dz - 1), hz = min(max((int)floorf(fz + r + mz), 0), L.dz - 1);
     if (hy - ly <= 2 && hz - lz <= 2) {
-        // the common case (seeded ICP iteration): one to nine rows, plain nested loops
+        // one to nine rows (the common case of a seeded query): plain nested loops.  Two flattened
+        // variants (one state-machine loop; row list in shared memory + one candidate loop) were
+        // measured and were not faster: the batch time is a chain of dependent L2 round trips.
         for (int kz = lz; kz <= hz; ++kz)
             for (int ky = ly; ky <= hy; ++ky)
                 ball_row(L, ky, kz, fx, fy, fz, mx, my, mz, lx, hx, px, py, pz, level0, bd, bi, bpos);

@@ -60,10 +60,8 @@ PW_HD double inverse6(const double* A, double* Ainv) {
 }
 
 // constructTransformationMatrix(alpha, beta, gamma, tx, ty, tz): R = Rz(gamma) Ry(beta) Rx(alpha)
-PW_HD void construct_T(const double* x, float* T) {
-    const double sa = sin(x[0]), ca = cos(x[0]);
-    const double sb = sin(x[1]), cb = cos(x[1]);
-    const double sg = sin(x[2]), cg = cos(x[2]);
+// (sines / cosines passed in so that a warp can evaluate them on three lanes)
+PW_HD void construct_T_sc(double sa, double ca, double sb, double cb, double sg, double cg, const double* x, float* T) {
     for (int i = 0; i < 16; ++i) T[i] = 0.0f;
     T[0] = (float)(cg * cb);
     T[1] = (float)(-sg * ca + cg * sb * sa);
@@ -78,6 +76,10 @@ PW_HD void construct_T(const double* x, float* T) {
     T[7] = (float)x[4];
     T[11] = (float)x[5];
     T[15] = 1.0f;
+}
+
+PW_HD void construct_T(const double* x, float* T) {
+    construct_T_sc(sin(x[0]), cos(x[0]), sin(x[1]), cos(x[1]), sin(x[2]), cos(x[2]), x, T);
 }
 
 // 28 accumulated values -> ATA (mirrored), ATb, x, T

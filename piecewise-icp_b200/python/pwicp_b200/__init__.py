@@ -33,7 +33,7 @@ class IcpParams(C.Structure):
 
 class IcpResult(C.Structure):
     _fields_ = [("n_iter", C.c_int), ("conv_state", C.c_int), ("grid_blocks", C.c_int),
-                ("warps_per_block", C.c_int), ("device_ms", C.c_float),
+                ("warps_per_block", C.c_int), ("group_batches", C.c_int), ("device_ms", C.c_float),
                 ("correspondences", C.c_longlong)]
 
 
@@ -276,6 +276,7 @@ class Context:
         self._chk(self.L.pwicp_icp_run(self.h, C.byref(prm), _ptr(T), C.byref(res), _ptr(mse), _ptr(Ttr), _ptr(itr)))
         out = {"T": T.reshape(4, 4), "n_iter": res.n_iter, "state": res.conv_state,
                "grid_blocks": res.grid_blocks, "warps_per_block": res.warps_per_block,
+               "group_batches": res.group_batches,
                "device_ms": res.device_ms, "correspondences": res.correspondences}
         if trace:
             out.update(mse=mse[:res.n_iter], T_trace=Ttr[:res.n_iter].reshape(-1, 4, 4),
@@ -298,7 +299,8 @@ class Context:
         self._n_icp = len(s)
         return {"T": T.reshape(4, 4), "n_iter": res.n_iter, "state": res.conv_state,
                 "device_ms": res.device_ms, "correspondences": res.correspondences,
-                "grid_blocks": res.grid_blocks, "warps_per_block": res.warps_per_block}
+                "grid_blocks": res.grid_blocks, "warps_per_block": res.warps_per_block,
+                "group_batches": res.group_batches}
 
     # -- outer iteration / loop
     def single_iteration(self, pp, state, prm=None, want_flags=True):

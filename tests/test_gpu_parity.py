@@ -139,7 +139,7 @@ def test_inner_loop_bit_exact_in_device_order(gpu_ctx, oracle, pair60k):
     assert sorted(perm.tolist()) == list(range(len(d["ct2"])))
     o = oracle.icp(d["ct1"], d["nrm1"], d["ct2"][perm],
                    oracle.icp_params(max_iter=12, force_iters=1, reduce_mode=1,
-                                     grid_blocks=r["grid_blocks"], warps_per_block=r["warps_per_block"]),
+                                     group_batches=r["group_batches"]),
                    trace=True)
     assert r["n_iter"] == o["n_iter"] == 12
     assert np.array_equal(r["idx_trace"][:, perm], o["idx_trace"])    # indices of every inner iteration
@@ -297,8 +297,7 @@ def test_full_size_properties_1m(gpu_ctx, oracle):
     r = gpu_ctx.icp_run(P.icp_params(max_iter=3, force_iters=1), trace=True)
     perm = gpu_ctx.icp_order()
     o1 = oracle.icp(d["ct1"], d["nrm1"], d["ct2"][perm],
-                    oracle.icp_params(max_iter=3, force_iters=1, reduce_mode=1, grid_blocks=r["grid_blocks"],
-                                      warps_per_block=r["warps_per_block"]), trace=True)
+                    oracle.icp_params(max_iter=3, force_iters=1, reduce_mode=1, group_batches=r["group_batches"]), trace=True)
     assert np.array_equal(r["T_trace"], o1["T_trace"]) and np.array_equal(r["idx_trace"][:, perm], o1["idx_trace"])
     o0 = oracle.icp(d["ct1"], d["nrm1"], d["ct2"], oracle.icp_params(max_iter=3, force_iters=1))
     da, dt = pose_diff(r["T"], o0["T"])
