@@ -38,8 +38,10 @@ struct IcpArgs {
     const float4* aux;        // level-0 order: nx, ny, nz, ctstd
     const float4* src;        // source set (read only)
     float4* work;             // transformed copy, updated in place every iteration
-    int* match;               // per source point: level-0 position of its last match (seed of the next search)
-    int use_seed0;            // match[] already holds seeds for the first iteration
+    int4* cand;               // per source point: candidate cache (nn_search.cuh), .x = last match = seed of the next search
+    float4* anchor;           // per source point: position the cache was built at, w = validity radius (0: none)
+    float slack;              // cache radius beyond the NN distance
+    float build_step2;        // a cache is built only when the point moved less than sqrt(this) in the last step
     int n;
     int max_iter;
     int force_iters;
@@ -237,15 +239,56 @@ __global__ void __launch_bounds__(kIcpThreads, PWICP_ICP_MINBLOCKS) icp_persiste
                 float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
                 if (active) {
                     float4 p = (it == 0) ? __ldg(a.src + i) : a.work[i];
+                    const int4 c = a.cand[i];
+                    const float4 an = a.anchor[i];
+                    float step2 = __int_as_float(0x7f800000);
                     if (it > 0) {
                         float x, y, z;
                         xform_point(T, p.x, p.y, p.z, x, y, z);
+                        step2 = l2_simple(x, y, z, p.x, p.y, p.z);
                         p.x = x; p.y = y; p.z = z;
                     }
                     a.work[i] = p;
-                    const int seed = (it > 0 || a.use_seed0) ? a.match[i] : -1;
-                    const Best bb = nn_search_seeded<true>(a.g, p.x, p.y, p.z, seed);
-                    a.match[i] = bb.pos;
+                    // (b) exact NN: best of the cached candidates when the cache still covers the
+                    // query (nn_search.cuh, "candidate cache"), else the seeded ball search
+                    Best bb;
+                    bool ok = false;
+                    int seed = c.x;
+                    if (seed >= 0) {
+                        const float4* __restrict__ pts = a.g.lv[0].pts;
+                        const float4 q0 = __ldg(pts + c.x), q1 = __ldg(pts + c.y), q2 = __ldg(pts + c.z), q3 = __ldg(pts + c.w);
+                        bb.d2 = l2_simple(p.x, p.y, p.z, q0.x, q0.y, q0.z);
+                        bb.idx = __float_as_int(q0.w); bb.pos = c.x; bb.qx = q0.x; bb.qy = q0.y; bb.qz = q0.z;
+#define PW_CAND(q, cp)                                                                         \
+                        {                                                                      \
+                            const float d = l2_simple(p.x, p.y, p.z, q.x, q.y, q.z);           \
+                            const int id = __float_as_int(q.w);                                \
+                            if (d < bb.d2 || (d == bb.d2 && id < bb.idx)) {                    \
+                                bb.d2 = d; bb.idx = id; bb.pos = cp; bb.qx = q.x; bb.qy = q.y; bb.qz = q.z; \
+                            }                                                                  \
+                        }
+                        PW_CAND(q1, c.y) PW_CAND(q2, c.z) PW_CAND(q3, c.w)
+#undef PW_CAND
+                        const float da = l2_simple(p.x, p.y, p.z, an.x, an.y, an.z);
+                        ok = sqrtf(bb.d2) + sqrtf(da) < an.w;
+                        seed = bb.pos;
+                    }
+                    if (!ok) {
+                        bb = nn_search_seeded<true>(a.g, p.x, p.y, p.z, seed);
+                        CandCache cc;
+                        cc.rho = 0.f;
+                        if (step2 < a.build_step2) {
+                            const float rm = sqrtf(bb.d2) + a.slack;
+                            cc = ball_collect(a.g.lv[0], a.g.ox, a.g.oy, a.g.oz, p.x, p.y, p.z, rm * rm);
+                        }
+                        if (cc.rho > 0.f) {
+                            a.cand[i] = make_int4(cc.pos[0], cc.pos[1], cc.pos[2], cc.pos[3]);
+                            a.anchor[i] = make_float4(p.x, p.y, p.z, cc.rho);
+                        } else {
+                            a.cand[i] = make_int4(bb.pos, bb.pos, bb.pos, bb.pos);
+                            if (an.w != 0.f) a.anchor[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
                     const float4 nq = __ldg(a.aux + bb.pos);
                     const float sx = p.x, sy = p.y, sz = p.z;
                     const float dx = bb.qx, dy = bb.qy, dz = bb.qz;
@@ -272,7 +315,8 @@ __global__ void __launch_bounds__(kIcpThreads, PWICP_ICP_MINBLOCKS) icp_persiste
                     for (int r = 0; r < 32; ++r) {
                         const double x = (double)s_rows[warp][r][va];
                         const double y = (lane == 27) ? 1.0 : (double)s_rows[warp][r][vb];
-                        acc += x * y;      // exact product of two float values, then one rounding
+                        acc = __fma_rn(x, y, acc);   // the product of two float values is exact in double, so
+                                                     // this is acc + x*y with one rounding, fused or not
                     }
                     __stcg(a.batch_part + (size_t)b * kNumVals + lane, acc);
                 }
@@ -362,14 +406,16 @@ __global__ void src_key_kernel(const float4* __restrict__ src, int n, float ox, 
 }
 
 __global__ void src_gather_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ order, int n, float4* out,
-                                  const int* __restrict__ seed_in, int* __restrict__ seed_out) {
+                                  const int* __restrict__ seed_in, int4* __restrict__ cand, float4* __restrict__ anchor) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t o = order[i];
     float4 p = src[o];
     p.w = __int_as_float((int)o);
     out[i] = p;
-    if (seed_in) seed_out[i] = seed_in[o];
+    const int sd = seed_in ? seed_in[o] : -1;
+    cand[i] = make_int4(sd, sd, sd, sd);
+    anchor[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // Sorts the source set by the target-grid cell it starts in (stable: ties keep the caller's
@@ -382,7 +428,7 @@ static int icp_sort_source(Ctx* ctx, int n, bool have_seed) {
     PW_TRY(ctx->keys2.reserve(ctx, (size_t)n * 8));
     PW_TRY(ctx->icp_perm.reserve(ctx, (size_t)n * 4));
     PW_TRY(ctx->icp_sorted.reserve(ctx, (size_t)n * sizeof(float4)));
-    PW_TRY(ctx->icp_match.reserve(ctx, (size_t)n * sizeof(int)));
+    PW_TRY(ctx->icp_match.reserve(ctx, (size_t)n * (sizeof(int4) + sizeof(float4))));
     const int blocks = (n + 255) / 256;
     src_key_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->icp_src.as<float4>(), n, ctx->tgt.dev.ox, ctx->tgt.dev.oy,
                                                     ctx->tgt.dev.oz, L.inv_h, L.dx, L.dy, L.dz,
@@ -399,7 +445,8 @@ static int icp_sort_source(Ctx* ctx, int n, bool have_seed) {
                                             ctx->vals.as<uint32_t>(), ctx->icp_perm.as<uint32_t>(), n, 0, bits, ctx->stream));
     src_gather_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->icp_src.as<float4>(), ctx->icp_perm.as<uint32_t>(), n,
                                                        ctx->icp_sorted.as<float4>(),
-                                                       have_seed ? ctx->icp_seed.as<int>() : nullptr, ctx->icp_match.as<int>());
+                                                       have_seed ? ctx->icp_seed.as<int>() : nullptr, ctx->icp_match.as<int4>(),
+                                                       reinterpret_cast<float4*>(ctx->icp_match.as<int4>() + n));
     ctx->launches += 5;
     PW_CUDA(cudaGetLastError());
     return PWICP_OK;
@@ -443,8 +490,10 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     a.aux = ctx->tgt_aux.as<float4>();
     a.src = ctx->icp_sorted.as<float4>();
     a.work = ctx->icp_work.as<float4>();
-    a.match = ctx->icp_match.as<int>();
-    a.use_seed0 = have_seed ? 1 : 0;
+    a.cand = ctx->icp_match.as<int4>();
+    a.anchor = reinterpret_cast<float4*>(a.cand + n);
+    a.slack = 0.03f / ctx->tgt.dev.lv[0].inv_h;
+    a.build_step2 = (0.25f * a.slack) * (0.25f * a.slack);
 
     a.n = n;
     a.max_iter = prm.max_iter;

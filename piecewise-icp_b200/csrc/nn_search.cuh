@@ -228,6 +228,72 @@ __device__ __forceinline__ Best nn_search_seeded(const GridDev& g, float px, flo
     return b;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Candidate cache (inner ICP loop).  Once the incremental transforms are small a query barely
+// moves between iterations, so the set  S = { q : d2(a, q) < rho2 }  collected around an anchor a
+// (the query's position when S was built) keeps containing every target that can be its nearest
+// neighbour: if  |p - best(S)| + |p - a| < rho  then any q at least as close to p as best(S) lies
+// within rho of a, i.e. in S, and best(S) under the tie rule is the exact answer.  S is tiny (the
+// ball of radius d_nn + slack meets the sampled surface in a small disc: 1-3 targets), so an
+// iteration costs kCacheCands gathered candidates instead of a cell walk.
+constexpr int kCacheCands = 4;
+
+struct CandCache {
+    int pos[kCacheCands];   // level-0 positions; unused slots repeat pos[0]
+    float rho;              // validity radius with its safety factor applied; 0 = no cache
+};
+
+// Collects the targets within sqrt(rho2max) of p on level 0: the kCacheCands nearest and the
+// radius up to which the list is complete.  Returns rho = 0 when the ball is too large for the
+// 3x3-row scan.  Out of line: runs once per query when its cache is (re)built.
+static __device__ __noinline__ CandCache ball_collect(const GridLevel& L, float ox, float oy, float oz,
+                                                      float px, float py, float pz, float rho2max) {
+    CandCache out;
+#pragma unroll
+    for (int k = 0; k < kCacheCands; ++k) out.pos[k] = -1;
+    out.rho = 0.f;
+    const float fx = (px - ox) * L.inv_h, fy = (py - oy) * L.inv_h, fz = (pz - oz) * L.inv_h;
+    const float mx = 0.01f + fabsf(fx) * 4e-6f, my = 0.01f + fabsf(fy) * 4e-6f, mz = 0.01f + fabsf(fz) * 4e-6f;
+    const float r = sqrtf(rho2max) * L.inv_h * 1.00001f;
+    const int lx = min(max((int)floorf(fx - r - mx), 0), L.dx - 1), hx = min(max((int)floorf(fx + r + mx), 0), L.dx - 1);
+    const int ly = min(max((int)floorf(fy - r - my), 0), L.dy - 1), hy = min(max((int)floorf(fy + r + my), 0), L.dy - 1);
+    const int lz = min(max((int)floorf(fz - r - mz), 0), L.dz - 1), hz = min(max((int)floorf(fz + r + mz), 0), L.dz - 1);
+    if (hy - ly > 2 || hz - lz > 2) return out;
+    float D[kCacheCands + 1];
+    int P[kCacheCands + 1];
+#pragma unroll
+    for (int k = 0; k <= kCacheCands; ++k) { D[k] = __int_as_float(0x7f800000); P[k] = -1; }
+    const float bc = rho2max * L.inv_h2;
+    for (int kz = lz; kz <= hz; ++kz)
+        for (int ky = ly; ky <= hy; ++ky) {
+            const float gy = axis_gap(fy, ky, my), gz = axis_gap(fz, kz, mz);
+            const float gyz = gy * gy + gz * gz;
+            if (gyz > bc) continue;
+            const float w = sqrtf(bc - gyz) * 1.00001f;
+            const int lxr = max(lx, (int)floorf(fx - w - mx)), hxr = min(hx, (int)floorf(fx + w + mx));
+            if (lxr > hxr) continue;
+            const uint32_t row = ((uint32_t)kz * (uint32_t)L.dy + (uint32_t)ky) * (uint32_t)L.dx;
+            const uint32_t s = __ldg(L.cell_start + row + lxr), e = __ldg(L.cell_start + row + hxr + 1);
+            for (uint32_t i = s; i < e; ++i) {
+                const float4 q = __ldg(L.pts + i);
+                float cd = l2_simple(px, py, pz, q.x, q.y, q.z);
+                if (cd <= rho2max) {
+                    int cp = (int)i;        // sorted insertion, ascending distance
+#pragma unroll
+                    for (int k = 0; k <= kCacheCands; ++k)
+                        if (cd < D[k]) { const float td = D[k]; const int tp = P[k]; D[k] = cd; P[k] = cp; cd = td; cp = tp; }
+                }
+            }
+        }
+    if (P[0] < 0) return out;
+    // complete up to rho2max, or only below the distance of the first target left out
+    const float rho2 = (P[kCacheCands] < 0) ? rho2max : D[kCacheCands];
+#pragma unroll
+    for (int k = 0; k < kCacheCands; ++k) out.pos[k] = (P[k] >= 0) ? P[k] : P[0];
+    out.rho = sqrtf(rho2) * 0.9999f;
+    return out;
+}
+
 __device__ __forceinline__ Best nn_search(const GridDev& g, float px, float py, float pz) {
     return nn_search_seeded(g, px, py, pz, -1);
 }
