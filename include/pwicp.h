@@ -102,7 +102,7 @@ typedef struct {
     int   conv_state;       /* PWICP_CONV_* */
     int   grid_blocks;      /* launch geometry (informational): CTAs x warps_per_block */
     int   warps_per_block;
-    int   group_batches;    /* reduction geometry: 32-point batches per group */
+    int   group_batches;    /* reduction geometry: fan-in of the summation hierarchy  */
     float device_ms;        /* whole inner loop, CUDA events */
     long long correspondences;  /* n_iter * n_source */
 } pwicp_icp_result;

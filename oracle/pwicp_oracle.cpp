@@ -199,7 +199,9 @@ bool inverse6(const double* A, double* Ainv, double* det_out) {
         }
     }
     if (det_out) *det_out = det;
-    /* solve LU * X = P * I column by column */
+    /* solve LU * X = P * I column by column (one reciprocal per pivot, as the device does) */
+    double rcp[6];
+    for (int r = 0; r < 6; ++r) rcp[r] = 1.0 / lu[r * 6 + r];
     for (int col = 0; col < 6; ++col) {
         double y[6];
         for (int r = 0; r < 6; ++r) {
@@ -210,7 +212,7 @@ bool inverse6(const double* A, double* Ainv, double* det_out) {
         for (int r = 5; r >= 0; --r) {
             double s = y[r];
             for (int c = r + 1; c < 6; ++c) s -= lu[r * 6 + c] * Ainv[c * 6 + col];
-            Ainv[r * 6 + col] = s / lu[r * 6 + r];
+            Ainv[r * 6 + col] = s * rcp[r];
         }
     }
     return ok;
@@ -277,15 +279,15 @@ void accumulate28(const float* u7, const float* d2, const unsigned char* valid, 
         return;
     }
     /* Summation order of the CUDA kernel (DESIGN.md "reduction geometry"): per 32-point batch the
-     * rows in order starting from 0; per group of `group_batches` consecutive batches: lane l sums the
-     * batch sums l, l+32, ... in order, then an xor butterfly 16,8,4,2,1 over the 32 lanes; the
-     * grand total applies the same lane-strided sum + butterfly to the group sums. */
+     * rows in order starting from 0; then a hierarchy with fan-in `group_batches` (default 32):
+     * every parent is the sum of its consecutive children in order, starting from 0; after at most
+     * two such levels (or once at most fan-in entries remain) the entries are summed in order into
+     * the grand total. */
     const long nb = ((long)n + 31) / 32;
-    const int gb = group_batches > 0 ? group_batches : 512;
-    const long ng = (nb + gb - 1) / gb;
-    std::vector<double> bsum((size_t)nb * 28, 0.0), gsum((size_t)ng * 28, 0.0);
+    const int fan = group_batches > 1 ? group_batches : 32;   /* a fan-in below 2 is meaningless */
+    std::vector<double> cur((size_t)nb * 28, 0.0);
     for (long b = 0; b < nb; ++b) {
-        double* acc = &bsum[(size_t)b * 28];
+        double* acc = &cur[(size_t)b * 28];
         for (int r = 0; r < 32; ++r) {
             long i = b * 32 + r;
             if (i >= n) break;
@@ -295,36 +297,29 @@ void accumulate28(const float* u7, const float* d2, const unsigned char* valid, 
             acc[27] += (double)d2[i];
         }
     }
-    for (long g = 0; g < ng; ++g) {
-        const long gsize = std::min((long)gb, nb - g * gb);
-        for (int v = 0; v < 28; ++v) {
-            double lane[32];
-            for (int l = 0; l < 32; ++l) {
+    long count = nb;
+    for (int level = 1; level < 3 && count > fan; ++level) {
+        const long np = (count + fan - 1) / fan;
+        std::vector<double> nxt((size_t)np * 28, 0.0);
+        for (long g = 0; g < np; ++g) {
+            const long size = std::min((long)fan, count - g * fan);
+            for (int v = 0; v < 28; ++v) {
                 double s = 0.0;
-                for (long k = l; k < gsize; k += 32) s += bsum[(size_t)(g * gb + k) * 28 + v];
-                lane[l] = s;
+                for (long k = 0; k < size; ++k) s += cur[(size_t)(g * fan + k) * 28 + v];
+                nxt[(size_t)g * 28 + v] = s;
             }
-            for (int off = 16; off >= 1; off >>= 1) {
-                double nxt[32];
-                for (int l = 0; l < 32; ++l) nxt[l] = lane[l] + lane[l ^ off];
-                std::memcpy(lane, nxt, sizeof(lane));
-            }
-            gsum[(size_t)g * 28 + v] = lane[0];
         }
+        cur.swap(nxt);
+        count = np;
     }
     for (int v = 0; v < 28; ++v) {
-        double lane[32];
-        for (int l = 0; l < 32; ++l) {
-            double s = 0.0;
-            for (long g = l; g < ng; g += 32) s += gsum[(size_t)g * 28 + v];
-            lane[l] = s;
+        double s = 0.0;
+        for (long k0 = 0; k0 < count; k0 += fan) {       /* chunks of fan-in entries, each from 0 */
+            double c = 0.0;
+            for (long k = k0; k < std::min(count, k0 + fan); ++k) c += cur[(size_t)k * 28 + v];
+            s += c;
         }
-        for (int off = 16; off >= 1; off >>= 1) {
-            double nxt[32];
-            for (int l = 0; l < 32; ++l) nxt[l] = lane[l] + lane[l ^ off];
-            std::memcpy(lane, nxt, sizeof(lane));
-        }
-        out28[v] = lane[0];
+        out28[v] = s;
     }
 }
 

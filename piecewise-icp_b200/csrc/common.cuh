@@ -16,7 +16,8 @@ constexpr int kRingsPerLevel = 2;  // rings searched on a level before moving to
 constexpr int kIcpThreads = 256;   // 8 warps per CTA (reduction geometry)
 constexpr int kIcpWarps = kIcpThreads / 32;
 constexpr int kNumVals = 28;       // 21 ATA + 6 ATb + sum d2
-constexpr int kGroupBatches = 512; // batches (of 32 points) per reduction group
+constexpr int kFanIn = 32;         // entries summed per parent on every level of the reduction hierarchy
+constexpr int kMaxRedLevels = 3;   // batches, groups, supergroups; the top level is summed by every CTA
 constexpr int kGrab = 1;           // batches a warp takes per atomic hand-out
 constexpr int kMaxIcpIter = 1024;
 

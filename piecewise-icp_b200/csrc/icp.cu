@@ -26,6 +26,9 @@
 #include "nn_search.cuh"
 #include "small_algebra.cuh"
 
+#ifndef PWICP_STATIC_EIGHTHS
+#define PWICP_STATIC_EIGHTHS 4     // share of a warp's batches that is assigned statically once the loop is calm
+#endif
 #ifndef PWICP_ICP_MINBLOCKS
 #define PWICP_ICP_MINBLOCKS 3
 #endif
@@ -46,9 +49,15 @@ struct IcpArgs {
     int max_iter;
     int force_iters;
     double rot_thr, transl_thr, mse_rel, mse_abs;
-    double* batch_part;       // [nb][28]: sums of one 32-point batch
-    double* group_part;       // [ng][28]: sums of kGroupBatches consecutive batches
+    double* part[kMaxRedLevels];  // [count[l]][28]: level 0 = sums of one 32-point batch, level l+1 = sums of
+                                  // kFanIn consecutive level-l entries
+    int* done;                    // [count[2]]: groups finished per supergroup, monotonic over iterations
+    int count[kMaxRedLevels];     // entries per level
+    int nlevels;
+    const double* top_part;       // = part[nlevels - 1]
+    int top_count;                // = count[nlevels - 1]
     int* batch_counter;       // [max_iter], zeroed before the launch: dynamic batch hand-out
+    int* fallbacks;           // [max_iter], zeroed before the launch: queries that ran the ball search
     float* out_T;             // 16: final transformation
     int* out_state;           // [0] n_iter, [1] conv_state
     double* mse_trace;        // nullable
@@ -61,19 +70,28 @@ struct IcpArgs {
 struct FinishSmem {
     double A[6][6];      // ATA, then its LU factors in place
     double inv[6][6];
-    double b[6], x[6];
+    double b[6], x[6], rcp[6];
     double sc[3][2];     // sin / cos of alpha, beta, gamma
+    double prev_mse;
     int piv[6];
     float Tn[16];
 };
 
+#ifdef PWICP_TIMING
+#define PW_TSF(k) do { if (lane == 0 && it == 30 && a.timing) a.timing[blockIdx.x * 16 + (k)] = clock64(); } while (0)
+#else
+#define PW_TSF(k)
+#endif
+
 // Warp 0 of every CTA: totals -> 6x6 solve -> float transform -> convergence decision.
 // Every scalar operation is the one small_algebra.cuh's sequential inverse6()/solve_from28()
 // performs (same operands, same order per element), so the result is bit-identical to the
-// single-thread version and to the oracle; the lanes only shorten the critical path (the
-// single-thread solve cost ~25 us per inner iteration, profiles/r01d_*).
-__device__ __forceinline__ int icp_finish_warp(const IcpArgs& a, int it, const double* s_tot, float* s_T,
-                                               float* s_Tfinal, double& prev_mse, FinishSmem& F, int lane) {
+// single-thread version and to the oracle; the lanes only shorten the critical path.
+// This code runs once per inner iteration on one warp, i.e. always from a cold instruction cache
+// (profiles/r01d_*: a straight-line version spent ~10 us mostly fetching instructions), hence the
+// rolled loops and the out-of-line placement: few instruction lines, re-used from L0.
+static __device__ __noinline__ int icp_finish_warp(const IcpArgs& a, int it, const double* s_tot, float* s_T,
+                                                   float* s_Tfinal, FinishSmem& F, int lane) {
     // ATA (mirrored) and ATb from the 28 totals
     for (int idx = lane; idx < 36; idx += 32) {
         const int r = idx / 6, c = idx % 6, lo = min(r, c), hi = max(r, c);
@@ -81,14 +99,18 @@ __device__ __forceinline__ int icp_finish_warp(const IcpArgs& a, int it, const d
     }
     if (lane < 6) { F.b[lane] = s_tot[21 + lane]; F.piv[lane] = lane; }
     __syncwarp();
-    // LU with partial pivoting (inverse6)
+    // LU with partial pivoting (inverse6); lanes 0..24 own the entries of the trailing 5x5 block
+    const int rr = lane / 5 + 1, cc = lane % 5 + 1;
+#pragma unroll 1
     for (int k = 0; k < 6; ++k) {
-        int p = k;
-        if (lane == 0) {
-            double big = fabs(F.A[k][k]);
-            for (int r = k + 1; r < 6; ++r) { const double v = fabs(F.A[r][k]); if (v > big) { big = v; p = r; } }
-        }
-        p = __shfl_sync(0xffffffffu, p, 0);
+        // first row r >= k with the largest |A[r][k]|: the bit pattern of a non-negative double
+        // orders like an unsigned integer
+        const bool part = lane >= k && lane < 6;
+        const double v = part ? fabs(F.A[lane][k]) : 0.0;
+        const unsigned vh = (unsigned)__double2hiint(v), vl = (unsigned)__double2loint(v);
+        const unsigned mh = __reduce_max_sync(0xffffffffu, vh);
+        const unsigned ml = __reduce_max_sync(0xffffffffu, vh == mh ? vl : 0u);
+        const int p = __ffs(__ballot_sync(0xffffffffu, part && vh == mh && vl == ml)) - 1;
         if (p != k) {
             if (lane < 6) { const double t = F.A[k][lane]; F.A[k][lane] = F.A[p][lane]; F.A[p][lane] = t; }
             if (lane == 0) { const int t = F.piv[k]; F.piv[k] = F.piv[p]; F.piv[p] = t; }
@@ -96,20 +118,20 @@ __device__ __forceinline__ int icp_finish_warp(const IcpArgs& a, int it, const d
         __syncwarp();
         const double d = F.A[k][k];
         if (d == 0.0) continue;
-        const int m = 5 - k;                                    // trailing block is m x m
+        const bool on = lane < 25 && rr > k && cc > k;
         double f = 0.0, upd = 0.0;
-        int r = 0, c = 0;
-        const bool on = lane < m * m;
         if (on) {
-            r = k + 1 + lane / m; c = k + 1 + lane % m;
-            f = F.A[r][k] / d;
-            upd = F.A[r][c] - f * F.A[k][c];
+            f = F.A[rr][k] / d;
+            upd = F.A[rr][cc] - f * F.A[k][cc];
         }
         __syncwarp();
-        if (on) { F.A[r][c] = upd; if (c == k + 1) F.A[r][k] = f; }
+        if (on) { F.A[rr][cc] = upd; if (cc == k + 1) F.A[rr][k] = f; }
         __syncwarp();
     }
-    // inverse: lane j solves L U x = P e_j
+    PW_TSF(8);
+    // inverse: lane j solves L U x = P e_j (one reciprocal per pivot, formed by six lanes at once)
+    if (lane < 6) F.rcp[lane] = 1.0 / F.A[lane][lane];
+    __syncwarp();
     if (lane < 6) {
         double y[6], xs[6];
 #pragma unroll
@@ -124,7 +146,7 @@ __device__ __forceinline__ int icp_finish_warp(const IcpArgs& a, int it, const d
             double sacc = y[r];
 #pragma unroll
             for (int c = r + 1; c < 6; ++c) sacc -= F.A[r][c] * xs[c];
-            xs[r] = sacc / F.A[r][r];
+            xs[r] = sacc * F.rcp[r];
         }
 #pragma unroll
         for (int r = 0; r < 6; ++r) F.inv[r][lane] = xs[r];
@@ -137,8 +159,10 @@ __device__ __forceinline__ int icp_finish_warp(const IcpArgs& a, int it, const d
         F.x[lane] = sacc;
     }
     __syncwarp();
-    if (lane < 3) { F.sc[lane][0] = sin(F.x[lane]); F.sc[lane][1] = cos(F.x[lane]); }
+    PW_TSF(6);
+    if (lane < 3) sincos(F.x[lane], &F.sc[lane][0], &F.sc[lane][1]);
     __syncwarp();
+    PW_TSF(7);
     if (lane == 0) {
         float Tn[16];
         construct_T_sc(F.sc[0][0], F.sc[0][1], F.sc[1][0], F.sc[1][1], F.sc[2][0], F.sc[2][1], F.x, Tn);
@@ -161,6 +185,7 @@ __device__ __forceinline__ int icp_finish_warp(const IcpArgs& a, int it, const d
     if (lane == 0) {
         const float* Tn = F.Tn;
         const double mse = s_tot[27] / (double)a.n;
+        const double prev_mse = F.prev_mse;
         const int iters = it + 1;
         // DefaultConvergenceCriteria<float>::hasConverged(), in PCL's order
         if (iters >= a.max_iter) state = PWICP_CONV_ITERATIONS;
@@ -171,7 +196,7 @@ __device__ __forceinline__ int icp_finish_warp(const IcpArgs& a, int it, const d
             else if (fabs(mse - prev_mse) < a.mse_abs) state = PWICP_CONV_ABS_MSE;
             else if (fabs(mse - prev_mse) / prev_mse < a.mse_rel) state = PWICP_CONV_REL_MSE;
         }
-        prev_mse = mse;
+        F.prev_mse = mse;
         if (blockIdx.x == 0) {
             if (a.mse_trace) a.mse_trace[it] = mse;
             if (a.T_trace) for (int k = 0; k < 16; ++k) a.T_trace[(size_t)it * 16 + k] = Tn[k];
@@ -185,6 +210,52 @@ __device__ __forceinline__ int icp_finish_warp(const IcpArgs& a, int it, const d
     return __shfl_sync(0xffffffffu, state, 0);
 }
 
+// The search path of a query whose candidate cache does not cover it: seeded ball search, and --
+// once the point has (nearly) stopped moving -- a new cache around its position.  Out of line on
+// purpose: it runs for every query during the first few iterations and (almost) never afterwards,
+// and the steady-state loop has to stay small enough to live in the instruction cache together
+// with the per-iteration solve (profiles/r01e_*: 6 us per iteration otherwise).
+static __device__ __noinline__ Best icp_search_fallback(const IcpArgs& a, int it, int i, float px, float py, float pz,
+                                                        int seed, float step2, float old_rho) {
+    {   // queries that needed the search this iteration (decides the scheduling of the next one)
+        const unsigned m = __activemask();
+        if ((int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(a.fallbacks + it, __popc(m));
+    }
+#ifdef PWICP_TIMING
+    if (a.timing && it < 64) {
+        atomicAdd((unsigned long long*)a.timing + 16 * 1024 + it * 2, 1ull);
+        if (step2 < a.build_step2) atomicAdd((unsigned long long*)a.timing + 16 * 1024 + it * 2 + 1, 1ull);
+    }
+#endif
+    const Best bb = nn_search_seeded<true>(a.g, px, py, pz, seed);
+    CandCache cc;
+    cc.rho = 0.f;
+    if (step2 < a.build_step2) {
+        const float rm = sqrtf(bb.d2) + a.slack;
+        cc = ball_collect(a.g.lv[0], a.g.ox, a.g.oy, a.g.oz, px, py, pz, rm * rm);
+    }
+    if (cc.rho > 0.f) {
+        a.cand[i] = make_int4(cc.pos[0], cc.pos[1], cc.pos[2], cc.pos[3]);
+        a.anchor[i] = make_float4(px, py, pz, cc.rho);
+    } else {
+        a.cand[i] = make_int4(bb.pos, bb.pos, bb.pos, bb.pos);
+        if (old_rho != 0.f) a.anchor[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    return bb;
+}
+
+// Sum of up to kFanIn entries (stride kNumVals doubles) in order, starting from 0.  All loads are
+// issued before the first add; absent entries contribute +0.0, which leaves the sum unchanged.
+__device__ __forceinline__ double sum_entries(const double* __restrict__ src, int size) {
+    double v[kFanIn];
+#pragma unroll
+    for (int k = 0; k < kFanIn; ++k) v[k] = (k < size) ? __ldcg(src + (size_t)k * kNumVals) : 0.0;
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < kFanIn; ++k) acc += v[k];
+    return acc;
+}
+
 __global__ void __launch_bounds__(kIcpThreads, PWICP_ICP_MINBLOCKS) icp_persistent_kernel(const IcpArgs a) {
     cg::grid_group grid = cg::this_grid();
     __shared__ __align__(16) float s_rows[kIcpWarps][32][8];
@@ -196,7 +267,6 @@ __global__ void __launch_bounds__(kIcpThreads, PWICP_ICP_MINBLOCKS) icp_persiste
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nb = (a.n + 31) / 32;                              // 32-point batches
-    const int ng = (nb + kGroupBatches - 1) / kGroupBatches;     // groups of kGroupBatches batches
 
     // which pair of row terms this lane accumulates: 21 upper-triangle ATA entries (row-major),
     // 6 ATb entries (u_r * u_6), lane 27 = sum of squared NN distances
@@ -209,12 +279,11 @@ __global__ void __launch_bounds__(kIcpThreads, PWICP_ICP_MINBLOCKS) icp_persiste
         if (lane == 27) { va = 7; vb = 7; }
     }
     if (tid < 16) { s_T[tid] = (tid % 5 == 0) ? 1.0f : 0.0f; s_Tfinal[tid] = s_T[tid]; }
-    if (tid == 0) s_stop = 0;
-    double prev_mse = 1.7976931348623157e308;   // DBL_MAX
+    if (tid == 0) { s_stop = 0; s_fin.prev_mse = 1.7976931348623157e308; }   // DBL_MAX
     __syncthreads();
 
 #ifdef PWICP_TIMING
-#define PW_TS(k) do { if (tid == 0 && it == 10 && a.timing) a.timing[blockIdx.x * 8 + (k)] = clock64(); } while (0)
+#define PW_TS(k) do { if (tid == 0 && it == 30 && a.timing) a.timing[blockIdx.x * 16 + (k)] = clock64(); } while (0)
 #else
 #define PW_TS(k)
 #endif
@@ -224,23 +293,36 @@ __global__ void __launch_bounds__(kIcpThreads, PWICP_ICP_MINBLOCKS) icp_persiste
 #pragma unroll
         for (int k = 0; k < 12; ++k) T[k] = s_T[k];
 
-        // ---- phase A: batches are handed out dynamically, kGrab at a time (the cost of a batch
-        // depends on the data), but every sum below is formed in an order that does not depend on
-        // which warp does it
-        for (;;) {
-            int b0 = 0;
-            if (lane == 0) b0 = atomicAdd(a.batch_counter + it, kGrab);
-            b0 = __shfl_sync(0xffffffffu, b0, 0);
-            if (b0 >= nb) break;
-            const int b1 = min(b0 + kGrab, nb);
-            for (int b = b0; b < b1; ++b) {
+        // ---- phase A.  Every warp first works through a static share of the batches (b = j * NW + W,
+        // half of its fair share), then takes single batches from a counter: the cost of a batch is
+        // data dependent while the ball search runs, and one atomic per batch on one address would
+        // serialise in L2 (~0.85 cycles each).  Every sum below is formed in an order that does not
+        // depend on which warp does it.  The loop is software pipelined: the loads of the next
+        // batch and the hand-out of the one after are in flight while the current one is processed.
+        {
+            const int NW = gridDim.x * kIcpWarps, W = blockIdx.x * kIcpWarps + warp;
+            // static batches per warp: half of the fair share once (nearly) every query is answered from its
+            // cache (uniform cost per batch), else only the two that cover the pipeline depth of the hand-out
+            const int fb_prev = (it > 0) ? __ldcg(a.fallbacks + it - 1) : a.n;
+            const bool calm = (long long)fb_prev * 64 < (long long)a.n;
+            const int J = (calm ? (nb / NW) * PWICP_STATIC_EIGHTHS / 8 : 0) + 2;
+            const float4* __restrict__ psrc = (it == 0) ? a.src : a.work;
+            int* counter = a.batch_counter + it;
+            int seq = 0;                                       // position in this warp's batch sequence
+            int tkt = 0;                                       // lane 0: hand-out ticket in flight
+            int b = W, bn = NW + W;                            // positions 0 and 1
+            float4 p = make_float4(0.f, 0.f, 0.f, 0.f), an = p, pn = p, ann = p;
+            int4 c = make_int4(-1, -1, -1, -1), cn = c;
+            if (b < nb && b * 32 + lane < a.n) { const int i = b * 32 + lane; p = psrc[i]; c = a.cand[i]; an = a.anchor[i]; }
+            while (b < nb) {
+                // loads of the next batch, ticket for the one after
+                if (bn < nb && bn * 32 + lane < a.n) { const int i = bn * 32 + lane; pn = psrc[i]; cn = a.cand[i]; ann = a.anchor[i]; }
+                if (seq + 2 >= J && lane == 0) tkt = atomicAdd(counter, 1);   // position seq+2 is dynamic
+
                 const int i = b * 32 + lane;
                 const bool active = i < a.n;
                 float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
                 if (active) {
-                    float4 p = (it == 0) ? __ldg(a.src + i) : a.work[i];
-                    const int4 c = a.cand[i];
-                    const float4 an = a.anchor[i];
                     float step2 = __int_as_float(0x7f800000);
                     if (it > 0) {
                         float x, y, z;
@@ -256,7 +338,12 @@ __global__ void __launch_bounds__(kIcpThreads, PWICP_ICP_MINBLOCKS) icp_persiste
                     int seed = c.x;
                     if (seed >= 0) {
                         const float4* __restrict__ pts = a.g.lv[0].pts;
-                        const float4 q0 = __ldg(pts + c.x), q1 = __ldg(pts + c.y), q2 = __ldg(pts + c.z), q3 = __ldg(pts + c.w);
+                        // unused cache slots repeat slot 0: their loads are predicated off (no L1 traffic)
+                        const float4 q0 = __ldg(pts + c.x);
+                        float4 q1 = q0, q2 = q0, q3 = q0;
+                        if (c.y != c.x) q1 = __ldg(pts + c.y);
+                        if (c.z != c.x) q2 = __ldg(pts + c.z);
+                        if (c.w != c.x) q3 = __ldg(pts + c.w);
                         bb.d2 = l2_simple(p.x, p.y, p.z, q0.x, q0.y, q0.z);
                         bb.idx = __float_as_int(q0.w); bb.pos = c.x; bb.qx = q0.x; bb.qy = q0.y; bb.qz = q0.z;
 #define PW_CAND(q, cp)                                                                         \
@@ -273,22 +360,7 @@ __global__ void __launch_bounds__(kIcpThreads, PWICP_ICP_MINBLOCKS) icp_persiste
                         ok = sqrtf(bb.d2) + sqrtf(da) < an.w;
                         seed = bb.pos;
                     }
-                    if (!ok) {
-                        bb = nn_search_seeded<true>(a.g, p.x, p.y, p.z, seed);
-                        CandCache cc;
-                        cc.rho = 0.f;
-                        if (step2 < a.build_step2) {
-                            const float rm = sqrtf(bb.d2) + a.slack;
-                            cc = ball_collect(a.g.lv[0], a.g.ox, a.g.oy, a.g.oz, p.x, p.y, p.z, rm * rm);
-                        }
-                        if (cc.rho > 0.f) {
-                            a.cand[i] = make_int4(cc.pos[0], cc.pos[1], cc.pos[2], cc.pos[3]);
-                            a.anchor[i] = make_float4(p.x, p.y, p.z, cc.rho);
-                        } else {
-                            a.cand[i] = make_int4(bb.pos, bb.pos, bb.pos, bb.pos);
-                            if (an.w != 0.f) a.anchor[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        }
-                    }
+                    if (!ok) bb = icp_search_fallback(a, it, i, p.x, p.y, p.z, seed, step2, an.w);
                     const float4 nq = __ldg(a.aux + bb.pos);
                     const float sx = p.x, sy = p.y, sz = p.z;
                     const float dx = bb.qx, dy = bb.qy, dz = bb.qz;
@@ -305,6 +377,8 @@ __global__ void __launch_bounds__(kIcpThreads, PWICP_ICP_MINBLOCKS) icp_persiste
                     // traces are reported in the caller's order (p.w = original source index)
                     if (a.idx_trace) a.idx_trace[(size_t)it * a.n + __float_as_int(p.w)] = bb.idx;
                 }
+                // rows through shared memory as floats: a broadcast LDS.32 is one wavefront, an LDS.64 two,
+                // and the L1/shared pipe is the busiest unit of this kernel (profiles/r01e_*)
                 float4* row = reinterpret_cast<float4*>(&s_rows[warp][lane][0]);
                 row[0] = lo; row[1] = hi;
                 __syncwarp();
@@ -318,47 +392,61 @@ __global__ void __launch_bounds__(kIcpThreads, PWICP_ICP_MINBLOCKS) icp_persiste
                         acc = __fma_rn(x, y, acc);   // the product of two float values is exact in double, so
                                                      // this is acc + x*y with one rounding, fused or not
                     }
-                    __stcg(a.batch_part + (size_t)b * kNumVals + lane, acc);
+                    __stcg(a.part[0] + (size_t)b * kNumVals + lane, acc);
                 }
                 __syncwarp();
+                // rotate the pipeline
+                ++seq;
+                b = bn; p = pn; c = cn; an = ann;
+                bn = (seq + 1 < J) ? (seq + 1) * NW + W : J * NW + __shfl_sync(0xffffffffu, tkt, 0);
             }
         }
         PW_TS(1);
         grid.sync();
         PW_TS(2);
 
-        // ---- phase B1: one warp per (group, value): lane l adds the group's batch sums l, l+32, ...
-        // in ascending order, then an xor butterfly 16,8,4,2,1 -- a fixed order, 16 independent loads
-        {
+        // ---- phase B1: one warp per group of kFanIn batches: lane v sums the group's entries of
+        // value v in order, starting from 0 (loads are independent, the adds sequential).  The warp
+        // that completes the last group of a kFanIn-group supergroup sums that one the same way.
+        if (a.nlevels > 1) {
             const int gwarp = blockIdx.x * kIcpWarps + warp, nwarps = gridDim.x * kIcpWarps;
-            for (int w = gwarp; w < ng * kNumVals; w += nwarps) {
-                const int g = w / kNumVals, v = w % kNumVals;
-                const int gsize = min(kGroupBatches, nb - g * kGroupBatches);
-                const double* bp = a.batch_part + (size_t)g * kGroupBatches * kNumVals + v;
-                double sg = 0.0;
-                for (int k = lane; k < gsize; k += 32) sg += __ldcg(bp + (size_t)k * kNumVals);
-#pragma unroll
-                for (int o = 16; o; o >>= 1) sg += __shfl_xor_sync(0xffffffffu, sg, o);
-                if (lane == 0) __stcg(a.group_part + (size_t)g * kNumVals + v, sg);
+            for (int g = gwarp; g < a.count[1]; g += nwarps) {
+                if (lane < kNumVals)
+                    __stcg(a.part[1] + (size_t)g * kNumVals + lane,
+                           sum_entries(a.part[0] + (size_t)g * kFanIn * kNumVals + lane, min(kFanIn, a.count[0] - g * kFanIn)));
+                if (a.nlevels > 2) {
+                    const int sg = g / kFanIn, size = min(kFanIn, a.count[1] - sg * kFanIn);
+                    __threadfence();
+                    __syncwarp();
+                    int last = 0;
+                    if (lane == 0) last = (atomicAdd(a.done + sg, 1) + 1 == (it + 1) * size);
+                    last = __shfl_sync(0xffffffffu, last, 0);
+                    if (last) {
+                        __threadfence();
+                        if (lane < kNumVals)
+                            __stcg(a.part[2] + (size_t)sg * kNumVals + lane,
+                                   sum_entries(a.part[1] + (size_t)sg * kFanIn * kNumVals + lane, size));
+                    }
+                }
             }
+            PW_TS(3);
+            grid.sync();
         }
-        PW_TS(3);
-        grid.sync();
+
+        // ---- phase B2: every CTA forms the same totals from the top-level entries, in order
+        if (warp == 0) {
+            if (lane < kNumVals) {
+                double acc = 0.0;
+                for (int k0 = 0; k0 < a.top_count; k0 += kFanIn)
+                    acc += sum_entries(a.top_part + (size_t)k0 * kNumVals + lane, min(kFanIn, a.top_count - k0));
+                s_tot[lane] = acc;
+            }
+            __syncwarp();
+        }
         PW_TS(4);
 
-        // ---- phase B2: the same pattern over the group sums (every CTA computes the same totals)
-        const double* P = a.group_part;
-        for (int v = warp; v < kNumVals; v += kIcpWarps) {
-            double sv = 0.0;
-            for (int g = lane; g < ng; g += 32) sv += __ldcg(P + (size_t)g * kNumVals + v);
-#pragma unroll
-            for (int o = 16; o; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
-            if (lane == 0) s_tot[v] = sv;
-        }
-        __syncthreads();
-
         if (warp == 0) {
-            const int st = icp_finish_warp(a, it, s_tot, s_T, s_Tfinal, prev_mse, s_fin, lane);
+            const int st = icp_finish_warp(a, it, s_tot, s_T, s_Tfinal, s_fin, lane);
             if (lane == 0) s_stop = st;
         }
         __syncthreads();
@@ -469,11 +557,20 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     int grid = (int)std::min<long>((long)occ * ctx->num_sms, std::max<long>(1, want));
 
     PW_TRY(ctx->icp_work.reserve(ctx, (size_t)n * sizeof(float4)));
-    const int ngroups = (int)((nb + kGroupBatches - 1) / kGroupBatches);
-    const size_t bytes_batch = (size_t)nb * kNumVals * sizeof(double);
-    const size_t bytes_group = (size_t)2 * ngroups * kNumVals * sizeof(double);
-    const size_t bytes_cnt = ((size_t)prm.max_iter + ngroups) * sizeof(int);
-    PW_TRY(ctx->icp_partials.reserve(ctx, bytes_batch + bytes_group + bytes_cnt + 64));
+    // reduction levels: level 0 = one entry per batch, then up to two levels that sum kFanIn
+    // consecutive entries each; the top level (any length) is summed in order by every CTA
+    int lcount[kMaxRedLevels], nlevels = 1;
+    lcount[0] = (int)nb;
+    while (nlevels < kMaxRedLevels && lcount[nlevels - 1] > kFanIn) {
+        lcount[nlevels] = (lcount[nlevels - 1] + kFanIn - 1) / kFanIn;
+        ++nlevels;
+    }
+    size_t part_entries = 0, done_entries = 0;
+    for (int l = 0; l < nlevels; ++l) part_entries += (size_t)lcount[l];
+    if (nlevels > 2) done_entries = (size_t)lcount[2];
+    const size_t bytes_part = part_entries * kNumVals * sizeof(double);
+    const size_t bytes_cnt = ((size_t)2 * prm.max_iter + done_entries) * sizeof(int);
+    PW_TRY(ctx->icp_partials.reserve(ctx, bytes_part + bytes_cnt + 64));
     const size_t out_bytes = 64 + 16 + (size_t)prm.max_iter * (8 + 64);
     PW_TRY(ctx->icp_out.reserve(ctx, out_bytes));
     char* ob = ctx->icp_out.as<char>();
@@ -502,10 +599,24 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     a.transl_thr = prm.tf_eps;
     a.mse_rel = prm.fit_eps;
     a.mse_abs = 1e-12;
-    a.batch_part = ctx->icp_partials.as<double>();
-    a.group_part = a.batch_part + (size_t)nb * kNumVals;
-    a.batch_counter = reinterpret_cast<int*>(ctx->icp_partials.as<char>() + bytes_batch + bytes_group);
-    PW_CUDA(cudaMemsetAsync(a.batch_counter, 0, bytes_cnt, ctx->stream));
+    {
+        double* pp = ctx->icp_partials.as<double>();
+        int* cc = reinterpret_cast<int*>(ctx->icp_partials.as<char>() + bytes_part);
+        PW_CUDA(cudaMemsetAsync(cc, 0, bytes_cnt, ctx->stream));
+        a.batch_counter = cc;
+        cc += prm.max_iter;
+        a.fallbacks = cc;
+        cc += prm.max_iter;
+        a.done = cc;
+        for (int l = 0; l < kMaxRedLevels; ++l) { a.part[l] = nullptr; a.count[l] = 0; }
+        for (int l = 0; l < nlevels; ++l) {
+            a.part[l] = pp; pp += (size_t)lcount[l] * kNumVals;
+            a.count[l] = lcount[l];
+        }
+        a.nlevels = nlevels;
+        a.top_part = a.part[nlevels - 1];
+        a.top_count = lcount[nlevels - 1];
+    }
     a.out_T = reinterpret_cast<float*>(ob);
     a.out_state = reinterpret_cast<int*>(ob + 64);
     a.mse_trace = mse_trace ? reinterpret_cast<double*>(ob + 80) : nullptr;
@@ -514,8 +625,8 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     a.timing = nullptr;
 #ifdef PWICP_TIMING
     static long long* d_timing = nullptr;
-    if (!d_timing) cudaMalloc(&d_timing, 1024 * 8 * sizeof(long long));
-    cudaMemsetAsync(d_timing, 0, 1024 * 8 * sizeof(long long), ctx->stream);
+    if (!d_timing) cudaMalloc(&d_timing, (1024 * 16 + 128) * sizeof(long long));
+    cudaMemsetAsync(d_timing, 0, (1024 * 16 + 128) * sizeof(long long), ctx->stream);
     a.timing = d_timing;
 #endif
 
@@ -532,20 +643,27 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     ctx->last_ms = ms;
 #ifdef PWICP_TIMING
     {
-        std::vector<long long> ht(1024 * 8);
+        std::vector<long long> ht(1024 * 16 + 128);
         cudaMemcpy(ht.data(), d_timing, ht.size() * 8, cudaMemcpyDeviceToHost);
-        long long t0min = -1;
-        for (int b = 0; b < grid; ++b) if (ht[b * 8]) t0min = (t0min < 0 || ht[b * 8] < t0min) ? ht[b * 8] : t0min;
-        double sum[6] = {0}, mx[6] = {0}, mn[6] = {1e30, 1e30, 1e30, 1e30, 1e30, 1e30};
-        for (int b = 0; b < grid; ++b) for (int k = 0; k < 6; ++k) { double v = (double)(ht[b * 8 + k] - t0min); sum[k] += v; mx[k] = std::max(mx[k], v); mn[k] = std::min(mn[k], v); }
-        if (t0min > 0) { printf("TIMING it=10 cycles (min/avg/max over %d CTAs):", grid); for (int k = 0; k < 6; ++k) printf(" [%d] %.0f/%.0f/%.0f", k, mn[k], sum[k] / grid, mx[k]); printf("\n"); }
+        // per-CTA deltas against its own first stamp (SM clocks are not synchronised)
+        double sum[16] = {0}, mx[16] = {0}, mn[16]; for (double& m : mn) m = 1e30;
+        int cnt = 0;
+        for (int b = 0; b < grid; ++b) {
+            if (!ht[b * 16]) continue;
+            ++cnt;
+            for (int k = 0; k < 9; ++k) { double v = (double)(ht[b * 16 + k] - ht[b * 16]); sum[k] += v; mx[k] = std::max(mx[k], v); mn[k] = std::min(mn[k], v); }
+        }
+        printf("FALLBACK lanes (cache builds) per iteration:");
+        for (int k = 0; k < std::min(64, host.st[0]); ++k) printf(" %lld(%lld)", ht[16 * 1024 + 2 * k], ht[16 * 1024 + 2 * k + 1]);
+        printf("\n");
+        if (cnt) { printf("TIMING it=30 n=%d cycles since iteration start (min/avg/max over %d CTAs):", n, cnt); for (int k : {1, 2, 3, 4, 8, 6, 7, 5}) printf(" [%d] %.0f/%.0f/%.0f", k, mn[k], sum[k] / cnt, mx[k]); printf("\n"); }
     }
 #endif
     const int n_iter = host.st[0];
     if (T16) for (int k = 0; k < 16; ++k) T16[k] = host.T[k];
     if (res) {
         res->n_iter = n_iter; res->conv_state = host.st[1];
-        res->grid_blocks = grid; res->warps_per_block = kIcpWarps; res->group_batches = kGroupBatches;
+        res->grid_blocks = grid; res->warps_per_block = kIcpWarps; res->group_batches = kFanIn;
         res->device_ms = ms; res->correspondences = (long long)n_iter * n;
     }
     if (mse_trace) PW_CUDA(cudaMemcpy(mse_trace, ob + 80, (size_t)n_iter * 8, cudaMemcpyDeviceToHost));

@@ -43,6 +43,8 @@ PW_HD double inverse6(const double* A, double* Ainv) {
             for (int c = k + 1; c < 6; ++c) lu[r * 6 + c] -= f * lu[k * 6 + c];
         }
     }
+    double rcp[6];
+    for (int r = 0; r < 6; ++r) rcp[r] = 1.0 / lu[r * 6 + r];
     for (int col = 0; col < 6; ++col) {
         double y[6];
         for (int r = 0; r < 6; ++r) {
@@ -53,7 +55,7 @@ PW_HD double inverse6(const double* A, double* Ainv) {
         for (int r = 5; r >= 0; --r) {
             double s = y[r];
             for (int c = r + 1; c < 6; ++c) s -= lu[r * 6 + c] * Ainv[c * 6 + col];
-            Ainv[r * 6 + col] = s / lu[r * 6 + r];
+            Ainv[r * 6 + col] = s * rcp[r];
         }
     }
     return det;
