@@ -4,6 +4,7 @@
 // (five per outer iteration over CTcloud1: src/Registration.cpp:738, :744, :1294 and two inside
 // pcl::IterativeClosestPoint; one per stage-1 iteration over cloud1: src/CommonFunc.cpp:269-273).
 #include <cub/cub.cuh>
+#include <thrust/iterator/reverse_iterator.h>
 #include <cfloat>
 #include <cmath>
 #include <cstring>
@@ -140,8 +141,7 @@ int bbox_packed_dev(Ctx* ctx, const float* xyz_dev, size_t n, float* mn3, float*
 
 // ---- build ---------------------------------------------------------------------------------
 __global__ void cell_key_kernel(const float* __restrict__ xyz, int n, float ox, float oy, float oz,
-                                float inv_h, int dx, int dy, int dz, uint32_t* keys, uint32_t* vals,
-                                uint32_t* counts) {
+                                float inv_h, int dx, int dy, int dz, uint32_t* keys, uint32_t* vals) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float x = xyz[3 * (size_t)i], y = xyz[3 * (size_t)i + 1], z = xyz[3 * (size_t)i + 2];
@@ -153,7 +153,18 @@ __global__ void cell_key_kernel(const float* __restrict__ xyz, int n, float ox, 
     uint32_t key = ((uint32_t)cz * (uint32_t)dy + (uint32_t)cy) * (uint32_t)dx + (uint32_t)cx;
     keys[i] = key;
     vals[i] = (uint32_t)i;
-    atomicAdd(counts + key, 1u);
+}
+
+// cell_start from the SORTED keys: the first point of every non-empty cell marks its cell (no
+// atomics: a histogram by atomicAdd serialises on the coarse levels, where thousands of points
+// share a cell -- it was 2/3 of the build, profiles/r01c_*); empty cells are filled afterwards by
+// a suffix minimum (the start of the next non-empty cell).
+__global__ void cell_mark_kernel(const uint32_t* __restrict__ sorted_keys, int n, uint32_t* cells, uint32_t ncells) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) cells[ncells] = (uint32_t)n;
+    if (i >= n) return;
+    const uint32_t k = sorted_keys[i];
+    if (i == 0 || sorted_keys[i - 1] != k) cells[k] = (uint32_t)i;
 }
 
 __global__ void gather_sorted_kernel(const float* __restrict__ xyz, const uint32_t* __restrict__ order,
@@ -215,27 +226,29 @@ int grid_build(Ctx* ctx, GridOwner& g, const float* xyz, int n) {
         PW_TRY(ctx->vals2.reserve(ctx, (size_t)n * 4));
         PW_TRY(g.cells[l].reserve(ctx, (ncells + 1) * sizeof(uint32_t)));
         uint32_t* cells = g.cells[l].as<uint32_t>();
-        PW_CUDA(cudaMemsetAsync(cells, 0, (ncells + 1) * sizeof(uint32_t), ctx->stream));
+        PW_CUDA(cudaMemsetAsync(cells, 0xff, (ncells + 1) * sizeof(uint32_t), ctx->stream));
         int blocks = (n + 255) / 256;
         cell_key_kernel<<<blocks, 256, 0, ctx->stream>>>(xyz, n, mn[0], mn[1], mn[2], inv_h, d[0], d[1], d[2],
-                                                         ctx->keys.as<uint32_t>(), ctx->vals.as<uint32_t>(), cells);
+                                                         ctx->keys.as<uint32_t>(), ctx->vals.as<uint32_t>());
         ctx->launches++;
-        // exclusive scan of the counts -> cell_start (in place)
+        auto rcells = thrust::make_reverse_iterator(cells + ncells + 1);
         size_t tmp_bytes = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cells, cells, (int)(ncells + 1), ctx->stream);
+        cub::DeviceScan::InclusiveScan(nullptr, tmp_bytes, rcells, rcells, cub::Min(), (int)(ncells + 1), ctx->stream);
         size_t tmp2 = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, tmp2, ctx->keys.as<uint32_t>(), ctx->keys2.as<uint32_t>(),
                                         ctx->vals.as<uint32_t>(), ctx->vals2.as<uint32_t>(), n, 0,
                                         bits_for(ncells), ctx->stream);
         PW_TRY(ctx->cub_tmp.reserve(ctx, std::max(tmp_bytes, tmp2)));
-        size_t cap = ctx->cub_tmp.cap;
-        PW_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, cap, cells, cells, (int)(ncells + 1), ctx->stream));
         // stable radix sort by cell key: points of one cell stay in ascending original index
-        cap = ctx->cub_tmp.cap;
+        size_t cap = ctx->cub_tmp.cap;
         PW_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, cap, ctx->keys.as<uint32_t>(),
                                                 ctx->keys2.as<uint32_t>(), ctx->vals.as<uint32_t>(),
                                                 ctx->vals2.as<uint32_t>(), n, 0, bits_for(ncells), ctx->stream));
-        ctx->launches += 6;
+        // cell_start: mark the first point of every non-empty cell, then suffix-min over the cells
+        cell_mark_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->keys2.as<uint32_t>(), n, cells, (uint32_t)ncells);
+        cap = ctx->cub_tmp.cap;
+        PW_CUDA(cub::DeviceScan::InclusiveScan(ctx->cub_tmp.p, cap, rcells, rcells, cub::Min(), (int)(ncells + 1), ctx->stream));
+        ctx->launches += 7;
         PW_TRY(g.pts[l].reserve(ctx, (size_t)n * sizeof(float4)));
         float4* pts = g.pts[l].as<float4>();
         uint32_t* invp = nullptr;
