@@ -43,6 +43,7 @@ struct IcpArgs {
     float4* work;             // transformed copy, updated in place every iteration
     int4* cand;               // per source point: candidate cache (nn_search.cuh), .x = last match = seed of the next search
     float4* anchor;           // per source point: position the cache was built at, w = validity radius (0: none)
+    int seed_exact;           // cand[].x is the exact NN of the untransformed source (iteration 0 needs no search)
     float slack;              // cache radius beyond the NN distance
     float build_step2;        // a cache is built only when the point moved less than sqrt(this) in the last step
     int n;
@@ -303,7 +304,7 @@ __global__ void __launch_bounds__(kIcpThreads, PWICP_ICP_MINBLOCKS) icp_persiste
             const int NW = gridDim.x * kIcpWarps, W = blockIdx.x * kIcpWarps + warp;
             // static batches per warp: half of the fair share once (nearly) every query is answered from its
             // cache (uniform cost per batch), else only the two that cover the pipeline depth of the hand-out
-            const int fb_prev = (it > 0) ? __ldcg(a.fallbacks + it - 1) : a.n;
+            const int fb_prev = (it > 1) ? __ldcg(a.fallbacks + it - 1) : a.n;
             const bool calm = (long long)fb_prev * 64 < (long long)a.n;
             const int J = (calm ? (nb / NW) * PWICP_STATIC_EIGHTHS / 8 : 0) + 2;
             const float4* __restrict__ psrc = (it == 0) ? a.src : a.work;
@@ -357,7 +358,7 @@ __global__ void __launch_bounds__(kIcpThreads, PWICP_ICP_MINBLOCKS) icp_persiste
                         PW_CAND(q1, c.y) PW_CAND(q2, c.z) PW_CAND(q3, c.w)
 #undef PW_CAND
                         const float da = l2_simple(p.x, p.y, p.z, an.x, an.y, an.z);
-                        ok = sqrtf(bb.d2) + sqrtf(da) < an.w;
+                        ok = (it == 0 && a.seed_exact) || sqrtf(bb.d2) + sqrtf(da) < an.w;
                         seed = bb.pos;
                     }
                     if (!ok) bb = icp_search_fallback(a, it, i, p.x, p.y, p.z, seed, step2, an.w);
@@ -506,6 +507,18 @@ __global__ void src_gather_kernel(const float4* __restrict__ src, const uint32_t
     anchor[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+// Iteration 0 of a source set without seeds: the plain search at full occupancy (the persistent
+// kernel is register-capped and runs it about twice as slowly, profiles/r01f_*).  The matches go
+// into the candidate slots; the persistent kernel takes them as the exact answer of iteration 0.
+__global__ void __launch_bounds__(256)
+icp_seed_kernel(GridDev g, const float4* __restrict__ src, int n, int4* __restrict__ cand) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = __ldg(src + i);
+    const Best b = nn_search_seeded(g, p.x, p.y, p.z, -1);
+    cand[i] = make_int4(b.pos, b.pos, b.pos, b.pos);
+}
+
 // Sorts the source set by the target-grid cell it starts in (stable: ties keep the caller's
 // order), so that the 8 queries of a tile group share a small candidate block.  The processing
 // order only affects the order of the double sums (DESIGN.md "reduction geometry").
@@ -581,6 +594,11 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     const bool have_seed = ctx->icp_seed_valid && ctx->icp_seed.p != nullptr;
     PW_TRY(icp_sort_source(ctx, n, have_seed));
     ctx->icp_seed_valid = false;                       // seeds belong to one source set
+    if (!have_seed) {
+        icp_seed_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->tgt.dev, ctx->icp_sorted.as<float4>(), n,
+                                                                  ctx->icp_match.as<int4>());
+        ctx->launches++;
+    }
 
     IcpArgs a;
     a.g = ctx->tgt.dev;
@@ -589,6 +607,7 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     a.work = ctx->icp_work.as<float4>();
     a.cand = ctx->icp_match.as<int4>();
     a.anchor = reinterpret_cast<float4*>(a.cand + n);
+    a.seed_exact = 1;         // classification matches (outer.cu) or icp_seed_kernel
     a.slack = 0.03f / ctx->tgt.dev.lv[0].inv_h;
     a.build_step2 = (0.25f * a.slack) * (0.25f * a.slack);
 

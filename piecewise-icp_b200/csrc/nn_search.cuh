@@ -52,7 +52,39 @@ __device__ __forceinline__ float axis_gap(float f, int k, float m) {
     return fmaxf(g, 0.0f);
 }
 
+// Candidates [s, e) of the sorted array against the current best.  kWide: four loads in flight at
+// a time -- in the register-capped persistent ICP kernel (24 warps per SM) the plain loop is a chain
+// of exposed L1/L2 round trips (its trip count is unknown to the compiler); the stand-alone search
+// kernels run at higher occupancy and are faster with the plain loop (profiles/r01f_*).
+template <bool kWide>
+__device__ __forceinline__ void scan_range(const float4* __restrict__ pts, uint32_t s, uint32_t e,
+                                           float px, float py, float pz, bool level0,
+                                           float& bd, int& bi, int& bpos) {
+    if (kWide) {
+        for (uint32_t i = s; i < e; i += 4) {
+            float4 q[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) q[k] = __ldg(pts + min(i + k, e - 1));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                // slots past the end repeat the last candidate: same distance, same index, no effect
+                const float d = l2_simple(px, py, pz, q[k].x, q[k].y, q[k].z);
+                const int id = __float_as_int(q[k].w);
+                if (d < bd || (d == bd && id < bi)) { bd = d; bi = id; bpos = level0 ? (int)min(i + k, e - 1) : -1; }
+            }
+        }
+    } else {
+        for (uint32_t i = s; i < e; ++i) {
+            const float4 q = __ldg(pts + i);
+            const float d = l2_simple(px, py, pz, q.x, q.y, q.z);
+            const int id = __float_as_int(q.w);
+            if (d < bd || (d == bd && id < bi)) { bd = d; bi = id; bpos = level0 ? (int)i : -1; }
+        }
+    }
+}
+
 // One cell row (ky, kz) of the ball: chord test against the CURRENT best, then a range scan.
+template <bool kWide>
 __device__ __forceinline__ void ball_row(const GridLevel& L, int ky, int kz, float fx, float fy, float fz,
                                          float mx, float my, float mz, int lx, int hx,
                                          float px, float py, float pz, bool level0,
@@ -65,19 +97,14 @@ __device__ __forceinline__ void ball_row(const GridLevel& L, int ky, int kz, flo
     if (lxr > hxr) return;
     const uint32_t row = ((uint32_t)kz * (uint32_t)L.dy + (uint32_t)ky) * (uint32_t)L.dx;
     const uint32_t s = __ldg(L.cell_start + row + lxr), e = __ldg(L.cell_start + row + hxr + 1);
-    const float4* __restrict__ pts = L.pts;
-    for (uint32_t i = s; i < e; ++i) {
-        const float4 q = __ldg(pts + i);
-        const float d = l2_simple(px, py, pz, q.x, q.y, q.z);
-        const int id = __float_as_int(q.w);
-        if (d < bd || (d == bd && id < bi)) { bd = d; bi = id; bpos = level0 ? (int)i : -1; }
-    }
+    scan_range<kWide>(L.pts, s, e, px, py, pz, level0, bd, bi, bpos);
 }
 
 // Large balls (more than 3x3 rows): rows nearest-first, as square rings in y/z around the home
 // row.  As soon as a closer target is met the ball shrinks and the remaining rings fall outside
 // it, so a query far from the surface does not pay for the whole initial ball.  Out of line: this
 // is the rare path and must not cost the common one registers.
+template <bool kWide>
 __device__ __forceinline__ void ball_scan_rings(const GridLevel& L, float fx, float fy, float fz,
                                                     float mx, float my, float mz,
                                                     int lx, int hx, int ly, int hy, int lz, int hz,
@@ -85,7 +112,7 @@ __device__ __forceinline__ void ball_scan_rings(const GridLevel& L, float fx, fl
                                                     float& bd, int& bi, int& bpos) {
     const int cy = min(max((int)floorf(fy), ly), hy), cz = min(max((int)floorf(fz), lz), hz);
     const int R = max(max(cy - ly, hy - cy), max(cz - lz, hz - cz));
-    ball_row(L, cy, cz, fx, fy, fz, mx, my, mz, lx, hx, px, py, pz, level0, bd, bi, bpos);
+    ball_row<kWide>(L, cy, cz, fx, fy, fz, mx, my, mz, lx, hx, px, py, pz, level0, bd, bi, bpos);
     for (int t = 1; t <= R; ++t) {
         // every row of ring t (and of all later rings) is at least this far away in y or z
         const float g = fminf(fminf(axis_gap(fy, cy - t, my), axis_gap(fy, cy + t, my)),
@@ -96,7 +123,7 @@ __device__ __forceinline__ void ball_scan_rings(const GridLevel& L, float fx, fl
             const bool full = (kz == cz - t || kz == cz + t);
             for (int ky = y0; ky <= y1; ++ky) {
                 if (!full && ky != cy - t && ky != cy + t) continue;
-                ball_row(L, ky, kz, fx, fy, fz, mx, my, mz, lx, hx, px, py, pz, level0, bd, bi, bpos);
+                ball_row<kWide>(L, ky, kz, fx, fy, fz, mx, my, mz, lx, hx, px, py, pz, level0, bd, bi, bpos);
             }
         }
     }
@@ -107,7 +134,7 @@ static __device__ __noinline__ void ball_scan_rings_ool(const GridLevel& L, floa
                                                         int lx, int hx, int ly, int hy, int lz, int hz,
                                                         float px, float py, float pz, bool level0,
                                                         float& bd, int& bi, int& bpos) {
-    ball_scan_rings(L, fx, fy, fz, mx, my, mz, lx, hx, ly, hy, lz, hz, px, py, pz, level0, bd, bi, bpos);
+    ball_scan_rings<true>(L, fx, fy, fz, mx, my, mz, lx, hx, ly, hy, lz, hz, px, py, pz, level0, bd, bi, bpos);
 }
 
 // Scans every cell of level L that the closed ball of radius sqrt(bd) around p touches.
@@ -131,11 +158,11 @@ __device__ __forceinline__ void ball_scan(const GridLevel& L, float ox, float oy
         // measured and were not faster: the batch time is a chain of dependent L2 round trips.
         for (int kz = lz; kz <= hz; ++kz)
             for (int ky = ly; ky <= hy; ++ky)
-                ball_row(L, ky, kz, fx, fy, fz, mx, my, mz, lx, hx, px, py, pz, level0, bd, bi, bpos);
+                ball_row<kLean>(L, ky, kz, fx, fy, fz, mx, my, mz, lx, hx, px, py, pz, level0, bd, bi, bpos);
     } else if (kLean) {
         ball_scan_rings_ool(L, fx, fy, fz, mx, my, mz, lx, hx, ly, hy, lz, hz, px, py, pz, level0, bd, bi, bpos);
     } else {
-        ball_scan_rings(L, fx, fy, fz, mx, my, mz, lx, hx, ly, hy, lz, hz, px, py, pz, level0, bd, bi, bpos);
+        ball_scan_rings<false>(L, fx, fy, fz, mx, my, mz, lx, hx, ly, hy, lz, hz, px, py, pz, level0, bd, bi, bpos);
     }
 }
 
