@@ -41,8 +41,10 @@ struct IcpArgs {
     const float4* aux;        // level-0 order: nx, ny, nz, ctstd
     const float4* src;        // source set (read only)
     float4* work;             // transformed copy, updated in place every iteration
-    int4* cand;               // per source point: candidate cache (nn_search.cuh), .x = last match = seed of the next search
-    float4* anchor;           // per source point: position the cache was built at, w = validity radius (0: none)
+    // per source point: the candidate cache (nn_search.cuh)
+    float4* anchor;           // position the cache was built at, w = validity radius (0: none)
+    float4* cq0;              // primary candidate INLINE: x, y, z of the last match, w = its level-0 position (int bits, -1: none)
+    int4* cmore;              // x, y, z: positions of up to three further candidates (unused = primary), w = original index of the primary
     int seed_exact;           // cand[].x is the exact NN of the untransformed source (iteration 0 needs no search)
     float slack;              // cache radius beyond the NN distance
     float build_step2;        // a cache is built only when the point moved less than sqrt(this) in the last step
@@ -235,15 +237,33 @@ static __device__ __noinline__ Best icp_search_fallback(const IcpArgs& a, int it
         const float rm = sqrtf(bb.d2) + a.slack;
         cc = ball_collect(a.g.lv[0], a.g.ox, a.g.oy, a.g.oz, px, py, pz, rm * rm);
     }
+    // the match is the primary candidate; the other cached targets follow in any order
+    int o1 = bb.pos, o2 = bb.pos, o3 = bb.pos;
     if (cc.rho > 0.f) {
-        a.cand[i] = make_int4(cc.pos[0], cc.pos[1], cc.pos[2], cc.pos[3]);
-        a.anchor[i] = make_float4(px, py, pz, cc.rho);
-    } else {
-        a.cand[i] = make_int4(bb.pos, bb.pos, bb.pos, bb.pos);
-        if (old_rho != 0.f) a.anchor[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        int k = 0;
+#pragma unroll
+        for (int j = 0; j < kCacheCands; ++j)
+            if (cc.pos[j] != bb.pos) { if (k == 0) o1 = cc.pos[j]; else if (k == 1) o2 = cc.pos[j]; else if (k == 2) o3 = cc.pos[j]; ++k; }
+        // all four slots taken by targets other than the match cannot happen (the match is the nearest
+        // of the collected set); guard anyway: no cache rather than a wrong one
+        if (k > 3) cc.rho = 0.f;
     }
+    if (cc.rho > 0.f) a.anchor[i] = make_float4(px, py, pz, cc.rho);
+    else { o1 = o2 = o3 = bb.pos; if (old_rho != 0.f) a.anchor[i] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    a.cq0[i] = make_float4(bb.qx, bb.qy, bb.qz, __int_as_float(bb.pos));
+    a.cmore[i] = make_int4(o1, o2, o3, bb.idx);
     return bb;
 }
+
+// 16-byte asynchronous copy global -> shared (LDGSTS, L2 only: the sources are rewritten by other
+// SMs every iteration), per-thread completion groups.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_group1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 // Sum of up to kFanIn entries (stride kNumVals doubles) in order, starting from 0.  All loads are
 // issued before the first add; absent entries contribute +0.0, which leaves the sum unchanged.
@@ -260,24 +280,38 @@ __device__ __forceinline__ double sum_entries(const double* __restrict__ src, in
 __global__ void __launch_bounds__(kIcpThreads, PWICP_ICP_MINBLOCKS) icp_persistent_kernel(const IcpArgs a) {
     cg::grid_group grid = cg::this_grid();
     __shared__ __align__(16) float s_rows[kIcpWarps][32][8];
+    // staging of the streamed per-point data, two batches deep per warp, filled by cp.async:
+    // [slot][field: point, anchor, primary candidate, further candidates, normal of the primary][lane]
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    float4 (*s_stage)[2][5][32] = reinterpret_cast<float4 (*)[2][5][32]>(s_dyn);
     __shared__ double s_tot[kNumVals];
     __shared__ float s_T[16];
     __shared__ float s_Tfinal[16];
     __shared__ int s_stop;
+    __shared__ int s_fb;      // queries that ran the search in the previous iteration
     __shared__ FinishSmem s_fin;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nb = (a.n + 31) / 32;                              // 32-point batches
 
-    // which pair of row terms this lane accumulates: 21 upper-triangle ATA entries (row-major),
-    // 6 ATb entries (u_r * u_6), lane 27 = sum of squared NN distances
-    int va = 0, vb = 0;
+    // DMMA fragment roles of this lane (row m = lane / 4 of A and column m of B; D[m][2k], D[m][2k+1]
+    // with k = lane % 4).  Row layout in shared memory: a b c nx ny nz e d2.  The 28 values are the
+    // 21 upper-triangle ATA entries (row-major), the 6 ATb entries, and the sum of squared NN distances.
+    const int offA = (lane >> 2) < 6 ? (lane >> 2) : 7;      // A row 6 (and the unused row 7): d2
+    const int offB = (lane >> 2) < 6 ? (lane >> 2) : 6;      // B column 6: e; column 7 is the constant 1
+    int v0 = -1, v1 = -1;
     {
-        int v = 0;
-        for (int r = 0; r < 6; ++r)
-            for (int c = r; c < 6; ++c) { if (v == lane) { va = r; vb = c; } ++v; }
-        for (int r = 0; r < 6; ++r) { if (v == lane) { va = r; vb = 6; } ++v; }
-        if (lane == 27) { va = 7; vb = 7; }
+        const int rD = lane >> 2;
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+            const int c = 2 * (lane & 3) + jj;
+            int v = -1;
+            if (rD < 6) {
+                if (c < 6 && c >= rD) v = rD * 6 - rD * (rD - 1) / 2 + (c - rD);
+                else if (c == 6) v = 21 + rD;
+            } else if (rD == 6 && c == 7) v = 27;
+            if (jj == 0) v0 = v; else v1 = v;
+        }
     }
     if (tid < 16) { s_T[tid] = (tid % 5 == 0) ? 1.0f : 0.0f; s_Tfinal[tid] = s_T[tid]; }
     if (tid == 0) { s_stop = 0; s_fin.prev_mse = 1.7976931348623157e308; }   // DBL_MAX
@@ -288,11 +322,32 @@ __global__ void __launch_bounds__(kIcpThreads, PWICP_ICP_MINBLOCKS) icp_persiste
 #else
 #define PW_TS(k)
 #endif
+    bool staged = false;      // the first batch of this iteration is already being copied
     for (int it = 0;; ++it) {
         PW_TS(0);
         float T[12];
 #pragma unroll
         for (int k = 0; k < 12; ++k) T[k] = s_T[k];
+        // stage-1 copies of a batch: point, anchor, primary candidate, further candidates
+        auto stage_batch = [&](const float4* __restrict__ psrc, int bb_, int slot) {
+            const int i_ = bb_ * 32 + lane;
+            if (bb_ < nb && i_ < a.n) {
+                cp_async16(&s_stage[warp][slot][0][lane], psrc + i_);
+                cp_async16(&s_stage[warp][slot][1][lane], a.anchor + i_);
+                cp_async16(&s_stage[warp][slot][2][lane], a.cq0 + i_);
+                cp_async16(&s_stage[warp][slot][3][lane], a.cmore + i_);
+            }
+            cp_async_commit();
+        };
+        // stage-2 copy: the normal of the primary candidate (its position arrives with stage 1)
+        auto stage_aux = [&](int bb_, int slot) {
+            const int i_ = bb_ * 32 + lane;
+            if (bb_ < nb && i_ < a.n) {
+                const int pos0 = __float_as_int(s_stage[warp][slot][2][lane].w);
+                if (pos0 >= 0) cp_async16(&s_stage[warp][slot][4][lane], a.aux + pos0);
+            }
+            cp_async_commit();
+        };
 
         // ---- phase A.  Every warp first works through a static share of the batches (b = j * NW + W,
         // half of its fair share), then takes single batches from a counter: the cost of a batch is
@@ -304,26 +359,36 @@ __global__ void __launch_bounds__(kIcpThreads, PWICP_ICP_MINBLOCKS) icp_persiste
             const int NW = gridDim.x * kIcpWarps, W = blockIdx.x * kIcpWarps + warp;
             // static batches per warp: half of the fair share once (nearly) every query is answered from its
             // cache (uniform cost per batch), else only the two that cover the pipeline depth of the hand-out
-            const int fb_prev = (it > 1) ? __ldcg(a.fallbacks + it - 1) : a.n;
+            const int fb_prev = (it > 1) ? s_fb : a.n;
             const bool calm = (long long)fb_prev * 64 < (long long)a.n;
             const int J = (calm ? (nb / NW) * PWICP_STATIC_EIGHTHS / 8 : 0) + 2;
+            const bool has_dyn = (long long)J * NW < (long long)nb;   // else no hand-out tickets at all
             const float4* __restrict__ psrc = (it == 0) ? a.src : a.work;
             int* counter = a.batch_counter + it;
             int seq = 0;                                       // position in this warp's batch sequence
             int tkt = 0;                                       // lane 0: hand-out ticket in flight
             int b = W, bn = NW + W;                            // positions 0 and 1
-            float4 p = make_float4(0.f, 0.f, 0.f, 0.f), an = p, pn = p, ann = p;
-            int4 c = make_int4(-1, -1, -1, -1), cn = c;
-            if (b < nb && b * 32 + lane < a.n) { const int i = b * 32 + lane; p = psrc[i]; c = a.cand[i]; an = a.anchor[i]; }
+            if (!staged) {                                     // else: issued during the previous iteration's solve
+                stage_batch(psrc, b, 0);
+                cp_async_wait_all();
+                stage_aux(b, 0);
+            }
             while (b < nb) {
-                // loads of the next batch, ticket for the one after
-                if (bn < nb && bn * 32 + lane < a.n) { const int i = bn * 32 + lane; pn = psrc[i]; cn = a.cand[i]; ann = a.anchor[i]; }
-                if (seq + 2 >= J && lane == 0) tkt = atomicAdd(counter, 1);   // position seq+2 is dynamic
+                const int slot = seq & 1;
+                // copies of the next batch and the ticket for the one after are in flight during this one
+                stage_batch(psrc, bn, slot ^ 1);
+                if (has_dyn && seq + 2 >= J && lane == 0) tkt = atomicAdd(counter, 1);   // position seq+2 is dynamic
+                cp_async_wait_group1();                        // everything but the copies just issued has landed
 
                 const int i = b * 32 + lane;
                 const bool active = i < a.n;
                 float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
                 if (active) {
+                    float4 p = s_stage[warp][slot][0][lane];
+                    const float4 an = s_stage[warp][slot][1][lane];
+                    const float4 q0 = s_stage[warp][slot][2][lane];
+                    const int4 cm = *reinterpret_cast<const int4*>(&s_stage[warp][slot][3][lane]);
+                    const int pos0 = __float_as_int(q0.w);
                     float step2 = __int_as_float(0x7f800000);
                     if (it > 0) {
                         float x, y, z;
@@ -336,33 +401,40 @@ __global__ void __launch_bounds__(kIcpThreads, PWICP_ICP_MINBLOCKS) icp_persiste
                     // query (nn_search.cuh, "candidate cache"), else the seeded ball search
                     Best bb;
                     bool ok = false;
-                    int seed = c.x;
-                    if (seed >= 0) {
+                    int seed = pos0;
+                    if (pos0 >= 0) {
                         const float4* __restrict__ pts = a.g.lv[0].pts;
-                        // unused cache slots repeat slot 0: their loads are predicated off (no L1 traffic)
-                        const float4 q0 = __ldg(pts + c.x);
-                        float4 q1 = q0, q2 = q0, q3 = q0;
-                        if (c.y != c.x) q1 = __ldg(pts + c.y);
-                        if (c.z != c.x) q2 = __ldg(pts + c.z);
-                        if (c.w != c.x) q3 = __ldg(pts + c.w);
                         bb.d2 = l2_simple(p.x, p.y, p.z, q0.x, q0.y, q0.z);
-                        bb.idx = __float_as_int(q0.w); bb.pos = c.x; bb.qx = q0.x; bb.qy = q0.y; bb.qz = q0.z;
-#define PW_CAND(q, cp)                                                                         \
-                        {                                                                      \
+                        bb.idx = cm.w; bb.pos = pos0; bb.qx = q0.x; bb.qy = q0.y; bb.qz = q0.z;
+                        // unused slots repeat the primary: their loads are predicated off (no L1 traffic)
+#define PW_CAND(cp)                                                                            \
+                        if ((cp) != pos0) {                                                    \
+                            const float4 q = __ldg(pts + (cp));                                \
                             const float d = l2_simple(p.x, p.y, p.z, q.x, q.y, q.z);           \
                             const int id = __float_as_int(q.w);                                \
                             if (d < bb.d2 || (d == bb.d2 && id < bb.idx)) {                    \
-                                bb.d2 = d; bb.idx = id; bb.pos = cp; bb.qx = q.x; bb.qy = q.y; bb.qz = q.z; \
+                                bb.d2 = d; bb.idx = id; bb.pos = (cp); bb.qx = q.x; bb.qy = q.y; bb.qz = q.z; \
                             }                                                                  \
                         }
-                        PW_CAND(q1, c.y) PW_CAND(q2, c.z) PW_CAND(q3, c.w)
+                        PW_CAND(cm.x) PW_CAND(cm.y) PW_CAND(cm.z)
 #undef PW_CAND
                         const float da = l2_simple(p.x, p.y, p.z, an.x, an.y, an.z);
                         ok = (it == 0 && a.seed_exact) || sqrtf(bb.d2) + sqrtf(da) < an.w;
                         seed = bb.pos;
                     }
-                    if (!ok) bb = icp_search_fallback(a, it, i, p.x, p.y, p.z, seed, step2, an.w);
-                    const float4 nq = __ldg(a.aux + bb.pos);
+                    float4 nq;
+                    if (ok && bb.pos == pos0) {
+                        nq = s_stage[warp][slot][4][lane];
+                    } else {
+                        if (!ok) bb = icp_search_fallback(a, it, i, p.x, p.y, p.z, seed, step2, an.w);
+                        else {
+                            // another cached target has become the nearest: make it the primary
+                            a.cq0[i] = make_float4(bb.qx, bb.qy, bb.qz, __int_as_float(bb.pos));
+                            a.cmore[i] = make_int4(cm.x == bb.pos ? pos0 : cm.x, cm.y == bb.pos ? pos0 : cm.y,
+                                                   cm.z == bb.pos ? pos0 : cm.z, bb.idx);
+                        }
+                        nq = __ldg(a.aux + bb.pos);
+                    }
                     const float sx = p.x, sy = p.y, sz = p.z;
                     const float dx = bb.qx, dy = bb.qy, dz = bb.qz;
                     const float nx = nq.x, ny = nq.y, nz = nq.z;
@@ -382,29 +454,46 @@ __global__ void __launch_bounds__(kIcpThreads, PWICP_ICP_MINBLOCKS) icp_persiste
                 // and the L1/shared pipe is the busiest unit of this kernel (profiles/r01e_*)
                 float4* row = reinterpret_cast<float4*>(&s_rows[warp][lane][0]);
                 row[0] = lo; row[1] = hi;
+                // the next batch's stage 1 has had the whole search to land: start its stage 2, which
+                // flies during the sums below
+                cp_async_wait_all();
+                stage_aux(bn, slot ^ 1);
                 __syncwarp();
-                // batch sums: lane v adds its product over rows 0..31 in order, starting from 0
-                if (lane < kNumVals) {
-                    double acc = 0.0;
-#pragma unroll 8
-                    for (int r = 0; r < 32; ++r) {
-                        const double x = (double)s_rows[warp][r][va];
-                        const double y = (lane == 27) ? 1.0 : (double)s_rows[warp][r][vb];
-                        acc = __fma_rn(x, y, acc);   // the product of two float values is exact in double, so
-                                                     // this is acc + x*y with one rounding, fused or not
+                // batch sums on the FP64 tensor cores: the 28 sums are entries of D = A * B with
+                // A = [a b c nx ny nz d2 -]^T (8 x 32) and B = [a b c nx ny nz e 1] (32 x 8), formed by eight
+                // chained DMMA.8x8x4.  On B200 a DMMA adds its four products to the accumulator one after
+                // the other, each with one rounding, in k order (scripts/micro/dmma_order.cu: 0 mismatches in
+                // 128 000 sums against a DFMA chain), and a product of two float values is exact in
+                // double: every sum is over rows 0..31 in order, starting from 0 -- the order the oracle uses.
+                {
+                    double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float* r = &s_rows[warp][4 * j + (lane & 3)][0];
+                        const double av = (double)r[offA];
+                        const double bv = (lane >= 28) ? 1.0 : (double)r[offB];
+                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                     : "+d"(c0), "+d"(c1) : "d"(av), "d"(bv));
                     }
-                    __stcg(a.part[0] + (size_t)b * kNumVals + lane, acc);
+                    double* dst = a.part[0] + (size_t)b * kNumVals;
+                    if (v0 >= 0) __stcg(dst + v0, c0);
+                    if (v1 >= 0) __stcg(dst + v1, c1);
                 }
                 __syncwarp();
                 // rotate the pipeline
                 ++seq;
-                b = bn; p = pn; c = cn; an = ann;
-                bn = (seq + 1 < J) ? (seq + 1) * NW + W : J * NW + __shfl_sync(0xffffffffu, tkt, 0);
+                b = bn;
+                bn = (seq + 1 < J) ? (seq + 1) * NW + W : (has_dyn ? J * NW + __shfl_sync(0xffffffffu, tkt, 0) : nb);
             }
+            cp_async_wait_all();
         }
         PW_TS(1);
         grid.sync();
         PW_TS(2);
+        // the next iteration's first batch (always position 0 = batch W): its copies do not depend on the
+        // transform being solved for, so they fly during the reduction and the solve
+        stage_batch(a.work, blockIdx.x * kIcpWarps + warp, 0);
+        staged = true;
 
         // ---- phase B1: one warp per group of kFanIn batches: lane v sums the group's entries of
         // value v in order, starting from 0 (loads are independent, the adds sequential).  The warp
@@ -434,6 +523,8 @@ __global__ void __launch_bounds__(kIcpThreads, PWICP_ICP_MINBLOCKS) icp_persiste
             grid.sync();
         }
 
+        cp_async_wait_all();
+        stage_aux(blockIdx.x * kIcpWarps + warp, 0);
         // ---- phase B2: every CTA forms the same totals from the top-level entries, in order
         if (warp == 0) {
             if (lane < kNumVals) {
@@ -442,6 +533,7 @@ __global__ void __launch_bounds__(kIcpThreads, PWICP_ICP_MINBLOCKS) icp_persiste
                     acc += sum_entries(a.top_part + (size_t)k0 * kNumVals + lane, min(kFanIn, a.top_count - k0));
                 s_tot[lane] = acc;
             }
+            if (lane == 31) s_fb = __ldcg(a.fallbacks + it);   // complete since the first grid barrier
             __syncwarp();
         }
         PW_TS(4);
@@ -454,6 +546,7 @@ __global__ void __launch_bounds__(kIcpThreads, PWICP_ICP_MINBLOCKS) icp_persiste
         PW_TS(5);
         if (s_stop) break;
     }
+    cp_async_wait_all();
 }
 
 __global__ void expand_xyz_kernel(const float* __restrict__ xyz, int n, float4* out) {
@@ -495,7 +588,8 @@ __global__ void src_key_kernel(const float4* __restrict__ src, int n, float ox, 
 }
 
 __global__ void src_gather_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ order, int n, float4* out,
-                                  const int* __restrict__ seed_in, int4* __restrict__ cand, float4* __restrict__ anchor) {
+                                  const int* __restrict__ seed_in, const float4* __restrict__ tgt_pts,
+                                  float4* __restrict__ anchor, float4* __restrict__ cq0, int4* __restrict__ cmore) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t o = order[i];
@@ -503,7 +597,11 @@ __global__ void src_gather_kernel(const float4* __restrict__ src, const uint32_t
     p.w = __int_as_float((int)o);
     out[i] = p;
     const int sd = seed_in ? seed_in[o] : -1;
-    cand[i] = make_int4(sd, sd, sd, sd);
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    int idx = 0;
+    if (sd >= 0) { q = __ldg(tgt_pts + sd); idx = __float_as_int(q.w); }
+    cq0[i] = make_float4(q.x, q.y, q.z, __int_as_float(sd));
+    cmore[i] = make_int4(sd, sd, sd, idx);
     anchor[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
@@ -511,12 +609,13 @@ __global__ void src_gather_kernel(const float4* __restrict__ src, const uint32_t
 // kernel is register-capped and runs it about twice as slowly, profiles/r01f_*).  The matches go
 // into the candidate slots; the persistent kernel takes them as the exact answer of iteration 0.
 __global__ void __launch_bounds__(256)
-icp_seed_kernel(GridDev g, const float4* __restrict__ src, int n, int4* __restrict__ cand) {
+icp_seed_kernel(GridDev g, const float4* __restrict__ src, int n, float4* __restrict__ cq0, int4* __restrict__ cmore) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4 p = __ldg(src + i);
     const Best b = nn_search_seeded(g, p.x, p.y, p.z, -1);
-    cand[i] = make_int4(b.pos, b.pos, b.pos, b.pos);
+    cq0[i] = make_float4(b.qx, b.qy, b.qz, __int_as_float(b.pos));
+    cmore[i] = make_int4(b.pos, b.pos, b.pos, b.idx);
 }
 
 // Sorts the source set by the target-grid cell it starts in (stable: ties keep the caller's
@@ -529,7 +628,7 @@ static int icp_sort_source(Ctx* ctx, int n, bool have_seed) {
     PW_TRY(ctx->keys2.reserve(ctx, (size_t)n * 8));
     PW_TRY(ctx->icp_perm.reserve(ctx, (size_t)n * 4));
     PW_TRY(ctx->icp_sorted.reserve(ctx, (size_t)n * sizeof(float4)));
-    PW_TRY(ctx->icp_match.reserve(ctx, (size_t)n * (sizeof(int4) + sizeof(float4))));
+    PW_TRY(ctx->icp_match.reserve(ctx, (size_t)n * 3 * sizeof(float4)));      // anchor, cq0, cmore
     const int blocks = (n + 255) / 256;
     src_key_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->icp_src.as<float4>(), n, ctx->tgt.dev.ox, ctx->tgt.dev.oy,
                                                     ctx->tgt.dev.oz, L.inv_h, L.dx, L.dy, L.dz,
@@ -546,8 +645,9 @@ static int icp_sort_source(Ctx* ctx, int n, bool have_seed) {
                                             ctx->vals.as<uint32_t>(), ctx->icp_perm.as<uint32_t>(), n, 0, bits, ctx->stream));
     src_gather_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->icp_src.as<float4>(), ctx->icp_perm.as<uint32_t>(), n,
                                                        ctx->icp_sorted.as<float4>(),
-                                                       have_seed ? ctx->icp_seed.as<int>() : nullptr, ctx->icp_match.as<int4>(),
-                                                       reinterpret_cast<float4*>(ctx->icp_match.as<int4>() + n));
+                                                       have_seed ? ctx->icp_seed.as<int>() : nullptr, ctx->tgt.dev.lv[0].pts,
+                                                       ctx->icp_match.as<float4>(), ctx->icp_match.as<float4>() + n,
+                                                       reinterpret_cast<int4*>(ctx->icp_match.as<float4>() + 2 * (size_t)n));
     ctx->launches += 5;
     PW_CUDA(cudaGetLastError());
     return PWICP_OK;
@@ -560,7 +660,8 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     if (n < 3) { set_error(ctx, "icp: fewer than 3 correspondences"); return PWICP_ERR_TOO_FEW_CORR; }
     if (prm.max_iter < 1 || prm.max_iter > kMaxIcpIter) { set_error(ctx, "icp: max_iter out of range"); return PWICP_ERR_ARG; }
 
-    const size_t smem = 0;
+    const size_t smem = (size_t)kIcpWarps * 2 * 5 * 32 * sizeof(float4);      // s_stage
+    PW_CUDA(cudaFuncSetAttribute(icp_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     PW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, icp_persistent_kernel, kIcpThreads, smem));
     if (occ < 1) { set_error(ctx, "icp: kernel does not fit on an SM"); return PWICP_ERR_CUDA; }
@@ -596,7 +697,8 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     ctx->icp_seed_valid = false;                       // seeds belong to one source set
     if (!have_seed) {
         icp_seed_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->tgt.dev, ctx->icp_sorted.as<float4>(), n,
-                                                                  ctx->icp_match.as<int4>());
+                                                                  ctx->icp_match.as<float4>() + n,
+                                                                  reinterpret_cast<int4*>(ctx->icp_match.as<float4>() + 2 * (size_t)n));
         ctx->launches++;
     }
 
@@ -605,8 +707,9 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     a.aux = ctx->tgt_aux.as<float4>();
     a.src = ctx->icp_sorted.as<float4>();
     a.work = ctx->icp_work.as<float4>();
-    a.cand = ctx->icp_match.as<int4>();
-    a.anchor = reinterpret_cast<float4*>(a.cand + n);
+    a.anchor = ctx->icp_match.as<float4>();
+    a.cq0 = a.anchor + n;
+    a.cmore = reinterpret_cast<int4*>(a.anchor + 2 * (size_t)n);
     a.seed_exact = 1;         // classification matches (outer.cu) or icp_seed_kernel
     a.slack = 0.03f / ctx->tgt.dev.lv[0].inv_h;
     a.build_step2 = (0.25f * a.slack) * (0.25f * a.slack);
