@@ -18,13 +18,13 @@ for n in (113664, 1000000):
     for _ in range(10):                      # clocks up, caches and allocations warm
         ctx.icp_run(P.icp_params(max_iter=300, force_iters=1))
     t = {}
-    for it in (1, 6, 51, 520, 1020):
+    for it in (1, 2, 3, 4, 5, 6, 51, 520, 1020):
         t[it] = min(ctx.icp_run(P.icp_params(max_iter=it, force_iters=1))["device_ms"] for _ in range(4))
     nn_ms = []
     for _ in range(3):
         ctx.nn(d["ct2"]); nn_ms.append(ctx.last_device_ms())
-    out.append("n=%%d: nn %%.3f ms, it1 %%.3f ms, it6 %%.3f, it51 %%.3f | steady us/iter %%.2f" %% (
-        len(d["ct2"]), min(nn_ms), t[1], t[6], t[51], (t[1020]-t[520])/500*1e3))
+    out.append("n=%%d: nn %%.3f ms, it1 %%.3f ms (+%%.0f +%%.0f +%%.0f +%%.0f +%%.0f us), it51 %%.3f | steady us/iter %%.2f" %% (
+        len(d["ct2"]), min(nn_ms), t[1], (t[2]-t[1])*1e3, (t[3]-t[2])*1e3, (t[4]-t[3])*1e3, (t[5]-t[4])*1e3, (t[6]-t[5])*1e3, t[51], (t[1020]-t[520])/500*1e3))
 print(os.path.basename(sys.argv[1]), " || ".join(out))
 ''' % ROOT
 for rep in range(2):

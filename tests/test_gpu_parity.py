@@ -148,6 +148,45 @@ def test_inner_loop_bit_exact_in_device_order(gpu_ctx, oracle, pair60k):
     assert np.array_equal(r["T"], o["T"])
 
 
+def test_candidate_cache_adversarial_clouds(gpu_ctx, oracle):
+    """The per-query candidate cache of the inner loop (exact by a ball-coverage certificate) on
+    inputs that are not a sampled surface: a volume-filling random cloud, exact duplicates, and a
+    lattice whose cell centres are equidistant from eight targets (exact float ties -> lowest
+    index).  Every index of every iteration, every transform and every MSE must equal the oracle's."""
+    rng = np.random.default_rng(7)
+    vol = rng.uniform(-1.0, 1.0, (40000, 3)).astype(np.float32)
+    dup = vol[rng.choice(len(vol), 3000, replace=False)]                       # exact duplicates
+    g = np.arange(-8, 9, dtype=np.float32) * 0.125
+    lat = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3) + np.float32(3.0)   # exact binary fractions
+    tgt = np.concatenate([vol, dup, lat]).astype(np.float32)
+    tgt = tgt[rng.permutation(len(tgt))]
+    nrm = rng.normal(0, 1, tgt.shape); nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    nrm = nrm.astype(np.float32)
+    centres = (lat[(np.abs(lat - 3.0) < 0.9).all(1)] + np.float32(0.0625)).astype(np.float32)   # 8-way ties
+    near = (vol[:20000] + rng.normal(0, 2e-3, (20000, 3))).astype(np.float32)
+    onto = dup[:2000].copy()                                                   # distance 0, duplicate indices
+    src0 = np.concatenate([near, centres, onto]).astype(np.float32)
+    T0 = synth.rigid_matrix(2e-4, -1e-4, 3e-4, 1e-4, -2e-4, 1e-4)
+    src = (src0 @ T0[:3, :3].T + T0[:3, 3]).astype(np.float32)
+    gpu_ctx.target_upload(tgt, nrm, np.full(len(tgt), 1e-4, np.float32))
+    gpu_ctx.icp_source_upload(src)
+    iters = 16
+    r = gpu_ctx.icp_run(P.icp_params(max_iter=iters, force_iters=1), trace=True)
+    perm = gpu_ctx.icp_order()
+    o = oracle.icp(tgt, nrm, src[perm], oracle.icp_params(max_iter=iters, force_iters=1, reduce_mode=1,
+                                                         group_batches=r["group_batches"]), trace=True)
+    assert r["n_iter"] == o["n_iter"] == iters
+    assert np.array_equal(r["idx_trace"][:, perm], o["idx_trace"])
+    assert np.array_equal(r["T_trace"], o["T_trace"]) and np.array_equal(r["mse"], o["mse"])
+    # the same source untransformed: the lattice centres sit exactly on 8-way ties in iteration 0
+    gpu_ctx.icp_source_upload(src0)
+    r = gpu_ctx.icp_run(P.icp_params(max_iter=6, force_iters=1), trace=True)
+    perm = gpu_ctx.icp_order()
+    o = oracle.icp(tgt, nrm, src0[perm], oracle.icp_params(max_iter=6, force_iters=1, reduce_mode=1,
+                                                          group_batches=r["group_batches"]), trace=True)
+    assert np.array_equal(r["idx_trace"][:, perm], o["idx_trace"]) and np.array_equal(r["T_trace"], o["T_trace"])
+
+
 def test_inner_loop_pose_vs_reference_order(gpu_ctx, oracle, pair60k, gold, pair2k):
     for d in (pair60k, pair2k):
         gpu_ctx.target_upload(d["ct1"], d["nrm1"], d["ctstd1"])
@@ -292,17 +331,47 @@ def test_full_size_properties_1m(gpu_ctx, oracle):
     # (d) whole set against the oracle KD-tree
     oi, od = oracle.nn(d["ct1"], d["ct2"])
     assert np.array_equal(idx, oi) and np.array_equal(d2, od)
-    # (e) three inner iterations, bit-exact in device order, pose within tolerance in reference order
+    # (e) eight inner iterations (search, cache build, cached iterations), bit-exact in device order,
+    # pose within tolerance in reference order
     gpu_ctx.icp_source_upload(d["ct2"])
-    r = gpu_ctx.icp_run(P.icp_params(max_iter=3, force_iters=1), trace=True)
+    r = gpu_ctx.icp_run(P.icp_params(max_iter=8, force_iters=1), trace=True)
     perm = gpu_ctx.icp_order()
     o1 = oracle.icp(d["ct1"], d["nrm1"], d["ct2"][perm],
-                    oracle.icp_params(max_iter=3, force_iters=1, reduce_mode=1, group_batches=r["group_batches"]), trace=True)
+                    oracle.icp_params(max_iter=8, force_iters=1, reduce_mode=1, group_batches=r["group_batches"]), trace=True)
     assert np.array_equal(r["T_trace"], o1["T_trace"]) and np.array_equal(r["idx_trace"][:, perm], o1["idx_trace"])
-    o0 = oracle.icp(d["ct1"], d["nrm1"], d["ct2"], oracle.icp_params(max_iter=3, force_iters=1))
+    assert np.array_equal(r["mse"], o1["mse"])
+    o0 = oracle.icp(d["ct1"], d["nrm1"], d["ct2"], oracle.icp_params(max_iter=8, force_iters=1))
     da, dt = pose_diff(r["T"], o0["T"])
     assert da <= POSE_TOL_RAD and dt <= POSE_TOL_M
     # (f) 50 forced iterations are deterministic run to run
     a = gpu_ctx.icp_run(P.icp_params(max_iter=50, force_iters=1))
     b = gpu_ctx.icp_run(P.icp_params(max_iter=50, force_iters=1))
     assert np.array_equal(a["T"], b["T"]) and a["correspondences"] == 50 * len(d["ct2"])
+
+
+def test_stress_10m_centroids(gpu_ctx, oracle):
+    """configs[4]: 10M-centroid pair.  Properties that do not need a 10M x 10M oracle pass, plus six
+    inner iterations (search, cache build, cached) bit-exact against the oracle in device order."""
+    d = synth.make_pair(10_000_000, with_clouds=False)
+    n = len(d["ct1"])
+    gpu_ctx.target_upload(d["ct1"], d["nrm1"], d["ctstd1"])
+    idx, d2 = gpu_ctx.nn(d["ct1"])
+    assert np.array_equal(idx, np.arange(n, dtype=np.int32)) and not d2.any()
+    idx, d2 = gpu_ctx.nn(d["ct2"])
+    df = d["ct2"] - d["ct1"][idx]
+    assert np.array_equal(d2, ((df[:, 0] * df[:, 0] + df[:, 1] * df[:, 1]) + df[:, 2] * df[:, 2]).astype(np.float32))
+    rng = np.random.default_rng(2)
+    pick = rng.choice(len(d["ct2"]), 100, replace=False)
+    oi, od = oracle.nn(d["ct1"], d["ct2"][pick], brute=True)
+    assert np.array_equal(idx[pick], oi) and np.array_equal(d2[pick], od)
+    gpu_ctx.icp_source_upload(d["ct2"])
+    r = gpu_ctx.icp_run(P.icp_params(max_iter=6, force_iters=1), trace=True)
+    perm = gpu_ctx.icp_order()
+    o = oracle.icp(d["ct1"], d["nrm1"], d["ct2"][perm],
+                   oracle.icp_params(max_iter=6, force_iters=1, reduce_mode=1, group_batches=r["group_batches"]), trace=True)
+    assert np.array_equal(r["T_trace"], o["T_trace"]) and np.array_equal(r["mse"], o["mse"])
+    assert np.array_equal(r["idx_trace"][:, perm], o["idx_trace"])
+    a = gpu_ctx.icp_run(P.icp_params(max_iter=30, force_iters=1))
+    b = gpu_ctx.icp_run(P.icp_params(max_iter=30, force_iters=1))
+    assert np.array_equal(a["T"], b["T"]) and a["correspondences"] == 30 * len(d["ct2"])
+    print(f"10M: 30 iterations {a['device_ms']:.2f} ms, {a['correspondences'] / a['device_ms'] / 1e6:.2f} G corr/s")
