@@ -36,6 +36,17 @@ ALG_BYTES_PER_CORR = 48          # 12 src + 12 tgt xyz + 12 tgt 
 METRIC = "correspondences/s/GPU (ICP iters/s on 1M-pt pair; pose err vs ref)"
 
 
+def profiled_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this
+    same configuration (profiles/traffic.json, written by scripts/summarize_profile.py)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        return float(t["dram_bytes_per_launch"]), t.get("source")
+    except Exception:
+        return None, None
+
+
 def measured_hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -240,6 +251,7 @@ def main():
 
     if rank == 0:
         peak, peak_kind = measured_hbm_peak()
+        traffic, traffic_src = profiled_traffic()
         icp_avg_ms = float(np.mean(icp_ms))
         achieved = ALG_BYTES_PER_CORR * INNER_ITERS * n2 / (icp_avg_ms * 1e-3) / 1e9
         line = {
@@ -262,15 +274,19 @@ def main():
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "icp_persistent_kernel", "achieved": achieved,
                          "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None,
-                         "note": "algorithmic 48 B/correspondence x 50 iterations x n_source per launch; "
-                                 "the 1M working set (64 MB) is L2-resident, DRAM traffic is far below it"},
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "algorithmic_bytes_per_launch": ALG_BYTES_PER_CORR * INNER_ITERS * n2,
+                         "launch_ms": icp_avg_ms,
+                         "note": "achieved = 48 B/correspondence x 50 iterations x n_source / launch time "
+                                 "(CUDA events on the library stream; the launch includes the Morton sort of the "
+                                 "source and the iteration-0 search pre-pass); peak = measured copy bandwidth "
+                                 "(MEASURED_PEAKS.json); traffic = dram read+write bytes of one launch (ncu)"},
         }
         # pose check against the oracle on a small pair (full size is covered by tests -m gpu)
         if not args.no_cpu_baseline:
             from oracle import oracle_py as O
             t0 = time.perf_counter()
-            sample_iters = 3
+            sample_iters = 20                # ~10 s of single-thread CPU work at 1M
             o = O.icp(d["ct1"], d["nrm1"], d["ct2"], O.icp_params(max_iter=sample_iters, force_iters=1))
             cpu_s = time.perf_counter() - t0
             g = ctx.icp_p2plane(h_t, h_n, h_s, P.icp_params(max_iter=sample_iters, force_iters=1))
