@@ -131,6 +131,7 @@ void pwicp_ctx_destroy(pwicp_ctx* p) {
     if (c->pinned) cudaFreeHost(c->pinned);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->stream);
+    if (c->copy_stream) { cudaStreamDestroy(c->copy_stream); for (auto& e : c->copy_ev) if (e) cudaEventDestroy(e); }
     delete c;
 }
 
@@ -381,10 +382,65 @@ int pwicp_icp_order(pwicp_ctx* p, int* perm) {
     return PWICP_OK;
 }
 
+// Host-buffer call in the shape of P2PICPwithPatchNormal (reference src/Registration.cpp:1255-1269).
+// The three uploads run on a copy stream; the grid build over the target overlaps the transfer of
+// the normals and of the source, the finite checks accumulate into one device flag that is read
+// once, right before the inner loop starts.
 int pwicp_icp_p2plane(pwicp_ctx* p, const float* tgt_xyz, const float* tgt_nrm, int n1, const float* src_xyz,
                       int n2, const pwicp_icp_params* prm, float* T16, pwicp_icp_result* res) {
-    PW_TRY(pwicp_target_upload(p, tgt_xyz, tgt_nrm, nullptr, nullptr, n1));
-    PW_TRY(pwicp_icp_source_upload(p, src_xyz, n2));
+    Ctx* ctx = reinterpret_cast<Ctx*>(p);
+    if (!ctx || n1 < 1 || n2 < 1 || !tgt_xyz || !tgt_nrm || !src_xyz) {
+        set_error(ctx, "icp_p2plane: bad arguments"); return PWICP_ERR_ARG;
+    }
+    PW_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->copy_stream) {
+        PW_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (auto& e : ctx->copy_ev) PW_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    ctx->n1 = 0;
+    PW_TRY(ctx->tgt_xyz.reserve(ctx, (size_t)3 * n1 * 4 + 64));
+    PW_TRY(ctx->tgt_nrm_raw.reserve(ctx, (size_t)3 * n1 * 4 + 64));
+    PW_TRY(ctx->scratch_a.reserve(ctx, (size_t)3 * n2 * 4 + 64));
+    PW_TRY(ctx->scratch_d.reserve(ctx, 256));
+    // earlier work on the library stream may still read these buffers
+    PW_CUDA(cudaEventRecord(ctx->copy_ev[3], ctx->stream));
+    PW_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[3], 0));
+    PW_CUDA(cudaMemcpyAsync(ctx->tgt_xyz.p, tgt_xyz, (size_t)3 * n1 * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+    PW_CUDA(cudaEventRecord(ctx->copy_ev[0], ctx->copy_stream));
+    PW_CUDA(cudaMemcpyAsync(ctx->tgt_nrm_raw.p, tgt_nrm, (size_t)3 * n1 * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+    PW_CUDA(cudaEventRecord(ctx->copy_ev[1], ctx->copy_stream));
+    PW_CUDA(cudaMemcpyAsync(ctx->scratch_a.p, src_xyz, (size_t)3 * n2 * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+    PW_CUDA(cudaEventRecord(ctx->copy_ev[2], ctx->copy_stream));
+
+    int* flag = ctx->scratch_d.as<int>() + 16;            // [0..5] belong to the bounding-box reduction
+    PW_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+    PW_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[0], 0));
+    PW_TRY(finite_accumulate_dev(ctx, ctx->tgt_xyz.as<float>(), (size_t)3 * n1, flag));
+    ctx->tgt_has_std = false;
+    ctx->tgt_has_ok = false;
+    // a non-finite coordinate would poison the bounding box: the build needs the verdict on the target
+    int bad = 0;
+    PW_CUDA(cudaMemcpyAsync(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PW_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (bad) { cudaStreamSynchronize(ctx->copy_stream); set_error(ctx, "target centroids: non-finite value in input"); return PWICP_ERR_NONFINITE; }
+    PW_TRY(grid_build(ctx, ctx->tgt, ctx->tgt_xyz.as<float>(), n1));
+    PW_TRY(reset_seeds(ctx));
+    PW_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[1], 0));
+    PW_TRY(finite_accumulate_dev(ctx, ctx->tgt_nrm_raw.as<float>(), (size_t)3 * n1, flag));
+    PW_TRY(ctx->tgt_aux.reserve(ctx, (size_t)n1 * sizeof(float4)));
+    PW_TRY(ctx->tgt_ok.reserve(ctx, (size_t)n1));
+    gather_aux_kernel<<<(n1 + 255) / 256, 256, 0, ctx->stream>>>(ctx->tgt_nrm_raw.as<float>(), nullptr, nullptr,
+                                                                 ctx->tgt.perm0, n1, ctx->tgt_aux.as<float4>(),
+                                                                 ctx->tgt_ok.as<unsigned char>());
+    ctx->launches++;
+    PW_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[2], 0));
+    PW_TRY(finite_accumulate_dev(ctx, ctx->scratch_a.as<float>(), (size_t)3 * n2, flag));
+    ctx->icp_seed_valid = false;
+    PW_TRY(icp_expand_source(ctx, ctx->scratch_a.as<float>(), n2));
+    PW_CUDA(cudaMemcpyAsync(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PW_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (bad) { set_error(ctx, "icp_p2plane: non-finite value in input"); return PWICP_ERR_NONFINITE; }
+    ctx->n1 = n1;
     return pwicp_icp_run(p, prm, T16, res, nullptr, nullptr, nullptr);
 }
 

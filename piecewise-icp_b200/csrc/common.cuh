@@ -80,6 +80,8 @@ void set_error(Ctx* c, const std::string& msg);
 struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;          // host-buffer calls: uploads overlap the grid build
+    cudaEvent_t copy_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
     float last_ms = 0.f;
@@ -122,6 +124,7 @@ int nn_query_packed(Ctx* ctx, const GridDev& g, const float* q_dev_packed, int n
 int self_nn_dev(Ctx* ctx, const GridDev& g, float* d2_dev);
 int upload_packed(Ctx* ctx, DevBuf& buf, const float* host_xyz, size_t n_floats);
 int check_finite_dev(Ctx* ctx, const float* dev, size_t n_floats, bool* ok);
+int finite_accumulate_dev(Ctx* ctx, const float* dev, size_t n_floats, int* flag_dev);   // no host sync
 
 // icp.cu
 int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_result* res,

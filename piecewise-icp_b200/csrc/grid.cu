@@ -81,6 +81,15 @@ int check_finite_dev(Ctx* ctx, const float* dev, size_t n_floats, bool* ok) {
     return PWICP_OK;
 }
 
+int finite_accumulate_dev(Ctx* ctx, const float* dev, size_t n_floats, int* flag_dev) {
+    if (!n_floats) return PWICP_OK;
+    int blocks = (int)std::min<size_t>((n_floats + 255) / 256, (size_t)ctx->num_sms * 8);
+    finite_kernel<<<blocks, 256, 0, ctx->stream>>>(dev, n_floats, flag_dev);
+    ctx->launches++;
+    PW_CUDA(cudaGetLastError());
+    return PWICP_OK;
+}
+
 // ---- bounding box -------------------------------------------------------------------------
 __device__ __forceinline__ int float_to_ordered(float f) {
     int i = __float_as_int(f);

@@ -40,10 +40,12 @@ struct IcpArgs {
     GridDev g;
     const float4* aux;        // level-0 order: nx, ny, nz, ctstd
     const float4* src;        // source set (read only)
-    float4* work;             // transformed copy, updated in place every iteration
+    float4* work;             // transformed copy, updated in place every iteration; w = path length since the
+                              // candidate cache of the point was built
     // per source point: the candidate cache (nn_search.cuh)
-    float4* anchor;           // position the cache was built at, w = validity radius (0: none)
     float4* cq0;              // primary candidate INLINE: x, y, z of the last match, w = its level-0 position (int bits, -1: none)
+    float4* cn0;              // normal of the primary candidate INLINE, w = validity radius of the cache (0: none); the
+                              // path length the query has travelled since the cache was built lives in work[].w
     int4* cmore;              // x, y, z: positions of up to three further candidates (unused = primary), w = original index of the primary
     int seed_exact;           // cand[].x is the exact NN of the untransformed source (iteration 0 needs no search)
     float slack;              // cache radius beyond the NN distance
@@ -218,8 +220,13 @@ static __device__ __noinline__ int icp_finish_warp(const IcpArgs& a, int it, con
 // purpose: it runs for every query during the first few iterations and (almost) never afterwards,
 // and the steady-state loop has to stay small enough to live in the instruction cache together
 // with the per-iteration solve (profiles/r01e_*: 6 us per iteration otherwise).
-static __device__ __noinline__ Best icp_search_fallback(const IcpArgs& a, int it, int i, float px, float py, float pz,
-                                                        int seed, float step2, float old_rho) {
+struct Fallback {
+    Best bb;
+    float nx, ny, nz;     // normal of the match
+    int built;            // a new cache was written: the caller restarts the path length
+};
+static __device__ __noinline__ Fallback icp_search_fallback(const IcpArgs& a, int it, int i, float px, float py, float pz,
+                                                            int seed, float step2) {
     {   // queries that needed the search this iteration (decides the scheduling of the next one)
         const unsigned m = __activemask();
         if ((int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(a.fallbacks + it, __popc(m));
@@ -230,7 +237,11 @@ static __device__ __noinline__ Best icp_search_fallback(const IcpArgs& a, int it
         if (step2 < a.build_step2) atomicAdd((unsigned long long*)a.timing + 16 * 1024 + it * 2 + 1, 1ull);
     }
 #endif
-    const Best bb = nn_search_seeded<true>(a.g, px, py, pz, seed);
+    Fallback f;
+    f.bb = nn_search_seeded<true>(a.g, px, py, pz, seed);
+    const Best& bb = f.bb;
+    const float4 nq = __ldg(a.aux + bb.pos);
+    f.nx = nq.x; f.ny = nq.y; f.nz = nq.z;
     CandCache cc;
     cc.rho = 0.f;
     if (step2 < a.build_step2) {
@@ -246,13 +257,13 @@ static __device__ __noinline__ Best icp_search_fallback(const IcpArgs& a, int it
             if (cc.pos[j] != bb.pos) { if (k == 0) o1 = cc.pos[j]; else if (k == 1) o2 = cc.pos[j]; else if (k == 2) o3 = cc.pos[j]; ++k; }
         // all four slots taken by targets other than the match cannot happen (the match is the nearest
         // of the collected set); guard anyway: no cache rather than a wrong one
-        if (k > 3) cc.rho = 0.f;
+        if (k > 3) { cc.rho = 0.f; o1 = o2 = o3 = bb.pos; }
     }
-    if (cc.rho > 0.f) a.anchor[i] = make_float4(px, py, pz, cc.rho);
-    else { o1 = o2 = o3 = bb.pos; if (old_rho != 0.f) a.anchor[i] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    f.built = cc.rho > 0.f;
     a.cq0[i] = make_float4(bb.qx, bb.qy, bb.qz, __int_as_float(bb.pos));
+    a.cn0[i] = make_float4(nq.x, nq.y, nq.z, cc.rho);
     a.cmore[i] = make_int4(o1, o2, o3, bb.idx);
-    return bb;
+    return f;
 }
 
 // 16-byte asynchronous copy global -> shared (LDGSTS, L2 only: the sources are rewritten by other
@@ -281,9 +292,9 @@ __global__ void __launch_bounds__(kIcpThreads, PWICP_ICP_MINBLOCKS) icp_persiste
     cg::grid_group grid = cg::this_grid();
     __shared__ __align__(16) float s_rows[kIcpWarps][32][8];
     // staging of the streamed per-point data, two batches deep per warp, filled by cp.async:
-    // [slot][field: point, anchor, primary candidate, further candidates, normal of the primary][lane]
+    // [slot][field: point + path length, normal of the primary + radius, primary candidate, further candidates][lane]
     extern __shared__ __align__(16) unsigned char s_dyn[];
-    float4 (*s_stage)[2][5][32] = reinterpret_cast<float4 (*)[2][5][32]>(s_dyn);
+    float4 (*s_stage)[2][4][32] = reinterpret_cast<float4 (*)[2][4][32]>(s_dyn);
     __shared__ double s_tot[kNumVals];
     __shared__ float s_T[16];
     __shared__ float s_Tfinal[16];
@@ -328,27 +339,17 @@ __global__ void __launch_bounds__(kIcpThreads, PWICP_ICP_MINBLOCKS) icp_persiste
         float T[12];
 #pragma unroll
         for (int k = 0; k < 12; ++k) T[k] = s_T[k];
-        // stage-1 copies of a batch: point, anchor, primary candidate, further candidates
+        // copies of a batch: point + path length, normal + radius, primary candidate, further candidates
         auto stage_batch = [&](const float4* __restrict__ psrc, int bb_, int slot) {
             const int i_ = bb_ * 32 + lane;
             if (bb_ < nb && i_ < a.n) {
                 cp_async16(&s_stage[warp][slot][0][lane], psrc + i_);
-                cp_async16(&s_stage[warp][slot][1][lane], a.anchor + i_);
+                cp_async16(&s_stage[warp][slot][1][lane], a.cn0 + i_);
                 cp_async16(&s_stage[warp][slot][2][lane], a.cq0 + i_);
                 cp_async16(&s_stage[warp][slot][3][lane], a.cmore + i_);
             }
             cp_async_commit();
         };
-        // stage-2 copy: the normal of the primary candidate (its position arrives with stage 1)
-        auto stage_aux = [&](int bb_, int slot) {
-            const int i_ = bb_ * 32 + lane;
-            if (bb_ < nb && i_ < a.n) {
-                const int pos0 = __float_as_int(s_stage[warp][slot][2][lane].w);
-                if (pos0 >= 0) cp_async16(&s_stage[warp][slot][4][lane], a.aux + pos0);
-            }
-            cp_async_commit();
-        };
-
         // ---- phase A.  Every warp first works through a static share of the batches (b = j * NW + W,
         // half of its fair share), then takes single batches from a counter: the cost of a batch is
         // data dependent while the ball search runs, and one atomic per batch on one address would
@@ -370,8 +371,6 @@ __global__ void __launch_bounds__(kIcpThreads, PWICP_ICP_MINBLOCKS) icp_persiste
             int b = W, bn = NW + W;                            // positions 0 and 1
             if (!staged) {                                     // else: issued during the previous iteration's solve
                 stage_batch(psrc, b, 0);
-                cp_async_wait_all();
-                stage_aux(b, 0);
             }
             while (b < nb) {
                 const int slot = seq & 1;
@@ -385,18 +384,19 @@ __global__ void __launch_bounds__(kIcpThreads, PWICP_ICP_MINBLOCKS) icp_persiste
                 float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
                 if (active) {
                     float4 p = s_stage[warp][slot][0][lane];
-                    const float4 an = s_stage[warp][slot][1][lane];
+                    const float4 cn = s_stage[warp][slot][1][lane];
                     const float4 q0 = s_stage[warp][slot][2][lane];
                     const int4 cm = *reinterpret_cast<const int4*>(&s_stage[warp][slot][3][lane]);
                     const int pos0 = __float_as_int(q0.w);
                     float step2 = __int_as_float(0x7f800000);
+                    float path = 0.f;                          // travelled since the cache was built (upper bound)
                     if (it > 0) {
                         float x, y, z;
                         xform_point(T, p.x, p.y, p.z, x, y, z);
                         step2 = l2_simple(x, y, z, p.x, p.y, p.z);
+                        path = p.w + sqrtf(step2) * 1.000001f;
                         p.x = x; p.y = y; p.z = z;
                     }
-                    a.work[i] = p;
                     // (b) exact NN: best of the cached candidates when the cache still covers the
                     // query (nn_search.cuh, "candidate cache"), else the seeded ball search
                     Best bb;
@@ -418,26 +418,27 @@ __global__ void __launch_bounds__(kIcpThreads, PWICP_ICP_MINBLOCKS) icp_persiste
                         }
                         PW_CAND(cm.x) PW_CAND(cm.y) PW_CAND(cm.z)
 #undef PW_CAND
-                        const float da = l2_simple(p.x, p.y, p.z, an.x, an.y, an.z);
-                        ok = (it == 0 && a.seed_exact) || sqrtf(bb.d2) + sqrtf(da) < an.w;
+                        // |p - anchor| <= path (triangle inequality over the steps actually taken)
+                        ok = (it == 0 && a.seed_exact) || sqrtf(bb.d2) + path * 1.00001f < cn.w;
                         seed = bb.pos;
                     }
-                    float4 nq;
-                    if (ok && bb.pos == pos0) {
-                        nq = s_stage[warp][slot][4][lane];
-                    } else {
-                        if (!ok) bb = icp_search_fallback(a, it, i, p.x, p.y, p.z, seed, step2, an.w);
-                        else {
-                            // another cached target has become the nearest: make it the primary
-                            a.cq0[i] = make_float4(bb.qx, bb.qy, bb.qz, __int_as_float(bb.pos));
-                            a.cmore[i] = make_int4(cm.x == bb.pos ? pos0 : cm.x, cm.y == bb.pos ? pos0 : cm.y,
-                                                   cm.z == bb.pos ? pos0 : cm.z, bb.idx);
-                        }
-                        nq = __ldg(a.aux + bb.pos);
+                    float nx = cn.x, ny = cn.y, nz = cn.z;
+                    if (!ok) {
+                        const Fallback f = icp_search_fallback(a, it, i, p.x, p.y, p.z, seed, step2);
+                        bb = f.bb; nx = f.nx; ny = f.ny; nz = f.nz;
+                        if (f.built) path = 0.f;
+                    } else if (bb.pos != pos0) {
+                        // another cached target has become the nearest: make it the primary
+                        const float4 nq = __ldg(a.aux + bb.pos);
+                        nx = nq.x; ny = nq.y; nz = nq.z;
+                        a.cq0[i] = make_float4(bb.qx, bb.qy, bb.qz, __int_as_float(bb.pos));
+                        a.cn0[i] = make_float4(nx, ny, nz, cn.w);
+                        a.cmore[i] = make_int4(cm.x == bb.pos ? pos0 : cm.x, cm.y == bb.pos ? pos0 : cm.y,
+                                               cm.z == bb.pos ? pos0 : cm.z, bb.idx);
                     }
+                    a.work[i] = make_float4(p.x, p.y, p.z, path);
                     const float sx = p.x, sy = p.y, sz = p.z;
                     const float dx = bb.qx, dy = bb.qy, dz = bb.qz;
-                    const float nx = nq.x, ny = nq.y, nz = nq.z;
                     // float expressions of TransformationEstimationPointToPlaneLLS (no FMA)
                     lo.x = nz * sy - ny * sz;
                     lo.y = nx * sz - nz * sx;
@@ -447,17 +448,13 @@ __global__ void __launch_bounds__(kIcpThreads, PWICP_ICP_MINBLOCKS) icp_persiste
                     hi.y = nz;
                     hi.z = nx * dx + ny * dy + nz * dz - nx * sx - ny * sy - nz * sz;
                     hi.w = bb.d2;
-                    // traces are reported in the caller's order (p.w = original source index)
-                    if (a.idx_trace) a.idx_trace[(size_t)it * a.n + __float_as_int(p.w)] = bb.idx;
+                    // traces are reported in the caller's order (src[].w = original source index)
+                    if (a.idx_trace) a.idx_trace[(size_t)it * a.n + __float_as_int(__ldg(a.src + i).w)] = bb.idx;
                 }
                 // rows through shared memory as floats: a broadcast LDS.32 is one wavefront, an LDS.64 two,
                 // and the L1/shared pipe is the busiest unit of this kernel (profiles/r01e_*)
                 float4* row = reinterpret_cast<float4*>(&s_rows[warp][lane][0]);
                 row[0] = lo; row[1] = hi;
-                // the next batch's stage 1 has had the whole search to land: start its stage 2, which
-                // flies during the sums below
-                cp_async_wait_all();
-                stage_aux(bn, slot ^ 1);
                 __syncwarp();
                 // batch sums on the FP64 tensor cores: the 28 sums are entries of D = A * B with
                 // A = [a b c nx ny nz d2 -]^T (8 x 32) and B = [a b c nx ny nz e 1] (32 x 8), formed by eight
@@ -523,8 +520,6 @@ __global__ void __launch_bounds__(kIcpThreads, PWICP_ICP_MINBLOCKS) icp_persiste
             grid.sync();
         }
 
-        cp_async_wait_all();
-        stage_aux(blockIdx.x * kIcpWarps + warp, 0);
         // ---- phase B2: every CTA forms the same totals from the top-level entries, in order
         if (warp == 0) {
             if (lane < kNumVals) {
@@ -589,7 +584,8 @@ __global__ void src_key_kernel(const float4* __restrict__ src, int n, float ox, 
 
 __global__ void src_gather_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ order, int n, float4* out,
                                   const int* __restrict__ seed_in, const float4* __restrict__ tgt_pts,
-                                  float4* __restrict__ anchor, float4* __restrict__ cq0, int4* __restrict__ cmore) {
+                                  const float4* __restrict__ tgt_aux,
+                                  float4* __restrict__ cn0, float4* __restrict__ cq0, int4* __restrict__ cmore) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t o = order[i];
@@ -599,22 +595,26 @@ __global__ void src_gather_kernel(const float4* __restrict__ src, const uint32_t
     const int sd = seed_in ? seed_in[o] : -1;
     float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
     int idx = 0;
-    if (sd >= 0) { q = __ldg(tgt_pts + sd); idx = __float_as_int(q.w); }
+    float4 nq = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (sd >= 0) { q = __ldg(tgt_pts + sd); idx = __float_as_int(q.w); nq = __ldg(tgt_aux + sd); }
     cq0[i] = make_float4(q.x, q.y, q.z, __int_as_float(sd));
     cmore[i] = make_int4(sd, sd, sd, idx);
-    anchor[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    cn0[i] = make_float4(nq.x, nq.y, nq.z, 0.f);
 }
 
 // Iteration 0 of a source set without seeds: the plain search at full occupancy (the persistent
 // kernel is register-capped and runs it about twice as slowly, profiles/r01f_*).  The matches go
 // into the candidate slots; the persistent kernel takes them as the exact answer of iteration 0.
 __global__ void __launch_bounds__(256)
-icp_seed_kernel(GridDev g, const float4* __restrict__ src, int n, float4* __restrict__ cq0, int4* __restrict__ cmore) {
+icp_seed_kernel(GridDev g, const float4* __restrict__ tgt_aux, const float4* __restrict__ src, int n,
+                float4* __restrict__ cn0, float4* __restrict__ cq0, int4* __restrict__ cmore) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4 p = __ldg(src + i);
     const Best b = nn_search_seeded(g, p.x, p.y, p.z, -1);
+    const float4 nq = __ldg(tgt_aux + b.pos);
     cq0[i] = make_float4(b.qx, b.qy, b.qz, __int_as_float(b.pos));
+    cn0[i] = make_float4(nq.x, nq.y, nq.z, 0.f);
     cmore[i] = make_int4(b.pos, b.pos, b.pos, b.idx);
 }
 
@@ -628,7 +628,7 @@ static int icp_sort_source(Ctx* ctx, int n, bool have_seed) {
     PW_TRY(ctx->keys2.reserve(ctx, (size_t)n * 8));
     PW_TRY(ctx->icp_perm.reserve(ctx, (size_t)n * 4));
     PW_TRY(ctx->icp_sorted.reserve(ctx, (size_t)n * sizeof(float4)));
-    PW_TRY(ctx->icp_match.reserve(ctx, (size_t)n * 3 * sizeof(float4)));      // anchor, cq0, cmore
+    PW_TRY(ctx->icp_match.reserve(ctx, (size_t)n * 3 * sizeof(float4)));      // cn0, cq0, cmore
     const int blocks = (n + 255) / 256;
     src_key_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->icp_src.as<float4>(), n, ctx->tgt.dev.ox, ctx->tgt.dev.oy,
                                                     ctx->tgt.dev.oz, L.inv_h, L.dx, L.dy, L.dz,
@@ -646,7 +646,7 @@ static int icp_sort_source(Ctx* ctx, int n, bool have_seed) {
     src_gather_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->icp_src.as<float4>(), ctx->icp_perm.as<uint32_t>(), n,
                                                        ctx->icp_sorted.as<float4>(),
                                                        have_seed ? ctx->icp_seed.as<int>() : nullptr, ctx->tgt.dev.lv[0].pts,
-                                                       ctx->icp_match.as<float4>(), ctx->icp_match.as<float4>() + n,
+                                                       ctx->tgt_aux.as<float4>(), ctx->icp_match.as<float4>(), ctx->icp_match.as<float4>() + n,
                                                        reinterpret_cast<int4*>(ctx->icp_match.as<float4>() + 2 * (size_t)n));
     ctx->launches += 5;
     PW_CUDA(cudaGetLastError());
@@ -660,7 +660,7 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     if (n < 3) { set_error(ctx, "icp: fewer than 3 correspondences"); return PWICP_ERR_TOO_FEW_CORR; }
     if (prm.max_iter < 1 || prm.max_iter > kMaxIcpIter) { set_error(ctx, "icp: max_iter out of range"); return PWICP_ERR_ARG; }
 
-    const size_t smem = (size_t)kIcpWarps * 2 * 5 * 32 * sizeof(float4);      // s_stage
+    const size_t smem = (size_t)kIcpWarps * 2 * 4 * 32 * sizeof(float4);      // s_stage
     PW_CUDA(cudaFuncSetAttribute(icp_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     PW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, icp_persistent_kernel, kIcpThreads, smem));
@@ -696,8 +696,9 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     PW_TRY(icp_sort_source(ctx, n, have_seed));
     ctx->icp_seed_valid = false;                       // seeds belong to one source set
     if (!have_seed) {
-        icp_seed_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->tgt.dev, ctx->icp_sorted.as<float4>(), n,
-                                                                  ctx->icp_match.as<float4>() + n,
+        icp_seed_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->tgt.dev, ctx->tgt_aux.as<float4>(),
+                                                                  ctx->icp_sorted.as<float4>(), n,
+                                                                  ctx->icp_match.as<float4>(), ctx->icp_match.as<float4>() + n,
                                                                   reinterpret_cast<int4*>(ctx->icp_match.as<float4>() + 2 * (size_t)n));
         ctx->launches++;
     }
@@ -707,9 +708,9 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     a.aux = ctx->tgt_aux.as<float4>();
     a.src = ctx->icp_sorted.as<float4>();
     a.work = ctx->icp_work.as<float4>();
-    a.anchor = ctx->icp_match.as<float4>();
-    a.cq0 = a.anchor + n;
-    a.cmore = reinterpret_cast<int4*>(a.anchor + 2 * (size_t)n);
+    a.cn0 = ctx->icp_match.as<float4>();
+    a.cq0 = a.cn0 + n;
+    a.cmore = reinterpret_cast<int4*>(a.cn0 + 2 * (size_t)n);
     a.seed_exact = 1;         // classification matches (outer.cu) or icp_seed_kernel
     a.slack = 0.03f / ctx->tgt.dev.lv[0].inv_h;
     a.build_step2 = (0.25f * a.slack) * (0.25f * a.slack);
