@@ -57,8 +57,9 @@ def measured_hbm_peak():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """Samples nvidia-smi clocks / throttle reasons; `stop(t0, t1)` keeps the samples taken inside the
+    timed region [t0, t1] (wall clock).  Started before the warm-up: nvidia-smi needs ~0.1 s to come up."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -70,7 +71,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -79,31 +80,41 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        rows = self.rows
+        window = "timed region"
+        if t0 is not None:
+            inside = [r for r in rows if t0 <= r[0] <= t1 + 0.03]
+            if len(inside) >= 2:
+                rows = inside
+            else:                       # a very short timed region: the samples closest to it
+                rows = sorted(rows, key=lambda r: abs(r[0] - 0.5 * (t0 + t1)))[:5]
+                window = "nearest samples (timed region shorter than the sampling period)"
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for _, r in rows:
             f = [x.strip() for x in r.split(",")]
-            if len(f) < 9:
+            if len(f) < 10:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                sm.append(float(f[2])); mx.append(float(f[3]))
             except ValueError:
                 continue
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[6:10]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": float(max(mx)) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def pose_error(T, T_ref, matrix2angle):
@@ -112,15 +123,19 @@ def pose_error(T, T_ref, matrix2angle):
 
 
 def run_reference(args, rank, world):
-    """CPU arm: the oracle's inner loop, single thread (the reference has no threads)."""
+    """CPU arm: the oracle's inner loop on the host cores.  The reference itself is single-threaded
+    (no OpenMP / threads anywhere in its tree); the figure reported here lets it use every host thread
+    for the independent NN queries and row terms (sums stay sequential), and states the single-thread
+    figure next to it."""
     if rank != 0:
         return
     from oracle import oracle_py as O
     from pwicp_b200 import synth
     d = synth.make_pair(N_CENTROIDS, with_clouds=False)
     n1, n2 = len(d["ct1"]), len(d["ct2"])
-    sample_iters = 2
-    prm = O.icp_params(max_iter=sample_iters, force_iters=1)
+    threads = os.cpu_count() or 1
+    sample_iters = 4
+    prm = O.icp_params(max_iter=sample_iters, force_iters=1, threads=threads)
     times = []
     for s in range(args.warmup + args.steps):
         t0 = time.perf_counter()
@@ -130,8 +145,11 @@ def run_reference(args, rank, world):
             times.append(dt)
     tot = sum(times)
     value = len(times) * sample_iters * n2 / tot
+    t0 = time.perf_counter()
+    O.icp(d["ct1"], d["nrm1"], d["ct2"], O.icp_params(max_iter=sample_iters, force_iters=1))
+    single = sample_iters * n2 / (time.perf_counter() - t0)
     sample = (f"{sample_iters} of {INNER_ITERS} inner iterations on the full {n1}x{n2} pair, KD-tree "
-              "build included, per step")
+              f"build (serial) included, per step; NN queries on {threads} threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "correspondences/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -139,8 +157,10 @@ def run_reference(args, rank, world):
         "vs_baseline": None, "dtype": "f32 distances / f64 normal equations", "data": "synthetic",
         "config": {"workload": "pairwise 1M-centroid synthetic planar-patch pair, 50 inner ICP iterations",
                    "n_target": n1, "n_source": n2, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "correspondences/s", "cores": 1, "kind": "port",
-                         "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "correspondences/s", "cores": threads, "kind": "port",
+                         "sample": sample, "single_thread_value": single,
+                         "note": "the reference is single-threaded; kind=port because PCL/Eigen/Boost are absent "
+                                 "(DESIGN.md section 7)"},
         "e2e": {"value": value, "unit": "correspondences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -150,7 +170,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=N_CENTROIDS, help=argparse.SUPPRESS)
@@ -194,15 +214,16 @@ def main():
         r = ctx.icp_run(prm)
         return b_ms, r
 
-    for _ in range(args.warmup):
-        step_resident()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    for _ in range(args.warmup):
+        step_resident()
     if dist:
         dist.barrier()
     torch.cuda.synchronize()
     launches0 = ctx.launch_count()
     wall0 = time.perf_counter()
+    epoch0 = time.time()
     build_ms, icp_ms, corr = [], [], 0
     last = None
     for _ in range(args.steps):
@@ -214,7 +235,7 @@ def main():
         dist.barrier()
     wall = time.perf_counter() - wall0
     launches = ctx.launch_count() - launches0 - args.steps    # minus the L2-flush fills
-    clocks = sampler.stop()
+    clocks = sampler.stop(epoch0, time.time())
     dev_s = (sum(build_ms) + sum(icp_ms)) / 1e3
 
     # ---- e2e arm: host buffers through the reference-shaped call ---------------------------
@@ -295,7 +316,16 @@ def main():
             line["cpu_baseline"] = {"value": sample_iters * n2 / cpu_s, "unit": "correspondences/s",
                                     "cores": 1, "kind": "port",
                                     "sample": f"{sample_iters} of {INNER_ITERS} inner iterations on the full "
-                                              f"{n1}x{n2} pair incl. KD-tree build ({cpu_s:.1f} s)"}
+                                              f"{n1}x{n2} pair incl. KD-tree build ({cpu_s:.1f} s); single "
+                                              "thread, like the reference"}
+            threads = os.cpu_count() or 1
+            t0 = time.perf_counter()
+            O.icp(d["ct1"], d["nrm1"], d["ct2"], O.icp_params(max_iter=sample_iters, force_iters=1, threads=threads))
+            mt_s = time.perf_counter() - t0
+            line["cpu_baseline_mt"] = {"value": sample_iters * n2 / mt_s, "unit": "correspondences/s",
+                                       "cores": threads, "kind": "port",
+                                       "sample": f"same sample, NN queries and row terms on {threads} threads "
+                                                 f"({mt_s:.1f} s); not what the reference does"}
         print(json.dumps(line), flush=True)
     ctx.close()
     if dist:

@@ -97,8 +97,9 @@ def _f32(a):
 
 
 def icp_params(max_iter=100, tf_eps=1e-8, fit_eps=1e-6, force_iters=0, reduce_mode=0,
-               group_batches=0, rot_thr_default=0):
-    return IcpParams(max_iter, tf_eps, fit_eps, force_iters, reduce_mode, group_batches, 0, rot_thr_default)
+               group_batches=0, rot_thr_default=0, threads=0):
+    """threads > 1: NN queries and row terms on that many threads (bench only; the reference is single-threaded)."""
+    return IcpParams(max_iter, tf_eps, fit_eps, force_iters, reduce_mode, group_batches, threads, rot_thr_default)
 
 
 def nn(tgt, qry, brute=False):

@@ -18,6 +18,7 @@
 #include <cstring>
 #include <limits>
 #include <numeric>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -362,6 +363,20 @@ orc_icp_params default_icp() {
     return p;
 }
 
+/* i = 0..n-1 on `threads` threads in contiguous chunks (1: a plain loop, what the reference does) */
+template <typename F>
+void parallel_for(int n, int threads, F&& f) {
+    if (threads <= 1 || n < 1024) { for (int i = 0; i < n; ++i) f(i); return; }
+    std::vector<std::thread> pool;
+    const int chunk = (n + threads - 1) / threads;
+    for (int t = 0; t < threads; ++t) {
+        const int lo = t * chunk, hi = std::min(n, lo + chunk);
+        if (lo >= hi) break;
+        pool.emplace_back([lo, hi, &f]() { for (int i = lo; i < hi; ++i) f(i); });
+    }
+    for (auto& th : pool) th.join();
+}
+
 /* A3/A6 on a prebuilt target tree */
 int icp_run(const KdTree& tree, const float* tgt, const float* nrm, const float* src, int n2s,
             const orc_icp_params& prm, float* Tfinal, int* n_iter, int* conv_state,
@@ -379,19 +394,21 @@ int icp_run(const KdTree& tree, const float* tgt, const float* nrm, const float*
     double prev_mse = std::numeric_limits<double>::max();
     if (n2s < 3) { *n_iter = 0; *conv_state = 5; return -1; }   /* min_number_correspondences_ = 3 */
     for (;;) {
-        for (int i = 0; i < n2s; ++i) tree.query(&cur[3 * (size_t)i], idx[i], d2[i]);
+        /* [reference: single thread]  prm.reserved > 1: the independent queries and rows on that many
+         * threads (bench.py's multi-thread CPU figure); every sum stays in its sequential order. */
+        const int threads = prm.reserved > 1 ? prm.reserved : 1;
+        parallel_for(n2s, threads, [&](int i) { tree.query(&cur[3 * (size_t)i], idx[i], d2[i]); });
         if (idx_trace) std::memcpy(idx_trace + (size_t)iters * n2s, idx.data(), sizeof(int) * (size_t)n2s);
-        for (int i = 0; i < n2s; ++i) {
+        parallel_for(n2s, threads, [&](int i) {
             const float* s = &cur[3 * (size_t)i];
             const float* d = tgt + 3 * (size_t)idx[i];
             const float* n = nrm + 3 * (size_t)idx[i];
             valid[i] = finite3(s) && finite3(d) && finite3(n);
             lls_row(s, d, n, &u7[7 * (size_t)i]);
-        }
+        });
         double s28[28], ATA[36], ATb[6], x[6];
         float T[16];
-        accumulate28(u7.data(), d2.data(), valid.data(), n2s, prm.reduce_mode, prm.group_batches,
-                     prm.reserved, s28);
+        accumulate28(u7.data(), d2.data(), valid.data(), n2s, prm.reduce_mode, prm.group_batches, 0, s28);
         solve_from28(s28, ATA, ATb, x, T);
         orc_transform(cur.data(), n2s, T);            /* transformCloud(input_transformed, ..) */
         mat4_mul(T, Tfinal, Tfinal);                  /* final = T * final */
