@@ -103,8 +103,10 @@ typedef struct {
     int   grid_blocks;      /* launch geometry (informational): CTAs x warps_per_block */
     int   warps_per_block;
     int   group_batches;    /* reduction geometry: fan-in of the summation hierarchy  */
-    float device_ms;        /* whole inner loop, CUDA events */
+    float device_ms;        /* whole inner loop (source sort, iteration-0 pre-pass, persistent kernel), CUDA events */
     long long correspondences;  /* n_iter * n_source */
+    float kernel_ms;        /* the persistent kernel alone (CUDA events around its launch) */
+    float reserved0;
 } pwicp_icp_result;
 
 /* source set of the inner loop: host upload (stand-alone use) ... */

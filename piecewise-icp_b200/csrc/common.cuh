@@ -18,7 +18,7 @@ constexpr int kIcpWarps = kIcpThreads / 32;
 constexpr int kNumVals = 28;       // 21 ATA + 6 ATb + sum d2
 constexpr int kFanIn = 32;         // entries summed per parent on every level of the reduction hierarchy
 constexpr int kMaxRedLevels = 3;   // batches, groups, supergroups; the top level is summed by every CTA
-constexpr int kGrab = 1;           // batches a warp takes per atomic hand-out
+constexpr int kHandoutLanes = 16;  // interleaved hand-out counters per inner iteration
 constexpr int kMaxIcpIter = 1024;
 
 struct GridLevel {
@@ -82,7 +82,7 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;          // host-buffer calls: uploads overlap the grid build
     cudaEvent_t copy_ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     std::string err;
     float last_ms = 0.f;
     long long launches = 0;

@@ -61,7 +61,8 @@ struct IcpArgs {
     int nlevels;
     const double* top_part;       // = part[nlevels - 1]
     int top_count;                // = count[nlevels - 1]
-    int* batch_counter;       // [max_iter], zeroed before the launch: dynamic batch hand-out
+    int* batch_counter;       // [max_iter][kHandoutLanes * 32], zeroed before the launch: dynamic batch hand-out
+                              // (kHandoutLanes counters per iteration, 128 bytes apart)
     int* fallbacks;           // [max_iter], zeroed before the launch: queries that ran the ball search
     float* out_T;             // 16: final transformation
     int* out_state;           // [0] n_iter, [1] conv_state
@@ -365,7 +366,11 @@ __global__ void __launch_bounds__(kIcpThreads, PWICP_ICP_MINBLOCKS) icp_persiste
             const int J = (calm ? (nb / NW) * PWICP_STATIC_EIGHTHS / 8 : 0) + 2;
             const bool has_dyn = (long long)J * NW < (long long)nb;   // else no hand-out tickets at all
             const float4* __restrict__ psrc = (it == 0) ? a.src : a.work;
-            int* counter = a.batch_counter + it;
+            // kHandoutLanes counters, counter c hands out the dynamic batches D0 + c, D0 + c + kHandoutLanes, ...:
+            // a single address makes every ticket queue behind thousands of others in the L2 atomic unit
+            // (16 % of all stall samples, profiles/r01h_*); interleaving keeps the lanes equally loaded
+            const int nl = min(kHandoutLanes, NW), hl = W % nl;
+            int* counter = a.batch_counter + ((size_t)it * kHandoutLanes + hl) * 32;
             int seq = 0;                                       // position in this warp's batch sequence
             int tkt = 0;                                       // lane 0: hand-out ticket in flight
             int b = W, bn = NW + W;                            // positions 0 and 1
@@ -480,7 +485,8 @@ __global__ void __launch_bounds__(kIcpThreads, PWICP_ICP_MINBLOCKS) icp_persiste
                 // rotate the pipeline
                 ++seq;
                 b = bn;
-                bn = (seq + 1 < J) ? (seq + 1) * NW + W : (has_dyn ? J * NW + __shfl_sync(0xffffffffu, tkt, 0) : nb);
+                bn = (seq + 1 < J) ? (seq + 1) * NW + W
+                                   : (has_dyn ? J * NW + __shfl_sync(0xffffffffu, tkt, 0) * nl + hl : nb);
             }
             cp_async_wait_all();
         }
@@ -683,7 +689,7 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     for (int l = 0; l < nlevels; ++l) part_entries += (size_t)lcount[l];
     if (nlevels > 2) done_entries = (size_t)lcount[2];
     const size_t bytes_part = part_entries * kNumVals * sizeof(double);
-    const size_t bytes_cnt = ((size_t)2 * prm.max_iter + done_entries) * sizeof(int);
+    const size_t bytes_cnt = ((size_t)prm.max_iter * (kHandoutLanes * 32 + 1) + done_entries) * sizeof(int);
     PW_TRY(ctx->icp_partials.reserve(ctx, bytes_part + bytes_cnt + 64));
     const size_t out_bytes = 64 + 16 + (size_t)prm.max_iter * (8 + 64);
     PW_TRY(ctx->icp_out.reserve(ctx, out_bytes));
@@ -727,7 +733,7 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
         int* cc = reinterpret_cast<int*>(ctx->icp_partials.as<char>() + bytes_part);
         PW_CUDA(cudaMemsetAsync(cc, 0, bytes_cnt, ctx->stream));
         a.batch_counter = cc;
-        cc += prm.max_iter;
+        cc += (size_t)prm.max_iter * kHandoutLanes * 32;
         a.fallbacks = cc;
         cc += prm.max_iter;
         a.done = cc;
@@ -754,6 +760,7 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
 #endif
 
     void* kargs[] = {(void*)&a};
+    PW_CUDA(cudaEventRecord(ctx->ev2, ctx->stream));
     PW_CUDA(cudaLaunchCooperativeKernel((void*)icp_persistent_kernel, dim3(grid), dim3(kIcpThreads), kargs, smem, ctx->stream));
     ctx->launches++;
     PW_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -761,8 +768,9 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     struct { float T[16]; int st[4]; } host;
     PW_CUDA(cudaMemcpyAsync(&host, ob, sizeof(host), cudaMemcpyDeviceToHost, ctx->stream));
     PW_CUDA(cudaStreamSynchronize(ctx->stream));
-    float ms = 0.f;
+    float ms = 0.f, kms = 0.f;
     PW_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    PW_CUDA(cudaEventElapsedTime(&kms, ctx->ev2, ctx->ev1));
     ctx->last_ms = ms;
 #ifdef PWICP_TIMING
     {
@@ -788,6 +796,7 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
         res->n_iter = n_iter; res->conv_state = host.st[1];
         res->grid_blocks = grid; res->warps_per_block = kIcpWarps; res->group_batches = kFanIn;
         res->device_ms = ms; res->correspondences = (long long)n_iter * n;
+        res->kernel_ms = kms; res->reserved0 = 0.f;
     }
     if (mse_trace) PW_CUDA(cudaMemcpy(mse_trace, ob + 80, (size_t)n_iter * 8, cudaMemcpyDeviceToHost));
     if (T_trace) PW_CUDA(cudaMemcpy(T_trace, ob + 80 + (size_t)prm.max_iter * 8, (size_t)n_iter * 64, cudaMemcpyDeviceToHost));

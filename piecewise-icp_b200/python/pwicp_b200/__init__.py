@@ -34,7 +34,7 @@ class IcpParams(C.Structure):
 class IcpResult(C.Structure):
     _fields_ = [("n_iter", C.c_int), ("conv_state", C.c_int), ("grid_blocks", C.c_int),
                 ("warps_per_block", C.c_int), ("group_batches", C.c_int), ("device_ms", C.c_float),
-                ("correspondences", C.c_longlong)]
+                ("correspondences", C.c_longlong), ("kernel_ms", C.c_float), ("reserved0", C.c_float)]
 
 
 class PairParams(C.Structure):
@@ -277,7 +277,7 @@ class Context:
         out = {"T": T.reshape(4, 4), "n_iter": res.n_iter, "state": res.conv_state,
                "grid_blocks": res.grid_blocks, "warps_per_block": res.warps_per_block,
                "group_batches": res.group_batches,
-               "device_ms": res.device_ms, "correspondences": res.correspondences}
+               "device_ms": res.device_ms, "kernel_ms": res.kernel_ms, "correspondences": res.correspondences}
         if trace:
             out.update(mse=mse[:res.n_iter], T_trace=Ttr[:res.n_iter].reshape(-1, 4, 4),
                        idx_trace=itr[:res.n_iter])
@@ -298,7 +298,7 @@ class Context:
         self.n1 = len(t)
         self._n_icp = len(s)
         return {"T": T.reshape(4, 4), "n_iter": res.n_iter, "state": res.conv_state,
-                "device_ms": res.device_ms, "correspondences": res.correspondences,
+                "device_ms": res.device_ms, "kernel_ms": res.kernel_ms, "correspondences": res.correspondences,
                 "grid_blocks": res.grid_blocks, "warps_per_block": res.warps_per_block,
                 "group_batches": res.group_batches}
 
