@@ -411,17 +411,21 @@ __global__ void __launch_bounds__(kIcpThreads, PWICP_ICP_MINBLOCKS) icp_persiste
                         const float4* __restrict__ pts = a.g.lv[0].pts;
                         bb.d2 = l2_simple(p.x, p.y, p.z, q0.x, q0.y, q0.z);
                         bb.idx = cm.w; bb.pos = pos0; bb.qx = q0.x; bb.qy = q0.y; bb.qz = q0.z;
-                        // unused slots repeat the primary: their loads are predicated off (no L1 traffic)
-#define PW_CAND(cp)                                                                            \
+                        // unused slots repeat the primary: their loads are predicated off (no L1 traffic); the
+                        // three loads are issued together, one round trip instead of up to three
+                        float4 q1 = q0, q2 = q0, q3 = q0;
+                        if (cm.x != pos0) q1 = __ldg(pts + cm.x);
+                        if (cm.y != pos0) q2 = __ldg(pts + cm.y);
+                        if (cm.z != pos0) q3 = __ldg(pts + cm.z);
+#define PW_CAND(q, cp)                                                                         \
                         if ((cp) != pos0) {                                                    \
-                            const float4 q = __ldg(pts + (cp));                                \
                             const float d = l2_simple(p.x, p.y, p.z, q.x, q.y, q.z);           \
                             const int id = __float_as_int(q.w);                                \
                             if (d < bb.d2 || (d == bb.d2 && id < bb.idx)) {                    \
                                 bb.d2 = d; bb.idx = id; bb.pos = (cp); bb.qx = q.x; bb.qy = q.y; bb.qz = q.z; \
                             }                                                                  \
                         }
-                        PW_CAND(cm.x) PW_CAND(cm.y) PW_CAND(cm.z)
+                        PW_CAND(q1, cm.x) PW_CAND(q2, cm.y) PW_CAND(q3, cm.z)
 #undef PW_CAND
                         // |p - anchor| <= path (triangle inequality over the steps actually taken)
                         ok = (it == 0 && a.seed_exact) || sqrtf(bb.d2) + path * 1.00001f < cn.w;
