@@ -131,6 +131,18 @@ int pwicp_icp_p2plane(pwicp_ctx* ctx, const float* tgt_xyz, const float* tgt_nrm
                       const float* src_xyz, int n2, const pwicp_icp_params* prm,
                       float* T16, pwicp_icp_result* res);
 
+/* ---- F3: constants of every planar patch of a cloud in one launch --------------
+ * Replaces, per patch: calPatchCTandBP (src/Segmentation.cpp:260-303: centroid + the six boundary
+ * points Xmax,Xmin,Ymax,Ymin,Zmax,Zmin), calPatchNormal (src/CommonFunc.cpp:284-333; the reference
+ * re-runs it 7*N2+N1+N2 times per outer iteration), calPatchSTD (src/CommonFunc.cpp:336-354) and the
+ * CTstd = std / n of calBPandCTSTD (src/Segmentation.cpp:306-321).
+ * patch_xyz: points packed patch by patch; patch_off[n_patches+1]: first point of every patch
+ * (patch_off[0] = 0).  Outputs (each may be NULL): ct3[n*3], bp18[n*18], nrm3[n*3], nrm_ok[n]
+ * (calPatchNormal's verdict: 0 and (0,0,1) for patches of 4 points or fewer), bp_std[n], ct_std[n]. */
+int pwicp_patch_stats(pwicp_ctx* ctx, const float* patch_xyz, const int* patch_off, int n_patches,
+                      float* ct3, float* bp18, float* nrm3, unsigned char* nrm_ok,
+                      float* bp_std, float* ct_std);
+
 /* ---- A2 + A7 + A8: one outer iteration / the outer loop ----------------------------------- */
 typedef struct {
     float Res1, Res2, SVRes1, SVRes2, DTmin;   /* src/Registration.cpp:706, :710 */

@@ -169,6 +169,20 @@ def patch_normal(pts):
     return n, bool(ok)
 
 
+def patch_stats(pts, off):
+    """calPatchCTandBP + calPatchNormal + calPatchSTD / calBPandCTSTD for every patch (points packed by patch)."""
+    pts = _f32(pts)
+    off = np.ascontiguousarray(off, np.int32)
+    n = len(off) - 1
+    ct = np.zeros((n, 3), np.float32); bp = np.zeros((n, 6, 3), np.float32); nrm = np.zeros((n, 3), np.float32)
+    ok = np.zeros(n, np.uint8); bs = np.zeros(n, np.float32); cs = np.zeros(n, np.float32)
+    L = lib()
+    L.orc_patch_stats.argtypes = [f32p, i32p, C.c_int, f32p, f32p, f32p, np.ctypeslib.ndpointer(np.uint8, flags="C"), f32p, f32p]
+    L.orc_patch_stats.restype = None
+    L.orc_patch_stats(pts, off, n, ct, bp, nrm, ok, bs, cs)
+    return {"ct": ct, "bp": bp, "nrm": nrm, "nrm_ok": ok, "bpstd": bs, "ctstd": cs}
+
+
 def matrix2angle(T):
     a = np.zeros(3, np.float32)
     lib().orc_matrix2angle(_f32(T).reshape(16), a)

@@ -750,6 +750,69 @@ int orc_patch_normal(const float* pts, int n, float* n3) {
     return (std::fabs(nLen2 - 1.0) < 1e-5) ? 1 : 0;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * F3. Patch constants next to the normal: calPatchCTandBP (src/Segmentation.cpp:260-303),
+ * calPatchSTD (src/CommonFunc.cpp:336-354) and calBPandCTSTD (src/Segmentation.cpp:306-321).
+ * [PCL] compute3DCentroid<PointXYZ, float>: float sums in point order, divided by n.
+ * [PCL] pcl::PCA (1.8.1): float mean, demeaned cloud, covariance = D D^T / (n - 1) in float,
+ * SelfAdjointEigenSolver<Matrix3f>, eigenvectors by descending eigenvalue -> col(2) = smallest.
+ * Eigen's float solver is not reproduced; the eigenvector comes from a double Jacobi sweep of the
+ * float covariance (agrees to ~1e-7, compared with a tolerance).
+ * [PCL] pointToPlaneDistance(p, a, b, c, d) = |a x + b y + c z + d| / sqrt(a^2 + b^2 + c^2) in double.
+ * ------------------------------------------------------------------------------------------ */
+void orc_patch_ct_bp(const float* pts, int n, float* ct3, float* bp18) {
+    float s[3] = {0, 0, 0};
+    float e[6][3] = {{-FLT_MAX, 0, 0}, {FLT_MAX, 0, 0}, {0, -FLT_MAX, 0}, {0, FLT_MAX, 0}, {0, 0, -FLT_MAX}, {0, 0, FLT_MAX}};
+    for (int i = 0; i < n; ++i) {
+        const float* p = pts + 3 * (size_t)i;
+        for (int c = 0; c < 3; ++c) s[c] += p[c];
+        for (int c = 0; c < 3; ++c) {
+            if (p[c] > e[2 * c][c]) std::memcpy(e[2 * c], p, 12);           /* :282-293, strict comparisons */
+            if (p[c] < e[2 * c + 1][c]) std::memcpy(e[2 * c + 1], p, 12);
+        }
+    }
+    for (int c = 0; c < 3; ++c) ct3[c] = s[c] / (float)n;
+    std::memcpy(bp18, e, sizeof(e));                                         /* Xmax Xmin Ymax Ymin Zmax Zmin, :295-300 */
+}
+
+float orc_patch_std(const float* pts, int n) {
+    float mean[3] = {0, 0, 0};
+    for (int i = 0; i < n; ++i) for (int c = 0; c < 3; ++c) mean[c] += pts[3 * (size_t)i + c];
+    for (int c = 0; c < 3; ++c) mean[c] /= (float)n;
+    float M[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (int i = 0; i < n; ++i) {
+        float d[3];
+        for (int c = 0; c < 3; ++c) d[c] = pts[3 * (size_t)i + c] - mean[c];
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) M[r][c] += d[r] * d[c];
+    }
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) M[r][c] /= (float)(n - 1);
+    float nv[3];
+    jacobi_smallest(M, nv);
+    const float A = nv[0], B = nv[1], C = nv[2];
+    const float D = -(A * mean[0] + B * mean[1] + C * mean[2]);
+    double acc = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const float* p = pts + 3 * (size_t)i;
+        const double dist = std::fabs((double)A * p[0] + (double)B * p[1] + (double)C * p[2] + (double)D) /
+                            std::sqrt((double)A * A + (double)B * B + (double)C * C);
+        acc += dist * dist;
+    }
+    return (float)std::sqrt(acc / double(n - 1));
+}
+
+/* all patch constants of a cloud: points packed patch by patch, off[np + 1] */
+void orc_patch_stats(const float* pts, const int* off, int np, float* ct, float* bp, float* nrm,
+                     unsigned char* ok, float* bpstd, float* ctstd) {
+    for (int i = 0; i < np; ++i) {
+        const float* p = pts + 3 * (size_t)off[i];
+        const int n = off[i + 1] - off[i];
+        orc_patch_ct_bp(p, n, ct + 3 * (size_t)i, bp + 18 * (size_t)i);
+        ok[i] = (unsigned char)orc_patch_normal(p, n, nrm + 3 * (size_t)i);
+        bpstd[i] = orc_patch_std(p, n);                  /* BPstd = sigma, :316 */
+        ctstd[i] = bpstd[i] / (float)n;                  /* CTstd = sigma / n, :319 */
+    }
+}
+
 /* A10 matrix2angle (src/CommonFunc.cpp:385-407) */
 void orc_matrix2angle(const float* T, float* ang) {
     double ax, ay, az;

@@ -83,6 +83,12 @@ int orc_vcm(const float* tgt, const float* nrm, int n1, const float* src_stable,
 /* ---- A9: calPatchNormal (src/CommonFunc.cpp:284-333) incl. pcl::computePointNormal/eigen33.
  * Returns 1 on success (normal written), 0 on failure (normal = 0,0,1). */
 int orc_patch_normal(const float* pts, int n, float* n3);
+/* ---- F3: calPatchCTandBP (src/Segmentation.cpp:260-303), calPatchSTD (src/CommonFunc.cpp:336-354),
+ * calBPandCTSTD (src/Segmentation.cpp:306-321) for every patch of a cloud (points packed patch by
+ * patch, off[np+1]).  ct np*3, bp np*18 (Xmax,Xmin,Ymax,Ymin,Zmax,Zmin), nrm np*3, ok np,
+ * bpstd np (= sigma), ctstd np (= sigma / n). */
+void orc_patch_stats(const float* pts, const int* off, int np, float* ct, float* bp, float* nrm,
+                     unsigned char* ok, float* bpstd, float* ctstd);
 
 /* ---- A10: matrix2angle (src/CommonFunc.cpp:385-407) */
 void orc_matrix2angle(const float* T16, float* ang3);

@@ -445,6 +445,39 @@ int pwicp_icp_p2plane(pwicp_ctx* p, const float* tgt_xyz, const float* tgt_nrm, 
     return pwicp_icp_run(p, prm, T16, res, nullptr, nullptr, nullptr);
 }
 
+// ---- F3: per-patch statistics -----------------------------------------------------------------
+int pwicp_patch_stats(pwicp_ctx* p, const float* patch_xyz, const int* patch_off, int n_patches,
+                      float* ct3, float* bp18, float* nrm3, unsigned char* nrm_ok, float* bp_std, float* ct_std) {
+    Ctx* ctx = reinterpret_cast<Ctx*>(p);
+    if (!ctx || n_patches < 1 || !patch_xyz || !patch_off) { set_error(ctx, "patch_stats: bad arguments"); return PWICP_ERR_ARG; }
+    PW_CUDA(cudaSetDevice(ctx->device));
+    const long long m = patch_off[n_patches];
+    if (patch_off[0] != 0 || m < 1) { set_error(ctx, "patch_stats: offsets must start at 0 and cover at least one point"); return PWICP_ERR_ARG; }
+    for (int i = 0; i < n_patches; ++i)
+        if (patch_off[i + 1] < patch_off[i]) { set_error(ctx, "patch_stats: offsets must be non-decreasing"); return PWICP_ERR_ARG; }
+    const size_t np = (size_t)n_patches;
+    PW_TRY(upload_checked(ctx, ctx->scratch_a, patch_xyz, (size_t)3 * m, "patch points"));
+    PW_TRY(ctx->scratch_b.reserve(ctx, (np + 1) * sizeof(int)));
+    PW_CUDA(cudaMemcpyAsync(ctx->scratch_b.p, patch_off, (np + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    // outputs: ct 3, bp 18, nrm 3, bpstd 1, ctstd 1 floats per patch, then the ok bytes
+    PW_TRY(ctx->scratch_c.reserve(ctx, np * 26 * sizeof(float) + np));
+    float* d = ctx->scratch_c.as<float>();
+    float *d_ct = d, *d_bp = d + 3 * np, *d_nrm = d + 21 * np, *d_bs = d + 24 * np, *d_cs = d + 25 * np;
+    unsigned char* d_ok = reinterpret_cast<unsigned char*>(d + 26 * np);
+    PW_TRY(patch_stats_dev(ctx, ctx->scratch_a.as<float>(), ctx->scratch_b.as<int>(), n_patches,
+                           (ct3 || bp18) ? d_ct : nullptr, bp18 ? d_bp : nullptr, (nrm3 || nrm_ok) ? d_nrm : nullptr,
+                           (nrm3 || nrm_ok) ? d_ok : nullptr, (bp_std || ct_std) ? d_bs : nullptr,
+                           (bp_std || ct_std) ? d_cs : nullptr));
+    if (ct3) PW_CUDA(cudaMemcpyAsync(ct3, d_ct, np * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (bp18) PW_CUDA(cudaMemcpyAsync(bp18, d_bp, np * 18 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (nrm3) PW_CUDA(cudaMemcpyAsync(nrm3, d_nrm, np * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (nrm_ok) PW_CUDA(cudaMemcpyAsync(nrm_ok, d_ok, np, cudaMemcpyDeviceToHost, ctx->stream));
+    if (bp_std) PW_CUDA(cudaMemcpyAsync(bp_std, d_bs, np * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ct_std) PW_CUDA(cudaMemcpyAsync(ct_std, d_cs, np * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    PW_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PWICP_OK;
+}
+
 // ---- outer iteration / loop -------------------------------------------------------------------
 int pwicp_single_iteration(pwicp_ctx* p, const pwicp_pair_params* pp, pwicp_state* st,
                            const pwicp_icp_params* icp, float* T16, double* vcm36,

@@ -144,4 +144,8 @@ int transform_packed_dev(Ctx* ctx, float* xyz_dev, size_t n, const float* T16);
 int bbox_packed_dev(Ctx* ctx, const float* xyz_dev, size_t n, float* mn3, float* mx3);
 void octree_cube(const float* mn, const float* mx, double res, double* bb6);
 
+// patch.cu
+int patch_stats_dev(Ctx* ctx, const float* xyz_dev, const int* off_dev, int np, float* ct, float* bp, float* nrm,
+                    unsigned char* ok, float* bpstd, float* ctstd);
+
 }  // namespace pwicp

@@ -27,7 +27,7 @@
 #include "small_algebra.cuh"
 
 #ifndef PWICP_STATIC_EIGHTHS
-#define PWICP_STATIC_EIGHTHS 4     // share of a warp's batches that is assigned statically once the loop is calm
+#define PWICP_STATIC_EIGHTHS 6     // share of a warp's batches that is assigned statically once the loop is calm
 #endif
 #ifndef PWICP_ICP_MINBLOCKS
 #define PWICP_ICP_MINBLOCKS 3
@@ -352,14 +352,14 @@ __global__ void __launch_bounds__(kIcpThreads, PWICP_ICP_MINBLOCKS) icp_persiste
             cp_async_commit();
         };
         // ---- phase A.  Every warp first works through a static share of the batches (b = j * NW + W,
-        // half of its fair share), then takes single batches from a counter: the cost of a batch is
+        // three quarters of its fair share once the loop is calm), then takes single batches from a counter: the cost of a batch is
         // data dependent while the ball search runs, and one atomic per batch on one address would
         // serialise in L2 (~0.85 cycles each).  Every sum below is formed in an order that does not
         // depend on which warp does it.  The loop is software pipelined: the loads of the next
         // batch and the hand-out of the one after are in flight while the current one is processed.
         {
             const int NW = gridDim.x * kIcpWarps, W = blockIdx.x * kIcpWarps + warp;
-            // static batches per warp: half of the fair share once (nearly) every query is answered from its
+            // static batches per warp: three quarters of the fair share once (nearly) every query is answered from its
             // cache (uniform cost per batch), else only the two that cover the pipeline depth of the hand-out
             const int fb_prev = (it > 1) ? s_fb : a.n;
             const bool calm = (long long)fb_prev * 64 < (long long)a.n;

@@ -15,6 +15,7 @@
 #include <unordered_map>
 
 #include "../../include/pwicp.h"
+#include "../csrc/patch_algebra.cuh"
 
 using namespace std;
 
@@ -273,67 +274,6 @@ double calPercentileDistBetween2PC(pcl::PointCloud<pcl::PointXYZ>::Ptr cloud1, p
 }
 
 // ---- patch normals (src/CommonFunc.cpp:284-333; pcl::computePointNormal + pcl::eigen33) --------
-namespace {
-
-void roots2(float b, float c, float* roots) {
-    roots[0] = 0.0f;
-    float d = (float)(b * b - 4.0 * c);
-    if (d < 0.0) d = 0.0f;
-    const float sd = std::sqrt(d);
-    roots[2] = 0.5f * (b + sd);
-    roots[1] = 0.5f * (b - sd);
-}
-
-void roots3(const float m[3][3], float* roots) {
-    const float c0 = m[0][0] * m[1][1] * m[2][2] + 2.0f * m[0][1] * m[0][2] * m[1][2] - m[0][0] * m[1][2] * m[1][2]
-                   - m[1][1] * m[0][2] * m[0][2] - m[2][2] * m[0][1] * m[0][1];
-    const float c1 = m[0][0] * m[1][1] - m[0][1] * m[0][1] + m[0][0] * m[2][2] - m[0][2] * m[0][2] + m[1][1] * m[2][2] - m[1][2] * m[1][2];
-    const float c2 = m[0][0] + m[1][1] + m[2][2];
-    if (std::fabs(c0) < FLT_EPSILON) { roots2(c2, c1, roots); return; }
-    const float inv3 = (float)(1.0 / 3.0), sqrt3 = std::sqrt(3.0f);
-    const float c2_3 = c2 * inv3;
-    float a_3 = (c1 - c2 * c2_3) * inv3;
-    if (a_3 > 0.0f) a_3 = 0.0f;
-    const float half_b = 0.5f * (c0 + c2_3 * (2.0f * c2_3 * c2_3 - c1));
-    float q = half_b * half_b + a_3 * a_3 * a_3;
-    if (q > 0.0f) q = 0.0f;
-    const float rho = std::sqrt(-a_3);
-    const float theta = std::atan2(std::sqrt(-q), half_b) * inv3;
-    const float ct = std::cos(theta), st = std::sin(theta);
-    roots[0] = c2_3 + 2.0f * rho * ct;
-    roots[1] = c2_3 - rho * (ct + sqrt3 * st);
-    roots[2] = c2_3 - rho * (ct - sqrt3 * st);
-    if (roots[0] >= roots[1]) std::swap(roots[0], roots[1]);
-    if (roots[1] >= roots[2]) { std::swap(roots[1], roots[2]); if (roots[0] >= roots[1]) std::swap(roots[0], roots[1]); }
-    if (roots[0] <= 0) roots2(c2, c1, roots);
-}
-
-void cross(const float* a, const float* b, float* o) {
-    o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
-}
-
-void smallestEigenvector(const float C[3][3], float* v) {
-    float scale = 0.0f;
-    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) scale = std::max(scale, std::fabs(C[i][j]));
-    if (scale <= FLT_MIN) scale = 1.0f;
-    float m[3][3];
-    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) m[i][j] = C[i][j] / scale;
-    float roots[3];
-    roots3(m, roots);
-    for (int i = 0; i < 3; ++i) m[i][i] -= roots[0];
-    float v1[3], v2[3], v3[3];
-    cross(m[0], m[1], v1); cross(m[0], m[2], v2); cross(m[1], m[2], v3);
-    const float l1 = v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2];
-    const float l2 = v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2];
-    const float l3 = v3[0] * v3[0] + v3[1] * v3[1] + v3[2] * v3[2];
-    const float* b; float l;
-    if (l1 >= l2 && l1 >= l3) { b = v1; l = l1; } else if (l2 >= l1 && l2 >= l3) { b = v2; l = l2; } else { b = v3; l = l3; }
-    const float s = std::sqrt(l);
-    v[0] = b[0] / s; v[1] = b[1] / s; v[2] = b[2] / s;
-}
-
-}  // namespace
-
 // symmetric 3x3 eigen decomposition (cyclic Jacobi, double): eigenvalues ascending, columns of V
 void pwicpJacobi3(double A[3][3], double w[3], double V[3][3]) {
     for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) V[i][j] = (i == j);
@@ -358,69 +298,27 @@ void pwicpJacobi3(double A[3][3], double w[3], double V[3][3]) {
     memcpy(V, Vs, sizeof(Vs));
 }
 
+// The arithmetic of calPatchNormal / calPatchSTD is csrc/patch_algebra.cuh, shared with the batched
+// device kernel (pwicp_patch_stats); these are the reference-shaped single-patch entry points.
 bool calPatchNormal(pcl::PointCloud<pcl::PointXYZ> cloud, float& nx, float& ny, float& nz) {
     if (!(cloud.size() > 4)) {
         std::cerr << "Patch normal calculation fails !!! Assigned with (0, 0, 1) \n\n";
         nx = 0; ny = 0; nz = 1;
         return false;
     }
-    // single-pass float mean + covariance (pcl::computeMeanAndCovarianceMatrix)
-    float acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (const auto& p : cloud.points) {
-        acc[0] += p.x * p.x; acc[1] += p.x * p.y; acc[2] += p.x * p.z;
-        acc[3] += p.y * p.y; acc[4] += p.y * p.z; acc[5] += p.z * p.z;
-        acc[6] += p.x; acc[7] += p.y; acc[8] += p.z;
-    }
-    for (float& a : acc) a /= (float)cloud.size();
-    float C[3][3];
-    C[0][0] = acc[0] - acc[6] * acc[6]; C[0][1] = acc[1] - acc[6] * acc[7]; C[0][2] = acc[2] - acc[6] * acc[8];
-    C[1][1] = acc[3] - acc[7] * acc[7]; C[1][2] = acc[4] - acc[7] * acc[8]; C[2][2] = acc[5] - acc[8] * acc[8];
-    C[1][0] = C[0][1]; C[2][0] = C[0][2]; C[2][1] = C[1][2];
-    float v[3];
-    smallestEigenvector(C, v);
-    const float nLen = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
-    if (fabs(nLen - 1.0) < 1e-5) { nx = v[0]; ny = v[1]; nz = v[2]; return true; }
-    // recalculation (src/CommonFunc.cpp:303-326): centred covariance, smallest singular vector
-    double mean[3] = {0, 0, 0};
-    for (const auto& p : cloud.points) { mean[0] += p.x; mean[1] += p.y; mean[2] += p.z; }
-    for (double& m : mean) m /= (double)cloud.size();
-    double M[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-    for (const auto& p : cloud.points) {
-        const double d[3] = {p.x - mean[0], p.y - mean[1], p.z - mean[2]};
-        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) M[r][c] += d[r] * d[c];
-    }
-    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) M[r][c] /= (double)cloud.size();
-    double w[3], V[3][3];
-    pwicpJacobi3(M, w, V);
-    nx = (float)V[0][0]; ny = (float)V[1][0]; nz = (float)V[2][0];
-    const float nLen2 = sqrt(nx * nx + ny * ny + nz * nz);
-    if (fabs(nLen2 - 1.0) < 1e-5) return true;
-    std::cerr << "Incalculable normals: " << nx << ", " << ny << ", " << nz << " !!! \n\n";
-    return false;
+    const vector<float> xyz = packXYZ(cloud);
+    float n3[3];
+    const bool ok = pwicp::pa_patch_normal(xyz.data(), (int)cloud.size(), n3) != 0;
+    nx = n3[0]; ny = n3[1]; nz = n3[2];
+    if (!ok) std::cerr << "Incalculable normals: " << nx << ", " << ny << ", " << nz << " !!! \n\n";
+    return ok;
 }
 
 // plane through the centroid with the smallest-eigenvalue direction, std of the point-to-plane
 // distances with (n - 1) (src/CommonFunc.cpp:336-354; pcl::PCA replaced by a Jacobi solve)
 float calPatchSTD(pcl::PointCloud<pcl::PointXYZ>::Ptr cloud) {
-    const int n = (int)cloud->size();
-    double mean[3] = {0, 0, 0};
-    for (const auto& p : cloud->points) { mean[0] += p.x; mean[1] += p.y; mean[2] += p.z; }
-    for (double& m : mean) m /= n;
-    double M[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-    for (const auto& p : cloud->points) {
-        const double d[3] = {p.x - mean[0], p.y - mean[1], p.z - mean[2]};
-        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) M[r][c] += d[r] * d[c];
-    }
-    double w[3], V[3][3];
-    pwicpJacobi3(M, w, V);
-    const float A = (float)V[0][0], B = (float)V[1][0], Cc = (float)V[2][0];
-    const float D = -(A * (float)mean[0] + B * (float)mean[1] + Cc * (float)mean[2]);
-    double s = 0.0;
-    for (const auto& p : cloud->points) {
-        const double dist = std::fabs(A * p.x + B * p.y + Cc * p.z + D) / std::sqrt((double)(A * A + B * B + Cc * Cc));
-        s += dist * dist;
-    }
-    return (float)sqrt(s / double(n - 1));
+    const vector<float> xyz = packXYZ(*cloud);
+    return pwicp::pa_patch_std(xyz.data(), (int)cloud->size());
 }
 
 void generateCentroidCloudWithPatchNormals(pcl::PointCloud<pcl::PointXYZ>::Ptr cloudCentroids,

@@ -45,6 +45,30 @@ void check(int status, const char* where) {
     fatal(string(where) + ": " + pwicp_last_error(pwicpHostContext()));
 }
 
+// calBPandCTSTD (src/Segmentation.cpp:306-321) for all patches of a cloud in one launch of the batched
+// device kernel (pwicp_patch_stats; the arithmetic of calPatchSTD, csrc/patch_algebra.cuh).
+// The per-patch host function of the same name stays available for callers without a device.
+void packPatches(pcl::PointCloud<pcl::PointXYZ>* patches, int n, vector<float>& xyz, vector<int>& off) {
+    off.assign(n + 1, 0);
+    for (int i = 0; i < n; ++i) off[i + 1] = off[i] + (int)patches[i].size();
+    xyz.resize(3 * (size_t)off[n]);
+    for (int i = 0; i < n; ++i)
+        for (size_t k = 0; k < patches[i].size(); ++k) {
+            const auto& p = patches[i].points[k];
+            float* o = &xyz[3 * ((size_t)off[i] + k)];
+            o[0] = p.x; o[1] = p.y; o[2] = p.z;
+        }
+}
+
+void calBPandCTSTDDevice(pcl::PointCloud<pcl::PointXYZ>* patches, int n, vector<float>& stdBP, vector<float>& stdCT) {
+    stdBP.assign(std::max(n, 0), 0.f); stdCT.assign(std::max(n, 0), 0.f);
+    if (n < 1) return;
+    vector<float> xyz; vector<int> off;
+    packPatches(patches, n, xyz, off);
+    check(pwicp_patch_stats(pwicpHostContext(), xyz.data(), off.data(), n, nullptr, nullptr, nullptr, nullptr,
+                            stdBP.data(), stdCT.data()), "patch sigmas");
+}
+
 // Everything a pair needs on the device, derived from the patch arrays the way
 // PwICP_singleIteration derives it every iteration (normals :821-824, concatenated patches).
 struct PairHost {
@@ -62,15 +86,17 @@ void buildPairHost(PairHost& h, const pcl::PointCloud<pcl::PointXYZ>& cloud1, co
     h.cloud1 = packXYZ(cloud1); h.cloud2 = packXYZ(cloud2);
     h.ctstd1 = CTstd1; h.bpstd2 = BPstd2;
     h.nrm1.assign(3 * (size_t)n1, 0.f); h.ok1.assign(n1, 1);
-    for (int i = 0; i < n1; ++i) {
-        // the constant target patch normals: computed once per pair.  The
-        // classification uses calPatchNormal's verdict (:783), the ICP target cloud the
-        // ">6 points, else (0,0,1)" rule of generateCentroidCloudWithPatchNormals (:367).
-        float nx = 0, ny = 0, nz = 1;
-        const bool ok = calPatchNormal(SVcloud1[i], nx, ny, nz);
-        h.ok1[i] = ok ? 1 : 0;
-        if (!(SVcloud1[i].size() > 6 && ok)) { nx = 0; ny = 0; nz = 1; }
-        h.nrm1[3 * i] = nx; h.nrm1[3 * i + 1] = ny; h.nrm1[3 * i + 2] = nz;
+    {
+        // the constant target patch normals: computed once per pair, all patches in
+        // one launch (pwicp_patch_stats = calPatchNormal per patch).  The classification uses
+        // calPatchNormal's verdict (:783), the ICP target cloud the ">6 points, else (0,0,1)" rule
+        // of generateCentroidCloudWithPatchNormals (:367).
+        vector<int> off1; vector<float> xyz1;
+        packPatches(SVcloud1, n1, xyz1, off1);
+        check(pwicp_patch_stats(pwicpHostContext(), xyz1.data(), off1.data(), n1, nullptr, nullptr, h.nrm1.data(),
+                                h.ok1.data(), nullptr, nullptr), "patch normals");
+        for (int i = 0; i < n1; ++i)
+            if (!(SVcloud1[i].size() > 6 && h.ok1[i])) { h.nrm1[3 * i] = 0; h.nrm1[3 * i + 1] = 0; h.nrm1[3 * i + 2] = 1; }
     }
     h.off2.assign(n2 + 1, 0);
     for (int i = 0; i < n2; ++i) h.off2[i + 1] = h.off2[i] + (int)SVcloud2[i].size();
@@ -184,8 +210,8 @@ void Piecewise_ICP(pcl::PointCloud<pcl::PointXYZ>::Ptr cloud1, pcl::PointCloud<p
     cout << "---------------------------------------------------------------------------- \n\n";
     if (num1 < 1) fatal("no patch in the target cloud!");
     std::vector<float> BPstd1, BPstd2, CTstd1, CTstd2;
-    calBPandCTSTD(SVcloud1, num1, BPstd1, CTstd1);                                                  // :663-664
-    calBPandCTSTD(SVcloud2, num2, BPstd2, CTstd2);
+    calBPandCTSTDDevice(SVcloud1, num1, BPstd1, CTstd1);                                            // :663-664
+    calBPandCTSTDDevice(SVcloud2, num2, BPstd2, CTstd2);
     if (4 > num2) fatal("No enough stable points left (<4)!");                                      // :728-731
 
     // one upload, the whole while(!g_toStage3) loop on the device (:680-694)

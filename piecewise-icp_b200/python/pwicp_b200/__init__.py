@@ -62,7 +62,7 @@ EXPORTS = [
     "pwicp_icp_source_upload", "pwicp_icp_source_all", "pwicp_icp_run", "pwicp_icp_order", "pwicp_icp_p2plane",
     "pwicp_single_iteration", "pwicp_piecewise_icp", "pwicp_percentile_nn", "pwicp_overlap_ratio",
     "pwicp_self_nn", "pwicp_vcm", "pwicp_transform", "pwicp_octree_bbox", "pwicp_bbox_corner_change",
-    "pwicp_matrix2angle", "pwicp_mat4_mul",
+    "pwicp_matrix2angle", "pwicp_mat4_mul", "pwicp_patch_stats",
 ]
 
 _lib = None
@@ -113,6 +113,7 @@ def load_library(path=None):
     L.pwicp_percentile_nn.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_float, C.POINTER(C.c_double)]
     L.pwicp_overlap_ratio.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_float, C.POINTER(C.c_float)]
     L.pwicp_self_nn.argtypes = [vp, vp, C.c_int, vp]
+    L.pwicp_patch_stats.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp]
     L.pwicp_vcm.argtypes = [vp, vp, C.c_int, vp, C.POINTER(C.c_int)]
     L.pwicp_transform.argtypes = [vp, vp, C.c_int, vp]
     L.pwicp_octree_bbox.argtypes = [vp, vp, C.c_int, C.c_double, vp]
@@ -343,6 +344,18 @@ class Context:
         d2 = np.zeros(len(p), np.float32)
         self._chk(self.L.pwicp_self_nn(self.h, _ptr(p), len(p), _ptr(d2)))
         return d2
+
+    def patch_stats(self, patch_xyz, patch_off):
+        """Constants of every planar patch in one launch: calPatchCTandBP + calPatchNormal + calPatchSTD.
+        Returns dict(ct (n,3), bp (n,6,3), nrm (n,3), nrm_ok (n,), bpstd (n,), ctstd (n,))."""
+        xyz = _f32(patch_xyz)
+        off = np.ascontiguousarray(patch_off, np.int32)
+        n = len(off) - 1
+        ct = np.zeros((n, 3), np.float32); bp = np.zeros((n, 6, 3), np.float32); nrm = np.zeros((n, 3), np.float32)
+        ok = np.zeros(n, np.uint8); bs = np.zeros(n, np.float32); cs = np.zeros(n, np.float32)
+        self._chk(self.L.pwicp_patch_stats(self.h, _ptr(xyz), _ptr(off), n, _ptr(ct), _ptr(bp), _ptr(nrm), _ptr(ok),
+                                           _ptr(bs), _ptr(cs)))
+        return {"ct": ct, "bp": bp, "nrm": nrm, "nrm_ok": ok, "bpstd": bs, "ctstd": cs}
 
     def vcm(self, src):
         s = _f32(src)

@@ -375,3 +375,39 @@ def test_stress_10m_centroids(gpu_ctx, oracle):
     b = gpu_ctx.icp_run(P.icp_params(max_iter=30, force_iters=1))
     assert np.array_equal(a["T"], b["T"]) and a["correspondences"] == 30 * len(d["ct2"])
     print(f"10M: 30 iterations {a['device_ms']:.2f} ms, {a['correspondences'] / a['device_ms'] / 1e6:.2f} G corr/s")
+
+
+# ------------------------------------------------------------------------------------- F3 (8f)
+def test_patch_stats_match_oracle(gpu_ctx, oracle):
+    """pwicp_patch_stats (one launch per cloud) against the oracle's calPatchCTandBP / calPatchNormal /
+    calPatchSTD restatement: centroids and boundary points bit-exact (sequential float sums, strict
+    comparisons), normals and sigmas within float-libm tolerance."""
+    rng = np.random.default_rng(11)
+    d = synth.make_pair(60000, pts_per_patch=16)
+    xyz, off = d["patch_pts2"], d["patch_off2"]
+    g = gpu_ctx.patch_stats(xyz, off)
+    o = oracle.patch_stats(xyz, off)
+    assert np.array_equal(g["ct"], o["ct"]) and np.array_equal(g["bp"], o["bp"])
+    assert np.array_equal(g["nrm_ok"], o["nrm_ok"])
+    assert np.abs(g["nrm"] - o["nrm"]).max() < 2e-5                 # atan2f/cosf/sinf: CUDA vs host libm
+    assert np.allclose(g["bpstd"], o["bpstd"], rtol=1e-4) and np.allclose(g["ctstd"], o["ctstd"], rtol=1e-4)
+    # ragged patch sizes, patches too small for a normal, a degenerate (collinear) patch
+    sizes = rng.integers(1, 60, 3000)
+    sizes[:5] = [1, 2, 4, 5, 6]
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    pts = (rng.normal(0, 1, (off[-1], 3)) * [0.05, 0.05, 0.002] + rng.uniform(-5, 5, 3)).astype(np.float32)
+    line = np.linspace(0, 1, sizes[10], dtype=np.float32)
+    pts[off[10]:off[11]] = np.stack([line, 2 * line, -line], 1)
+    g = gpu_ctx.patch_stats(pts, off)
+    o = oracle.patch_stats(pts, off)
+    assert np.array_equal(g["ct"], o["ct"]) and np.array_equal(g["bp"], o["bp"])
+    assert np.array_equal(g["nrm_ok"][:3], [0, 0, 0]) and np.array_equal(g["nrm"][:3], np.tile([0, 0, 1], (3, 1)))
+    big = sizes >= 8
+    big[10] = False                                                  # the collinear patch has no defined normal
+    assert np.array_equal(g["nrm_ok"][big], o["nrm_ok"][big])
+    dn = np.minimum(np.abs(g["nrm"] - o["nrm"]).max(1), np.abs(g["nrm"] + o["nrm"]).max(1))
+    assert dn[big].max() < 1e-3                                      # near-isotropic small patches amplify libm ulps
+    ok = big & (sizes >= 3)
+    assert np.allclose(g["bpstd"][ok], o["bpstd"][ok], rtol=1e-3)
+    with pytest.raises(P.PwicpError):
+        gpu_ctx.patch_stats(pts, off[::-1].copy())

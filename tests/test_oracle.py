@@ -220,3 +220,26 @@ def test_golden_vectors(oracle, gold, pair2k):
     assert np.allclose(res["VCM"], gold["outer_VCM"], rtol=1e-12)
     res2 = oracle.piecewise_icp(oracle.PairData(d), 0, 0.0)
     assert np.array_equal(res2["DTseries"], gold["outer_auto_DTseries"])
+
+
+def test_patch_stats_match_numpy(oracle):
+    """F3: centroid / boundary points / sigma of every patch against float64 numpy; the normal is the
+    reference's single-pass float covariance (loses digits by design), so it is only checked loosely."""
+    d = synth.make_pair(1500, pts_per_patch=24)
+    r = oracle.patch_stats(d["patch_pts2"], d["patch_off2"])
+    pp = d["patch_pts2"].reshape(-1, 24, 3)
+    assert np.abs(pp.astype(np.float64).mean(1) - r["ct"]).max() < 1e-6
+    for k, (axis, fn) in enumerate([(0, np.argmax), (0, np.argmin), (1, np.argmax), (1, np.argmin), (2, np.argmax), (2, np.argmin)]):
+        pick = fn(pp[:, :, axis], axis=1)                       # first extremal point wins, like the strict comparisons
+        assert np.array_equal(r["bp"][:, k], pp[np.arange(len(pp)), pick])
+    c = pp.astype(np.float64) - pp.astype(np.float64).mean(1, keepdims=True)
+    w, v = np.linalg.eigh(np.einsum("nki,nkj->nij", c, c))
+    nn = v[:, :, 0]
+    sd = np.sqrt((np.einsum("nki,ni->nk", c, nn) ** 2).sum(1) / 23)
+    assert np.allclose(r["bpstd"], sd, rtol=1e-5) and np.allclose(r["ctstd"], sd / 24, rtol=1e-5)
+    assert r["nrm_ok"].all()
+    assert np.minimum(np.abs(nn - r["nrm"]).max(1), np.abs(nn + r["nrm"]).max(1)).max() < 1e-2
+    # ragged patches incl. too-small ones: calPatchNormal refuses 4 points or fewer
+    off = np.array([0, 3, 7, 12, 40], np.int32)
+    r = oracle.patch_stats(d["patch_pts2"][:40], off)
+    assert r["nrm_ok"].tolist() == [0, 0, 1, 1] and np.array_equal(r["nrm"][0], [0, 0, 1])
