@@ -147,5 +147,6 @@ void octree_cube(const float* mn, const float* mx, double res, double* bb6);
 // patch.cu
 int patch_stats_dev(Ctx* ctx, const float* xyz_dev, const int* off_dev, int np, float* ct, float* bp, float* nrm,
                     unsigned char* ok, float* bpstd, float* ctstd);
+int dmma_order_dev(Ctx* ctx, const float* A_dev, const float* B_dev, double* D_dev, int nchunks);
 
 }  // namespace pwicp

@@ -411,3 +411,14 @@ def test_patch_stats_match_oracle(gpu_ctx, oracle):
     assert np.allclose(g["bpstd"][ok], o["bpstd"][ok], rtol=1e-3)
     with pytest.raises(P.PwicpError):
         gpu_ctx.patch_stats(pts, off[::-1].copy())
+
+
+def test_dmma_accumulates_in_row_order(gpu_ctx):
+    """The inner loop forms its 28 batch sums with chained DMMA.8x8x4 and claims the oracle's
+    sequential order; that holds iff the tensor core adds its four products one after the other in
+    k order with one rounding each.  Checked bit for bit on wide-dynamic-range inputs."""
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        A = (rng.uniform(-0.5, 0.5, (32, 8)) * 10.0 ** rng.integers(-3, 4, (32, 8))).astype(np.float32)
+        B = (rng.uniform(-0.5, 0.5, (32, 8)) * 10.0 ** rng.integers(-3, 4, (32, 8))).astype(np.float32)
+        assert gpu_ctx.dmma_order_mismatches(A, B) == 0
