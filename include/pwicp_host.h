@@ -49,6 +49,16 @@ int  PiecewiseICP_4D_shard(const char* confile, int startEpoch, int epochNum, in
  * the reference epoch; call on rank 0 only. */
 bool PiecewiseICP_4D_finalize(const char* confile, int startEpoch, int epochNum, int pairMode,
                               const pwicp_epoch_record* records);
+/* Segmenter plug-in.  The supervoxel segmentation in front of the hot path (src/Segmentation.cpp:17-66: kNN-45 PCA
+ * normals + Lin's supervoxels, all in the reference's header-only codelibrary) is out of scope of this library, which
+ * ships a documented stand-in (cubic cells).  A caller that owns a segmentation registers it here: it receives the packed
+ * xyz of a pre-processed cloud, the supervoxel resolution and kNN (include/CommonFunc.h:41), writes one label per point
+ * (the reference's lin_labels) and returns the number of supervoxels (< 0 = failure).  PatchGenerationAndRefinement then
+ * groups the points as src/Segmentation.cpp:95-100 does and applies the reference's refinement / planarity gates.
+ * NULL restores the stand-in.  Not thread-safe (like the reference's globals). */
+typedef int (*pwicp_segmenter_fn)(const float* xyz, int n, float svResolution, int knn, int* labels);
+void pwicp_host_set_segmenter(pwicp_segmenter_fn fn);
+
 /* device used by the reference-shaped entry points (default: PWICP_DEVICE, LOCAL_RANK or 0) */
 void pwicp_host_set_device(int device);
 

@@ -110,6 +110,45 @@ def nn(tgt, qry, brute=False):
     return idx, d2
 
 
+# ---- oracle/_ref: the reference's own KD-tree (codelibrary/util/tree/kd_tree.h), compiled where it lies ----
+REF_KDTREE = os.path.join(_HERE, "_ref", "libref_kdtree.so")
+_REF = None
+
+
+def ref_available():
+    """True when oracle/_ref/libref_kdtree.so exists (built by `make -C oracle` wherever /root/reference is
+    present; the built file travels to the GPU box, the reference sources do not)."""
+    return os.path.exists(REF_KDTREE)
+
+
+def _ref():
+    global _REF
+    if _REF is None:
+        L = C.CDLL(REF_KDTREE)
+        L.ref_kdtree_nn.argtypes = [f32p, C.c_int, f32p, C.c_int, i32p, f64p]
+        L.ref_kdtree_knn.argtypes = [f32p, C.c_int, f32p, C.c_int, C.c_int, i32p]
+        _REF = L
+    return _REF
+
+
+def ref_nn(tgt, qry):
+    """1-NN by the reference's KD-tree; d2 in its own (double) metric."""
+    tgt, qry = _f32(tgt), _f32(qry)
+    idx = np.empty(len(qry), np.int32)
+    d2 = np.empty(len(qry), np.float64)
+    if _ref().ref_kdtree_nn(tgt, len(tgt), qry, len(qry), idx, d2) != 0:
+        raise ValueError("ref_kdtree_nn: empty target")
+    return idx, d2
+
+
+def ref_knn(tgt, qry, k):
+    tgt, qry = _f32(tgt), _f32(qry)
+    idx = np.empty((len(qry), k), np.int32)
+    if _ref().ref_kdtree_knn(tgt, len(tgt), qry, len(qry), k, idx) != 0:
+        raise ValueError("ref_kdtree_knn: bad k / empty target")
+    return idx
+
+
 def transform(pts, T):
     out = _f32(pts).copy()
     lib().orc_transform(out, len(out), _f32(T).reshape(16))

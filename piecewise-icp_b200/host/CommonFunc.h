@@ -14,7 +14,7 @@ const double ARC_TO_DEG = 57.29577951308238;   ///< include/CommonFunc.h:37
 const double DEG_TO_ARC = 0.0174532925199433;
 const double GON_TO_ARC = 0.0157079632679;
 const double ARC_TO_GON = 63.6619772368;       ///< include/CommonFunc.h:40
-const int kNN = 45;                             ///< include/CommonFunc.h:41 (unused by the stand-in segmentation)
+const int kNN = 45;                             ///< include/CommonFunc.h:41 (passed to a registered segmenter; unused by the stand-in segmentation)
 const int minPtNum = 20;                        ///< include/CommonFunc.h:42
 
 /// include/CommonFunc.h:48-61

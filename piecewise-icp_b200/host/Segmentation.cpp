@@ -3,6 +3,7 @@
 // reference's supervoxel segmentation).  Everything after that follows the reference's
 // per-patch post-processing: src/Segmentation.cpp:107-150, :195-321.
 #include "Segmentation.h"
+#include "../../include/pwicp_host.h"
 
 #include <algorithm>
 #include <cfloat>
@@ -97,12 +98,74 @@ void calBPandCTSTD(pcl::PointCloud<pcl::PointXYZ>* cloudPatches, int patchNum, s
     }
 }
 
+// ---- segmenter plug-in (include/pwicp_host.h: pwicp_host_set_segmenter) ----------------------------------------
+// Segmentation is out of scope here; a caller that owns one (the reference does: Lin's supervoxels,
+// src/Segmentation.cpp:17-66) registers it and gets the reference's grouping (:95-100: points appended to their
+// supervoxel in cloud order, supervoxels visited in label order) followed by the same per-patch post-processing.
+static pwicp_segmenter_fn g_segmenter = nullptr;
+extern "C" void pwicp_host_set_segmenter(pwicp_segmenter_fn fn) { g_segmenter = fn; }
+
+namespace {
+
+// src/Segmentation.cpp:107-150 for one initial patch; returns true when the patch is kept
+bool acceptPatch(pcl::PointCloud<pcl::PointXYZ>::Ptr raw, pcl::PointCloud<pcl::PointXYZ>::Ptr refined,
+                 pcl::PointCloud<pcl::PointXYZ>::Ptr cloudCentroid, pcl::PointCloud<pcl::PointXYZ>::Ptr cloudBoundary,
+                 pcl::PointCloud<pcl::PointXYZ>& slot) {
+    if ((int)raw->size() < minPtNum) return false;                                        // :109-112
+    const int kept = PatchRefinement(raw, refined, 2.0);                                  // :116
+    if (kept < minPtNum) return false;                                                    // :119-122
+    float variation, planarity, linearity;
+    calPatchFeature(refined, variation, planarity, linearity);
+    if (variation > 0.02f || planarity < 0.25f) return false;                             // :127
+    slot = *refined;
+    pcl::PointXYZ centroid;
+    pcl::PointCloud<pcl::PointXYZ>::Ptr bp(new pcl::PointCloud<pcl::PointXYZ>);
+    if (calPatchCTandBP(*refined, centroid, bp) != 6) {
+        std::cerr << "Error: Incorrect number of boundary points calculated! Aborting.\n";
+        std::exit(EXIT_FAILURE);
+    }
+    cloudCentroid->push_back(centroid);
+    *cloudBoundary += *bp;
+    return true;
+}
+
+int patchesFromSegmenter(pcl::PointCloud<pcl::PointXYZ>::Ptr cloud, float svResolution,
+                         pcl::PointCloud<pcl::PointXYZ>::Ptr cloudCentroid, pcl::PointCloud<pcl::PointXYZ>::Ptr cloudBoundary,
+                         pcl::PointCloud<pcl::PointXYZ>*& cloudPatches) {
+    const int n = (int)cloud->size();
+    vector<float> xyz(3 * (size_t)n);
+    for (int i = 0; i < n; ++i) { xyz[3 * i] = cloud->points[i].x; xyz[3 * i + 1] = cloud->points[i].y; xyz[3 * i + 2] = cloud->points[i].z; }
+    vector<int> labels(n, -1);
+    const int numSV = g_segmenter(xyz.data(), n, svResolution, kNN, labels.data());
+    if (numSV < 0) { std::cerr << "Error: the registered segmenter failed! Aborting.\n"; std::exit(EXIT_FAILURE); }
+    cout << "--->>> " << numSV << " supervoxels are generated." << endl;
+    vector<pcl::PointCloud<pcl::PointXYZ>> all(std::max(numSV, 1));
+    for (int i = 0; i < n; ++i)
+        if (labels[i] >= 0 && labels[i] < numSV) all[labels[i]].push_back(cloud->points[i]);                       // :95-100
+    cloudPatches = new pcl::PointCloud<pcl::PointXYZ>[std::max(numSV, 1)];
+    int validSV = 0, validSVPtNum = 0;
+    pcl::PointCloud<pcl::PointXYZ>::Ptr refined(new pcl::PointCloud<pcl::PointXYZ>);
+    for (int i = 0; i < numSV; ++i) {
+        if (!acceptPatch(all[i].makeShared(), refined, cloudCentroid, cloudBoundary, cloudPatches[validSV])) continue;
+        validSVPtNum += (int)cloudPatches[validSV].size();
+        ++validSV;
+    }
+    cout << "--->>> Number of selected patches = " << validSV << "   Ratio of selected patches = "
+         << 100.0 * validSV / std::max(numSV, 1) << "% \n"
+         << "--->>> Number of points in selected patches = " << validSVPtNum << "   Ratio of selected points = "
+         << 100.0 * validSVPtNum / std::max(n, 1) << "% \n\n";
+    return validSV;
+}
+
+}  // namespace
+
 int PatchGenerationAndRefinement(pcl::PointCloud<pcl::PointXYZ>::Ptr cloud, float svResolution,
                                  pcl::PointCloud<pcl::PointXYZ>::Ptr cloudCentroid,
                                  pcl::PointCloud<pcl::PointXYZ>::Ptr cloudBoundary,
                                  pcl::PointCloud<pcl::PointXYZ>*& cloudPatches, bool /*isVis*/) {
     cloudCentroid->clear(); cloudBoundary->clear();
     const int n = (int)cloud->size();
+    if (g_segmenter) return patchesFromSegmenter(cloud, svResolution, cloudCentroid, cloudBoundary, cloudPatches);
     // stand-in segmentation: sort points by cubic cell of side svResolution
     float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX};
     for (const auto& p : cloud->points) { mn[0] = min(mn[0], p.x); mn[1] = min(mn[1], p.y); mn[2] = min(mn[2], p.z); }
@@ -129,22 +192,8 @@ int PatchGenerationAndRefinement(pcl::PointCloud<pcl::PointXYZ>::Ptr cloud, floa
         raw->clear();
         while (j < n && keyed[j].first == keyed[i].first) { raw->push_back(cloud->points[keyed[j].second]); ++j; }
         i = j;
-        if ((int)raw->size() < minPtNum) { ++invalidSV; continue; }                       // :109-112
-        const int kept = PatchRefinement(raw, refined, 2.0);                              // :116
-        if (kept < minPtNum) { ++invalidSV; continue; }                                   // :119-122
-        float variation, planarity, linearity;
-        calPatchFeature(refined, variation, planarity, linearity);
-        if (variation > 0.02f || planarity < 0.25f) { ++invalidSV; continue; }            // :127
-        cloudPatches[validSV] = *refined;
-        validSVPtNum += (int)refined->size();
-        pcl::PointXYZ centroid;
-        pcl::PointCloud<pcl::PointXYZ>::Ptr bp(new pcl::PointCloud<pcl::PointXYZ>);
-        if (calPatchCTandBP(*refined, centroid, bp) != 6) {
-            std::cerr << "Error: Incorrect number of boundary points calculated! Aborting.\n";
-            std::exit(EXIT_FAILURE);
-        }
-        cloudCentroid->push_back(centroid);
-        *cloudBoundary += *bp;
+        if (!acceptPatch(raw, refined, cloudCentroid, cloudBoundary, cloudPatches[validSV])) { ++invalidSV; continue; }
+        validSVPtNum += (int)cloudPatches[validSV].size();
         ++validSV;
     }
     cout << "--->>> Number of selected patches = " << validSV << "   Ratio of selected patches = "

@@ -73,6 +73,56 @@ int pwicp_host_patches(const float* xyz, int n, float svRes, float* ct, float* b
     return np;
 }
 
+// Input side of one 4D pair on the host, no device needed: PCpreprocessing of both clouds (src/Registration.cpp:415-416),
+// the shift by -centroid(cloud1_prep) (:420-436) and PatchGenerationAndRefinement of both (:653-654).  Outputs are packed
+// xyz; patch points are concatenated by patch with CSR offsets.  Every out pointer may be NULL (sizes only); sizes[8] =
+// {m1, m2, np1, np2, patch points 1, patch points 2, 0, 0}.  Returns 0, or -1 when a capacity is too small.
+int pwicp_host_prepare_pair(const float* xyz1, int n1, const float* xyz2, int n2, float Res1, float Res2, float SV1, float SV2,
+                            float* cloud1, float* cloud2, int capCloud, float* patch1, int* off1, float* patch2, int* off2,
+                            int capPatchPts, int capPatches, float* shift3, int* sizes) {
+    typedef pcl::PointCloud<pcl::PointXYZ> Cloud;
+    Cloud::Ptr in1(new Cloud), in2(new Cloud), p1(new Cloud), p2(new Cloud), r1(new Cloud), r2(new Cloud);
+    in1->resize(n1); in2->resize(n2);
+    for (int i = 0; i < n1; ++i) { in1->points[i].x = xyz1[3 * i]; in1->points[i].y = xyz1[3 * i + 1]; in1->points[i].z = xyz1[3 * i + 2]; }
+    for (int i = 0; i < n2; ++i) { in2->points[i].x = xyz2[3 * i]; in2->points[i].y = xyz2[3 * i + 1]; in2->points[i].z = xyz2[3 * i + 2]; }
+    PCpreprocessing(in1, p1, true, Res1, 14, 5.0);
+    PCpreprocessing(in2, p2, true, Res2, 14, 5.0);
+    Eigen::Vector4f c;
+    pcl::compute3DCentroid(*p1, c);
+    Eigen::Matrix4f S = Eigen::Matrix4f::Identity();
+    S(0, 3) = -1 * c[0]; S(1, 3) = -1 * c[1]; S(2, 3) = -1 * c[2];
+    pcl::transformPointCloud(*p1, *r1, S);
+    pcl::transformPointCloud(*p2, *r2, S);
+    if (shift3) { shift3[0] = S(0, 3); shift3[1] = S(1, 3); shift3[2] = S(2, 3); }
+    Cloud::Ptr CT1(new Cloud), CT2(new Cloud), BP1(new Cloud), BP2(new Cloud);
+    Cloud* SV1c = nullptr; Cloud* SV2c = nullptr;
+    const int np1 = PatchGenerationAndRefinement(r1, SV1, CT1, BP1, SV1c, false);
+    const int np2 = PatchGenerationAndRefinement(r2, SV2, CT2, BP2, SV2c, false);
+    int tot1 = 0, tot2 = 0;
+    for (int i = 0; i < np1; ++i) tot1 += (int)SV1c[i].size();
+    for (int i = 0; i < np2; ++i) tot2 += (int)SV2c[i].size();
+    const int sz[8] = {(int)r1->size(), (int)r2->size(), np1, np2, tot1, tot2, 0, 0};
+    if (sizes) std::memcpy(sizes, sz, sizeof(sz));
+    int rc = 0;
+    if ((cloud1 || cloud2) && (sz[0] > capCloud || sz[1] > capCloud)) rc = -1;
+    if ((patch1 || patch2) && (tot1 > capPatchPts || tot2 > capPatchPts || np1 > capPatches || np2 > capPatches)) rc = -1;
+    if (rc == 0) {
+        auto packCloud = [](const Cloud& cl, float* o) { if (o) for (size_t i = 0; i < cl.size(); ++i) { o[3 * i] = cl.points[i].x; o[3 * i + 1] = cl.points[i].y; o[3 * i + 2] = cl.points[i].z; } };
+        packCloud(*r1, cloud1); packCloud(*r2, cloud2);
+        auto packPatches = [](Cloud* sv, int np, float* o, int* off) {
+            if (!o || !off) return;
+            int k = 0; off[0] = 0;
+            for (int i = 0; i < np; ++i) {
+                for (const auto& p : sv[i].points) { o[3 * k] = p.x; o[3 * k + 1] = p.y; o[3 * k + 2] = p.z; ++k; }
+                off[i + 1] = k;
+            }
+        };
+        packPatches(SV1c, np1, patch1, off1); packPatches(SV2c, np2, patch2, off2);
+    }
+    delete[] SV1c; delete[] SV2c;
+    return rc;
+}
+
 // calTransToReferenceEpoch as a file-to-file operation (F2)
 void pwicp_host_chain_to_reference(const char* transMatFile, int pairMode, const char* pairFile, int epochNum,
                                    const char* outTM, const char* outTP) {

@@ -49,3 +49,31 @@ def gpu_ctx():
     ctx = pwicp_b200.Context(0)
     yield ctx
     ctx.close()
+
+
+# ---- BASELINE configs[0]: the reference's shipped two-epoch pair + the result the reference recorded for it ----------
+def load_refpair(patch_stats, path=None):
+    """tests/golden/refpair_e2.npz (made by tests/golden/make_refpair.py) -> the centroid-level pair Piecewise_ICP holds after
+    PatchGenerationAndRefinement + calBPandCTSTD (src/Registration.cpp:653-664).  patch_stats(points, offsets) supplies the
+    per-patch constants: the oracle's on the CPU, the device's (pwicp_patch_stats) on the GPU."""
+    import numpy as np
+    z = np.load(path or os.path.join(ROOT, "tests", "golden", "refpair_e2.npz"))
+
+    def patches(cloud, lab):
+        keep = np.nonzero(lab >= 0)[0]
+        order = keep[np.argsort(lab[keep], kind="stable")]            # patch k = its cloud points in cloud order
+        return cloud[order], np.concatenate([[0], np.cumsum(np.bincount(lab[keep]))]).astype(np.int32)
+
+    p1, o1 = patches(z["cloud1"], z["lab1"])
+    p2, o2 = patches(z["cloud2"], z["lab2"])
+    s1, s2 = patch_stats(p1, o1), patch_stats(p2, o2)
+    nrm1 = s1["nrm"].copy()
+    nrm1[~((np.diff(o1) > 6) & (s1["nrm_ok"] != 0))] = (0, 0, 1)     # generateCentroidCloudWithPatchNormals, src/CommonFunc.cpp:367
+    res, sv, dtinit, dtmin = (float(v) for v in z["config"])
+    d = {"cloud1": z["cloud1"], "ct1": s1["ct"], "nrm1": nrm1, "nrm1_ok": s1["nrm_ok"], "ctstd1": s1["ctstd"],
+         "cloud2": z["cloud2"], "ct2": s2["ct"], "bp2": s2["bp"].reshape(-1, 3), "bpstd2": s2["bpstd"],
+         "patch_off2": o2, "patch_pts2": p2, "Res1": res, "Res2": res, "SVRes1": sv, "SVRes2": sv, "DTmin": dtmin}
+    S = np.eye(4, dtype=np.float32); S[:3, 3] = z["shift"]
+    Si = np.eye(4, dtype=np.float32); Si[:3, 3] = -z["shift"]
+    return {"pair": d, "DTinit": dtinit, "S": S, "Sinv": Si, "T_recorded": z["T_recorded"], "VCM_recorded": z["VCM_recorded"],
+            "T_truth": z["T_truth"]}

@@ -52,6 +52,22 @@ def test_nn_matches_oracle_bit_exact(gpu_ctx, oracle, pair60k):
     assert np.array_equal(d2, od)
 
 
+def test_nn_matches_reference_kdtree(gpu_ctx, oracle, pair60k):
+    """The device search against reference-authored code (oracle/_ref: the reference's codelibrary KD-tree)."""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref/libref_kdtree.so not built")
+    d = pair60k
+    gpu_ctx.target_upload(d["ct1"], d["nrm1"], d["ctstd1"])
+    q = np.concatenate([d["ct2"], d["bp2"]])
+    idx, d2 = gpu_ctx.nn(q)
+    ri, rd = oracle.ref_nn(d["ct1"], q)
+    bad = np.nonzero(ri != idx)[0]                      # only rounding-level ties may differ (double vs float metric)
+    dr = q[bad] - d["ct1"][ri[bad]]
+    fr = ((dr[:, 0] * dr[:, 0] + dr[:, 1] * dr[:, 1]) + dr[:, 2] * dr[:, 2]).astype(np.float32)
+    assert (fr >= d2[bad]).all() and (fr <= d2[bad] * np.float32(1 + 3e-7)).all()          # within 2 ulp in float
+    assert len(bad) < 5 and np.allclose(d2, rd, rtol=3e-7, atol=1e-12)
+
+
 def test_nn_golden_vectors(gpu_ctx, gold, pair2k):
     d = pair2k
     gpu_ctx.target_upload(d["ct1"], d["nrm1"], d["ctstd1"])
@@ -331,6 +347,15 @@ def test_full_size_properties_1m(gpu_ctx, oracle):
     # (d) whole set against the oracle KD-tree
     oi, od = oracle.nn(d["ct1"], d["ct2"])
     assert np.array_equal(idx, oi) and np.array_equal(d2, od)
+    # (d2) whole set against the reference's own KD-tree (oracle/_ref, codelibrary/util/tree/kd_tree.h compiled from
+    # /root/reference; metric in double, so indices may differ only where the two float distances are within rounding)
+    if oracle.ref_available():
+        ri, rd = oracle.ref_nn(d["ct1"], d["ct2"])
+        bad = np.nonzero(ri != idx)[0]
+        dr = d["ct2"][bad] - d["ct1"][ri[bad]]
+        fr = ((dr[:, 0] * dr[:, 0] + dr[:, 1] * dr[:, 1]) + dr[:, 2] * dr[:, 2]).astype(np.float32)
+        assert (fr >= d2[bad]).all() and (fr <= d2[bad] * np.float32(1 + 3e-7)).all()      # within 2 ulp in float
+        assert len(bad) < 10 and np.allclose(d2, rd, rtol=3e-7, atol=1e-12)
     # (e) eight inner iterations (search, cache build, cached iterations), bit-exact in device order,
     # pose within tolerance in reference order
     gpu_ctx.icp_source_upload(d["ct2"])
@@ -422,3 +447,28 @@ def test_dmma_accumulates_in_row_order(gpu_ctx):
         A = (rng.uniform(-0.5, 0.5, (32, 8)) * 10.0 ** rng.integers(-3, 4, (32, 8))).astype(np.float32)
         B = (rng.uniform(-0.5, 0.5, (32, 8)) * 10.0 ** rng.integers(-3, 4, (32, 8))).astype(np.float32)
         assert gpu_ctx.dmma_order_mismatches(A, B) == 0
+
+
+# ---------------------------------------------------------------- configs[0]: the reference's own pair and recorded result
+def test_reference_pair_reproduces_recorded_result(gpu_ctx, oracle):
+    """BASELINE configs[0] on the device: the reference's shipped Epoch_001 -> Epoch_002 pair at the hot-path boundary
+    (tests/golden/refpair_e2.npz, segmented by the reference's own supervoxel code), per-patch constants from the device
+    (pwicp_patch_stats), outer loop on the device (pwicp_piecewise_icp).  The result must be the 4x4 the reference recorded
+    for this pair (results/4DPCReg/2_Direct2Ref_TransMatrix.txt) within 1e-6 rad / 1e-6 m, and the oracle's."""
+    from conftest import load_refpair
+    f = load_refpair(gpu_ctx.patch_stats)
+    d = f["pair"]
+    gpu_ctx.upload_pair(d)
+    g = gpu_ctx.piecewise_icp(P.PairParams(d["Res1"], d["Res2"], d["SVRes1"], d["SVRes2"], d["DTmin"]), 1, f["DTinit"])
+    T = P.mat4_mul(P.mat4_mul(f["Sinv"], g["T"]), f["S"])                       # src/Registration.cpp:461
+    da, dt = pose_diff(T, f["T_recorded"].astype(np.float32))
+    assert da <= POSE_TOL_RAD and dt <= POSE_TOL_M, (da, dt)
+    sd, sd_rec = np.sqrt(np.diag(g["VCM"])), np.sqrt(np.diag(f["VCM_recorded"]))
+    assert np.allclose(sd, sd_rec, rtol=2e-3)
+    # same pair through the oracle (its own patch constants): identical schedule, pose within tolerance
+    fo = load_refpair(oracle.patch_stats)
+    o = oracle.piecewise_icp(oracle.PairData(fo["pair"]), 1, fo["DTinit"])
+    assert np.array_equal(g["DTseries"], o["DTseries"])
+    assert [s.n_stable for s in g["stats"]] == [s.n_stable for s in o["stats"]]
+    da, dt = pose_diff(g["T"], o["T"])
+    assert da <= POSE_TOL_RAD and dt <= POSE_TOL_M, (da, dt)

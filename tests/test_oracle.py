@@ -37,6 +37,56 @@ def test_nn_matches_brute_force_and_scipy(oracle):
         assert np.allclose(np.sqrt(d1), dd, rtol=1e-5, atol=1e-7)
 
 
+def _assert_same_nn(tgt, qry, idx_a, idx_ref):
+    """Indices must agree except on rounding-level ties: the reference KD-tree's metric is accumulated in double
+    (codelibrary/util/metric/squared_euclidean.h:33-36), the hot path's in float (flann::L2_Simple<float>)."""
+    bad = np.nonzero(idx_a != idx_ref)[0]
+    if len(bad):
+        def f32d2(i):
+            d = qry[bad] - tgt[i[bad]]
+            return ((d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]).astype(np.float32)
+        a, r = f32d2(idx_a), f32d2(idx_ref)           # idx_a is the float minimum; the other within 2 ulp of it
+        assert (r >= a).all() and (r <= a * np.float32(1 + 3e-7)).all(), f"{len(bad)} real NN mismatches"
+    return len(bad)
+
+
+def test_nn_pinned_by_reference_kdtree(oracle, gold, pair2k):
+    """oracle/_ref: the reference's own KD-tree (codelibrary/util/tree/kd_tree.h, the structure FLANN's
+    KDTreeSingleIndex shares) compiled from /root/reference where it lies.  The oracle's exact 1-NN and the
+    committed golden index vectors must be what reference-authored code returns."""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref/libref_kdtree.so not built (no /root/reference on this machine)")
+    # (i) the golden vectors
+    q = np.concatenate([pair2k["ct2"], pair2k["bp2"]])
+    ri, rd = oracle.ref_nn(pair2k["ct1"], q)
+    assert _assert_same_nn(pair2k["ct1"], q, gold["nn_pair_idx"], ri) == 0
+    rng = np.random.default_rng(7)
+    tgt = rng.uniform(-5, 5, (100000, 3)).astype(np.float32)
+    qry = rng.uniform(-6, 6, (20000, 3)).astype(np.float32)
+    ri, rd = oracle.ref_nn(tgt, qry)
+    assert _assert_same_nn(tgt, qry, gold["nn_rand_idx"], ri) == 0
+    assert np.allclose(gold["nn_rand_d2"], rd, rtol=3e-7)
+    # (ii) the oracle itself on a fresh 60k centroid pair (420k queries incl. boundary points) and on clustered data
+    d = synth.make_pair(60000, seed=11)
+    q = np.concatenate([d["ct2"], d["bp2"]])
+    oi, od = oracle.nn(d["ct1"], q)
+    ri, rd = oracle.ref_nn(d["ct1"], q)
+    _assert_same_nn(d["ct1"], q, oi, ri)
+    assert np.allclose(od, rd, rtol=3e-7, atol=1e-12)
+    rng = np.random.default_rng(3)
+    centres = rng.normal(0, 10, (50, 3))
+    tgt = (centres[rng.integers(0, 50, 30000)] + rng.normal(0, 0.05, (30000, 3))).astype(np.float32)
+    qry = (centres[rng.integers(0, 50, 20000)] + rng.normal(0, 0.3, (20000, 3))).astype(np.float32)
+    oi, _ = oracle.nn(tgt, qry)
+    ri, _ = oracle.ref_nn(tgt, qry)
+    _assert_same_nn(tgt, qry, oi, ri)
+    # (iii) the k = 2 self search behind calPCresolution (src/CommonFunc.cpp:239-263): neighbour 0 is the point itself
+    kn = oracle.ref_knn(tgt[:5000], tgt[:5000], 2)
+    oi2, _ = oracle.nn(tgt[:5000], tgt[:5000])
+    assert np.array_equal(kn[:, 0], np.arange(5000)) or (np.linalg.norm(tgt[kn[:, 0]] - tgt[:5000], axis=1) == 0).all()
+    assert (np.linalg.norm(tgt[oi2] - tgt[:5000], axis=1) == 0).all()
+
+
 def test_nn_ties_resolve_to_lowest_index(oracle):
     tgt = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [1, 0, 0]], np.float32)
     idx, d2 = oracle.nn(tgt, np.zeros((1, 3), np.float32))
@@ -243,3 +293,31 @@ def test_patch_stats_match_numpy(oracle):
     off = np.array([0, 3, 7, 12, 40], np.int32)
     r = oracle.patch_stats(d["patch_pts2"][:40], off)
     assert r["nrm_ok"].tolist() == [0, 0, 1, 1] and np.array_equal(r["nrm"][0], [0, 0, 1])
+
+
+# ---------------------------------------------------------------- pinned by the reference's own recorded result
+def test_outer_loop_reproduces_the_references_recorded_result(oracle):
+    """BASELINE configs[0].  The reference ships the scans (data/data_synthetic), the configuration
+    (configuration_files/configuration_4d.txt) and the result its own build wrote for them
+    (results/4DPCReg/2_Direct2Ref_TransMatrix.txt).  tests/golden/refpair_e2.npz holds that pair at the hot-path boundary,
+    segmented by the reference's own supervoxel code (oracle/_ref, tests/golden/make_refpair.py).  The oracle's outer loop
+    on it must land on the recorded 4x4 within the north-star tolerance (1e-6 rad / 1e-6 m; the file prints 12 decimals
+    of float32 values) and on the recorded VCM."""
+    from conftest import load_refpair
+    f = load_refpair(oracle.patch_stats)
+    d = f["pair"]
+    assert len(d["ct1"]) == 1822 and len(d["ct2"]) == 1846
+    res = oracle.piecewise_icp(oracle.PairData(d), 1, f["DTinit"])
+    T = oracle.mat4_mul(oracle.mat4_mul(f["Sinv"], res["T"]), f["S"])          # src/Registration.cpp:461
+    da = np.abs(oracle.matrix2angle(T) - oracle.matrix2angle(f["T_recorded"].astype(np.float32))).max()
+    dt = np.abs(T[:3, 3] - f["T_recorded"][:3, 3]).max()
+    assert da <= 1e-6 and dt <= 1e-6, (da, dt)
+    assert np.abs(T - f["T_recorded"]).max() <= 1e-6
+    sd, sd_rec = np.sqrt(np.diag(res["VCM"])), np.sqrt(np.diag(f["VCM_recorded"]))
+    assert np.allclose(sd, sd_rec, rtol=2e-3)                                   # recorded with ~3-4 significant digits
+    assert np.allclose(res["VCM"], f["VCM_recorded"], rtol=0, atol=2e-3 * np.abs(f["VCM_recorded"]).max())
+    assert len(res["DTseries"]) - 1 == 4 and (np.diff(res["DTseries"]) <= 0).all()
+    # and it is a good registration: the recorded result's own distance to the ground truth (1.1 mm, 1e-4 rad)
+    G = f["T_truth"]
+    e = min(np.abs(T - X).max() for X in (G, np.linalg.inv(G)))
+    assert e < 1.5e-3
