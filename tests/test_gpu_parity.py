@@ -465,9 +465,8 @@ def test_reference_pair_reproduces_recorded_result(gpu_ctx, oracle):
     assert da <= POSE_TOL_RAD and dt <= POSE_TOL_M, (da, dt)
     sd, sd_rec = np.sqrt(np.diag(g["VCM"])), np.sqrt(np.diag(f["VCM_recorded"]))
     assert np.allclose(sd, sd_rec, rtol=2e-3)
-    # same pair through the oracle (its own patch constants): identical schedule, pose within tolerance
-    fo = load_refpair(oracle.patch_stats)
-    o = oracle.piecewise_icp(oracle.PairData(fo["pair"]), 1, fo["DTinit"])
+    # the same centroid-level pair (device patch constants) through the oracle: identical schedule, pose within tolerance
+    o = oracle.piecewise_icp(oracle.PairData(d), 1, f["DTinit"])
     assert np.array_equal(g["DTseries"], o["DTseries"])
     assert [s.n_stable for s in g["stats"]] == [s.n_stable for s in o["stats"]]
     da, dt = pose_diff(g["T"], o["T"])
