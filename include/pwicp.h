@@ -51,6 +51,8 @@ void pwicp_ctx_destroy(pwicp_ctx* ctx);
 const char* pwicp_last_error(const pwicp_ctx* ctx);  /* ctx may be NULL: last global error */
 /* device time (ms, CUDA events on the context's stream) of the last timed entry point */
 float pwicp_last_device_ms(const pwicp_ctx* ctx);
+/* duration of the k-NN kernel alone in the last pwicp_knn_mean_dist / pwicp_preprocess call (CUDA events) */
+float pwicp_last_knn_kernel_ms(const pwicp_ctx* ctx);
 /* number of kernels this library launched on the context so far (bench "gpu_launches") */
 long long pwicp_launch_count(const pwicp_ctx* ctx);
 /* writes a buffer larger than L2 (bench hygiene between timed steps) */
@@ -194,6 +196,18 @@ int pwicp_overlap_ratio(pwicp_ctx* ctx, const float* cloud1, int m1, const float
 /* squared distance of every point to its nearest OTHER point of the same cloud: the second
  * neighbour of KdTreeFLANN::nearestKSearch(i, 2) in calPCresolution (src/CommonFunc.cpp:239-263) */
 int pwicp_self_nn(pwicp_ctx* ctx, const float* xyz, int n, float* d2);
+/* ---- F4: PCpreprocessing (src/CommonFunc.cpp:423-452), [PCL 1.8.1 VoxelGrid / StatisticalOutlierRemoval] ---- */
+/* pcl::VoxelGrid with a cubic leaf (:430-433): one centroid per occupied voxel, ascending voxel index; points of a
+ * voxel are summed in input order (float).  out_xyz must hold n points. */
+int pwicp_voxel_grid(pwicp_ctx* ctx, const float* xyz, int n, float leaf, float* out_xyz, int* n_out);
+/* first pass of pcl::StatisticalOutlierRemoval (:446-451): mean distance of every point to its k nearest other
+ * points (nearestKSearch(point, k + 1) without the point itself), float(dist_sum / k).  1 <= k <= 32 < n. */
+int pwicp_knn_mean_dist(pwicp_ctx* ctx, const float* xyz, int n, int k, float* mean_dist);
+/* PCpreprocessing(cloud_in, cloud_out, isDownSamp, voxelSize, SOR_NeighborNum, SOR_StdMult) (:423-439): VoxelGrid
+ * (when downsample != 0) then StatisticalOutlierRemoval; points with mean distance <= mean + std_mult * stddev are
+ * kept in order.  out_xyz must hold n points. */
+int pwicp_preprocess(pwicp_ctx* ctx, const float* xyz, int n, int downsample, float leaf, int k, double std_mult,
+                     float* out_xyz, int* n_out);
 /* calTransParaVCM (src/Registration.cpp:1273-1343) on the resident centroid target */
 int pwicp_vcm(pwicp_ctx* ctx, const float* src_stable_xyz, int n, double* vcm36, int* singular);
 /* pcl::transformPointCloud (src/Registration.cpp:943-954), in place on a host array */

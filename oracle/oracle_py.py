@@ -222,6 +222,44 @@ def patch_stats(pts, off):
     return {"ct": ct, "bp": bp, "nrm": nrm, "nrm_ok": ok, "bpstd": bs, "ctstd": cs}
 
 
+def voxel_grid(xyz, leaf):
+    """pcl::VoxelGrid with a cubic leaf (F4)."""
+    p = _f32(xyz)
+    out = np.zeros_like(p)
+    L = lib()
+    L.orc_voxel_grid.argtypes = [f32p, C.c_int, C.c_float, f32p]
+    m = L.orc_voxel_grid(p, len(p), leaf, out)
+    return out[:m].copy()
+
+
+def knn_mean_dist(xyz, k):
+    """first pass of pcl::StatisticalOutlierRemoval: mean distance to the k nearest other points (F4)."""
+    p = _f32(xyz)
+    out = np.zeros(len(p), np.float32)
+    L = lib()
+    L.orc_knn_mean_dist.argtypes = [f32p, C.c_int, C.c_int, f32p]
+    if L.orc_knn_mean_dist(p, len(p), k, out) != 0:
+        raise ValueError("knn_mean_dist: need 1 <= k < n")
+    return out
+
+
+def sor_select(xyz, mean_dist, std_mult):
+    p = _f32(xyz)
+    md = _f32(mean_dist)
+    out = np.zeros_like(p)
+    thr = C.c_double(0)
+    L = lib()
+    L.orc_sor_select.argtypes = [f32p, C.c_int, f32p, C.c_double, f32p, C.POINTER(C.c_double)]
+    m = L.orc_sor_select(p, len(p), md, std_mult, out, C.byref(thr))
+    return out[:m].copy(), thr.value
+
+
+def preprocess(xyz, leaf, k=14, std_mult=5.0):
+    """PCpreprocessing(cloud, out, true, leaf, k, std_mult) (src/CommonFunc.cpp:423-439)."""
+    v = voxel_grid(xyz, leaf)
+    return sor_select(v, knn_mean_dist(v, k), std_mult)[0]
+
+
 def matrix2angle(T):
     a = np.zeros(3, np.float32)
     lib().orc_matrix2angle(_f32(T).reshape(16), a)

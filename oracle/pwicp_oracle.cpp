@@ -164,6 +164,50 @@ struct KdTree {
         idx = (b.idx == INT32_MAX) ? -1 : b.idx;
         d2 = b.d2;
     }
+
+    /* k nearest neighbours (F4: StatisticalOutlierRemoval's nearestKSearch): best[] holds the k
+     * smallest float distances in ascending order; `skip` (an original index, or -1) is left out. */
+    void search_k(int ni, const float* q, double mindist, double* dists, int skip, int k, float* best) const {
+        const Node& nd = nodes[ni];
+        if (nd.dim < 0) {
+            for (int i = nd.lo; i < nd.hi; ++i) {
+                if (ids[i] == skip) continue;
+                float d = l2_simple(q, &pts[3 * (size_t)i]);
+                if (d < best[k - 1]) {
+                    int j = k - 1;
+                    while (j > 0 && best[j - 1] > d) { best[j] = best[j - 1]; --j; }
+                    best[j] = d;
+                }
+            }
+            return;
+        }
+        int dim = nd.dim;
+        double val = q[dim];
+        double diff1 = val - (double)nd.divlow, diff2 = val - (double)nd.divhigh;
+        int nearc, farc; double cut;
+        if (diff1 + diff2 < 0) { nearc = nd.left; farc = nd.right; cut = diff2 * diff2; }
+        else                   { nearc = nd.right; farc = nd.left; cut = diff1 * diff1; }
+        search_k(nearc, q, mindist, dists, skip, k, best);
+        double dsave = dists[dim];
+        double md = mindist + cut - dsave;
+        if (md * 0.999999 <= (double)best[k - 1]) {
+            dists[dim] = cut;
+            search_k(farc, q, md, dists, skip, k, best);
+            dists[dim] = dsave;
+        }
+    }
+
+    void query_k(const float* q, int skip, int k, float* best) const {
+        for (int j = 0; j < k; ++j) best[j] = std::numeric_limits<float>::infinity();
+        if (n <= 0) return;
+        double dists[3] = {0, 0, 0}, md = 0;
+        for (int c = 0; c < 3; ++c) {
+            if (q[c] < bbmin[c]) { double d = (double)q[c] - bbmin[c]; dists[c] = d * d; }
+            if (q[c] > bbmax[c]) { double d = (double)q[c] - bbmax[c]; dists[c] = d * d; }
+            md += dists[c];
+        }
+        search_k(0, q, md, dists, skip, k, best);
+    }
 };
 
 /* ------------------------------------------------------------------------------------------
@@ -1012,6 +1056,88 @@ int orc_piecewise_icp(orc_pair* pr, int isManualDTinit, float DTinit, const orc_
     *n_series = ns;
     std::memcpy(T16, transMat, sizeof(transMat));
     return count;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * F4: PCpreprocessing (src/CommonFunc.cpp:423-452) = pcl::VoxelGrid + pcl::StatisticalOutlierRemoval
+ * [PCL-recalled, PCL 1.8.1 filters/voxel_grid.hpp applyFilter, statistical_outlier_removal.hpp
+ * applyFilterIndices].
+ * ------------------------------------------------------------------------------------------ */
+
+/* VoxelGrid with a cubic leaf: inverse_leaf = 1/leaf (float); min_b/max_b = floor(min/max * inverse_leaf);
+ * voxel index = ijk . (1, div_x, div_x*div_y) with ijk = floor(p * inverse_leaf) - min_b; points sorted by
+ * voxel index; one output point per occupied voxel in ascending index order, the float centroid of its
+ * points.  The order of the points INSIDE a voxel follows std::sort in PCL (unspecified); here it is the
+ * input order (what a stable sort gives), which fixes the float summation order.  Returns the number of
+ * output points (out has room for n). */
+int orc_voxel_grid(const float* xyz, int n, float leaf, float* out) {
+    if (n <= 0) return 0;
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int i = 0; i < n; ++i)
+        for (int c = 0; c < 3; ++c) { mn[c] = std::min(mn[c], xyz[3 * (size_t)i + c]); mx[c] = std::max(mx[c], xyz[3 * (size_t)i + c]); }
+    const float inv = 1.0f / leaf;
+    long long minb[3], div[3];
+    for (int c = 0; c < 3; ++c) {
+        minb[c] = (long long)std::floor(mn[c] * inv);
+        div[c] = (long long)std::floor(mx[c] * inv) - minb[c] + 1;
+    }
+    std::vector<std::pair<long long, int>> keyed((size_t)n);
+    for (int i = 0; i < n; ++i) {
+        const float* p = xyz + 3 * (size_t)i;
+        const long long ix = (long long)std::floor(p[0] * inv) - minb[0];
+        const long long iy = (long long)std::floor(p[1] * inv) - minb[1];
+        const long long iz = (long long)std::floor(p[2] * inv) - minb[2];
+        keyed[i] = {ix + iy * div[0] + iz * div[0] * div[1], i};
+    }
+    std::stable_sort(keyed.begin(), keyed.end(),
+                     [](const std::pair<long long, int>& a, const std::pair<long long, int>& b) { return a.first < b.first; });
+    int m = 0;
+    size_t i = 0;
+    while (i < keyed.size()) {
+        size_t j = i;
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+        while (j < keyed.size() && keyed[j].first == keyed[i].first) {
+            const float* p = xyz + 3 * (size_t)keyed[j].second;
+            sx += p[0]; sy += p[1]; sz += p[2]; ++j;
+        }
+        const float cnt = (float)(j - i);
+        out[3 * (size_t)m] = sx / cnt; out[3 * (size_t)m + 1] = sy / cnt; out[3 * (size_t)m + 2] = sz / cnt;
+        ++m;
+        i = j;
+    }
+    return m;
+}
+
+/* StatisticalOutlierRemoval, first pass: for every point the mean distance to its k nearest OTHER points
+ * (nearestKSearch(point, k + 1), first hit = the point itself, skipped): dist_sum (double) of sqrt(d2) (float d2,
+ * float sqrt) in ascending order, distances[i] = float(dist_sum / k).  n must exceed k. */
+int orc_knn_mean_dist(const float* xyz, int n, int k, float* mean_dist) {
+    if (k < 1 || k > 256 || n <= k) return -1;
+    KdTree tree;
+    tree.build(xyz, n);
+    std::vector<float> best((size_t)k);
+    for (int i = 0; i < n; ++i) {
+        tree.query_k(xyz + 3 * (size_t)i, i, k, best.data());
+        double s = 0.0;
+        for (int j = 0; j < k; ++j) s += std::sqrt(best[j]);
+        mean_dist[i] = (float)(s / k);
+    }
+    return 0;
+}
+
+/* second pass: mean and standard deviation of the mean distances (double, sequential), threshold = mean + mult * stddev,
+ * points with distance <= threshold are kept in input order (negative = false).  Returns the number kept. */
+int orc_sor_select(const float* xyz, int n, const float* mean_dist, double std_mult, float* out, double* threshold) {
+    double sum = 0, sq = 0;
+    for (int i = 0; i < n; ++i) { sum += mean_dist[i]; sq += (double)mean_dist[i] * mean_dist[i]; }
+    const double mean = sum / n;
+    const double var = (sq - sum * sum / n) / (n - 1);
+    const double thr = mean + std_mult * std::sqrt(std::max(var, 0.0));
+    if (threshold) *threshold = thr;
+    int m = 0;
+    for (int i = 0; i < n; ++i)
+        if (mean_dist[i] <= thr) { std::memcpy(out + 3 * (size_t)m, xyz + 3 * (size_t)i, 12); ++m; }
+    return m;
 }
 
 }  // extern "C"

@@ -97,6 +97,12 @@ int orc_patch_normal(const float* pts, int n, float* n3);
 void orc_patch_stats(const float* pts, const int* off, int np, float* ct, float* bp, float* nrm,
                      unsigned char* ok, float* bpstd, float* ctstd);
 
+/* ---- F4: PCpreprocessing (src/CommonFunc.cpp:423-452): pcl::VoxelGrid (cubic leaf) and the two passes of
+ * pcl::StatisticalOutlierRemoval (mean distance to the k nearest other points; mean + mult * stddev selection). */
+int orc_voxel_grid(const float* xyz, int n, float leaf, float* out);
+int orc_knn_mean_dist(const float* xyz, int n, int k, float* mean_dist);
+int orc_sor_select(const float* xyz, int n, const float* mean_dist, double std_mult, float* out, double* threshold);
+
 /* ---- A10: matrix2angle (src/CommonFunc.cpp:385-407) */
 void orc_matrix2angle(const float* T16, float* ang3);
 

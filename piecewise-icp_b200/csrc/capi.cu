@@ -123,7 +123,7 @@ void pwicp_ctx_destroy(pwicp_ctx* p) {
     Ctx* c = reinterpret_cast<Ctx*>(p);
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    c->tgt.release(); c->c1.release();
+    c->tgt.release(); c->c1.release(); c->prep.release();
     DevBuf* bufs[] = {&c->tgt_aux, &c->tgt_ok, &c->ct2, &c->bp2, &c->bpstd2, &c->patch_xyz, &c->patch_id,
                       &c->patch_off, &c->cloud2, &c->icp_src, &c->icp_work, &c->icp_partials, &c->icp_out,
                       &c->icp_idx, &c->icp_sorted, &c->icp_perm, &c->icp_seed, &c->icp_match, &c->ct_seed, &c->bp_seed, &c->pp_seed, &c->ct_order, &c->tgt_xyz, &c->tgt_nrm_raw, &c->tgt_std_raw, &c->tgt_ok_raw, &c->keys, &c->vals, &c->keys2, &c->vals2, &c->cub_tmp, &c->scratch_a,
@@ -137,6 +137,7 @@ void pwicp_ctx_destroy(pwicp_ctx* p) {
 }
 
 float pwicp_last_device_ms(const pwicp_ctx* p) { return p ? reinterpret_cast<const Ctx*>(p)->last_ms : 0.f; }
+float pwicp_last_knn_kernel_ms(const pwicp_ctx* p) { return p ? reinterpret_cast<const Ctx*>(p)->prep_kernel_ms : 0.f; }
 long long pwicp_launch_count(const pwicp_ctx* p) { return p ? reinterpret_cast<const Ctx*>(p)->launches : 0; }
 
 int pwicp_sync(pwicp_ctx* p) {
@@ -562,12 +563,11 @@ int pwicp_percentile_nn(pwicp_ctx* p, const float* cloud1, int m1, const float* 
     Ctx* ctx = reinterpret_cast<Ctx*>(p);
     if (!ctx || m1 < 1 || m2 < 1 || !out) { set_error(ctx, "percentile_nn: bad arguments"); return PWICP_ERR_ARG; }
     PW_CUDA(cudaSetDevice(ctx->device));
-    GridOwner g;
+    GridOwner& g = ctx->prep;            // persistent buffers (cudaMalloc/cudaFree cost ms), rebuilt per call
     PW_TRY(upload_checked(ctx, ctx->scratch_a, cloud1, (size_t)3 * m1, "cloud1"));
     int rc = grid_build(ctx, g, ctx->scratch_a.as<float>(), m1);
     if (rc == PWICP_OK) rc = upload_checked(ctx, ctx->scratch_c, cloud2, (size_t)3 * m2, "cloud2");
     if (rc == PWICP_OK) rc = percentile_dev(ctx, g.dev, ctx->scratch_c.as<float>(), m2, nullptr, nullptr, m2, pct, out, nullptr);
-    g.release();
     return rc;
 }
 
@@ -576,7 +576,7 @@ int pwicp_overlap_ratio(pwicp_ctx* p, const float* cloud1, int m1, const float* 
     Ctx* ctx = reinterpret_cast<Ctx*>(p);
     if (!ctx || m1 < 1 || m2 < 1 || !out) { set_error(ctx, "overlap_ratio: bad arguments"); return PWICP_ERR_ARG; }
     PW_CUDA(cudaSetDevice(ctx->device));
-    GridOwner g;
+    GridOwner& g = ctx->prep;            // persistent buffers (cudaMalloc/cudaFree cost ms), rebuilt per call
     PW_TRY(upload_checked(ctx, ctx->scratch_a, cloud1, (size_t)3 * m1, "cloud1"));
     int rc = grid_build(ctx, g, ctx->scratch_a.as<float>(), m1);
     if (rc == PWICP_OK) rc = upload_checked(ctx, ctx->scratch_c, cloud2, (size_t)3 * m2, "cloud2");
@@ -594,7 +594,6 @@ int pwicp_overlap_ratio(pwicp_ctx* p, const float* cloud1, int m1, const float* 
                 cudaStreamSynchronize(ctx->stream) != cudaSuccess) { set_error(ctx, "overlap_ratio: copy failed"); rc = PWICP_ERR_CUDA; }
         }
     }
-    g.release();
     if (rc == PWICP_OK) *out = float((int)cnt) / float(m2);        // :613
     return rc;
 }
@@ -603,7 +602,7 @@ int pwicp_self_nn(pwicp_ctx* p, const float* xyz, int n, float* d2) {
     Ctx* ctx = reinterpret_cast<Ctx*>(p);
     if (!ctx || !xyz || !d2 || n < 2) { set_error(ctx, "self_nn: bad arguments"); return PWICP_ERR_ARG; }
     PW_CUDA(cudaSetDevice(ctx->device));
-    GridOwner g;
+    GridOwner& g = ctx->prep;            // persistent buffers (cudaMalloc/cudaFree cost ms), rebuilt per call
     PW_TRY(upload_checked(ctx, ctx->scratch_a, xyz, (size_t)3 * n, "cloud"));
     int rc = grid_build(ctx, g, ctx->scratch_a.as<float>(), n);
     if (rc == PWICP_OK) rc = ctx->scratch_b.reserve(ctx, (size_t)n * 4);
@@ -612,8 +611,88 @@ int pwicp_self_nn(pwicp_ctx* p, const float* xyz, int n, float* d2) {
         if (cudaMemcpyAsync(d2, ctx->scratch_b.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
             cudaStreamSynchronize(ctx->stream) != cudaSuccess) { set_error(ctx, "self_nn: copy failed"); rc = PWICP_ERR_CUDA; }
     }
-    g.release();
     return rc;
+}
+
+// ---- F4: PCpreprocessing (src/CommonFunc.cpp:423-452) ----------------------------------------------------------------
+int pwicp_voxel_grid(pwicp_ctx* p, const float* xyz, int n, float leaf, float* out_xyz, int* n_out) {
+    Ctx* ctx = reinterpret_cast<Ctx*>(p);
+    if (!ctx || !xyz || !out_xyz || !n_out || n < 1 || !(leaf > 0.f)) { set_error(ctx, "voxel_grid: bad arguments"); return PWICP_ERR_ARG; }
+    PW_CUDA(cudaSetDevice(ctx->device));
+    PW_TRY(upload_checked(ctx, ctx->scratch_a, xyz, (size_t)3 * n, "cloud"));
+    PW_TRY(ctx->scratch_c.reserve(ctx, (size_t)3 * n * 4));
+    PW_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    PW_TRY(voxel_grid_dev(ctx, ctx->scratch_a.as<float>(), n, leaf, ctx->scratch_c.as<float>(), n_out));
+    PW_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    PW_CUDA(cudaMemcpyAsync(out_xyz, ctx->scratch_c.p, (size_t)3 * *n_out * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PW_CUDA(cudaStreamSynchronize(ctx->stream));
+    PW_CUDA(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    return PWICP_OK;
+}
+
+static int knn_mean_dist_resident(Ctx* ctx, const float* xyz_dev, int n, int k, float* mean_dist_host) {
+    GridOwner& g = ctx->prep;                      // persistent buffers, rebuilt for this cloud
+    PW_TRY(grid_build(ctx, g, xyz_dev, n));
+    PW_TRY(ctx->scratch_b.reserve(ctx, (size_t)n * 4));
+    PW_CUDA(cudaEventRecord(ctx->ev2, ctx->stream));
+    PW_TRY(knn_mean_dist_dev(ctx, g.dev, k, ctx->scratch_b.as<float>()));
+    PW_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    PW_CUDA(cudaMemcpyAsync(mean_dist_host, ctx->scratch_b.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PW_CUDA(cudaStreamSynchronize(ctx->stream));
+    PW_CUDA(cudaEventElapsedTime(&ctx->prep_kernel_ms, ctx->ev2, ctx->ev1));
+    return PWICP_OK;
+}
+
+int pwicp_knn_mean_dist(pwicp_ctx* p, const float* xyz, int n, int k, float* mean_dist) {
+    Ctx* ctx = reinterpret_cast<Ctx*>(p);
+    if (!ctx || !xyz || !mean_dist || k < 1 || k > 32 || n <= k) { set_error(ctx, "knn_mean_dist: bad arguments (1 <= k <= 32 < n)"); return PWICP_ERR_ARG; }
+    PW_CUDA(cudaSetDevice(ctx->device));
+    PW_TRY(upload_checked(ctx, ctx->scratch_a, xyz, (size_t)3 * n, "cloud"));
+    PW_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    PW_TRY(knn_mean_dist_resident(ctx, ctx->scratch_a.as<float>(), n, k, mean_dist));
+    PW_CUDA(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));      // grid build + k-NN kernel
+    return PWICP_OK;
+}
+
+// VoxelGrid (optional) + StatisticalOutlierRemoval in one call: the cloud stays on the device between the two steps; the
+// selection (mean + mult * stddev of the mean distances, sequential double sums like PCL) runs on the host over the
+// downloaded 4 bytes per point.  out_xyz must hold n points.
+int pwicp_preprocess(pwicp_ctx* p, const float* xyz, int n, int downsample, float leaf, int k, double std_mult,
+                     float* out_xyz, int* n_out) {
+    Ctx* ctx = reinterpret_cast<Ctx*>(p);
+    if (!ctx || !xyz || !out_xyz || !n_out || n < 1 || (downsample && !(leaf > 0.f)) || k < 1 || k > 32) {
+        set_error(ctx, "preprocess: bad arguments"); return PWICP_ERR_ARG;
+    }
+    PW_CUDA(cudaSetDevice(ctx->device));
+    PW_TRY(upload_checked(ctx, ctx->scratch_a, xyz, (size_t)3 * n, "cloud"));
+    PW_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    const float* cur = ctx->scratch_a.as<float>();
+    int m = n;
+    if (downsample) {
+        PW_TRY(ctx->scratch_c.reserve(ctx, (size_t)3 * n * 4));
+        PW_TRY(voxel_grid_dev(ctx, ctx->scratch_a.as<float>(), n, leaf, ctx->scratch_c.as<float>(), &m));
+        cur = ctx->scratch_c.as<float>();
+    }
+    std::vector<float> pts((size_t)3 * m), md((size_t)m);
+    PW_CUDA(cudaMemcpyAsync(pts.data(), cur, (size_t)3 * m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (m <= k) {                                  // StatisticalOutlierRemoval needs more than k points: pass through
+        PW_CUDA(cudaStreamSynchronize(ctx->stream));
+        std::memcpy(out_xyz, pts.data(), (size_t)3 * m * 4);
+        *n_out = m;
+        return PWICP_OK;
+    }
+    PW_TRY(knn_mean_dist_resident(ctx, cur, m, k, md.data()));
+    PW_CUDA(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));      // voxel grid + cloud download + grid build + k-NN kernel
+    double sum = 0, sq = 0;
+    for (int i = 0; i < m; ++i) { sum += md[i]; sq += (double)md[i] * md[i]; }
+    const double mean = sum / m;
+    const double var = (sq - sum * sum / m) / (m - 1);
+    const double thr = mean + std_mult * std::sqrt(std::max(var, 0.0));
+    int kept = 0;
+    for (int i = 0; i < m; ++i)
+        if (md[i] <= thr) { std::memcpy(out_xyz + 3 * (size_t)kept, pts.data() + 3 * (size_t)i, 12); ++kept; }
+    *n_out = kept;
+    return PWICP_OK;
 }
 
 int pwicp_vcm(pwicp_ctx* p, const float* src, int n, double* vcm36, int* singular) {

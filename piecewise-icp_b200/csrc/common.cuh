@@ -13,7 +13,10 @@ namespace pwicp {
 constexpr int kMaxLevels = 3;      // grid pyramid: cell sizes h, 8h, 64h
 constexpr int kLevelFactor = 8;
 constexpr int kRingsPerLevel = 2;  // rings searched on a level before moving to the coarser one
-constexpr int kIcpThreads = 256;   // 8 warps per CTA (reduction geometry)
+#ifndef PWICP_ICP_THREADS
+#define PWICP_ICP_THREADS 256
+#endif
+constexpr int kIcpThreads = PWICP_ICP_THREADS;   // 8 warps per CTA; the sums do not depend on it
 constexpr int kIcpWarps = kIcpThreads / 32;
 constexpr int kNumVals = 28;       // 21 ATA + 6 ATb + sum d2
 constexpr int kFanIn = 32;         // entries summed per parent on every level of the reduction hierarchy
@@ -99,6 +102,9 @@ struct Ctx {
     // full cloud1
     GridOwner c1;
     int m1 = 0;
+    // F4 pre-processing: grid over the cloud being filtered (buffers persist across calls: cudaMalloc/cudaFree cost ms)
+    GridOwner prep;
+    float prep_kernel_ms = 0.f;                  // duration of the last k-NN kernel alone
     // source
     DevBuf ct2, bp2, bpstd2, patch_xyz, patch_id, patch_off, cloud2;
     int n2 = 0, m2 = 0, mp2 = 0;
@@ -143,6 +149,10 @@ int vcm_dev(Ctx* ctx, const float4* src_dev, int n, double* vcm36, int* singular
 int transform_packed_dev(Ctx* ctx, float* xyz_dev, size_t n, const float* T16);
 int bbox_packed_dev(Ctx* ctx, const float* xyz_dev, size_t n, float* mn3, float* mx3);
 void octree_cube(const float* mn, const float* mx, double res, double* bb6);
+
+// prep.cu (F4)
+int voxel_grid_dev(Ctx* ctx, const float* xyz_dev, int n, float leaf, float* out_dev, int* n_out);
+int knn_mean_dist_dev(Ctx* ctx, const GridDev& g, int k, float* out_dev);
 
 // patch.cu
 int patch_stats_dev(Ctx* ctx, const float* xyz_dev, const int* off_dev, int np, float* ct, float* bp, float* nrm,

@@ -349,7 +349,11 @@ float calBoundingBoxCornerChange(const double* boundingBox, const Eigen::Matrix4
     return pwicp_bbox_corner_change(boundingBox, transMat.m);
 }
 
-// ---- pre-processing stand-ins (OUT OF SCOPE) ---------------------------
+// ---- pre-processing -------------------------------------------------
+// PCpreprocessing / SORfilter run on the device (pwicp_preprocess: csrc/prep.cu).  The plain host statements of the
+// same two PCL filters below (PCpreprocessingHost / SORfilterHost) are kept for tools that must work without a
+// device (c_hooks.cpp: pwicp_host_prepare_pair, the CPU pinning harness); both give identical clouds
+// (tests/test_host_gpu.py).
 static void voxelGrid(const pcl::PointCloud<pcl::PointXYZ>& in, float leaf, pcl::PointCloud<pcl::PointXYZ>& out) {
     out.clear();
     if (in.empty()) return;
@@ -382,8 +386,8 @@ static void voxelGrid(const pcl::PointCloud<pcl::PointXYZ>& in, float leaf, pcl:
     }
 }
 
-void SORfilter(pcl::PointCloud<pcl::PointXYZ>::Ptr cloud_in, pcl::PointCloud<pcl::PointXYZ>::Ptr cloud_out,
-               int SOR_NeighborNum, double SOR_StdMult) {
+void SORfilterHost(pcl::PointCloud<pcl::PointXYZ>::Ptr cloud_in, pcl::PointCloud<pcl::PointXYZ>::Ptr cloud_out,
+                   int SOR_NeighborNum, double SOR_StdMult) {
     const auto& pts = cloud_in->points;
     const int n = (int)pts.size(), k = SOR_NeighborNum;
     cloud_out->clear();
@@ -439,12 +443,43 @@ void SORfilter(pcl::PointCloud<pcl::PointXYZ>::Ptr cloud_in, pcl::PointCloud<pcl
     for (int i = 0; i < n; ++i) if (meanDist[i] <= thr) cloud_out->push_back(pts[i]);
 }
 
-void PCpreprocessing(pcl::PointCloud<pcl::PointXYZ>::Ptr cloud_in, pcl::PointCloud<pcl::PointXYZ>::Ptr cloud_out,
-                     bool isDownSamp, float voxelSize, int SOR_NeighborNum, double SOR_StdMult) {
+void PCpreprocessingHost(pcl::PointCloud<pcl::PointXYZ>::Ptr cloud_in, pcl::PointCloud<pcl::PointXYZ>::Ptr cloud_out,
+                         bool isDownSamp, float voxelSize, int SOR_NeighborNum, double SOR_StdMult) {
     pcl::PointCloud<pcl::PointXYZ>::Ptr filtered(new pcl::PointCloud<pcl::PointXYZ>);
     if (isDownSamp) voxelGrid(*cloud_in, voxelSize, *filtered);
     else pcl::copyPointCloud(*cloud_in, *filtered);
-    SORfilter(filtered, cloud_out, SOR_NeighborNum, SOR_StdMult);
+    SORfilterHost(filtered, cloud_out, SOR_NeighborNum, SOR_StdMult);
+}
+
+// src/CommonFunc.cpp:423-439 and :442-452 on the device
+static void preprocessDevice(const pcl::PointCloud<pcl::PointXYZ>& in, pcl::PointCloud<pcl::PointXYZ>& out,
+                             bool isDownSamp, float voxelSize, int k, double mult) {
+    const int n = (int)in.size();
+    out.clear();
+    if (n < 1) return;
+    vector<float> xyz(3 * (size_t)n), res(3 * (size_t)n);
+    for (int i = 0; i < n; ++i) { xyz[3 * i] = in.points[i].x; xyz[3 * i + 1] = in.points[i].y; xyz[3 * i + 2] = in.points[i].z; }
+    int m = 0;
+    if (pwicp_preprocess(pwicpHostContext(), xyz.data(), n, isDownSamp ? 1 : 0, voxelSize, k, mult, res.data(), &m) != PWICP_OK) {
+        std::cerr << "Error: pre-processing failed on the device: " << pwicp_last_error(pwicpHostContext()) << "\n";
+        std::exit(EXIT_FAILURE);
+    }
+    out.resize(m);
+    for (int i = 0; i < m; ++i) { out.points[i].x = res[3 * i]; out.points[i].y = res[3 * i + 1]; out.points[i].z = res[3 * i + 2]; }
+}
+
+void SORfilter(pcl::PointCloud<pcl::PointXYZ>::Ptr cloud_in, pcl::PointCloud<pcl::PointXYZ>::Ptr cloud_out,
+               int SOR_NeighborNum, double SOR_StdMult) {
+    pcl::PointCloud<pcl::PointXYZ> res;
+    preprocessDevice(*cloud_in, res, false, 0.f, SOR_NeighborNum, SOR_StdMult);
+    *cloud_out = res;
+}
+
+void PCpreprocessing(pcl::PointCloud<pcl::PointXYZ>::Ptr cloud_in, pcl::PointCloud<pcl::PointXYZ>::Ptr cloud_out,
+                     bool isDownSamp, float voxelSize, int SOR_NeighborNum, double SOR_StdMult) {
+    pcl::PointCloud<pcl::PointXYZ> res;
+    preprocessDevice(*cloud_in, res, isDownSamp, voxelSize, SOR_NeighborNum, SOR_StdMult);
+    *cloud_out = res;
 }
 
 void visualizeTwoPC(pcl::PointCloud<pcl::PointXYZ>::Ptr, std::string, double, double, double, int,

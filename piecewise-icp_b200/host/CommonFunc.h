@@ -54,6 +54,11 @@ void matrix2angle(Eigen::Matrix4f transMat, Eigen::Vector3f& rotAngle);
 float calBoundingBoxCornerChange(const double* boundingBox, const Eigen::Matrix4f transMat);
 /// src/CommonFunc.cpp:423-452.  OUT OF SCOPE stand-ins: plain host voxel-grid
 /// centroiding + statistical outlier removal with PCL's documented semantics, not parity-checked.
+/// host-only statements of the same two filters (no device; used by c_hooks.cpp tools)
+void PCpreprocessingHost(pcl::PointCloud<pcl::PointXYZ>::Ptr cloud_in, pcl::PointCloud<pcl::PointXYZ>::Ptr cloud_out,
+                         bool isDownSamp, float voxelSize, int SOR_NeighborNum, double SOR_StdMult);
+void SORfilterHost(pcl::PointCloud<pcl::PointXYZ>::Ptr cloud_in, pcl::PointCloud<pcl::PointXYZ>::Ptr cloud_out,
+                   int SOR_NeighborNum, double SOR_StdMult);
 void PCpreprocessing(pcl::PointCloud<pcl::PointXYZ>::Ptr cloud_in, pcl::PointCloud<pcl::PointXYZ>::Ptr cloud_out,
                      bool isDownSamp, float voxelSize, int SOR_NeighborNum, double SOR_StdMult);
 void SORfilter(pcl::PointCloud<pcl::PointXYZ>::Ptr cloud_in, pcl::PointCloud<pcl::PointXYZ>::Ptr cloud_out,

@@ -85,8 +85,8 @@ int pwicp_host_prepare_pair(const float* xyz1, int n1, const float* xyz2, int n2
     in1->resize(n1); in2->resize(n2);
     for (int i = 0; i < n1; ++i) { in1->points[i].x = xyz1[3 * i]; in1->points[i].y = xyz1[3 * i + 1]; in1->points[i].z = xyz1[3 * i + 2]; }
     for (int i = 0; i < n2; ++i) { in2->points[i].x = xyz2[3 * i]; in2->points[i].y = xyz2[3 * i + 1]; in2->points[i].z = xyz2[3 * i + 2]; }
-    PCpreprocessing(in1, p1, true, Res1, 14, 5.0);
-    PCpreprocessing(in2, p2, true, Res2, 14, 5.0);
+    PCpreprocessingHost(in1, p1, true, Res1, 14, 5.0);
+    PCpreprocessingHost(in2, p2, true, Res2, 14, 5.0);
     Eigen::Vector4f c;
     pcl::compute3DCentroid(*p1, c);
     Eigen::Matrix4f S = Eigen::Matrix4f::Identity();
@@ -121,6 +121,18 @@ int pwicp_host_prepare_pair(const float* xyz1, int n1, const float* xyz2, int n2
     }
     delete[] SV1c; delete[] SV2c;
     return rc;
+}
+
+// PCpreprocessing on a host array: device != 0 -> the driver's path (pwicp_preprocess), else the host statements
+int pwicp_host_preprocess(const float* xyz, int n, int downsample, float leaf, int k, double mult, int device, float* out, int cap) {
+    pcl::PointCloud<pcl::PointXYZ>::Ptr in(new pcl::PointCloud<pcl::PointXYZ>), res(new pcl::PointCloud<pcl::PointXYZ>);
+    in->resize(n);
+    for (int i = 0; i < n; ++i) { in->points[i].x = xyz[3 * i]; in->points[i].y = xyz[3 * i + 1]; in->points[i].z = xyz[3 * i + 2]; }
+    if (device) PCpreprocessing(in, res, downsample != 0, leaf, k, mult);
+    else PCpreprocessingHost(in, res, downsample != 0, leaf, k, mult);
+    const int m = (int)res->size();
+    for (int i = 0; i < m && i < cap; ++i) { out[3 * i] = res->points[i].x; out[3 * i + 1] = res->points[i].y; out[3 * i + 2] = res->points[i].z; }
+    return m;
 }
 
 // calTransToReferenceEpoch as a file-to-file operation (F2)

@@ -63,6 +63,7 @@ EXPORTS = [
     "pwicp_single_iteration", "pwicp_piecewise_icp", "pwicp_percentile_nn", "pwicp_overlap_ratio",
     "pwicp_self_nn", "pwicp_vcm", "pwicp_transform", "pwicp_octree_bbox", "pwicp_bbox_corner_change",
     "pwicp_matrix2angle", "pwicp_mat4_mul", "pwicp_patch_stats", "pwicp_dmma_order_check",
+    "pwicp_voxel_grid", "pwicp_knn_mean_dist", "pwicp_preprocess", "pwicp_last_knn_kernel_ms",
 ]
 
 _lib = None
@@ -115,6 +116,11 @@ def load_library(path=None):
     L.pwicp_self_nn.argtypes = [vp, vp, C.c_int, vp]
     L.pwicp_patch_stats.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp]
     L.pwicp_dmma_order_check.argtypes = [vp, vp, vp, C.c_int, C.POINTER(C.c_longlong)]
+    L.pwicp_last_knn_kernel_ms.argtypes = [vp]
+    L.pwicp_last_knn_kernel_ms.restype = C.c_float
+    L.pwicp_voxel_grid.argtypes = [vp, vp, C.c_int, C.c_float, vp, C.POINTER(C.c_int)]
+    L.pwicp_knn_mean_dist.argtypes = [vp, vp, C.c_int, C.c_int, vp]
+    L.pwicp_preprocess.argtypes = [vp, vp, C.c_int, C.c_int, C.c_float, C.c_int, C.c_double, vp, C.POINTER(C.c_int)]
     L.pwicp_vcm.argtypes = [vp, vp, C.c_int, vp, C.POINTER(C.c_int)]
     L.pwicp_transform.argtypes = [vp, vp, C.c_int, vp]
     L.pwicp_octree_bbox.argtypes = [vp, vp, C.c_int, C.c_double, vp]
@@ -364,6 +370,31 @@ class Context:
         self._chk(self.L.pwicp_patch_stats(self.h, _ptr(xyz), _ptr(off), n, _ptr(ct), _ptr(bp), _ptr(nrm), _ptr(ok),
                                            _ptr(bs), _ptr(cs)))
         return {"ct": ct, "bp": bp, "nrm": nrm, "nrm_ok": ok, "bpstd": bs, "ctstd": cs}
+
+    # -- F4: PCpreprocessing
+    def voxel_grid(self, xyz, leaf):
+        p = _f32(xyz)
+        out = np.zeros_like(p)
+        m = C.c_int(0)
+        self._chk(self.L.pwicp_voxel_grid(self.h, _ptr(p), len(p), C.c_float(leaf), _ptr(out), C.byref(m)))
+        return out[:m.value].copy()
+
+    def last_knn_kernel_ms(self):
+        return float(self.L.pwicp_last_knn_kernel_ms(self.h))
+
+    def knn_mean_dist(self, xyz, k):
+        p = _f32(xyz)
+        out = np.zeros(len(p), np.float32)
+        self._chk(self.L.pwicp_knn_mean_dist(self.h, _ptr(p), len(p), int(k), _ptr(out)))
+        return out
+
+    def preprocess(self, xyz, leaf, k=14, std_mult=5.0, downsample=True):
+        p = _f32(xyz)
+        out = np.zeros_like(p)
+        m = C.c_int(0)
+        self._chk(self.L.pwicp_preprocess(self.h, _ptr(p), len(p), int(bool(downsample)), C.c_float(leaf), int(k),
+                                          C.c_double(std_mult), _ptr(out), C.byref(m)))
+        return out[:m.value].copy()
 
     def vcm(self, src):
         s = _f32(src)

@@ -158,6 +158,16 @@ def patches(xyz, sv_res, cap=1 << 20):
     return {"ct": ct[:n], "bp": bp[:n].reshape(-1, 3), "bpstd": sb[:n], "ctstd": sc[:n]}
 
 
+def preprocess(xyz, leaf, k=14, mult=5.0, downsample=True, device=True):
+    """PCpreprocessing (src/CommonFunc.cpp:423-439): on the device like the drivers (device=True) or the host statements."""
+    p = np.ascontiguousarray(xyz, np.float32)
+    out = np.zeros_like(p)
+    L = lib()
+    L.pwicp_host_preprocess.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_int]
+    m = L.pwicp_host_preprocess(p.ctypes.data, len(p), int(downsample), leaf, k, mult, int(device), out.ctypes.data, len(p))
+    return out[:m].copy()
+
+
 def register_clouds(xyz1, xyz2, res, sv, dtinit, dtmin, mode=0):
     """Piecewise_ICP on two in-memory clouds (already pre-processed and shifted).  mode 0: the
     device outer loop; mode 1: the reference's while(!stage3) PwICP_singleIteration loop."""

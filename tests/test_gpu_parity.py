@@ -471,3 +471,61 @@ def test_reference_pair_reproduces_recorded_result(gpu_ctx, oracle):
     assert [s.n_stable for s in g["stats"]] == [s.n_stable for s in o["stats"]]
     da, dt = pose_diff(g["T"], o["T"])
     assert da <= POSE_TOL_RAD and dt <= POSE_TOL_M, (da, dt)
+
+
+# ---------------------------------------------------------------- F4: PCpreprocessing (VoxelGrid + StatisticalOutlierRemoval)
+def _prep_clouds():
+    rng = np.random.default_rng(42)
+    scan = synth.make_scan(extent=2.0, spacing=0.005, seed=9)                      # a sampled surface, ~160k points
+    vol = rng.uniform(-1, 1, (40000, 3)).astype(np.float32)                         # volume filling
+    neg = (rng.normal(0, 0.3, (30000, 3)) + (-5.0, 7.0, -0.2)).astype(np.float32)   # negative / offset coordinates
+    dup = np.repeat(rng.uniform(0, 1, (3000, 3)).astype(np.float32), 4, axis=0)     # exact duplicates
+    return {"scan": scan, "volume": vol, "offset": neg, "duplicates": dup}
+
+
+def test_voxel_grid_matches_oracle(gpu_ctx, oracle):
+    """pcl::VoxelGrid (src/CommonFunc.cpp:430-433): same voxels, same order, bit-identical float centroids."""
+    for name, c in _prep_clouds().items():
+        for leaf in (0.005, 0.02, 0.3):
+            g, o = gpu_ctx.voxel_grid(c, leaf), oracle.voxel_grid(c, leaf)
+            assert g.shape == o.shape and np.array_equal(g, o), (name, leaf)
+    one = np.array([[0.1, -0.2, 0.3]], np.float32)
+    assert np.array_equal(gpu_ctx.voxel_grid(one, 0.01), one)
+    same = np.tile(np.array([[0.101, 0.102, 0.103]], np.float32), (1000, 1)) + np.float32(1e-4) * np.arange(1000, dtype=np.float32)[:, None] / 1000
+    g, o = gpu_ctx.voxel_grid(same, 1.0), oracle.voxel_grid(same, 1.0)              # everything in one voxel: 1000-term float sum
+    assert len(g) == 1 and np.array_equal(g, o)
+    with pytest.raises(P.PwicpError):
+        gpu_ctx.voxel_grid(one, 0.0)
+
+
+def test_knn_mean_dist_matches_oracle(gpu_ctx, oracle):
+    """First pass of pcl::StatisticalOutlierRemoval (src/CommonFunc.cpp:446-451): bit-identical mean k-NN distances."""
+    clouds = _prep_clouds()
+    for name, c in clouds.items():
+        for k in ((14, 1, 8, 20, 32) if name == "scan" else (14,)):
+            g, o = gpu_ctx.knn_mean_dist(c, k), oracle.knn_mean_dist(c, k)
+            assert np.array_equal(g, o), (name, k, int((g != o).sum()))
+    tiny = clouds["volume"][:15]                                                    # n = k + 1: every other point is a neighbour
+    assert np.array_equal(gpu_ctx.knn_mean_dist(tiny, 14), oracle.knn_mean_dist(tiny, 14))
+    far = np.concatenate([clouds["volume"][:5000], np.array([[50, 50, 50], [-80, 3, 9]], np.float32)])   # isolated outliers
+    assert np.array_equal(gpu_ctx.knn_mean_dist(far, 14), oracle.knn_mean_dist(far, 14))
+    with pytest.raises(P.PwicpError):
+        gpu_ctx.knn_mean_dist(tiny[:14], 14)
+
+
+def test_preprocess_matches_oracle(gpu_ctx, oracle):
+    """PCpreprocessing(cloud, out, true, Res, 14, 5.0) as the 4D driver calls it (src/Registration.cpp:415-416) and with the
+    pairwise driver's multiplier 2.7 (:272-273); SOR alone (isDownSamp = false)."""
+    rng = np.random.default_rng(5)
+    scan = synth.make_scan(extent=2.0, spacing=0.005, seed=10)
+    noisy = np.concatenate([scan, (scan[rng.choice(len(scan), 300)] + rng.normal(0, 0.05, (300, 3))).astype(np.float32)])
+    for mult in (5.0, 2.7):
+        g, o = gpu_ctx.preprocess(noisy, 0.005, 14, mult), oracle.preprocess(noisy, 0.005, 14, mult)
+        assert g.shape == o.shape and np.array_equal(g, o) and len(g) < len(noisy)
+    md = oracle.knn_mean_dist(noisy, 14)
+    o, _ = oracle.sor_select(noisy, md, 5.0)
+    assert np.array_equal(gpu_ctx.preprocess(noisy, 0.0, 14, 5.0, downsample=False), o)
+    # full size: 1M points, bit-identical
+    big = synth.make_pair(1_000_000, with_clouds=False)["ct1"]
+    assert np.array_equal(gpu_ctx.knn_mean_dist(big, 14), oracle.knn_mean_dist(big, 14))
+    assert np.array_equal(gpu_ctx.voxel_grid(big, 0.08), oracle.voxel_grid(big, 0.08))

@@ -135,3 +135,13 @@ def test_4d_epoch_sharding_matches_single_process(series, tmp_path, monkeypatch)
         outs[name] = out
     for f in ("TransMatrices.txt", "TransParameters.txt", "TransMatrices_toRef.txt", "TransParameters_toRef.txt"):
         assert open(outs["single"] + f).read() == open(outs["sharded"] + f).read(), f
+
+
+def test_preprocessing_device_equals_host_statements():
+    """PCpreprocessing in the drivers runs on the device (pwicp_preprocess); the host statements of the same PCL filters
+    (used by the CPU tools) give the identical cloud."""
+    scan = synth.make_scan(extent=1.5, spacing=0.005, seed=3)
+    for mult in (5.0, 2.7):
+        a = host.preprocess(scan, 0.005, 14, mult, device=True)
+        b = host.preprocess(scan, 0.005, 14, mult, device=False)
+        assert a.shape == b.shape and np.array_equal(a, b) and 0 < len(a) <= len(scan)

@@ -321,3 +321,29 @@ def test_outer_loop_reproduces_the_references_recorded_result(oracle):
     G = f["T_truth"]
     e = min(np.abs(T - X).max() for X in (G, np.linalg.inv(G)))
     assert e < 1.5e-3
+
+
+# ---------------------------------------------------------------- F4: VoxelGrid / StatisticalOutlierRemoval restatement
+def test_preprocessing_restatement(oracle):
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(8)
+    c = rng.uniform(-1, 1, (20000, 3)).astype(np.float32)
+    v = oracle.voxel_grid(c, 0.1)
+    key = np.floor(c * np.float32(1.0 / np.float32(0.1))).astype(np.int64)
+    key -= key.min(0)
+    dims = key.max(0) + 1
+    lin = key[:, 0] + key[:, 1] * dims[0] + key[:, 2] * dims[0] * dims[1]
+    uniq = np.unique(lin)
+    assert len(v) == len(uniq)
+    ref = np.stack([c[lin == u].astype(np.float64).mean(0) for u in uniq[:200]])       # ascending voxel index
+    assert np.allclose(v[:200], ref, atol=1e-6)
+    md = oracle.knn_mean_dist(c, 14)
+    dd, _ = cKDTree(c.astype(np.float64)).query(c.astype(np.float64), 15)
+    assert np.allclose(md, dd[:, 1:].mean(1), rtol=1e-5)
+    out, thr = oracle.sor_select(c, md, 1.0)
+    assert np.isclose(thr, md.astype(np.float64).mean() + md.astype(np.float64).std(ddof=1), rtol=1e-9)
+    assert np.array_equal(out, c[md <= thr])
+    # the host mirror's statements of the same filters give the identical cloud
+    from pwicp_b200 import host
+    scan = synth.make_scan(extent=1.0, spacing=0.005, seed=4)
+    assert np.array_equal(host.preprocess(scan, 0.005, 14, 5.0, device=False), oracle.preprocess(scan, 0.005, 14, 5.0))
