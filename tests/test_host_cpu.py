@@ -84,6 +84,44 @@ def test_patch_generation_stand_in():
     assert (np.abs(bp - p["ct"][:, None, :]).max(axis=(1, 2)) < 0.11).all()
 
 
+def test_segmenter_plugin_groups_points_like_the_reference():
+    """pwicp_host_set_segmenter: labels from the caller's segmentation replace the cubic-cell stand-in; points are grouped per
+    label in cloud order (src/Segmentation.cpp:95-100) and go through the reference's refinement / planarity gates."""
+    import ctypes as C
+    pts = synth.make_scan(extent=1.0, spacing=0.01, seed=6)
+    calls = {}
+
+    @C.CFUNCTYPE(C.c_int, C.POINTER(C.c_float), C.c_int, C.c_float, C.c_int, C.POINTER(C.c_int))
+    def stripes(xyz, n, sv, knn, labels):
+        a = np.ctypeslib.as_array(xyz, shape=(n, 3))
+        lab = np.floor((a[:, 0] - a[:, 0].min()) / sv).astype(np.int32) * 64 + np.floor((a[:, 1] - a[:, 1].min()) / sv).astype(np.int32)
+        uniq, inv = np.unique(lab, return_inverse=True)
+        np.ctypeslib.as_array(labels, shape=(n,))[:] = inv
+        calls["n"], calls["knn"], calls["sv"], calls["labels"] = n, knn, sv, inv.copy()
+        return len(uniq)
+
+    L = host.lib()
+    L.pwicp_host_set_segmenter.argtypes = [C.c_void_p]
+    L.pwicp_host_set_segmenter(C.cast(stripes, C.c_void_p))
+    try:
+        p = host.patches(pts, 0.1)
+    finally:
+        L.pwicp_host_set_segmenter(None)
+    assert calls["n"] == len(pts) and calls["knn"] == 45 and abs(calls["sv"] - 0.1) < 1e-7
+    n = len(p["ct"])
+    assert 50 < n <= calls["labels"].max() + 1
+    # every centroid is the mean of a refined subset of one label's points: it lies inside that label's bounding box
+    lab = calls["labels"]
+    for k in range(0, n, 7):
+        d = np.abs(pts - p["ct"][k]).max(axis=1)
+        owner = lab[np.argmin(d)]
+        box = pts[lab == owner]
+        assert (p["ct"][k] >= box.min(0) - 1e-6).all() and (p["ct"][k] <= box.max(0) + 1e-6).all()
+    # a failing segmenter is fatal in the reference-shaped mirror only through its return code: here it just restores
+    q = host.patches(pts, 0.1)                       # stand-in again
+    assert len(q["ct"]) > 0 and len(q["ct"]) != n or not np.array_equal(q["ct"], p["ct"])
+
+
 def _write_transmatrices(path, Ts, Vs):
     with open(path, "w") as f:
         for k, (T, V) in enumerate(zip(Ts, Vs)):
