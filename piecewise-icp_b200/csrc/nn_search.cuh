@@ -28,6 +28,17 @@
 
 namespace pwicp {
 
+// Squared distance (in cells) beyond which a seed counts as stale and the home cell is tried as well.  Stand-alone
+// searches: half a cell.  Inner loop: one cell -- after the large first ICP steps the previous match IS stale (at 10M
+// centroids the first transform moves the cloud edge by several cells: second iteration 5.7 -> 3.2 ms with the
+// re-seed), but at half a cell the extra home-cell scan costs more than the larger ball on the following
+// iterations (profiles/r01k_ab_reseed.txt: 1M loop 2.85 ms without, 3.18 ms at 0.25, 2.77 ms at 1.0).
+#ifndef PWICP_RESEED_CELLS2
+#define PWICP_RESEED_CELLS2 0.25f
+#endif
+#ifndef PWICP_RESEED_CELLS2_LOOP
+#define PWICP_RESEED_CELLS2_LOOP 1.0f
+#endif
 constexpr float kBallMaxCells = 6.0f;   // scan on the finest level whose ball radius is <= this many cells
                                         // (finer is cheaper unless the ball is mostly empty space: rows ~ (2r+1)^2)
 
@@ -234,7 +245,8 @@ __device__ __forceinline__ Best nn_search_seeded(const GridDev& g, float px, flo
         bpos = seed_pos;
         // a stale seed (the cloud moved by a good part of a cell since it was recorded) would make
         // the ball large: the home cell usually holds a better candidate
-        if (!kLean && bd * g.lv[0].inv_h2 > 0.25f) find_seed(g, px, py, pz, bd, bi, bpos);
+        if (kLean) { if (bd * g.lv[0].inv_h2 > PWICP_RESEED_CELLS2_LOOP) find_seed_ool(g, px, py, pz, bd, bi, bpos); }
+        else if (bd * g.lv[0].inv_h2 > PWICP_RESEED_CELLS2) find_seed(g, px, py, pz, bd, bi, bpos);
     } else if (kLean) {
         find_seed_ool(g, px, py, pz, bd, bi, bpos);
     } else {
