@@ -71,6 +71,21 @@ def test_pair_call_end_to_end(series, tmp_path):
     assert not host.pair_call(cfg, prefix)
 
 
+def test_pair_call_automatic_resolution_and_dtinit(series, tmp_path):
+    """isSetResSVsize = 0 and isSetDTinit = 0 (src/Registration.cpp:259-262, :627-630): the point spacing comes from
+    calPCresolution (device self-NN), the supervoxel size is 10 x spacing, DTinit = 3 x P75 of the cloud-to-cloud distances
+    (device percentile); the registration must still land on the ground truth."""
+    root, folder, gt = series
+    cfg = str(tmp_path / "configuration_pair.txt")
+    synth.write_config(cfg, os.path.join(folder, "Epoch_001.pcd"), os.path.join(folder, "Epoch_002.pcd"), manual_res=0, manual_dt=0)
+    prefix = str(tmp_path) + "/"
+    assert host.pair_call(cfg, prefix)
+    T, V = read_transmatrix_file(prefix + "TransMatrix.txt")
+    da, dt = pose_err(T, gt[1])
+    assert da < 3e-4 and dt < 1.5e-3, (da, dt)
+    assert (np.diag(V) > 0).all()
+
+
 def test_device_loop_equals_reference_shaped_loop(series):
     """Piecewise_ICP (device loop) == while(!stage3) PwICP_singleIteration (mirror function)."""
     root, folder, gt = series
