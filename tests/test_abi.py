@@ -66,3 +66,16 @@ def test_host_helpers_match_oracle(oracle):
     # gimbal branch of matrix2angle (src/CommonFunc.cpp:388-399)
     G = np.eye(4, dtype=np.float32); G[:3, :3] = [[0, 0, 1], [0, 1, 0], [-1, 0, 0]]
     assert np.array_equal(P.matrix2angle(G), oracle.matrix2angle(G))
+
+
+def test_drivers_have_no_cpu_fallback():
+    """The reference-shaped drivers (host/Registration.cpp) reach the device for every hot-path and pre-processing step: the
+    host-only statements kept for device-less tools (PCpreprocessingHost / SORfilterHost, c_hooks.cpp) are never called
+    from them, and a missing CUDA device is fatal (pwicpHostContext), not a switch to CPU code."""
+    reg = open(os.path.join(ROOT, "piecewise-icp_b200", "host", "Registration.cpp")).read()
+    assert "PCpreprocessingHost" not in reg and "SORfilterHost" not in reg
+    assert "PCpreprocessing(" in reg and "pwicp_piecewise_icp" in reg
+    cf = open(os.path.join(ROOT, "piecewise-icp_b200", "host", "CommonFunc.cpp")).read()
+    i = cf.index("pwicp_ctx* pwicpHostContext()")
+    body = cf[i:i + 900]
+    assert "pwicp_ctx_create" in body and ("exit(EXIT_FAILURE)" in body or "std::exit" in body)

@@ -347,3 +347,26 @@ def test_preprocessing_restatement(oracle):
     from pwicp_b200 import host
     scan = synth.make_scan(extent=1.0, spacing=0.005, seed=4)
     assert np.array_equal(host.preprocess(scan, 0.005, 14, 5.0, device=False), oracle.preprocess(scan, 0.005, 14, 5.0))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/data/data_synthetic"), reason="needs the reference tree (absent on the GPU box)")
+def test_recorded_results_reproduced_on_more_shipped_pairs(oracle):
+    """scripts/refdata_oracle.py on three more of the reference's shipped pairs (epochs with 4, 6 and 6 outer iterations, all
+    three DT stages): host pre-processing mirror + the reference's own segmentation (oracle/_ref) + the oracle's outer loop
+    against results/4DPCReg/<e>_Direct2Ref_TransMatrix.txt, within the north-star tolerance.  (All 19 pairs:
+    profiles/r01i_refdata_oracle_cpu.txt -- 16 within 1e-6, the rest input-side)"""
+    import sys
+    if not os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libref_supervoxel.so")):
+        pytest.skip("oracle/_ref/libref_supervoxel.so not built")
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    import refdata_oracle as R
+    from pwicp_b200 import host
+    scans = os.path.join(R.REF, "data/data_synthetic/syntheticPC_with_transformations")
+    e1 = host.load_pcd(os.path.join(scans, "Epoch_001.pcd"))
+    for e, n_outer in ((4, 4), (12, 6), (16, 6)):
+        T, res, d = R.register(e1, host.load_pcd(os.path.join(scans, "Epoch_%03d.pcd" % e)))
+        Tr, Vr = R.read_T(os.path.join(R.REF, "results/4DPCReg/%d_Direct2Ref_TransMatrix.txt" % e))
+        da, dt = R.pose_err(T, Tr)
+        assert da <= 1e-6 and dt <= 1e-6, (e, da, dt)
+        assert len(res["DTseries"]) - 1 == n_outer
+        assert np.allclose(np.sqrt(np.diag(res["VCM"])), np.sqrt(np.diag(Vr)), rtol=2e-3)
