@@ -299,6 +299,10 @@ def main():
                          "traffic": traffic, "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch": ALG_BYTES_PER_CORR * INNER_ITERS * n2,
                          "launch_ms": kern_avg_ms, "share_of_step": kern_avg_ms * args.steps / (1e3 * dev_s) if world == 1 else None,
+                         # what the kernel actually moves per correspondence (four 16-byte reads + one write; at 1M the
+                         # streams are L2-resident, so this is L2 traffic, see "traffic" for the DRAM share)
+                         "streamed": {"bytes_per_correspondence": 80,
+                                      "gbs": achieved * 80.0 / ALG_BYTES_PER_CORR, "frac_of_hbm_peak": achieved * 80.0 / ALG_BYTES_PER_CORR / peak},
                          "note": "achieved = 48 B/correspondence x 50 iterations x n_source / average duration of "
                                  "the icp_persistent_kernel launch (CUDA events around the launch on the library "
                                  "stream); the rest of a step is the grid build, the Morton sort of the source and "
