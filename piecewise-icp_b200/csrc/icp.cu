@@ -27,6 +27,14 @@
 #include "small_algebra.cuh"
 
 #ifndef PWICP_STATIC_EIGHTHS
+// candidate cache: radius beyond the NN distance (in level-0 cells) and the largest last step (as a fraction of it) at
+// which a cache is built
+#ifndef PWICP_SLACK_CELLS
+#define PWICP_SLACK_CELLS 0.03f
+#endif
+#ifndef PWICP_BUILD_FRAC
+#define PWICP_BUILD_FRAC 0.25f
+#endif
 #define PWICP_STATIC_EIGHTHS 6     // share of a warp's batches that is assigned statically once the loop is calm
 #endif
 #ifndef PWICP_ICP_MINBLOCKS
@@ -722,8 +730,8 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     a.cq0 = a.cn0 + n;
     a.cmore = reinterpret_cast<int4*>(a.cn0 + 2 * (size_t)n);
     a.seed_exact = 1;         // classification matches (outer.cu) or icp_seed_kernel
-    a.slack = 0.03f / ctx->tgt.dev.lv[0].inv_h;
-    a.build_step2 = (0.25f * a.slack) * (0.25f * a.slack);
+    a.slack = PWICP_SLACK_CELLS / ctx->tgt.dev.lv[0].inv_h;
+    a.build_step2 = (PWICP_BUILD_FRAC * a.slack) * (PWICP_BUILD_FRAC * a.slack);
 
     a.n = n;
     a.max_iter = prm.max_iter;
