@@ -14,7 +14,8 @@
  *   - the results its own build recorded for its shipped scans (results/4DPCReg, 12 decimals): behind
  *     the reference's own segmentation (oracle/_ref/libref_supervoxel.so, compiled from its
  *     codelibrary) this outer loop reproduces 16 of the 19 recorded 4x4 within 1e-6 rad / 1e-6 m
- *     (scripts/refdata_oracle.py; committed fixture tests/golden/refpair_e2.npz, tests/test_oracle.py);
+ *     (scripts/refdata_oracle.py; committed fixture tests/golden/refpair_e2.npz, tests/test_oracle.py), and 34 of the
+ *     46 distinct pairs of the three recorded pair modes (reference-epoch, fixed interval 3, adaptive);
  *     the other three differ on the input side (PCL VoxelGrid/SOR summation order);
  *   - the reference's own KD-tree (oracle/_ref/libref_kdtree.so): identical nearest neighbours up to
  *     rounding-level ties of the float metric;

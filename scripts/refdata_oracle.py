@@ -8,7 +8,12 @@ CPU only.  For every pair of the reference's shipped synthetic series (data/data
 with the shipped configuration (configuration_files/configuration_4d.txt) and compares the final 4x4 with
 results/4DPCReg/<epoch>_Direct2Ref_TransMatrix.txt and with the ground truth (defined_transformations.txt).
 
-    python scripts/refdata_oracle.py [first_epoch last_epoch] [--standin]
+    python scripts/refdata_oracle.py [first_epoch last_epoch] [--standin] [--mode direct|fixed|adaptive]
+
+--mode fixed: the recorded <e>_Fixed_TransMatrix.txt files (interval 3: epoch e against epoch e - 3, the reference epoch
+for e <= 4; the interval is not recorded, 3 is the one that reproduces the files).  --mode adaptive: the recorded
+<e>_Adaptive_TransMatrix.txt files with the pairs calAdaptivePairSequence selects for this series (overlap threshold 0.75,
+DTinit 0.05; RegPairFile.txt of the device run, gpurun_out/refdata_4d/Adaptive).
 
 Remaining differences to the recorded numbers come from the pre-processing in front of the segmentation, which is PCL in
 the reference (VoxelGrid / StatisticalOutlierRemoval; summation order inside a voxel is unspecified) and a host mirror here.
@@ -95,24 +100,37 @@ def pose_err(T, G):
 
 
 def main():
-    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    args = [a for a in sys.argv[1:] if a.isdigit()]
     first, last = (int(args[0]), int(args[1])) if len(args) == 2 else (2, 20)
     standin = "--standin" in sys.argv
     scans = os.path.join(REF, "data/data_synthetic/syntheticPC_with_transformations")
     gt = ground_truth(os.path.join(REF, "data/data_synthetic/defined_transformations.txt"))
-    e1 = host.load_pcd(os.path.join(scans, "Epoch_001.pcd"))
-    print("epoch | n1 n2 outer | vs recorded: rot[rad] transl[m] VCM rel | vs truth ours: rot transl | vs truth recorded: rot transl | s")
+    mode = sys.argv[sys.argv.index("--mode") + 1] if "--mode" in sys.argv else "direct"
+    tag = {"direct": "Direct2Ref", "fixed": "Fixed", "adaptive": "Adaptive"}[mode]
+    load = lambda k: host.load_pcd(os.path.join(scans, "Epoch_%03d.pcd" % k))
+    # 1-based target epoch of every source epoch
+    adaptive = {2: 1, 3: 1, 4: 1, 5: 1, 6: 1, 7: 3, 8: 4, 9: 4, 10: 5, 11: 6, 12: 6, 13: 7, 14: 9, 15: 12, 16: 13, 17: 14, 18: 14, 19: 14, 20: 14}
+    target_of = {"direct": lambda e: 1, "fixed": lambda e: max(1, e - 3), "adaptive": lambda e: adaptive[e]}[mode]
+    print("mode %s" % mode)
+    print("epoch target | n1 n2 outer | vs recorded: rot[rad] transl[m] VCM rel | vs truth ours: rot transl | vs truth recorded: rot transl | s")
+    n_ok = 0
     for e in range(first, last + 1):
         t0 = time.time()
-        T, res, d = register(e1, host.load_pcd(os.path.join(scans, "Epoch_%03d.pcd" % e)), not standin)
-        Tr, Vr = read_T(os.path.join(REF, "results/4DPCReg/%d_Direct2Ref_TransMatrix.txt" % e))
-        G = np.linalg.inv(gt[e])                                         # the files hold reference -> epoch
+        tgt = target_of(e)
+        T, res, d = register(load(tgt), load(e), not standin)
+        Tr, Vr = read_T(os.path.join(REF, "results/4DPCReg/%d_%s_TransMatrix.txt" % (e, tag)))
         a, b = pose_err(T, Tr)
-        g1, g2 = min((pose_err(T, X) for X in (gt[e], G)), key=lambda x: x[0])
-        r1, r2 = min((pose_err(Tr, X) for X in (gt[e], G)), key=lambda x: x[0])
+        n_ok += int(a <= 1e-6 and b <= 1e-6)
+        if tgt == 1:
+            G = np.linalg.inv(gt[e])                                     # the files hold reference -> epoch
+            g1, g2 = min((pose_err(T, X) for X in (gt[e], G)), key=lambda x: x[0])
+            r1, r2 = min((pose_err(Tr, X) for X in (gt[e], G)), key=lambda x: x[0])
+        else:
+            g1 = g2 = r1 = r2 = float("nan")                             # the truth is given against the reference epoch only
         vrel = np.abs(np.sqrt(np.diag(res["VCM"])) / np.sqrt(np.diag(Vr)) - 1).max()
-        print("%5d | %4d %4d %2d | %.2e %.2e %.1e | %.2e %.2e | %.2e %.2e | %.1f" %
-              (e, len(d["ct1"]), len(d["ct2"]), len(res["DTseries"]) - 1, a, b, vrel, g1, g2, r1, r2, time.time() - t0), flush=True)
+        print("%5d %6d | %4d %4d %2d | %.2e %.2e %.1e | %.2e %.2e | %.2e %.2e | %.1f" %
+              (e, tgt, len(d["ct1"]), len(d["ct2"]), len(res["DTseries"]) - 1, a, b, vrel, g1, g2, r1, r2, time.time() - t0), flush=True)
+    print("within 1e-6 rad / 1e-6 m of the recorded matrix: %d of %d" % (n_ok, last - first + 1))
 
 
 if __name__ == "__main__":
