@@ -164,7 +164,8 @@ knn_mean_dist_kernel(GridDev g, int k_runtime, float r0, float* __restrict__ out
 
 int knn_mean_dist_dev(Ctx* ctx, const GridDev& g, int k, float* out_dev) {
     if (k < 1 || k > 32 || g.n <= k) { set_error(ctx, "knn_mean_dist: need 1 <= k <= 32 and more than k points"); return PWICP_ERR_ARG; }
-    // first cube: a ball of about one cell and a half (on a sampled surface ~ cells_per_point^(-1/3) spacings per cell)
+    // first cube: one cell around the point in every direction (3 x 3 x 3 cells; on a sampled surface a cell holds ~10 points,
+    // so the 14 nearest usually lie inside; otherwise the second pass scans the cube of the k-th distance found)
     const float r0 = 1.0f;
     const int blocks = (g.n + 127) / 128;
     // K is a compile-time bound of the register-resident list; k <= K entries are summed
