@@ -235,6 +235,24 @@ void Piecewise_ICP(pcl::PointCloud<pcl::PointXYZ>::Ptr cloud1, pcl::PointCloud<p
              << stats[k].n_stable << " | inner iterations: " << stats[k].icp_iters << " | bbox change: " << stats[k].maxBBchange * 100
              << " cm | device " << stats[k].device_ms << " ms\n";
     g_toStage2 = g_toStage3 = true;
+    if (const char* tr = getenv("PWICP_TRACE_JSON")) {
+        // machine-readable trace (one JSON line per registered pair, appended): what the reference only prints
+        // (:691-693, :870-871, :888) plus the device time of every outer iteration
+        ofstream js(tr, std::ios::app);
+        if (js) {
+            js << std::setprecision(9) << "{\"n1\": " << num1 << ", \"n2\": " << num2 << ", \"outer_iterations\": " << n_outer << ", \"iterations\": [";
+            for (int k = 0; k < n_outer; ++k) {
+                const pwicp_iter_stats& st = stats[k];
+                js << (k ? ", " : "") << "{\"DT\": " << series[k] << ", \"DT_next\": " << series[k + 1] << ", \"n_stable\": " << st.n_stable
+                   << ", \"n_stable_points\": " << st.n_stable_pts << ", \"inner_iterations\": " << st.icp_iters
+                   << ", \"bbox_change_m\": " << st.maxBBchange << ", \"vcm_written\": " << st.vcm_written
+                   << ", \"device_ms\": " << st.device_ms << "}";
+            }
+            js << "], \"T\": [";
+            for (int k = 0; k < 16; ++k) js << (k ? ", " : "") << T16[k];
+            js << "]}\n";
+        }
+    }
     DTseries.assign(series.begin(), series.begin() + ns);                                           // :675-688
     memcpy(transMat.m, T16, sizeof(T16));
     VCM.resize(6, 6);

@@ -86,6 +86,25 @@ def test_pair_call_automatic_resolution_and_dtinit(series, tmp_path):
     assert (np.diag(V) > 0).all()
 
 
+def test_json_trace_of_the_outer_loop(series, tmp_path, monkeypatch):
+    """PWICP_TRACE_JSON: one JSON line per registered pair with what the reference only prints per outer iteration."""
+    import json
+    root, folder, gt = series
+    trace = tmp_path / "trace.jsonl"
+    monkeypatch.setenv("PWICP_TRACE_JSON", str(trace))
+    a = host.load_pcd(os.path.join(folder, "Epoch_001.pcd"))[::2]
+    b = host.load_pcd(os.path.join(folder, "Epoch_002.pcd"))[::2]
+    r = host.register_clouds(a, b, 0.01, 0.1, 0.05, 0.004, mode=0)
+    lines = [json.loads(l) for l in open(trace).read().splitlines()]
+    assert len(lines) == 1
+    t = lines[0]
+    assert t["outer_iterations"] == len(t["iterations"]) == len(r["DTseries"]) - 1
+    assert [np.float32(i["DT"]) for i in t["iterations"]] == list(r["DTseries"][:-1])
+    assert all(i["n_stable"] >= 4 and i["inner_iterations"] >= 1 and i["device_ms"] > 0 for i in t["iterations"])
+    assert t["iterations"][-1]["vcm_written"] == 1
+    assert np.allclose(np.array(t["T"], np.float32).reshape(4, 4), r["T"], atol=1e-7)
+
+
 def test_device_loop_equals_reference_shaped_loop(series):
     """Piecewise_ICP (device loop) == while(!stage3) PwICP_singleIteration (mirror function)."""
     root, folder, gt = series
