@@ -59,6 +59,15 @@ bool PiecewiseICP_4D_finalize(const char* confile, int startEpoch, int epochNum,
 typedef int (*pwicp_segmenter_fn)(const float* xyz, int n, float svResolution, int knn, int* labels);
 void pwicp_host_set_segmenter(pwicp_segmenter_fn fn);
 
+/* Result-file tools (no device needed).  pwicp_host_write_transmatrix: the per-pair file of src/Registration.cpp:340-388
+ * (TransMatrix.txt / <time>_<mode>_TransMatrix.txt) from a row-major 4x4 and a 6x6; returns 1 on success.
+ * pwicp_host_chain_to_reference: calTransToReferenceEpoch (:977-1153) file to file.  pwicp_host_abs_error:
+ * calAbsErrorOfTransPara (:1157-1251) file to file. */
+int  pwicp_host_write_transmatrix(const char* path, const float* T16, const double* vcm36);
+void pwicp_host_chain_to_reference(const char* transMatFile, int pairMode, const char* pairFile, int epochNum,
+                                   const char* outTM, const char* outTP);
+void pwicp_host_abs_error(const char* transMatFile, const char* gtFile, int allEpochNum, int startEpoch, const char* outFile);
+
 /* device used by the reference-shaped entry points (default: PWICP_DEVICE, LOCAL_RANK or 0) */
 void pwicp_host_set_device(int device);
 

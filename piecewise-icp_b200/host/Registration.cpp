@@ -152,6 +152,24 @@ void writeTransMatrixFile(ofstream& out, const Eigen::Matrix4f& T, const Eigen::
         << "Std_tz = " << 1000 * sqrt(VCM(5, 5)) << " mm\n";
 }
 
+}  // namespace
+
+// the per-pair result file (TransMatrix.txt / <time>_<mode>_TransMatrix.txt) from a 4x4 and a 6x6, for tools and tests
+extern "C" int pwicp_host_write_transmatrix(const char* path, const float* T16, const double* vcm36) {
+    Eigen::Matrix4f T; std::memcpy(T.m, T16, sizeof(T.m));
+    Eigen::MatrixXd V; V.resize(6, 6);
+    for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) V(r, c) = vcm36[r * 6 + c];
+    Eigen::Vector3f ang, tr;
+    matrix2angle(T, ang);
+    tr[0] = T(0, 3); tr[1] = T(1, 3); tr[2] = T(2, 3);
+    ofstream out(path);
+    if (!out) return 0;
+    writeTransMatrixFile(out, T, ang, tr, V);
+    return 1;
+}
+
+namespace {
+
 // shift by -centroid(cloud1_prep), run the core, conjugate back (src/Registration.cpp:276-319, :419-461)
 struct CoreResult { Eigen::Matrix4f T_final; Eigen::Vector3f ang, tr; Eigen::MatrixXd VCM; vector<float> DTseries; };
 

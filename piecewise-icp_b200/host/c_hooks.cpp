@@ -142,6 +142,11 @@ void pwicp_host_chain_to_reference(const char* transMatFile, int pairMode, const
     calTransToReferenceEpoch(transMatFile, pairMode, pairFile, epochNum, outTM, outTP, ts, T, V);
 }
 
+// calAbsErrorOfTransPara as a file-to-file operation (src/Registration.cpp:1157-1251)
+void pwicp_host_abs_error(const char* transMatFile, const char* gtFile, int allEpochNum, int startEpoch, const char* outFile) {
+    calAbsErrorOfTransPara(transMatFile, gtFile, allEpochNum, startEpoch, outFile);
+}
+
 }  // extern "C"
 
 // ---- the reference's outer loop written with the mirror's per-iteration function ---------------

@@ -184,6 +184,42 @@ def test_chain_to_reference_epoch(tmp_path):
     assert hdr.startswith("Epoch  Rx[gon]  Ry[gon]  Rz[gon]  tx[m]  ty[m]  tz[m]  Std_Rx[mgon]")
 
 
+def test_chain_and_error_report_reproduce_the_references_recorded_files(tmp_path):
+    """F2 and A10 against the reference's own recorded outputs (tests/golden/recorded_4d, copied from results/4DPCReg and
+    data/data_synthetic): from the recorded TransMatrices.txt (adaptive run) and the adaptive pair list,
+    calTransToReferenceEpoch (src/Registration.cpp:977-1153, adjoint covariance propagation :1072-1083) must write the
+    recorded TransMatrices_toRef.txt / TransParameters_toRef.txt, and calAbsErrorOfTransPara (:1157-1251, matrix2angle
+    src/CommonFunc.cpp:385-407) the recorded TransPara_AbsError.txt -- text for text."""
+    import ctypes as C
+    rec = os.path.join(ROOT, "tests", "golden", "recorded_4d")
+    norm = lambda path: open(path).read().replace("\r", "").rstrip("\n")
+    L = host.lib()
+    out_tm, out_tp = str(tmp_path / "TransMatrices_toRef.txt"), str(tmp_path / "TransParameters_toRef.txt")
+    L.pwicp_host_chain_to_reference(os.path.join(rec, "TransMatrices.txt").encode(), -1, os.path.join(rec, "RegPairFile.txt").encode(), 19,
+                                    out_tm.encode(), out_tp.encode())
+    assert norm(out_tm) == norm(os.path.join(rec, "TransMatrices_toRef.txt"))
+    assert norm(out_tp) == norm(os.path.join(rec, "TransParameters_toRef.txt"))
+    L.pwicp_host_abs_error.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_char_p]
+    L.pwicp_host_abs_error.restype = None
+    out_err = str(tmp_path / "TransPara_AbsError.txt")
+    L.pwicp_host_abs_error(os.path.join(rec, "TransMatrices_toRef.txt").encode(), os.path.join(rec, "defined_transformations.txt").encode(), 20, 0,
+                           out_err.encode())
+    assert norm(out_err) == norm(os.path.join(rec, "TransPara_AbsError.txt"))
+    # the per-pair result file: layout, 12 / 10 decimals, gon angles of matrix2angle -- line for line down to the VCM; the six
+    # standard deviations only to the 4 digits the printed VCM still carries
+    L.pwicp_host_write_transmatrix.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p]
+    for f in ("2_Direct2Ref_TransMatrix.txt", "12_Adaptive_TransMatrix.txt"):
+        want = norm(os.path.join(rec, f)).splitlines()
+        T = np.array([[float(v) for v in want[1 + r].split()] for r in range(4)], np.float32)
+        V = np.array([[float(v) for v in want[16 + r].split()] for r in range(6)])
+        assert L.pwicp_host_write_transmatrix(str(tmp_path / f).encode(), T.ctypes.data, V.ctypes.data)
+        got = norm(str(tmp_path / f)).splitlines()
+        assert len(got) == len(want) == 30 and got[:24] == want[:24]
+        for a, b in zip(got[24:], want[24:]):
+            assert a.split()[:2] == b.split()[:2] and a.split()[-1] == b.split()[-1]
+            assert abs(float(a.split()[2]) / float(b.split()[2]) - 1) < 2e-3
+
+
 _GLOO_WORKER = r'''
 import os, sys
 sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "piecewise-icp_b200", "python"))
