@@ -329,7 +329,11 @@ void accumulate28(const float* u7, const float* d2, const unsigned char* valid, 
      * two such levels (or once at most fan-in entries remain) the entries are summed in order into
      * the grand total. */
     const long nb = ((long)n + 31) / 32;
-    const int fan = group_batches > 1 ? group_batches : 32;   /* a fan-in below 2 is meaningless */
+    /* group_batches: low 16 bits = fan-in of every level; bits 16..30 (optional) = a different fan-in for the first level
+     * (batches -> groups), for kernels that sum a short run of consecutive batches in registers before the hierarchy */
+    const int fan_hi = group_batches & 0xffff, fan_lo = (group_batches >> 16) & 0x7fff;
+    const int fan = fan_hi > 1 ? fan_hi : 32;                 /* a fan-in below 2 is meaningless */
+    const int fan0 = fan_lo > 1 ? fan_lo : fan;
     std::vector<double> cur((size_t)nb * 28, 0.0);
     for (long b = 0; b < nb; ++b) {
         double* acc = &cur[(size_t)b * 28];
@@ -343,14 +347,15 @@ void accumulate28(const float* u7, const float* d2, const unsigned char* valid, 
         }
     }
     long count = nb;
-    for (int level = 1; level < 3 && count > fan; ++level) {
-        const long np = (count + fan - 1) / fan;
+    for (int level = 1; level < 3 && count > (level == 1 ? fan0 : fan); ++level) {
+        const long f = (level == 1) ? fan0 : fan;
+        const long np = (count + f - 1) / f;
         std::vector<double> nxt((size_t)np * 28, 0.0);
         for (long g = 0; g < np; ++g) {
-            const long size = std::min((long)fan, count - g * fan);
+            const long size = std::min(f, count - g * f);
             for (int v = 0; v < 28; ++v) {
                 double s = 0.0;
-                for (long k = 0; k < size; ++k) s += cur[(size_t)(g * fan + k) * 28 + v];
+                for (long k = 0; k < size; ++k) s += cur[(size_t)(g * f + k) * 28 + v];
                 nxt[(size_t)g * 28 + v] = s;
             }
         }

@@ -370,3 +370,18 @@ def test_recorded_results_reproduced_on_more_shipped_pairs(oracle):
         assert da <= 1e-6 and dt <= 1e-6, (e, da, dt)
         assert len(res["DTseries"]) - 1 == n_outer
         assert np.allclose(np.sqrt(np.diag(res["VCM"])), np.sqrt(np.diag(Vr)), rtol=2e-3)
+
+
+def test_device_order_sums_with_a_separate_first_level_fan_in(oracle):
+    """reduce_mode = 1 (the kernel's hierarchical summation order): group_batches may carry a different fan-in for the first
+    level in bits 16.. (one-barrier reduction); absent or equal it is the uniform hierarchy."""
+    d = synth.make_pair(40000, seed=3)
+    idx, _ = oracle.nn(d["ct1"], d["ct2"])
+    args = (d["ct2"], idx, d["ct1"], d["nrm1"])
+    base = oracle.lls_step(*args, reduce_mode=1, group_batches=32)
+    assert np.array_equal(base[0], oracle.lls_step(*args, reduce_mode=1, group_batches=32 | (32 << 16))[0])
+    two = oracle.lls_step(*args, reduce_mode=1, group_batches=32 | (8 << 16))
+    seq = oracle.lls_step(*args, reduce_mode=0)
+    assert not np.array_equal(two[0], base[0])                       # another order ...
+    assert np.allclose(two[0], seq[0], rtol=1e-12) and np.allclose(two[1], seq[1], rtol=1e-10, atol=1e-18)   # ... of the same sums
+    assert np.abs(two[3] - seq[3]).max() <= 1e-7
