@@ -260,6 +260,30 @@ def preprocess(xyz, leaf, k=14, std_mult=5.0):
     return sor_select(v, knn_mean_dist(v, k), std_mult)[0]
 
 
+def knn_normals(xyz, k=45):
+    """k nearest neighbours (self first) + PCA normal of every point, as the reference's segmentation front end computes them."""
+    p = _f32(xyz)
+    nb = np.zeros((len(p), k), np.int32)
+    nrm = np.zeros((len(p), 3), np.float64)
+    L = lib()
+    L.orc_knn_normals.argtypes = [f32p, C.c_int, C.c_int, i32p, f64p]
+    if L.orc_knn_normals(p, len(p), k, nb.reshape(-1), nrm.reshape(-1)) != 0:
+        raise ValueError("knn_normals: need 1 <= k <= n")
+    return nb, nrm
+
+
+def ref_knn_normals(xyz, k=45):
+    """the same through the reference's own code (oracle/_ref/libref_supervoxel.so)"""
+    p = _f32(xyz)
+    nb = np.zeros((len(p), k), np.int32)
+    nrm = np.zeros((len(p), 3), np.float64)
+    L = C.CDLL(os.path.join(_HERE, "_ref", "libref_supervoxel.so"))
+    L.ref_knn_normals.argtypes = [f32p, C.c_int, C.c_int, i32p, f64p]
+    if L.ref_knn_normals(p, len(p), k, nb.reshape(-1), nrm.reshape(-1)) != 0:
+        raise ValueError("ref_knn_normals: need n > k")
+    return nb, nrm
+
+
 def matrix2angle(T):
     a = np.zeros(3, np.float32)
     lib().orc_matrix2angle(_f32(T).reshape(16), a)

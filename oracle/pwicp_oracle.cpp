@@ -197,6 +197,55 @@ struct KdTree {
         }
     }
 
+    /* k nearest neighbours WITH indices in the metric of the reference's codelibrary (F4 segmentation front end,
+     * codelibrary/util/metric/squared_euclidean.h:33-36): t += double(a - b) * (a - b) over x, y, z on double coordinates
+     * (float inputs widened).  bd / bi ascending; equal distances keep the lower original index first. */
+    static double l2_double(const float* a, const float* b) {
+        double t = 0.0;
+        for (int c = 0; c < 3; ++c) { const double d = (double)a[c] - (double)b[c]; t += d * d; }
+        return t;
+    }
+    void search_kd(int ni, const float* q, double mindist, double* dists, int k, double* bd, int* bi) const {
+        const Node& nd = nodes[ni];
+        if (nd.dim < 0) {
+            for (int i = nd.lo; i < nd.hi; ++i) {
+                const double d = l2_double(q, &pts[3 * (size_t)i]);
+                const int id = ids[i];
+                if (d < bd[k - 1] || (d == bd[k - 1] && id < bi[k - 1])) {
+                    int j = k - 1;
+                    while (j > 0 && (bd[j - 1] > d || (bd[j - 1] == d && bi[j - 1] > id))) { bd[j] = bd[j - 1]; bi[j] = bi[j - 1]; --j; }
+                    bd[j] = d; bi[j] = id;
+                }
+            }
+            return;
+        }
+        int dim = nd.dim;
+        double val = q[dim];
+        double diff1 = val - (double)nd.divlow, diff2 = val - (double)nd.divhigh;
+        int nearc, farc; double cut;
+        if (diff1 + diff2 < 0) { nearc = nd.left; farc = nd.right; cut = diff2 * diff2; }
+        else                   { nearc = nd.right; farc = nd.left; cut = diff1 * diff1; }
+        search_kd(nearc, q, mindist, dists, k, bd, bi);
+        double dsave = dists[dim];
+        double md = mindist + cut - dsave;
+        if (md * 0.999999 <= bd[k - 1]) {
+            dists[dim] = cut;
+            search_kd(farc, q, md, dists, k, bd, bi);
+            dists[dim] = dsave;
+        }
+    }
+    void query_kd(const float* q, int k, double* bd, int* bi) const {
+        for (int j = 0; j < k; ++j) { bd[j] = std::numeric_limits<double>::infinity(); bi[j] = INT32_MAX; }
+        if (n <= 0) return;
+        double dists[3] = {0, 0, 0}, md = 0;
+        for (int c = 0; c < 3; ++c) {
+            if (q[c] < bbmin[c]) { double d = (double)q[c] - bbmin[c]; dists[c] = d * d; }
+            if (q[c] > bbmax[c]) { double d = (double)q[c] - bbmax[c]; dists[c] = d * d; }
+            md += dists[c];
+        }
+        search_kd(0, q, md, dists, k, bd, bi);
+    }
+
     void query_k(const float* q, int skip, int k, float* best) const {
         for (int j = 0; j < k; ++j) best[j] = std::numeric_limits<float>::infinity();
         if (n <= 0) return;
@@ -1143,6 +1192,61 @@ int orc_sor_select(const float* xyz, int n, const float* mean_dist, double std_m
     for (int i = 0; i < n; ++i)
         if (mean_dist[i] <= thr) { std::memcpy(out + 3 * (size_t)m, xyz + 3 * (size_t)i, 12); ++m; }
     return m;
+}
+
+/* F4, segmentation front end (src/Segmentation.cpp:28-46): for every point its k nearest neighbours (itself included, ascending
+ * distance in the codelibrary's double metric, ties by index) and the normal of
+ * cl::geometry::point_cloud::PCAEstimateNormal over them (codelibrary/geometry/point_cloud/pca_estimate_normals.h:47-117,
+ * unit weights): centroid and covariance sums in neighbour order, smallest eigenvalue in closed form
+ * (trigonometric solution of the characteristic cubic), eigenvector from the cross product of two rows, normalised;
+ * (0,0,1) when degenerate.  The orientation of the normal is not defined (the reference says so).
+ * neighbors: n x k, normals: n x 3 doubles. */
+int orc_knn_normals(const float* xyz, int n, int k, int* neighbors, double* normals) {
+    if (k < 1 || k > 256 || n < k) return -1;
+    KdTree tree;
+    tree.build(xyz, n);
+    std::vector<double> bd((size_t)k);
+    std::vector<int> bi((size_t)k);
+    for (int i = 0; i < n; ++i) {
+        tree.query_kd(xyz + 3 * (size_t)i, k, bd.data(), bi.data());
+        for (int j = 0; j < k; ++j) neighbors[(size_t)i * k + j] = bi[j];
+        double cx = 0, cy = 0, cz = 0, sum = 0;                               /* Centroid3D, center_3d.h:82-108 */
+        for (int j = 0; j < k; ++j) {
+            const float* p = xyz + 3 * (size_t)bi[j];
+            const double w = 1.0;
+            cx += w * p[0]; cy += w * p[1]; cz += w * p[2]; sum += w;
+        }
+        sum = 1.0 / sum; cx *= sum; cy *= sum; cz *= sum;
+        double a00 = 0, a01 = 0, a02 = 0, a11 = 0, a12 = 0, a22 = 0, wsum = 0;
+        for (int j = 0; j < k; ++j) {
+            const float* p = xyz + 3 * (size_t)bi[j];
+            const double x = p[0] - cx, y = p[1] - cy, z = p[2] - cz, w = 1.0;
+            a00 += w * x * x; a01 += w * x * y; a02 += w * x * z; a11 += w * y * y; a12 += w * y * z; a22 += w * z * z;
+            wsum += w;
+        }
+        const double t = 1.0 / wsum;
+        a00 *= t; a01 *= t; a02 *= t; a11 *= t; a12 *= t; a22 *= t;
+        const double q = (a00 + a11 + a22) / 3.0;
+        double pq = (a00 - q) * (a00 - q) + (a11 - q) * (a11 - q) + (a22 - q) * (a22 - q) + 2.0 * (a01 * a01 + a02 * a02 + a12 * a12);
+        pq = std::sqrt(pq / 6.0);
+        const double mpq = std::pow(1.0 / pq, 3.0);
+        const double det_b = mpq * ((a00 - q) * ((a11 - q) * (a22 - q) - a12 * a12) - a01 * (a01 * (a22 - q) - a12 * a02) +
+                                    a02 * (a01 * a12 - (a11 - q) * a02));
+        const double r = 0.5 * det_b;
+        double phi = 0.0;
+        if (r <= -1.0) phi = M_PI / 3.0;
+        else if (r >= 1.0) phi = 0.0;
+        else phi = std::acos(r) / 3.0;
+        const double eig = q + 2.0 * pq * std::cos(phi + M_PI * (2.0 / 3.0));
+        double nx = a01 * a12 - a02 * (a11 - eig);
+        double ny = a01 * a02 - a12 * (a00 - eig);
+        double nz = (a00 - eig) * (a11 - eig) - a01 * a01;
+        const double norm = std::sqrt(nx * nx + ny * ny + nz * nz);
+        if (norm == 0.0) { nx = 0.0; ny = 0.0; nz = 1.0; }
+        else { const double s = 1.0 / norm; nx *= s; ny *= s; nz *= s; }
+        normals[3 * (size_t)i] = nx; normals[3 * (size_t)i + 1] = ny; normals[3 * (size_t)i + 2] = nz;
+    }
+    return 0;
 }
 
 }  // extern "C"

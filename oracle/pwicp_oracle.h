@@ -104,6 +104,10 @@ int orc_voxel_grid(const float* xyz, int n, float leaf, float* out);
 int orc_knn_mean_dist(const float* xyz, int n, int k, float* mean_dist);
 int orc_sor_select(const float* xyz, int n, const float* mean_dist, double std_mult, float* out, double* threshold);
 
+/* segmentation front end (src/Segmentation.cpp:28-46): k nearest neighbours (self first, codelibrary double metric) and
+ * cl::geometry::point_cloud::PCAEstimateNormal over them.  neighbors n x k, normals n x 3 doubles (orientation undefined). */
+int orc_knn_normals(const float* xyz, int n, int k, int* neighbors, double* normals);
+
 /* ---- A10: matrix2angle (src/CommonFunc.cpp:385-407) */
 void orc_matrix2angle(const float* T16, float* ang3);
 

@@ -79,3 +79,24 @@ extern "C" int ref_supervoxel_labels(const float* xyz, int n, float sv_resolutio
     for (int i = 0; i < numPoints; ++i) labels[i] = lin_labels[i];
     return lin_supervoxels.size();
 }
+
+// The first half of src/Segmentation.cpp:17-66 alone (statements :28-46): the k nearest neighbours of every point (the point
+// itself first) and the PCA normal over them, as the reference computes them.  neighbors: n x knn indices; normals: n x 3 doubles.
+extern "C" int ref_knn_normals(const float* xyz, int n, int knn, int32_t* neighbors_out, double* normals_out) {
+    if (n <= knn || knn <= 0) return -1;
+    cl::Array<cl::RPoint3D> points;
+    for (int i = 0; i < n; ++i) points.emplace_back(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+    cl::KDTree<cl::RPoint3D> kdtree;
+    kdtree.SwapPoints(&points);
+    cl::Array<int> nb;
+    cl::Array<cl::RPoint3D> neighbor_points(knn);
+    for (int i = 0; i < n; ++i) {
+        kdtree.FindKNearestNeighbors(kdtree.points()[i], knn, &nb);
+        for (int k = 0; k < knn; ++k) { neighbor_points[k] = kdtree.points()[nb[k]]; neighbors_out[(size_t)i * knn + k] = nb[k]; }
+        cl::RVector3D nrm;
+        cl::geometry::point_cloud::PCAEstimateNormal(neighbor_points.begin(), neighbor_points.end(), &nrm);
+        normals_out[3 * (size_t)i] = nrm.x; normals_out[3 * (size_t)i + 1] = nrm.y; normals_out[3 * (size_t)i + 2] = nrm.z;
+    }
+    return 0;
+}
+

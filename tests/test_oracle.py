@@ -385,3 +385,22 @@ def test_device_order_sums_with_a_separate_first_level_fan_in(oracle):
     assert not np.array_equal(two[0], base[0])                       # another order ...
     assert np.allclose(two[0], seq[0], rtol=1e-12) and np.allclose(two[1], seq[1], rtol=1e-10, atol=1e-18)   # ... of the same sums
     assert np.abs(two[3] - seq[3]).max() <= 1e-7
+
+
+def test_knn_normals_restatement_matches_the_references_code(oracle):
+    """Groundwork for the next F4 kernel (kNN-45 PCA normals, src/Segmentation.cpp:28-46): the oracle's restatement against the
+    reference's own codelibrary (oracle/_ref) on the reference pair's target cloud -- identical neighbour lists, bit-identical
+    normals (the closed-form smallest eigenvector of pca_estimate_normals.h)."""
+    if not oracle.ref_available() or not os.path.exists(os.path.join(os.path.dirname(oracle.REF_KDTREE), "libref_supervoxel.so")):
+        pytest.skip("oracle/_ref not built")
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "refpair_e2.npz"))
+    c = z["cloud1"][:40000]
+    nb, nr = oracle.knn_normals(c, 45)
+    rnb, rnr = oracle.ref_knn_normals(c, 45)
+    assert (nb[:, 0] == np.arange(len(c))).all()                       # the point itself first
+    same = (nb == rnb).all(axis=1)
+    assert same.mean() > 0.999                                         # exact ties may be visited in another order ...
+    for a, b in zip(nb[~same], rnb[~same]):
+        assert set(a) == set(b)                                        # ... but the set is the same
+    assert np.array_equal(nr[same], rnr[same])
+    assert np.allclose(np.linalg.norm(nr, axis=1), 1.0, atol=1e-12)
