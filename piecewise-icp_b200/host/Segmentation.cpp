@@ -165,6 +165,10 @@ int PatchGenerationAndRefinement(pcl::PointCloud<pcl::PointXYZ>::Ptr cloud, floa
                                  pcl::PointCloud<pcl::PointXYZ>*& cloudPatches, bool /*isVis*/) {
     cloudCentroid->clear(); cloudBoundary->clear();
     const int n = (int)cloud->size();
+    if (!g_segmenter) {
+        const char* e = getenv("PWICP_SEGMENTER");
+        if (e && std::string(e) == "supervoxel") g_segmenter = &pwicp_host_builtin_supervoxels;
+    }
     if (g_segmenter) return patchesFromSegmenter(cloud, svResolution, cloudCentroid, cloudBoundary, cloudPatches);
     // stand-in segmentation: sort points by cubic cell of side svResolution
     float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX};
