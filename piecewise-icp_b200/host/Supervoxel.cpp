@@ -25,6 +25,7 @@
 #include <cmath>
 #include <cstdint>
 #include <queue>
+#include <thread>
 #include <unordered_set>
 #include <vector>
 
@@ -174,12 +175,21 @@ extern "C" int pwicp_host_builtin_supervoxels(const float* xyz, int n, float svR
     vector<int> nbr((size_t)n * knn);
     vector<P3> nrm(n);
     {
-        vector<double> bd(knn); vector<int> bi(knn);
-        for (int i = 0; i < n; ++i) {
-            knnOf(p, g, i, knn, bd, bi);
-            std::copy(bi.begin(), bi.end(), nbr.begin() + (size_t)i * knn);
-            nrm[i] = pcaNormal(p, &nbr[(size_t)i * knn], knn);
-        }
+        // every point is independent: host threads (the fusion below is sequential by nature)
+        const int nt = (int)std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+        auto work = [&](int t) {
+            vector<double> bd(knn); vector<int> bi(knn);
+            const int lo = (int)((long long)n * t / nt), hi = (int)((long long)n * (t + 1) / nt);     // contiguous: scan order is local
+            for (int i = lo; i < hi; ++i) {
+                knnOf(p, g, i, knn, bd, bi);
+                std::copy(bi.begin(), bi.end(), nbr.begin() + (size_t)i * knn);
+                nrm[i] = pcaNormal(p, &nbr[(size_t)i * knn], knn);
+            }
+        };
+        vector<std::thread> pool;
+        for (int t = 1; t < nt; ++t) pool.emplace_back(work, t);
+        work(0);
+        for (auto& th : pool) th.join();
     }
     auto metric = [&](int a, int b) {
         const double dot = nrm[a].x * nrm[b].x + nrm[a].y * nrm[b].y + nrm[a].z * nrm[b].z;
