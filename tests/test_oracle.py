@@ -351,8 +351,8 @@ def test_preprocessing_restatement(oracle):
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/data/data_synthetic"), reason="needs the reference tree (absent on the GPU box)")
 def test_recorded_results_reproduced_on_more_shipped_pairs(oracle):
-    """scripts/refdata_oracle.py on three more of the reference's shipped pairs (epochs with 4, 6 and 6 outer iterations, all
-    three DT stages): host pre-processing mirror + the reference's own segmentation (oracle/_ref) + the oracle's outer loop
+    """scripts/refdata_oracle.py on more of the reference's shipped pairs, all three recorded pair modes (epochs with 4 to 6 outer
+    iterations, all three DT stages): host pre-processing mirror + the reference's own segmentation (oracle/_ref) + the oracle's outer loop
     against results/4DPCReg/<e>_Direct2Ref_TransMatrix.txt, within the north-star tolerance.  (All 19 pairs:
     profiles/r01i_refdata_oracle_cpu.txt -- 16 within 1e-6, the rest input-side)"""
     import sys
@@ -362,14 +362,21 @@ def test_recorded_results_reproduced_on_more_shipped_pairs(oracle):
     import refdata_oracle as R
     from pwicp_b200 import host
     scans = os.path.join(R.REF, "data/data_synthetic/syntheticPC_with_transformations")
-    e1 = host.load_pcd(os.path.join(scans, "Epoch_001.pcd"))
-    for e, n_outer in ((4, 4), (12, 6), (16, 6)):
-        T, res, d = R.register(e1, host.load_pcd(os.path.join(scans, "Epoch_%03d.pcd" % e)))
-        Tr, Vr = R.read_T(os.path.join(R.REF, "results/4DPCReg/%d_Direct2Ref_TransMatrix.txt" % e))
+    load = lambda k: host.load_pcd(os.path.join(scans, "Epoch_%03d.pcd" % k))
+    # (source epoch, target epoch, recorded family, outer iterations): reference-epoch mode, fixed interval 3, adaptive
+    for e, tgt, tag, n_outer in ((4, 1, "Direct2Ref", 4), (12, 1, "Direct2Ref", 6), (16, 1, "Direct2Ref", 6),
+                                 (12, 9, "Fixed", 6), (14, 9, "Adaptive", 5)):
+        T, res, d = R.register(load(tgt), load(e))
+        Tr, Vr = R.read_T(os.path.join(R.REF, "results/4DPCReg/%d_%s_TransMatrix.txt" % (e, tag)))
         da, dt = R.pose_err(T, Tr)
-        assert da <= 1e-6 and dt <= 1e-6, (e, da, dt)
+        assert da <= 1e-6 and dt <= 1e-6, (e, tag, da, dt)
         assert len(res["DTseries"]) - 1 == n_outer
         assert np.allclose(np.sqrt(np.diag(res["VCM"])), np.sqrt(np.diag(Vr)), rtol=2e-3)
+    # the library's own supervoxels (host/Supervoxel.cpp) instead of the reference's code: same result
+    T, res, d = R.register(load(1), load(12), "builtin")
+    Tr, _ = R.read_T(os.path.join(R.REF, "results/4DPCReg/12_Direct2Ref_TransMatrix.txt"))
+    da, dt = R.pose_err(T, Tr)
+    assert da <= 1e-6 and dt <= 1e-6, ("builtin", da, dt)
 
 
 def test_device_order_sums_with_a_separate_first_level_fan_in(oracle):
