@@ -222,13 +222,15 @@ def patch_stats(pts, off):
     return {"ct": ct, "bp": bp, "nrm": nrm, "nrm_ok": ok, "bpstd": bs, "ctstd": cs}
 
 
-def voxel_grid(xyz, leaf):
-    """pcl::VoxelGrid with a cubic leaf (F4)."""
+def voxel_grid(xyz, leaf, msvc_order=False):
+    """pcl::VoxelGrid with a cubic leaf (F4).  msvc_order: points of a voxel summed in the order the Microsoft STL's
+    std::sort leaves them (the reference's Windows build) instead of the input order."""
     p = _f32(xyz)
     out = np.zeros_like(p)
     L = lib()
-    L.orc_voxel_grid.argtypes = [f32p, C.c_int, C.c_float, f32p]
-    m = L.orc_voxel_grid(p, len(p), leaf, out)
+    fn = L.orc_voxel_grid_msvc if msvc_order else L.orc_voxel_grid
+    fn.argtypes = [f32p, C.c_int, C.c_float, f32p]
+    m = fn(p, len(p), leaf, out)
     return out[:m].copy()
 
 
@@ -254,9 +256,9 @@ def sor_select(xyz, mean_dist, std_mult):
     return out[:m].copy(), thr.value
 
 
-def preprocess(xyz, leaf, k=14, std_mult=5.0):
+def preprocess(xyz, leaf, k=14, std_mult=5.0, msvc_order=False):
     """PCpreprocessing(cloud, out, true, leaf, k, std_mult) (src/CommonFunc.cpp:423-439)."""
-    v = voxel_grid(xyz, leaf)
+    v = voxel_grid(xyz, leaf, msvc_order)
     return sor_select(v, knn_mean_dist(v, k), std_mult)[0]
 
 

@@ -9,6 +9,7 @@
  * All "[PCL]" comments restate PCL 1.8.1 / FLANN / Eigen behaviour from the published sources
  * (not present in this container); each is tied to the reference call site that triggers it.
  */
+#include "msvc_sort.h"
 #include "pwicp_oracle.h"
 
 #include <algorithm>
@@ -1124,7 +1125,12 @@ int orc_piecewise_icp(orc_pair* pr, int isManualDTinit, float DTinit, const orc_
  * points.  The order of the points INSIDE a voxel follows std::sort in PCL (unspecified); here it is the
  * input order (what a stable sort gives), which fixes the float summation order.  Returns the number of
  * output points (out has room for n). */
-int orc_voxel_grid(const float* xyz, int n, float leaf, float* out) {
+static int voxel_grid_impl(const float* xyz, int n, float leaf, float* out, int msvc_order);
+int orc_voxel_grid(const float* xyz, int n, float leaf, float* out) { return voxel_grid_impl(xyz, n, leaf, out, 0); }
+/* the same with the points of a voxel in the order the Microsoft STL's std::sort leaves them (msvc_sort.h): what the
+ * reference's Windows build, which recorded results/4DPCReg, computed */
+int orc_voxel_grid_msvc(const float* xyz, int n, float leaf, float* out) { return voxel_grid_impl(xyz, n, leaf, out, 1); }
+static int voxel_grid_impl(const float* xyz, int n, float leaf, float* out, int msvc_order) {
     if (n <= 0) return 0;
     float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     for (int i = 0; i < n; ++i)
@@ -1143,8 +1149,9 @@ int orc_voxel_grid(const float* xyz, int n, float leaf, float* out) {
         const long long iz = (long long)std::floor(p[2] * inv) - minb[2];
         keyed[i] = {ix + iy * div[0] + iz * div[0] * div[1], i};
     }
-    std::stable_sort(keyed.begin(), keyed.end(),
-                     [](const std::pair<long long, int>& a, const std::pair<long long, int>& b) { return a.first < b.first; });
+    auto by_key = [](const std::pair<long long, int>& a, const std::pair<long long, int>& b) { return a.first < b.first; };
+    if (msvc_order) msvc::sort(keyed.begin(), keyed.end(), by_key);
+    else std::stable_sort(keyed.begin(), keyed.end(), by_key);
     int m = 0;
     size_t i = 0;
     while (i < keyed.size()) {

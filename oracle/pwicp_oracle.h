@@ -13,7 +13,8 @@
  * PCL 1.8.1 algorithms those statements call.  It is pinned by what the reference does hold:
  *   - the results its own build recorded for its shipped scans (results/4DPCReg, 12 decimals): behind
  *     the reference's own segmentation (oracle/_ref/libref_supervoxel.so, compiled from its
- *     codelibrary) this outer loop reproduces 16 of the 19 recorded 4x4 within 1e-6 rad / 1e-6 m
+ *     codelibrary) this outer loop reproduces 16 of the 19 recorded 4x4 within 1e-6 rad / 1e-6 m -- all 19 when
+ *     pcl::VoxelGrid's within-voxel order is the Microsoft STL's (msvc_sort.h; the files come from a Windows build) --
  *     (scripts/refdata_oracle.py; committed fixture tests/golden/refpair_e2.npz, tests/test_oracle.py), and 34 of the
  *     46 distinct pairs of the three recorded pair modes (reference-epoch, fixed interval 3, adaptive);
  *     the other three differ on the input side (PCL VoxelGrid/SOR summation order);
@@ -101,6 +102,7 @@ void orc_patch_stats(const float* pts, const int* off, int np, float* ct, float*
 /* ---- F4: PCpreprocessing (src/CommonFunc.cpp:423-452): pcl::VoxelGrid (cubic leaf) and the two passes of
  * pcl::StatisticalOutlierRemoval (mean distance to the k nearest other points; mean + mult * stddev selection). */
 int orc_voxel_grid(const float* xyz, int n, float leaf, float* out);
+int orc_voxel_grid_msvc(const float* xyz, int n, float leaf, float* out);   /* within-voxel order of the Microsoft STL's std::sort */
 int orc_knn_mean_dist(const float* xyz, int n, int k, float* mean_dist);
 int orc_sor_select(const float* xyz, int n, const float* mean_dist, double std_mult, float* out, double* threshold);
 

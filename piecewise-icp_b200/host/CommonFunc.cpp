@@ -1,6 +1,7 @@
 // CommonFunc.cpp -- host mirror of the reference's src/CommonFunc.cpp on top of libpwicp.so.
 // Same function names, argument meaning and error behaviour; see CommonFunc.h.
 #include "CommonFunc.h"
+#include "msvc_sort.h"
 
 #include <dirent.h>
 #include <sys/stat.h>
@@ -371,7 +372,12 @@ static void voxelGrid(const pcl::PointCloud<pcl::PointXYZ>& in, float leaf, pcl:
         const long long ix = (long long)floor(p.x * inv) - minb[0], iy = (long long)floor(p.y * inv) - minb[1], iz = (long long)floor(p.z * inv) - minb[2];
         keyed[i] = {ix + iy * div[0] + iz * div[0] * div[1], (int)i};
     }
-    sort(keyed.begin(), keyed.end());
+    // order of the points inside a voxel = order of the float sums: input order (what a stable sort gives, and what the
+    // device path does), or -- PWICP_VOXEL_ORDER=msvc -- the order the reference's Windows build produced (msvc_sort.h)
+    const char* vo = getenv("PWICP_VOXEL_ORDER");
+    if (vo && string(vo) == "msvc")
+        msvc::sort(keyed.begin(), keyed.end(), [](const pair<long long, int>& a, const pair<long long, int>& b) { return a.first < b.first; });
+    else sort(keyed.begin(), keyed.end());
     size_t i = 0;
     while (i < keyed.size()) {
         size_t j = i;

@@ -10,7 +10,9 @@ results/4DPCReg/<epoch>_Direct2Ref_TransMatrix.txt and with the ground truth (de
 
     python scripts/refdata_oracle.py [first_epoch last_epoch] [--standin | --builtin] [--mode direct|fixed|adaptive]
 
---standin: the library's cubic-cell stand-in; --builtin: the library's own supervoxels (host/Supervoxel.cpp, same labels as
+--msvc-order: pcl::VoxelGrid sums the points of a voxel in the order its (unstable) std::sort leaves them; the recorded results
+come from the reference's Windows build, i.e. the Microsoft STL's order (host/msvc_sort.h) -- with it every recorded pair is
+reproduced.  --standin: the library's cubic-cell stand-in; --builtin: the library's own supervoxels (host/Supervoxel.cpp, same labels as
 the reference's code) instead of oracle/_ref.
 
 --mode fixed: the recorded <e>_Fixed_TransMatrix.txt files (interval 3: epoch e against epoch e - 3, the reference epoch
@@ -112,6 +114,9 @@ def main():
     scans = os.path.join(REF, "data/data_synthetic/syntheticPC_with_transformations")
     gt = ground_truth(os.path.join(REF, "data/data_synthetic/defined_transformations.txt"))
     mode = sys.argv[sys.argv.index("--mode") + 1] if "--mode" in sys.argv else "direct"
+    if "--msvc-order" in sys.argv:
+        os.environ["PWICP_VOXEL_ORDER"] = "msvc"     # host/msvc_sort.h: the within-voxel summation order of the reference's Windows build
+        print("VoxelGrid: points of a voxel in the order of the Microsoft STL's std::sort")
     tag = {"direct": "Direct2Ref", "fixed": "Fixed", "adaptive": "Adaptive"}[mode]
     load = lambda k: host.load_pcd(os.path.join(scans, "Epoch_%03d.pcd" % k))
     # 1-based target epoch of every source epoch

@@ -347,6 +347,16 @@ def test_preprocessing_restatement(oracle):
     from pwicp_b200 import host
     scan = synth.make_scan(extent=1.0, spacing=0.005, seed=4)
     assert np.array_equal(host.preprocess(scan, 0.005, 14, 5.0, device=False), oracle.preprocess(scan, 0.005, 14, 5.0))
+    # within-voxel order of the Microsoft STL's std::sort (the reference's Windows build): same voxels, same points up to the
+    # last bit of some centroids; host statements (PWICP_VOXEL_ORDER=msvc) and oracle agree bit for bit
+    dense = (scan[:, None, :] + rng.normal(0, 4e-4, (len(scan), 4, 3))).reshape(-1, 3).astype(np.float32)    # ~4 points per voxel
+    a, b = oracle.voxel_grid(dense, 0.005), oracle.voxel_grid(dense, 0.005, msvc_order=True)
+    assert a.shape == b.shape and np.allclose(a, b, atol=1e-6) and (a != b).any()
+    os.environ["PWICP_VOXEL_ORDER"] = "msvc"
+    try:
+        assert np.array_equal(host.preprocess(dense, 0.005, 14, 5.0, device=False), oracle.preprocess(dense, 0.005, 14, 5.0, msvc_order=True))
+    finally:
+        del os.environ["PWICP_VOXEL_ORDER"]
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/data/data_synthetic"), reason="needs the reference tree (absent on the GPU box)")
@@ -372,6 +382,19 @@ def test_recorded_results_reproduced_on_more_shipped_pairs(oracle):
         assert da <= 1e-6 and dt <= 1e-6, (e, tag, da, dt)
         assert len(res["DTseries"]) - 1 == n_outer
         assert np.allclose(np.sqrt(np.diag(res["VCM"])), np.sqrt(np.diag(Vr)), rtol=2e-3)
+    # the three pairs of the reference-epoch family that miss with the input order inside a voxel (2.9e-6, 1.8e-5, 8.7e-4 rad)
+    # are reproduced once pcl::VoxelGrid's points are summed in the order of the Microsoft STL's std::sort (host/msvc_sort.h):
+    # the recorded files come from the reference's Windows build
+    os.environ["PWICP_VOXEL_ORDER"] = "msvc"
+    try:
+        for e in (3, 8, 19):
+            T, res, d = R.register(load(1), load(e))
+            Tr, Vr = R.read_T(os.path.join(R.REF, "results/4DPCReg/%d_Direct2Ref_TransMatrix.txt" % e))
+            da, dt = R.pose_err(T, Tr)
+            assert da <= 1e-6 and dt <= 1e-6, (e, "msvc order", da, dt)
+            assert np.allclose(np.sqrt(np.diag(res["VCM"])), np.sqrt(np.diag(Vr)), rtol=2e-3)
+    finally:
+        del os.environ["PWICP_VOXEL_ORDER"]
     # the library's own supervoxels (host/Supervoxel.cpp) instead of the reference's code: same result
     T, res, d = R.register(load(1), load(12), "builtin")
     Tr, _ = R.read_T(os.path.join(R.REF, "results/4DPCReg/12_Direct2Ref_TransMatrix.txt"))
