@@ -484,7 +484,16 @@ void SORfilter(pcl::PointCloud<pcl::PointXYZ>::Ptr cloud_in, pcl::PointCloud<pcl
 void PCpreprocessing(pcl::PointCloud<pcl::PointXYZ>::Ptr cloud_in, pcl::PointCloud<pcl::PointXYZ>::Ptr cloud_out,
                      bool isDownSamp, float voxelSize, int SOR_NeighborNum, double SOR_StdMult) {
     pcl::PointCloud<pcl::PointXYZ> res;
-    preprocessDevice(*cloud_in, res, isDownSamp, voxelSize, SOR_NeighborNum, SOR_StdMult);
+    const char* vo = getenv("PWICP_VOXEL_ORDER");
+    if (isDownSamp && vo && string(vo) == "msvc") {
+        // the reference's Windows build: the voxel centroids in the Microsoft std::sort order (host, msvc_sort.h), then
+        // the outlier removal on the device as usual
+        pcl::PointCloud<pcl::PointXYZ> vox;
+        voxelGrid(*cloud_in, voxelSize, vox);
+        preprocessDevice(vox, res, false, 0.f, SOR_NeighborNum, SOR_StdMult);
+    } else {
+        preprocessDevice(*cloud_in, res, isDownSamp, voxelSize, SOR_NeighborNum, SOR_StdMult);
+    }
     *cloud_out = res;
 }
 
