@@ -434,3 +434,37 @@ def test_knn_normals_restatement_matches_the_references_code(oracle):
         assert set(a) == set(b)                                        # ... but the set is the same
     assert np.array_equal(nr[same], rnr[same])
     assert np.allclose(np.linalg.norm(nr, axis=1), 1.0, atol=1e-12)
+
+
+# ---------------------------------------------------------------- property tests (hypothesis)
+def test_properties_nn_and_knn_against_brute_force(oracle):
+    """Random small clouds incl. duplicates, lattice points (exact ties) and far queries: the KD-tree search equals brute force
+    bit for bit (index and float distance, lowest index on ties); the k-NN mean distance equals a numpy restatement."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    coords = st.integers(min_value=-6, max_value=6)
+
+    @settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+    @given(st.lists(st.tuples(coords, coords, coords), min_size=1, max_size=60),
+           st.lists(st.tuples(coords, coords, coords), min_size=1, max_size=30), st.floats(0.01, 3.0), st.integers(0, 2**31 - 1))
+    def check(tgt, qry, scale, seed):
+        rng = np.random.default_rng(seed)
+        t = (np.array(tgt, np.float32) * np.float32(scale)).astype(np.float32)
+        q = (np.array(qry, np.float32) * np.float32(scale) + rng.choice([0.0, 0.0, 0.37], (len(qry), 3))).astype(np.float32)
+        i1, d1 = oracle.nn(t, q)
+        i2, d2 = oracle.nn(t, q, brute=True)
+        assert np.array_equal(i1, i2) and np.array_equal(d1, d2)
+        d = q[:, None, :] - t[None, :, :]
+        ref = ((d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]).astype(np.float32)
+        assert np.array_equal(d1, ref.min(axis=1)) and np.array_equal(i1, ref.argmin(axis=1))        # argmin = lowest index on ties
+        k = min(5, len(t) - 1)
+        if k >= 1:
+            md = oracle.knn_mean_dist(t, k)
+            dd = t[:, None, :] - t[None, :, :]
+            full = ((dd[..., 0] * dd[..., 0] + dd[..., 1] * dd[..., 1]) + dd[..., 2] * dd[..., 2]).astype(np.float32)
+            np.fill_diagonal(full, np.inf)
+            near = np.sort(full, axis=1)[:, :k]
+            want = (np.sqrt(near).astype(np.float64).cumsum(axis=1)[:, -1] / k).astype(np.float32)
+            assert np.array_equal(md, want)
+
+    check()
