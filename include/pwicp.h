@@ -104,11 +104,13 @@ typedef struct {
     int   conv_state;       /* PWICP_CONV_* */
     int   grid_blocks;      /* launch geometry (informational): CTAs x warps_per_block */
     int   warps_per_block;
-    int   group_batches;    /* reduction geometry: fan-in of the summation hierarchy  */
+    int   group_batches;    /* reduction geometry: total warps of the grid | warps per CTA << 16;
+                               the summation order is a function of (n_source, this) alone */
     float device_ms;        /* whole inner loop (source sort, iteration-0 pre-pass, persistent kernel), CUDA events */
     long long correspondences;  /* n_iter * n_source */
     float kernel_ms;        /* the persistent kernel alone (CUDA events around its launch) */
-    float reserved0;
+    int   natural_iters;    /* first iteration at which DefaultConvergenceCriteria was met (= n_iter unless force_iters) */
+    int   natural_state;    /* ... and the PWICP_CONV_* state it reported */
 } pwicp_icp_result;
 
 /* source set of the inner loop: host upload (stand-alone use) ... */
@@ -122,6 +124,11 @@ int pwicp_icp_source_all(pwicp_ctx* ctx);
  * idx_trace[max_iter*n] (int, correspondence indices of every inner iteration). */
 int pwicp_icp_run(pwicp_ctx* ctx, const pwicp_icp_params* prm, float* T16, pwicp_icp_result* res,
                   double* mse_trace, float* T_trace, int* idx_trace);
+/* Per-iteration profile of the last pwicp_icp_run (diagnostic): iter_us[k] = device time of inner iteration k
+ * (%globaltimer of CTA 0, microseconds), searched[k] = queries of iteration k that were not answered from their
+ * candidate cache and ran the ball search.  cap = entries available in each array (either may be NULL);
+ * returns the number of iterations written. */
+int pwicp_icp_profile(pwicp_ctx* ctx, double* iter_us, int* searched, int cap);
 /* Processing order of the last pwicp_icp_run: perm[k] = index (in the uploaded source set) of the
  * k-th point in the order the device accumulated the normal equations (source points are sorted
  * by the target-grid cell they start in).  Only the order of the double sums depends on it; the

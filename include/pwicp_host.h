@@ -58,11 +58,9 @@ bool PiecewiseICP_4D_finalize(const char* confile, int startEpoch, int epochNum,
  * NULL restores the stand-in.  Not thread-safe (like the reference's globals). */
 typedef int (*pwicp_segmenter_fn)(const float* xyz, int n, float svResolution, int knn, int* labels);
 void pwicp_host_set_segmenter(pwicp_segmenter_fn fn);
-/* A built-in segmenter of that signature: boundary-preserving supervoxels after Lin et al. 2018, the algorithm of the
- * reference's front end (kNN normals, lambda-doubling fusion, boundary refinement; host C++, host/Supervoxel.cpp); same
- * labels as the reference's code on the reference's shipped scans.  Used when registered, or when the environment has
- * PWICP_SEGMENTER=supervoxel; the default stays the cubic-cell stand-in until it is validated on the device drivers. */
-int pwicp_host_builtin_supervoxels(const float* xyz, int n, float svResolution, int knn, int* labels);
+/* A segmentation can also be named by the environment, for the file-level drivers: PWICP_SEGMENTER_PLUGIN=<shared object>:<symbol>
+ * is dlopen()ed on first use and the symbol (of type pwicp_segmenter_fn) registered.  The library itself ships no
+ * supervoxel implementation (out of scope); without a plug-in the drivers use the stand-in and say so. */
 
 /* Result-file tools (no device needed).  pwicp_host_write_transmatrix: the per-pair file of src/Registration.cpp:340-388
  * (TransMatrix.txt / <time>_<mode>_TransMatrix.txt) from a row-major 4x4 and a 6x6; returns 1 on success.

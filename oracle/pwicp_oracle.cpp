@@ -1,6 +1,8 @@
 /*
  * pwicp_oracle.cpp -- CPU ORACLE (test infrastructure; see pwicp_oracle.h for the rules).
- * PARITY UNPINNED (no reference fixture exists at this boundary).
+ * PARITY PINNED by the reference: the reference's recorded results/4DPCReg matrices on its shipped
+ * scans (tests/test_oracle.py, tests/golden/refpair_e2.npz), its own KD-tree compiled into oracle/_ref, and its recorded
+ * aggregate files (tests/golden/recorded_4d).
  *
  * Build: g++ -O2 -std=c++17 -ffp-contract=off -fno-fast-math -fPIC -shared (oracle/Makefile).
  * -ffp-contract=off matters: the reference was built with MSVC /fp:precise for x64/SSE2, which
@@ -9,7 +11,7 @@
  * All "[PCL]" comments restate PCL 1.8.1 / FLANN / Eigen behaviour from the published sources
  * (not present in this container); each is tied to the reference call site that triggers it.
  */
-#include "msvc_sort.h"
+#include "../piecewise-icp_b200/host/msvc_sort.h"   /* the Microsoft STL's std::sort order: one copy, shared with the host mirror */
 #include "pwicp_oracle.h"
 
 #include <algorithm>
@@ -373,7 +375,52 @@ void accumulate28(const float* u7, const float* d2, const unsigned char* valid, 
         }
         return;
     }
-    /* Summation order of the CUDA kernel (DESIGN.md "reduction geometry"): per 32-point batch the
+    if (reduce_mode == 2) {
+        /* Summation order of the round-2 CUDA kernel (DESIGN.md 3.2 "reduction geometry").  group_batches = total
+         * warps of the grid NWT | warps per CTA WPC << 16.  Batch b (rows 32 b .. 32 b + 31) belongs to warp
+         * b mod NWT; lane l of that warp adds row l of its batches b = w, w + NWT, ... in that order to 28 sums of
+         * its own (fused multiply-add: the product of two float values is exact in double); the 32 lanes are
+         * folded as a balanced tree with partner distances 16, 8, 4, 2, 1; a CTA adds its WPC warps in order; the
+         * CTA sums are added in chunks of ceil(G / WPC) consecutive CTAs, each from 0, and the chunks in order. */
+        const long nb = ((long)n + 31) / 32;
+        const int NWT = group_batches & 0xffff, WPC = (group_batches >> 16) & 0x7fff;
+        for (int v = 0; v < 28; ++v) out28[v] = 0.0;
+        if (NWT < 1 || WPC < 1 || NWT % WPC) return;
+        const int G = NWT / WPC;
+        std::vector<double> cta((size_t)G * 28, 0.0);
+        std::vector<double> lanes(32 * 28);
+        for (int w = 0; w < NWT; ++w) {
+            std::fill(lanes.begin(), lanes.end(), 0.0);
+            for (long b = w; b < nb; b += NWT)
+                for (int l = 0; l < 32; ++l) {
+                    const long i = b * 32 + l;
+                    if (i >= n) break;
+                    double* acc = &lanes[(size_t)l * 28];
+                    const float* u = u7 + 7 * (size_t)i;
+                    if (valid[i])
+                        for (int v = 0; v < 27; ++v) acc[v] = std::fma((double)u[g_vt.a[v]], (double)u[g_vt.b[v]], acc[v]);
+                    acc[27] += (double)d2[i];
+                }
+            for (int stride = 16; stride >= 1; stride >>= 1)
+                for (int l = 0; l < stride; ++l)
+                    for (int v = 0; v < 28; ++v) lanes[(size_t)l * 28 + v] += lanes[(size_t)(l + stride) * 28 + v];
+            /* CTA sum: warps in order, starting from 0 */
+            double* c = &cta[(size_t)(w / WPC) * 28];
+            for (int v = 0; v < 28; ++v) c[v] += lanes[v];
+        }
+        const int per = (G + WPC - 1) / WPC;
+        for (int v = 0; v < 28; ++v) {
+            double s = 0.0;
+            for (int g0 = 0; g0 < G; g0 += per) {
+                double ch = 0.0;
+                for (int g = g0; g < std::min(G, g0 + per); ++g) ch += cta[(size_t)g * 28 + v];
+                s += ch;
+            }
+            out28[v] = s;
+        }
+        return;
+    }
+    /* Summation order of the round-1 CUDA kernel: per 32-point batch the
      * rows in order starting from 0; then a hierarchy with fan-in `group_batches` (default 32):
      * every parent is the sum of its consecutive children in order, starting from 0; after at most
      * two such levels (or once at most fan-in entries remain) the entries are summed in order into
@@ -1186,18 +1233,20 @@ int orc_knn_mean_dist(const float* xyz, int n, int k, float* mean_dist) {
     return 0;
 }
 
-/* second pass: mean and standard deviation of the mean distances (double, sequential), threshold = mean + mult * stddev,
- * points with distance <= threshold are kept in input order (negative = false).  Returns the number kept. */
+/* second pass [PCL 1.8.1 StatisticalOutlierRemoval::applyFilterIndices]: mean and standard deviation of the mean distances
+ * (double sums over a vector<float>: `sq_sum += distances[i] * distances[i]` is a FLOAT product, rounded before it is
+ * widened; the variance is not clamped), threshold = mean + mult * stddev, a point is an outlier iff distance > threshold;
+ * the others are kept in input order (negative = false).  Returns the number kept. */
 int orc_sor_select(const float* xyz, int n, const float* mean_dist, double std_mult, float* out, double* threshold) {
     double sum = 0, sq = 0;
-    for (int i = 0; i < n; ++i) { sum += mean_dist[i]; sq += (double)mean_dist[i] * mean_dist[i]; }
+    for (int i = 0; i < n; ++i) { const float d_sq = mean_dist[i] * mean_dist[i]; sum += mean_dist[i]; sq += d_sq; }
     const double mean = sum / n;
     const double var = (sq - sum * sum / n) / (n - 1);
-    const double thr = mean + std_mult * std::sqrt(std::max(var, 0.0));
+    const double thr = mean + std_mult * std::sqrt(var);
     if (threshold) *threshold = thr;
     int m = 0;
     for (int i = 0; i < n; ++i)
-        if (mean_dist[i] <= thr) { std::memcpy(out + 3 * (size_t)m, xyz + 3 * (size_t)i, 12); ++m; }
+        if (!(mean_dist[i] > thr)) { std::memcpy(out + 3 * (size_t)m, xyz + 3 * (size_t)i, 12); ++m; }
     return m;
 }
 

@@ -49,7 +49,8 @@ void orc_transform(float* pts, int n, const float* T16);
 
 /* ---- A4: TransformationEstimationPointToPlaneLLS::estimateRigidTransformation
  * (reached from src/Registration.cpp:1266).  reduce_mode 0 = sequential double sums in
- * correspondence order (what PCL does); reduce_mode 1 = the summation order of the CUDA kernel
+ * correspondence order (what PCL does); reduce_mode 2 = the summation order of the round-2 CUDA kernel
+ * (group_batches = total warps | warps per CTA << 16); reduce_mode 1 = that of the round-1 kernel
  * (32-point batches, then a hierarchy of fan-in group_batches; see DESIGN.md "reduction geometry"),
  * used to prove the GPU loop bit-exactly. Outputs: ATA (36), ATb (6), x (6), T (16 f32). */
 int orc_lls_step(const float* src, const int* match, int n, const float* tgt, const float* nrm,
@@ -64,7 +65,7 @@ typedef struct {
     double fit_eps;         /* 1e-6 (src/Registration.cpp:877, :1263) */
     int    force_iters;     /* !=0: benchmark mode, run exactly max_iter iterations */
     int    reduce_mode;     /* see orc_lls_step */
-    int    group_batches;   /* reduce_mode 1: fan-in of the summation hierarchy (device: 32)       */
+    int    group_batches;   /* reduce_mode 1: fan-in of the summation hierarchy; 2: total warps | warps per CTA << 16 */
     int    reserved;
     int    rot_thr_default; /* !=0: leave the rotation threshold at PCL's default 0.99999 */
 } orc_icp_params;

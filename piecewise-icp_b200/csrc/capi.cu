@@ -376,6 +376,20 @@ int pwicp_icp_run(pwicp_ctx* p, const pwicp_icp_params* prm, float* T16, pwicp_i
     return icp_run_device(ctx, prm ? *prm : d, T16, res, mse_trace, T_trace, idx_trace);
 }
 
+int pwicp_icp_profile(pwicp_ctx* p, double* iter_us, int* searched, int cap) {
+    Ctx* ctx = reinterpret_cast<Ctx*>(p);
+    if (!ctx || cap < 0 || ctx->icp_prof_iters < 1 || !ctx->icp_partials.p) { set_error(ctx, "icp_profile: no inner loop has run"); return 0; }
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return 0;
+    const int m = std::min(cap, ctx->icp_prof_iters);
+    if (searched && m) cudaMemcpy(searched, ctx->icp_partials.as<char>() + ctx->icp_prof_off_searched, (size_t)m * 4, cudaMemcpyDeviceToHost);
+    if (iter_us && m) {
+        std::vector<unsigned long long> ns((size_t)m + 1);
+        cudaMemcpy(ns.data(), ctx->icp_partials.as<char>() + ctx->icp_prof_off_ns, ((size_t)m + 1) * 8, cudaMemcpyDeviceToHost);
+        for (int k = 0; k < m; ++k) iter_us[k] = (double)(ns[k + 1] - ns[k]) * 1e-3;
+    }
+    return m;
+}
+
 int pwicp_icp_order(pwicp_ctx* p, int* perm) {
     Ctx* ctx = reinterpret_cast<Ctx*>(p);
     if (!ctx || !perm || ctx->n_icp < 1 || !ctx->icp_perm.p) { set_error(ctx, "icp_order: no inner loop has run"); return PWICP_ERR_ARG; }
@@ -684,13 +698,15 @@ int pwicp_preprocess(pwicp_ctx* p, const float* xyz, int n, int downsample, floa
     PW_TRY(knn_mean_dist_resident(ctx, cur, m, k, md.data()));
     PW_CUDA(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));      // voxel grid + cloud download + grid build + k-NN kernel
     double sum = 0, sq = 0;
-    for (int i = 0; i < m; ++i) { sum += md[i]; sq += (double)md[i] * md[i]; }
+    // [PCL 1.8.1 StatisticalOutlierRemoval::applyFilterIndices] distances is a vector<float>: the square is a float
+    // product, rounded before it is widened; no clamp of the variance; a point is an outlier iff distance > threshold
+    for (int i = 0; i < m; ++i) { const float d_sq = md[i] * md[i]; sum += md[i]; sq += d_sq; }
     const double mean = sum / m;
     const double var = (sq - sum * sum / m) / (m - 1);
-    const double thr = mean + std_mult * std::sqrt(std::max(var, 0.0));
+    const double thr = mean + std_mult * std::sqrt(var);
     int kept = 0;
     for (int i = 0; i < m; ++i)
-        if (md[i] <= thr) { std::memcpy(out_xyz + 3 * (size_t)kept, pts.data() + 3 * (size_t)i, 12); ++kept; }
+        if (!(md[i] > thr)) { std::memcpy(out_xyz + 3 * (size_t)kept, pts.data() + 3 * (size_t)i, 12); ++kept; }
     *n_out = kept;
     return PWICP_OK;
 }

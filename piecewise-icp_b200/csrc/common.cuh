@@ -14,14 +14,12 @@ constexpr int kMaxLevels = 3;      // grid pyramid: cell sizes h, 8h, 64h
 constexpr int kLevelFactor = 8;
 constexpr int kRingsPerLevel = 2;  // rings searched on a level before moving to the coarser one
 #ifndef PWICP_ICP_THREADS
-#define PWICP_ICP_THREADS 256
+#define PWICP_ICP_THREADS 512
 #endif
-constexpr int kIcpThreads = PWICP_ICP_THREADS;   // 8 warps per CTA; the sums do not depend on it
+constexpr int kIcpThreads = PWICP_ICP_THREADS;   // one CTA of 16 warps per SM; part of the reduction geometry
 constexpr int kIcpWarps = kIcpThreads / 32;
 constexpr int kNumVals = 28;       // 21 ATA + 6 ATb + sum d2
-constexpr int kFanIn = 32;         // entries summed per parent on every level of the reduction hierarchy
-constexpr int kMaxRedLevels = 3;   // batches, groups, supergroups; the top level is summed by every CTA
-constexpr int kHandoutLanes = 16;  // interleaved hand-out counters per inner iteration
+constexpr int kStageSlots = 3;     // batches of streamed per-point data in flight per warp (cp.async ring)
 constexpr int kMaxIcpIter = 1024;
 
 struct GridLevel {
@@ -116,6 +114,8 @@ struct Ctx {
     DevBuf ct_seed, bp_seed, pp_seed, ct_order;
     bool ct_order_valid = false;
     int n_icp = 0;
+    int icp_prof_iters = 0;                      // pwicp_icp_profile: iterations of the last run, offsets into icp_partials
+    size_t icp_prof_off_searched = 0, icp_prof_off_ns = 0;
     // scratch
     DevBuf keys, vals, keys2, vals2, cub_tmp, scratch_a, scratch_b, scratch_c, scratch_d, flags, pos;
     DevBuf l2flush;

@@ -4,20 +4,27 @@
 // pcl::IterativeClosestPointWithNormals::align with TransformationEstimationPointToPlaneLLS and
 // DefaultConvergenceCriteria.
 //
-// Per inner iteration every thread: (a) applies the previous incremental transform to its
-// source point in place (float, pcl::transformPointCloudWithNormals order), (b) finds the exact
-// nearest target centroid in the grid, (c) forms the 7 float row terms of the LLS system; each
-// warp accumulates the 27 (+1: sum of squared NN distances) double sums of its 32-point batch
-// sequentially through shared memory, CTAs publish partials, ONE grid-wide barrier, then every
-// CTA redundantly reduces the partials in a fixed order, solves the 6x6 system, builds the float
-// transform and evaluates the convergence criteria -- identical instructions on identical
+// Layout (round 2).  One CTA of 16 warps per SM.  The 32-point batches of the Morton-ordered source
+// are dealt out round robin to the warps of the whole grid (batch b belongs to warp b mod NWT) and stay with that
+// warp for the whole loop: every piece of per-point state -- the transformed point, its matched target and normal,
+// the candidate cache -- is read and written by one thread only, so no iteration needs a grid-wide fence for it, and
+// every warp samples the whole cloud, so the data-dependent cost of the search iterations is balanced without a
+// hand-out counter.  Per inner iteration every lane (a) applies the previous incremental transform to its point in
+// place (float, pcl::transformPointCloudWithNormals order), (b) confirms the cached match as the exact nearest
+// target (nn_search.cuh, "candidate cache") or runs the seeded ball search, (c) forms the 7 float row terms of the
+// LLS system and adds its 27 products + d2 to 28 double accumulators of its own (DFMA; a product of two float
+// values is exact in double, so fma(a, b, acc) is the separately rounded acc + a*b of the reference).  At the end
+// of the iteration a warp folds its 32 lanes with a reduce-scatter butterfly (partners 16, 8, 4, 2, 1), the CTA
+// adds its warps in order, ONE grid barrier, every CTA adds the CTA sums in the same fixed order, solves the 6x6
+// system, builds the float transform and evaluates the convergence criteria -- identical instructions on identical
 // inputs, so all CTAs take the same decision without a second barrier or a host round trip.
 //
-// Batches of 32 points are handed out dynamically (their cost is data dependent; a static split
-// left half of the SM time waiting at the grid barrier, profiles/r01c_*), yet the summation order
-// ("reduction geometry") is fixed: rows of a batch in order, batches of a 64-batch group
-// in order (a second, cheap grid-wide pass), groups by a lane-strided sum + butterfly.
-// The oracle's reduce_mode=1 reproduces it for the bit-exact whole-loop parity test.
+// Why not the FP64 tensor cores (round 1 formed the batch sums by DMMA.8x8x4): profiles/r02a_hw_rates.txt -- on
+// B200 a DMMA.8x8x4 issues every 3.9 cycles per SM and a warp-wide DFMA every 0.55, i.e. the same FLOP rate, but
+// the 8x8 tile spends 64 outputs on 28 sums and needs 16 F2F.F64.F32 per batch (2 cycles per SM each, the slowest
+// instruction of the loop) against 8 for the per-lane sums: 64 against 31 FP64-pipe cycles per batch.
+// The summation order ("reduction geometry") is fixed by (n, gridDim.x, warps per CTA) alone and the oracle's
+// reduce_mode = 2 reproduces it for the bit-exact whole-loop parity tests.
 #include <cooperative_groups.h>
 
 #include "common.cuh"
@@ -26,7 +33,6 @@
 #include "nn_search.cuh"
 #include "small_algebra.cuh"
 
-#ifndef PWICP_STATIC_EIGHTHS
 // candidate cache: radius beyond the NN distance (in level-0 cells) and the largest last step (as a fraction of it) at
 // which a cache is built
 #ifndef PWICP_SLACK_CELLS
@@ -35,49 +41,48 @@
 #ifndef PWICP_BUILD_FRAC
 #define PWICP_BUILD_FRAC 0.25f
 #endif
-#define PWICP_STATIC_EIGHTHS 6     // share of a warp's batches that is assigned statically once the loop is calm
-#endif
-#ifndef PWICP_ICP_MINBLOCKS
-#define PWICP_ICP_MINBLOCKS 3
-#endif
 namespace cg = cooperative_groups;
 
 namespace pwicp {
 
+constexpr int kMoreBit = 0x40000000;      // in cq[].w: further cached candidates in cmore[]
+constexpr float kPadMargin = 1e18f;       // margin of a padding point: its square is finite, no step ever uses it up
+
+// target-only prefix of the point-to-plane residual: ((nx*dx + ny*dy) + nz*dz), float, no FMA (-fmad=false)
+__device__ __forceinline__ float nq_dot(float nx, float ny, float nz, float qx, float qy, float qz) {
+    return nx * qx + ny * qy + nz * qz;
+}
+
 struct IcpArgs {
     GridDev g;
     const float4* aux;        // level-0 order: nx, ny, nz, ctstd
-    const float4* src;        // source set (read only)
-    float4* work;             // transformed copy, updated in place every iteration; w = path length since the
-                              // candidate cache of the point was built
-    // per source point: the candidate cache (nn_search.cuh)
-    float4* cq0;              // primary candidate INLINE: x, y, z of the last match, w = its level-0 position (int bits, -1: none)
-    float4* cn0;              // normal of the primary candidate INLINE, w = validity radius of the cache (0: none); the
-                              // path length the query has travelled since the cache was built lives in work[].w
+    const float4* src;        // source set in processing order (read only): x, y, z, w = index in the caller's order
+    float4* work;             // x, y, z: transformed copy, updated in place every iteration; w = what is left of the
+                              // validity radius of the point's candidate cache after the path it has travelled since
+                              // the cache was built (<= 0: no cache)
+    // per source point: the candidate cache (nn_search.cuh); rewritten only when the match changes
+    float4* cq;               // matched target INLINE: x, y, z, w = its level-0 position (int bits) | kMoreBit when
+                              // cmore[] holds further cached candidates
+    float4* cn;               // its normal INLINE: x, y, z, w = (nx*qx + ny*qy) + nz*qz, the target-only prefix of the
+                              // residual expression of TransformationEstimationPointToPlaneLLS (float, unfused, in order)
     int4* cmore;              // x, y, z: positions of up to three further candidates (unused = primary), w = original index of the primary
-    int seed_exact;           // cand[].x is the exact NN of the untransformed source (iteration 0 needs no search)
+    // all per-point arrays are padded to a multiple of 32 points: a pad has a zero normal (every row term and product is
+    // exactly zero), a huge margin (never searches) and is excluded from the sum of squared distances
+    int seed_exact;           // cq[] is the exact NN of the untransformed source (iteration 0 needs no search)
     float slack;              // cache radius beyond the NN distance
-    float build_step2;        // a cache is built only when the point moved less than sqrt(this) in the last step
+    float build_step;         // a cache is built only when the point moved less than this in the last step (L1 length)
     int n;
     int max_iter;
     int force_iters;
     double rot_thr, transl_thr, mse_rel, mse_abs;
-    double* part[kMaxRedLevels];  // [count[l]][28]: level 0 = sums of one 32-point batch, level l+1 = sums of
-                                  // kFanIn consecutive level-l entries
-    int* done;                    // [count[2]]: groups finished per supergroup, monotonic over iterations
-    int count[kMaxRedLevels];     // entries per level
-    int nlevels;
-    const double* top_part;       // = part[nlevels - 1]
-    int top_count;                // = count[nlevels - 1]
-    int* batch_counter;       // [max_iter][kHandoutLanes * 32], zeroed before the launch: dynamic batch hand-out
-                              // (kHandoutLanes counters per iteration, 128 bytes apart)
-    int* fallbacks;           // [max_iter], zeroed before the launch: queries that ran the ball search
+    double* part;             // [2][gridDim.x][28]: CTA sums of an iteration, double buffered
+    int* searched;            // [max_iter], zeroed before the launch: queries that ran the ball search (diagnostic)
     float* out_T;             // 16: final transformation
-    int* out_state;           // [0] n_iter, [1] conv_state
+    int* out_state;           // [0] n_iter, [1] conv_state, [2] first iteration at which the criteria were met, [3] its state
     double* mse_trace;        // nullable
     float* T_trace;           // nullable
     int* idx_trace;           // nullable, [iter][n]
-    long long* timing;        // debug build only
+    unsigned long long* iter_ns;   // [max_iter + 1]: %globaltimer at the start of the loop and after every iteration (CTA 0)
 };
 
 // Shared scratch of the per-iteration solve.
@@ -88,14 +93,9 @@ struct FinishSmem {
     double sc[3][2];     // sin / cos of alpha, beta, gamma
     double prev_mse;
     int piv[6];
+    int met;             // the convergence criteria have been met before (force_iters keeps looping)
     float Tn[16];
 };
-
-#ifdef PWICP_TIMING
-#define PW_TSF(k) do { if (lane == 0 && it == 30 && a.timing) a.timing[blockIdx.x * 16 + (k)] = clock64(); } while (0)
-#else
-#define PW_TSF(k)
-#endif
 
 // Warp 0 of every CTA: totals -> 6x6 solve -> float transform -> convergence decision.
 // Every scalar operation is the one small_algebra.cuh's sequential inverse6()/solve_from28()
@@ -142,7 +142,6 @@ static __device__ __noinline__ int icp_finish_warp(const IcpArgs& a, int it, con
         if (on) { F.A[rr][cc] = upd; if (cc == k + 1) F.A[rr][k] = f; }
         __syncwarp();
     }
-    PW_TSF(8);
     // inverse: lane j solves L U x = P e_j (one reciprocal per pivot, formed by six lanes at once)
     if (lane < 6) F.rcp[lane] = 1.0 / F.A[lane][lane];
     __syncwarp();
@@ -173,10 +172,8 @@ static __device__ __noinline__ int icp_finish_warp(const IcpArgs& a, int it, con
         F.x[lane] = sacc;
     }
     __syncwarp();
-    PW_TSF(6);
     if (lane < 3) sincos(F.x[lane], &F.sc[lane][0], &F.sc[lane][1]);
     __syncwarp();
-    PW_TSF(7);
     if (lane == 0) {
         float Tn[16];
         construct_T_sc(F.sc[0][0], F.sc[0][1], F.sc[1][0], F.sc[1][1], F.sc[2][0], F.sc[2][1], F.x, Tn);
@@ -202,13 +199,20 @@ static __device__ __noinline__ int icp_finish_warp(const IcpArgs& a, int it, con
         const double prev_mse = F.prev_mse;
         const int iters = it + 1;
         // DefaultConvergenceCriteria<float>::hasConverged(), in PCL's order
-        if (iters >= a.max_iter) state = PWICP_CONV_ITERATIONS;
-        else if (!a.force_iters) {
+        // force_iters (benchmark mode): the criteria are evaluated and recorded but may not stop the loop
+        int crit = 0;
+        if (iters >= a.max_iter) crit = PWICP_CONV_ITERATIONS;
+        else {
             const double cos_angle = 0.5 * (double)(Tn[0] + Tn[5] + Tn[10] - 1.0f);
             const double transl_sq = (double)(Tn[3] * Tn[3] + Tn[7] * Tn[7] + Tn[11] * Tn[11]);
-            if (cos_angle >= a.rot_thr && transl_sq <= a.transl_thr) state = PWICP_CONV_TRANSFORM;
-            else if (fabs(mse - prev_mse) < a.mse_abs) state = PWICP_CONV_ABS_MSE;
-            else if (fabs(mse - prev_mse) / prev_mse < a.mse_rel) state = PWICP_CONV_REL_MSE;
+            if (cos_angle >= a.rot_thr && transl_sq <= a.transl_thr) crit = PWICP_CONV_TRANSFORM;
+            else if (fabs(mse - prev_mse) < a.mse_abs) crit = PWICP_CONV_ABS_MSE;
+            else if (fabs(mse - prev_mse) / prev_mse < a.mse_rel) crit = PWICP_CONV_REL_MSE;
+        }
+        state = (crit == PWICP_CONV_ITERATIONS || !a.force_iters) ? crit : 0;
+        if (crit && !F.met) {
+            F.met = 1;
+            if (blockIdx.x == 0) { a.out_state[2] = iters; a.out_state[3] = crit; }
         }
         F.prev_mse = mse;
         if (blockIdx.x == 0) {
@@ -232,20 +236,15 @@ static __device__ __noinline__ int icp_finish_warp(const IcpArgs& a, int it, con
 struct Fallback {
     Best bb;
     float nx, ny, nz;     // normal of the match
-    int built;            // a new cache was written: the caller restarts the path length
+    float nq;             // nq_dot(normal, match)
+    float rho;            // validity radius of the cache that was written (0: none)
 };
 static __device__ __noinline__ Fallback icp_search_fallback(const IcpArgs& a, int it, int i, float px, float py, float pz,
-                                                            int seed, float step2) {
-    {   // queries that needed the search this iteration (decides the scheduling of the next one)
+                                                            int seed, float step) {
+    {   // queries that needed the search this iteration (diagnostic: pwicp_icp_profile)
         const unsigned m = __activemask();
-        if ((int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(a.fallbacks + it, __popc(m));
+        if ((int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(a.searched + it, __popc(m));
     }
-#ifdef PWICP_TIMING
-    if (a.timing && it < 64) {
-        atomicAdd((unsigned long long*)a.timing + 16 * 1024 + it * 2, 1ull);
-        if (step2 < a.build_step2) atomicAdd((unsigned long long*)a.timing + 16 * 1024 + it * 2 + 1, 1ull);
-    }
-#endif
     Fallback f;
     f.bb = nn_search_seeded<true>(a.g, px, py, pz, seed);
     const Best& bb = f.bb;
@@ -253,310 +252,287 @@ static __device__ __noinline__ Fallback icp_search_fallback(const IcpArgs& a, in
     f.nx = nq.x; f.ny = nq.y; f.nz = nq.z;
     CandCache cc;
     cc.rho = 0.f;
-    if (step2 < a.build_step2) {
+    if (step < a.build_step) {
         const float rm = sqrtf(bb.d2) + a.slack;
         cc = ball_collect(a.g.lv[0], a.g.ox, a.g.oy, a.g.oz, px, py, pz, rm * rm);
     }
     // the match is the primary candidate; the other cached targets follow in any order
-    int o1 = bb.pos, o2 = bb.pos, o3 = bb.pos;
+    int o1 = bb.pos, o2 = bb.pos, o3 = bb.pos, k = 0;
     if (cc.rho > 0.f) {
-        int k = 0;
 #pragma unroll
         for (int j = 0; j < kCacheCands; ++j)
             if (cc.pos[j] != bb.pos) { if (k == 0) o1 = cc.pos[j]; else if (k == 1) o2 = cc.pos[j]; else if (k == 2) o3 = cc.pos[j]; ++k; }
         // all four slots taken by targets other than the match cannot happen (the match is the nearest
         // of the collected set); guard anyway: no cache rather than a wrong one
-        if (k > 3) { cc.rho = 0.f; o1 = o2 = o3 = bb.pos; }
+        if (k > 3) { cc.rho = 0.f; k = 0; }
     }
-    f.built = cc.rho > 0.f;
-    a.cq0[i] = make_float4(bb.qx, bb.qy, bb.qz, __int_as_float(bb.pos));
-    a.cn0[i] = make_float4(nq.x, nq.y, nq.z, cc.rho);
-    a.cmore[i] = make_int4(o1, o2, o3, bb.idx);
+    f.rho = cc.rho;
+    f.nq = nq_dot(nq.x, nq.y, nq.z, bb.qx, bb.qy, bb.qz);
+    a.cq[i] = make_float4(bb.qx, bb.qy, bb.qz, __int_as_float(bb.pos | (k > 0 ? kMoreBit : 0)));
+    a.cn[i] = make_float4(nq.x, nq.y, nq.z, f.nq);
+    if (k > 0) a.cmore[i] = make_int4(o1, o2, o3, bb.idx);
     return f;
 }
 
-// 16-byte asynchronous copy global -> shared (LDGSTS, L2 only: the sources are rewritten by other
-// SMs every iteration), per-thread completion groups.
+// 16-byte asynchronous copy global -> shared (LDGSTS through L2), per-thread completion groups.
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_group1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-
-// Sum of up to kFanIn entries (stride kNumVals doubles) in order, starting from 0.  All loads are
-// issued before the first add; absent entries contribute +0.0, which leaves the sum unchanged.
-__device__ __forceinline__ double sum_entries(const double* __restrict__ src, int size) {
-    double v[kFanIn];
-#pragma unroll
-    for (int k = 0; k < kFanIn; ++k) v[k] = (k < size) ? __ldcg(src + (size_t)k * kNumVals) : 0.0;
-    double acc = 0.0;
-#pragma unroll
-    for (int k = 0; k < kFanIn; ++k) acc += v[k];
-    return acc;
+__device__ __forceinline__ void cp_async_wait_group2() { asm volatile("cp.async.wait_group 2;" ::: "memory"); }
+// 16-byte load from the shared window (volatile: never hoisted out of the loop, never cached in registers)
+__device__ __forceinline__ void lds128(float4& v, unsigned addr) {
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
 }
 
-__global__ void __launch_bounds__(kIcpThreads, PWICP_ICP_MINBLOCKS) icp_persistent_kernel(const IcpArgs a) {
+// Reduce-scatter butterfly over the lanes of a warp.  One step with partner distance kS: the lanes whose bit kS is
+// clear keep entries [0, kS) of their array, the others [kS, 2 kS); every lane adds what its partner (lane ^ kS)
+// held of the kept half.  After the steps 16, 8, 4, 2, 1 lane v holds the sum over all lanes of entry v, each
+// formed as the balanced tree ((x[l] + x[l + 16]) + ...) -- addition commutes bit for bit, so it does not matter
+// which partner does the add.  The first step takes the 28 sums (entries 28..31 are implicit zeros).
+__device__ __forceinline__ void fold_lanes16(const double (&x)[kNumVals], double (&y)[16], int lane) {
+    const bool upper = (lane & 16) != 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const double hi = (j + 16 < kNumVals) ? x[(j + 16 < kNumVals) ? j + 16 : 0] : 0.0;
+        const double keep = upper ? hi : x[j];
+        const double send = upper ? x[j] : hi;
+        y[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+}
+template <int kS>
+__device__ __forceinline__ void fold_lanes(double (&x)[16], int lane) {
+    const bool upper = (lane & kS) != 0;
+#pragma unroll
+    for (int j = 0; j < kS; ++j) {
+        const double keep = upper ? x[j + kS] : x[j];
+        const double send = upper ? x[j] : x[j + kS];
+        x[j] = keep + __shfl_xor_sync(0xffffffffu, send, kS);
+    }
+}
+
+// kTrace: the variant that also records the correspondence indices of every iteration (parity tests).
+template <bool kTrace>
+__global__ void __launch_bounds__(kIcpThreads, 1) icp_persistent_kernel(const IcpArgs a) {
     cg::grid_group grid = cg::this_grid();
-    __shared__ __align__(16) float s_rows[kIcpWarps][32][8];
-    // staging of the streamed per-point data, two batches deep per warp, filled by cp.async:
-    // [slot][field: point + path length, normal of the primary + radius, primary candidate, further candidates][lane]
+    // landing zone of the streamed per-point data, kStageSlots batches deep per warp, filled by cp.async; every lane
+    // reads back only the 16-byte cells it copied itself: [warp][slot][point + margin, matched target, normal][lane]
     extern __shared__ __align__(16) unsigned char s_dyn[];
-    float4 (*s_stage)[2][4][32] = reinterpret_cast<float4 (*)[2][4][32]>(s_dyn);
+    __shared__ double s_wsum[kIcpWarps][kNumVals];   // warp sums of the iteration, then the chunk sums of the CTA partials
     __shared__ double s_tot[kNumVals];
     __shared__ float s_T[16];
     __shared__ float s_Tfinal[16];
     __shared__ int s_stop;
-    __shared__ int s_fb;      // queries that ran the search in the previous iteration
     __shared__ FinishSmem s_fin;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nb = (a.n + 31) / 32;                              // 32-point batches
-
-    // DMMA fragment roles of this lane (row m = lane / 4 of A and column m of B; D[m][2k], D[m][2k+1]
-    // with k = lane % 4).  Row layout in shared memory: a b c nx ny nz e d2.  The 28 values are the
-    // 21 upper-triangle ATA entries (row-major), the 6 ATb entries, and the sum of squared NN distances.
-    const int offA = (lane >> 2) < 6 ? (lane >> 2) : 7;      // A row 6 (and the unused row 7): d2
-    const int offB = (lane >> 2) < 6 ? (lane >> 2) : 6;      // B column 6: e; column 7 is the constant 1
-    int v0 = -1, v1 = -1;
+    const int G = gridDim.x, NWT = G * kIcpWarps, ws = blockIdx.x * kIcpWarps + warp;
+    const int K = (ws < nb) ? (nb - 1 - ws) / NWT + 1 : 0;       // batches ws, ws + NWT, ... of this warp
+    const int per = (G + kIcpWarps - 1) / kIcpWarps;             // CTA partials per chunk of the final sum
+    const int nchunks = (G + per - 1) / per;
+    const int stride = NWT * 32;                                 // distance of this lane's consecutive points
+    const int i0 = ws * 32 + lane;
+    constexpr int kSlotBytes = 3 * 32 * (int)sizeof(float4);
+    // shared-window address of this lane's landing cells, pinned in a register (an opaque move: otherwise the compiler
+    // re-derives it from the thread index in every trip of the loop, 15 instructions)
+    unsigned s_lane_sh;
     {
-        const int rD = lane >> 2;
-#pragma unroll
-        for (int jj = 0; jj < 2; ++jj) {
-            const int c = 2 * (lane & 3) + jj;
-            int v = -1;
-            if (rD < 6) {
-                if (c < 6 && c >= rD) v = rD * 6 - rD * (rD - 1) / 2 + (c - rD);
-                else if (c == 6) v = 21 + rD;
-            } else if (rD == 6 && c == 7) v = 27;
-            if (jj == 0) v0 = v; else v1 = v;
-        }
+        const unsigned v = (unsigned)__cvta_generic_to_shared(s_dyn + (size_t)warp * (kStageSlots * kSlotBytes)) + lane * 16;
+        asm volatile("mov.u32 %0, %1;" : "=r"(s_lane_sh) : "r"(v));
     }
+
     if (tid < 16) { s_T[tid] = (tid % 5 == 0) ? 1.0f : 0.0f; s_Tfinal[tid] = s_T[tid]; }
-    if (tid == 0) { s_stop = 0; s_fin.prev_mse = 1.7976931348623157e308; }   // DBL_MAX
+    if (tid == 0) { s_stop = 0; s_fin.prev_mse = 1.7976931348623157e308; s_fin.met = 0; }   // DBL_MAX
+    if (blockIdx.x == 0 && tid == 0) a.iter_ns[0] = globaltimer_ns();
     __syncthreads();
 
-#ifdef PWICP_TIMING
-#define PW_TS(k) do { if (tid == 0 && it == 30 && a.timing) a.timing[blockIdx.x * 16 + (k)] = clock64(); } while (0)
-#else
-#define PW_TS(k)
-#endif
-    bool staged = false;      // the first batch of this iteration is already being copied
+    // copies of point i_ of this lane (one of the batches of this warp; past the end: an empty group): point +
+    // margin, matched target, its normal
+    const int n_pad = nb * 32;
+    auto stage_point = [&](const float4* __restrict__ psrc, int i_, int slot_off) {
+        if (i_ < n_pad) {
+            const unsigned d = s_lane_sh + slot_off;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(psrc + i_) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 512), "l"(a.cq + i_) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 1024), "l"(a.cn + i_) : "memory");
+        }
+        cp_async_commit();
+    };
+    stage_point(a.src, i0, 0);
+    stage_point(a.src, i0 + stride, kSlotBytes);
+    const unsigned s_T_sh = (unsigned)__cvta_generic_to_shared(s_T);
+
     for (int it = 0;; ++it) {
-        PW_TS(0);
-        float T[12];
+        double acc[kNumVals];
 #pragma unroll
-        for (int k = 0; k < 12; ++k) T[k] = s_T[k];
-        // copies of a batch: point + path length, normal + radius, primary candidate, further candidates
-        auto stage_batch = [&](const float4* __restrict__ psrc, int bb_, int slot) {
-            const int i_ = bb_ * 32 + lane;
-            if (bb_ < nb && i_ < a.n) {
-                cp_async16(&s_stage[warp][slot][0][lane], psrc + i_);
-                cp_async16(&s_stage[warp][slot][1][lane], a.cn0 + i_);
-                cp_async16(&s_stage[warp][slot][2][lane], a.cq0 + i_);
-                cp_async16(&s_stage[warp][slot][3][lane], a.cmore + i_);
-            }
-            cp_async_commit();
-        };
-        // ---- phase A.  Every warp first works through a static share of the batches (b = j * NW + W,
-        // three quarters of its fair share once the loop is calm), then takes single batches from a counter: the cost of a batch is
-        // data dependent while the ball search runs, and one atomic per batch on one address would
-        // serialise in L2 (~0.85 cycles each).  Every sum below is formed in an order that does not
-        // depend on which warp does it.  The loop is software pipelined: the loads of the next
-        // batch and the hand-out of the one after are in flight while the current one is processed.
-        {
-            const int NW = gridDim.x * kIcpWarps, W = blockIdx.x * kIcpWarps + warp;
-            // static batches per warp: three quarters of the fair share once (nearly) every query is answered from its
-            // cache (uniform cost per batch), else only the two that cover the pipeline depth of the hand-out
-            const int fb_prev = (it > 1) ? s_fb : a.n;
-            const bool calm = (long long)fb_prev * 64 < (long long)a.n;
-            const int J = (calm ? (nb / NW) * PWICP_STATIC_EIGHTHS / 8 : 0) + 2;
-            const bool has_dyn = (long long)J * NW < (long long)nb;   // else no hand-out tickets at all
-            const float4* __restrict__ psrc = (it == 0) ? a.src : a.work;
-            // kHandoutLanes counters, counter c hands out the dynamic batches D0 + c, D0 + c + kHandoutLanes, ...:
-            // a single address makes every ticket queue behind thousands of others in the L2 atomic unit
-            // (16 % of all stall samples, profiles/r01h_*); interleaving keeps the lanes equally loaded
-            const int nl = min(kHandoutLanes, NW), hl = W % nl;
-            int* counter = a.batch_counter + ((size_t)it * kHandoutLanes + hl) * 32;
-            int seq = 0;                                       // position in this warp's batch sequence
-            int tkt = 0;                                       // lane 0: hand-out ticket in flight
-            int b = W, bn = NW + W;                            // positions 0 and 1
-            if (!staged) {                                     // else: issued during the previous iteration's solve
-                stage_batch(psrc, b, 0);
-            }
-            while (b < nb) {
-                const int slot = seq & 1;
-                // copies of the next batch and the ticket for the one after are in flight during this one
-                stage_batch(psrc, bn, slot ^ 1);
-                if (has_dyn && seq + 2 >= J && lane == 0) tkt = atomicAdd(counter, 1);   // position seq+2 is dynamic
-                cp_async_wait_group1();                        // everything but the copies just issued has landed
+        for (int v = 0; v < kNumVals; ++v) acc[v] = 0.0;
+        const float4* __restrict__ psrc = (it == 0) ? a.src : a.work;
+        const float4* __restrict__ pts = a.g.lv[0].pts;
+        const bool first = it == 0;
 
-                const int i = b * 32 + lane;
-                const bool active = i < a.n;
-                float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
-                if (active) {
-                    float4 p = s_stage[warp][slot][0][lane];
-                    const float4 cn = s_stage[warp][slot][1][lane];
-                    const float4 q0 = s_stage[warp][slot][2][lane];
-                    const int4 cm = *reinterpret_cast<const int4*>(&s_stage[warp][slot][3][lane]);
-                    const int pos0 = __float_as_int(q0.w);
-                    float step2 = __int_as_float(0x7f800000);
-                    float path = 0.f;                          // travelled since the cache was built (upper bound)
-                    if (it > 0) {
-                        float x, y, z;
-                        xform_point(T, p.x, p.y, p.z, x, y, z);
-                        step2 = l2_simple(x, y, z, p.x, p.y, p.z);
-                        path = p.w + sqrtf(step2) * 1.000001f;
-                        p.x = x; p.y = y; p.z = z;
-                    }
-                    // (b) exact NN: best of the cached candidates when the cache still covers the
-                    // query (nn_search.cuh, "candidate cache"), else the seeded ball search
-                    Best bb;
-                    bool ok = false;
-                    int seed = pos0;
-                    if (pos0 >= 0) {
-                        const float4* __restrict__ pts = a.g.lv[0].pts;
-                        bb.d2 = l2_simple(p.x, p.y, p.z, q0.x, q0.y, q0.z);
-                        bb.idx = cm.w; bb.pos = pos0; bb.qx = q0.x; bb.qy = q0.y; bb.qz = q0.z;
-                        // unused slots repeat the primary: their loads are predicated off (no L1 traffic); the
-                        // three loads are issued together, one round trip instead of up to three
-                        float4 q1 = q0, q2 = q0, q3 = q0;
-                        if (cm.x != pos0) q1 = __ldg(pts + cm.x);
-                        if (cm.y != pos0) q2 = __ldg(pts + cm.y);
-                        if (cm.z != pos0) q3 = __ldg(pts + cm.z);
+        // ---- phase A: this warp's batches, two batches of copies in flight ahead of the one being processed
+        int slot = 0, pslot = 2 * kSlotBytes, i = i0;            // byte offsets of the ring slots
+#pragma unroll 1
+        for (int k = 0; k < K; ++k, i += stride) {
+            stage_point(psrc, i + 2 * stride, pslot);
+            cp_async_wait_group2();                              // everything but the two youngest groups has landed
+            float4 p, q0, cn;
+            lds128(p, s_lane_sh + slot);
+            lds128(q0, s_lane_sh + slot + 512);
+            lds128(cn, s_lane_sh + slot + 1024);
+            const int pos0 = __float_as_int(q0.w) & ~kMoreBit;
+            float step = __int_as_float(0x7f800000);             // L1 length of the last step (>= its Euclidean length)
+            float margin;                                        // cache radius left after the path travelled (lower bound)
+            float mchk;                                          // ... as the certificate below uses it
+            if (!first) {
+                // the transform is read from shared memory where it is used (three broadcast loads): twelve more
+                // live registers across the loop would spill the accumulators
+                float4 r0, r1, r2;
+                lds128(r0, s_T_sh); lds128(r1, s_T_sh + 16); lds128(r2, s_T_sh + 32);
+                const float x = r0.x * p.x + r0.y * p.y + r0.z * p.z + r0.w;      // xform_point (small_algebra.cuh)
+                const float y = r1.x * p.x + r1.y * p.y + r1.z * p.z + r1.w;
+                const float z = r2.x * p.x + r2.y * p.y + r2.z * p.z + r2.w;
+                step = (fabsf(x - p.x) + fabsf(y - p.y)) + fabsf(z - p.z);
+                margin = __fmaf_rn(step, -1.00001f, p.w);
+                mchk = margin;
+                p.x = x; p.y = y; p.z = z;
+            } else {
+                margin = (i < a.n) ? 0.f : kPadMargin;            // no cache yet; pads never search
+                mchk = (a.seed_exact || i >= a.n) ? kPadMargin : 0.f;
+            }
+            // (b) exact NN: best of the cached candidates when the cache still covers the
+            // query (nn_search.cuh, "candidate cache"), else the seeded ball search
+            float bd2 = l2_simple(p.x, p.y, p.z, q0.x, q0.y, q0.z);
+            float qx = q0.x, qy = q0.y, qz = q0.z;
+            float nx = cn.x, ny = cn.y, nz = cn.z, nq = cn.w;
+            int bpos = pos0;
+            if (__float_as_int(q0.w) & kMoreBit) {
+                // further cached candidates (a minority of the points): positions from the side array, the
+                // three loads are issued together, unused slots repeat the primary and are predicated off
+                const int4 cm = __ldcg(a.cmore + i);
+                int bidx = cm.w;
+                float4 q1 = q0, q2 = q0, q3 = q0;
+                if (cm.x != pos0) q1 = __ldg(pts + cm.x);
+                if (cm.y != pos0) q2 = __ldg(pts + cm.y);
+                if (cm.z != pos0) q3 = __ldg(pts + cm.z);
 #define PW_CAND(q, cp)                                                                         \
-                        if ((cp) != pos0) {                                                    \
-                            const float d = l2_simple(p.x, p.y, p.z, q.x, q.y, q.z);           \
-                            const int id = __float_as_int(q.w);                                \
-                            if (d < bb.d2 || (d == bb.d2 && id < bb.idx)) {                    \
-                                bb.d2 = d; bb.idx = id; bb.pos = (cp); bb.qx = q.x; bb.qy = q.y; bb.qz = q.z; \
-                            }                                                                  \
-                        }
-                        PW_CAND(q1, cm.x) PW_CAND(q2, cm.y) PW_CAND(q3, cm.z)
+                if ((cp) != pos0) {                                                            \
+                    const float d = l2_simple(p.x, p.y, p.z, q.x, q.y, q.z);                   \
+                    const int id = __float_as_int(q.w);                                        \
+                    if (d < bd2 || (d == bd2 && id < bidx)) {                                  \
+                        bd2 = d; bidx = id; bpos = (cp); qx = q.x; qy = q.y; qz = q.z;         \
+                    }                                                                          \
+                }
+                PW_CAND(q1, cm.x) PW_CAND(q2, cm.y) PW_CAND(q3, cm.z)
 #undef PW_CAND
-                        // |p - anchor| <= path (triangle inequality over the steps actually taken)
-                        ok = (it == 0 && a.seed_exact) || sqrtf(bb.d2) + path * 1.00001f < cn.w;
-                        seed = bb.pos;
-                    }
-                    float nx = cn.x, ny = cn.y, nz = cn.z;
-                    if (!ok) {
-                        const Fallback f = icp_search_fallback(a, it, i, p.x, p.y, p.z, seed, step2);
-                        bb = f.bb; nx = f.nx; ny = f.ny; nz = f.nz;
-                        if (f.built) path = 0.f;
-                    } else if (bb.pos != pos0) {
-                        // another cached target has become the nearest: make it the primary
-                        const float4 nq = __ldg(a.aux + bb.pos);
-                        nx = nq.x; ny = nq.y; nz = nq.z;
-                        a.cq0[i] = make_float4(bb.qx, bb.qy, bb.qz, __int_as_float(bb.pos));
-                        a.cn0[i] = make_float4(nx, ny, nz, cn.w);
-                        a.cmore[i] = make_int4(cm.x == bb.pos ? pos0 : cm.x, cm.y == bb.pos ? pos0 : cm.y,
-                                               cm.z == bb.pos ? pos0 : cm.z, bb.idx);
-                    }
-                    a.work[i] = make_float4(p.x, p.y, p.z, path);
-                    const float sx = p.x, sy = p.y, sz = p.z;
-                    const float dx = bb.qx, dy = bb.qy, dz = bb.qz;
-                    // float expressions of TransformationEstimationPointToPlaneLLS (no FMA)
-                    lo.x = nz * sy - ny * sz;
-                    lo.y = nx * sz - nz * sx;
-                    lo.z = ny * sx - nx * sy;
-                    lo.w = nx;
-                    hi.x = ny;
-                    hi.y = nz;
-                    hi.z = nx * dx + ny * dy + nz * dz - nx * sx - ny * sy - nz * sz;
-                    hi.w = bb.d2;
-                    // traces are reported in the caller's order (src[].w = original source index)
-                    if (a.idx_trace) a.idx_trace[(size_t)it * a.n + __float_as_int(__ldg(a.src + i).w)] = bb.idx;
-                }
-                // rows through shared memory as floats: a broadcast LDS.32 is one wavefront, an LDS.64 two,
-                // and the L1/shared pipe is the busiest unit of this kernel (profiles/r01e_*)
-                float4* row = reinterpret_cast<float4*>(&s_rows[warp][lane][0]);
-                row[0] = lo; row[1] = hi;
-                __syncwarp();
-                // batch sums on the FP64 tensor cores: the 28 sums are entries of D = A * B with
-                // A = [a b c nx ny nz d2 -]^T (8 x 32) and B = [a b c nx ny nz e 1] (32 x 8), formed by eight
-                // chained DMMA.8x8x4.  On B200 a DMMA adds its four products to the accumulator one after
-                // the other, each with one rounding, in k order (scripts/micro/dmma_order.cu: 0 mismatches in
-                // 128 000 sums against a DFMA chain), and a product of two float values is exact in
-                // double: every sum is over rows 0..31 in order, starting from 0 -- the order the oracle uses.
-                {
-                    double c0 = 0.0, c1 = 0.0;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float* r = &s_rows[warp][4 * j + (lane & 3)][0];
-                        const double av = (double)r[offA];
-                        const double bv = (lane >= 28) ? 1.0 : (double)r[offB];
-                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                                     : "+d"(c0), "+d"(c1) : "d"(av), "d"(bv));
-                    }
-                    double* dst = a.part[0] + (size_t)b * kNumVals;
-                    if (v0 >= 0) __stcg(dst + v0, c0);
-                    if (v1 >= 0) __stcg(dst + v1, c1);
-                }
-                __syncwarp();
-                // rotate the pipeline
-                ++seq;
-                b = bn;
-                bn = (seq + 1 < J) ? (seq + 1) * NW + W
-                                   : (has_dyn ? J * NW + __shfl_sync(0xffffffffu, tkt, 0) * nl + hl : nb);
-            }
-            cp_async_wait_all();
-        }
-        PW_TS(1);
-        grid.sync();
-        PW_TS(2);
-        // the next iteration's first batch (always position 0 = batch W): its copies do not depend on the
-        // transform being solved for, so they fly during the reduction and the solve
-        stage_batch(a.work, blockIdx.x * kIcpWarps + warp, 0);
-        staged = true;
-
-        // ---- phase B1: one warp per group of kFanIn batches: lane v sums the group's entries of
-        // value v in order, starting from 0 (loads are independent, the adds sequential).  The warp
-        // that completes the last group of a kFanIn-group supergroup sums that one the same way.
-        if (a.nlevels > 1) {
-            const int gwarp = blockIdx.x * kIcpWarps + warp, nwarps = gridDim.x * kIcpWarps;
-            for (int g = gwarp; g < a.count[1]; g += nwarps) {
-                if (lane < kNumVals)
-                    __stcg(a.part[1] + (size_t)g * kNumVals + lane,
-                           sum_entries(a.part[0] + (size_t)g * kFanIn * kNumVals + lane, min(kFanIn, a.count[0] - g * kFanIn)));
-                if (a.nlevels > 2) {
-                    const int sg = g / kFanIn, size = min(kFanIn, a.count[1] - sg * kFanIn);
-                    __threadfence();
-                    __syncwarp();
-                    int last = 0;
-                    if (lane == 0) last = (atomicAdd(a.done + sg, 1) + 1 == (it + 1) * size);
-                    last = __shfl_sync(0xffffffffu, last, 0);
-                    if (last) {
-                        __threadfence();
-                        if (lane < kNumVals)
-                            __stcg(a.part[2] + (size_t)sg * kNumVals + lane,
-                                   sum_entries(a.part[1] + (size_t)sg * kFanIn * kNumVals + lane, size));
-                    }
+                if (bpos != pos0 && mchk > 0.f && bd2 * 1.00003f < mchk * mchk) {
+                    // another cached target has become the nearest: make it the primary
+                    const float4 nv = __ldg(a.aux + bpos);
+                    nx = nv.x; ny = nv.y; nz = nv.z;
+                    nq = nq_dot(nx, ny, nz, qx, qy, qz);
+                    a.cq[i] = make_float4(qx, qy, qz, __int_as_float(bpos | kMoreBit));
+                    a.cn[i] = make_float4(nx, ny, nz, nq);
+                    a.cmore[i] = make_int4(cm.x == bpos ? pos0 : cm.x, cm.y == bpos ? pos0 : cm.y,
+                                           cm.z == bpos ? pos0 : cm.z, bidx);
                 }
             }
-            PW_TS(3);
-            grid.sync();
-        }
-
-        // ---- phase B2: every CTA forms the same totals from the top-level entries, in order
-        if (warp == 0) {
-            if (lane < kNumVals) {
-                double acc = 0.0;
-                for (int k0 = 0; k0 < a.top_count; k0 += kFanIn)
-                    acc += sum_entries(a.top_part + (size_t)k0 * kNumVals + lane, min(kFanIn, a.top_count - k0));
-                s_tot[lane] = acc;
+            // |p - anchor| <= path (triangle inequality over the steps actually taken): every target at least as
+            // close to p as the best cached one lies within the cache radius of the anchor; compared as squares
+            if (!(mchk > 0.f && bd2 * 1.00003f < mchk * mchk)) {
+                const Fallback f = icp_search_fallback(a, it, i, p.x, p.y, p.z, bpos, step);
+                bd2 = f.bb.d2; bpos = f.bb.pos; qx = f.bb.qx; qy = f.bb.qy; qz = f.bb.qz;
+                nx = f.nx; ny = f.ny; nz = f.nz; nq = f.nq;
+                margin = f.rho;
             }
-            if (lane == 31) s_fb = __ldcg(a.fallbacks + it);   // complete since the first grid barrier
-            __syncwarp();
+            a.work[i] = make_float4(p.x, p.y, p.z, margin);
+            // float expressions of TransformationEstimationPointToPlaneLLS (no FMA); nq = (nx*dx + ny*dy) + nz*dz
+            const float u0 = nz * p.y - ny * p.z;
+            const float u1 = nx * p.z - nz * p.x;
+            const float u2 = ny * p.x - nx * p.y;
+            const float u6 = nq - nx * p.x - ny * p.y - nz * p.z;
+            const float u7 = (i < a.n) ? bd2 : 0.f;              // a pad's rows are zero through its zero normal
+            // traces are reported in the caller's order (src[].w = original source index)
+            if (kTrace && i < a.n)
+                a.idx_trace[(size_t)it * a.n + __float_as_int(__ldg(a.src + i).w)] = __float_as_int(__ldg(pts + bpos).w);
+            // 27 products + d2 into this lane's sums
+            {
+                const double d0 = (double)u0, d1 = (double)u1, d2 = (double)u2, d3 = (double)nx, d4 = (double)ny,
+                             d5 = (double)nz, d6 = (double)u6;
+                acc[0] = fma(d0, d0, acc[0]);   acc[1] = fma(d0, d1, acc[1]);   acc[2] = fma(d0, d2, acc[2]);
+                acc[3] = fma(d0, d3, acc[3]);   acc[4] = fma(d0, d4, acc[4]);   acc[5] = fma(d0, d5, acc[5]);
+                acc[6] = fma(d1, d1, acc[6]);   acc[7] = fma(d1, d2, acc[7]);   acc[8] = fma(d1, d3, acc[8]);
+                acc[9] = fma(d1, d4, acc[9]);   acc[10] = fma(d1, d5, acc[10]); acc[11] = fma(d2, d2, acc[11]);
+                acc[12] = fma(d2, d3, acc[12]); acc[13] = fma(d2, d4, acc[13]); acc[14] = fma(d2, d5, acc[14]);
+                acc[15] = fma(d3, d3, acc[15]); acc[16] = fma(d3, d4, acc[16]); acc[17] = fma(d3, d5, acc[17]);
+                acc[18] = fma(d4, d4, acc[18]); acc[19] = fma(d4, d5, acc[19]); acc[20] = fma(d5, d5, acc[20]);
+                acc[21] = fma(d0, d6, acc[21]); acc[22] = fma(d1, d6, acc[22]); acc[23] = fma(d2, d6, acc[23]);
+                acc[24] = fma(d3, d6, acc[24]); acc[25] = fma(d4, d6, acc[25]); acc[26] = fma(d5, d6, acc[26]);
+                acc[27] += (double)u7;
+            }
+            slot = (slot == (kStageSlots - 1) * kSlotBytes) ? 0 : slot + kSlotBytes;
+            pslot = (pslot == (kStageSlots - 1) * kSlotBytes) ? 0 : pslot + kSlotBytes;
         }
-        PW_TS(4);
 
-        if (warp == 0) {
-            const int st = icp_finish_warp(a, it, s_tot, s_T, s_Tfinal, s_fin, lane);
-            if (lane == 0) s_stop = st;
+        // ---- warp sums (lane v ends up with value v), CTA sum over the warps in order, published for the grid
+        {
+            double y[16];
+            fold_lanes16(acc, y, lane);
+            fold_lanes<8>(y, lane);
+            fold_lanes<4>(y, lane);
+            fold_lanes<2>(y, lane);
+            fold_lanes<1>(y, lane);
+            if (lane < kNumVals) s_wsum[warp][lane] = y[0];
         }
         __syncthreads();
-        PW_TS(5);
+        if (warp == 0 && lane < kNumVals) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < kIcpWarps; ++w) s += s_wsum[w][lane];
+            __stcg(a.part + ((size_t)(it & 1) * G + blockIdx.x) * kNumVals + lane, s);
+        }
+        grid.sync();
+        // the next iteration's first two batches: their copies do not depend on the transform being solved
+        // for, so they fly during the reduction and the solve
+        stage_point(a.work, i0, 0);
+        stage_point(a.work, i0 + stride, kSlotBytes);
+
+        // ---- every CTA forms the same totals: warp w adds the CTA sums w*per .. in order, warp 0 the chunks
+        if (warp < nchunks && lane < kNumVals) {
+            const double* __restrict__ src = a.part + ((size_t)(it & 1) * G + (size_t)warp * per) * kNumVals + lane;
+            const int cnt = min(per, G - warp * per);
+            double v[10];
+            double s = 0.0;
+            for (int g0 = 0; g0 < cnt; g0 += 10) {               // loads of a round are issued before its first add
+#pragma unroll
+                for (int g = 0; g < 10; ++g) v[g] = (g0 + g < cnt) ? __ldcg(src + (size_t)(g0 + g) * kNumVals) : 0.0;
+#pragma unroll
+                for (int g = 0; g < 10; ++g) if (g0 + g < cnt) s += v[g];
+            }
+            s_wsum[warp][lane] = s;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            if (lane < kNumVals) {
+                double s = 0.0;
+                for (int c = 0; c < nchunks; ++c) s += s_wsum[c][lane];
+                s_tot[lane] = s;
+            }
+            __syncwarp();
+            const int st = icp_finish_warp(a, it, s_tot, s_T, s_Tfinal, s_fin, lane);
+            if (lane == 0) {
+                s_stop = st;
+                if (blockIdx.x == 0) a.iter_ns[it + 1] = globaltimer_ns();
+            }
+        }
+        __syncthreads();
         if (s_stop) break;
     }
     cp_async_wait_all();
@@ -600,24 +576,29 @@ __global__ void src_key_kernel(const float4* __restrict__ src, int n, float ox, 
     vals[i] = (uint32_t)i;
 }
 
-__global__ void src_gather_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ order, int n, float4* out,
-                                  const int* __restrict__ seed_in, const float4* __restrict__ tgt_pts,
+// a padding point (i >= n, up to the next multiple of 32): zero normal, see IcpArgs
+__device__ __forceinline__ void write_pad(int i, float4* out, float4* cn0, float4* cq0) {
+    out[i] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+    cq0[i] = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
+    cn0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+__global__ void src_gather_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ order, int n, int n_pad,
+                                  float4* out, const int* __restrict__ seed_in, const float4* __restrict__ tgt_pts,
                                   const float4* __restrict__ tgt_aux,
-                                  float4* __restrict__ cn0, float4* __restrict__ cq0, int4* __restrict__ cmore) {
+                                  float4* __restrict__ cn0, float4* __restrict__ cq0) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= n_pad) return;
+    if (i >= n) { write_pad(i, out, cn0, cq0); return; }
     const uint32_t o = order[i];
     float4 p = src[o];
     p.w = __int_as_float((int)o);
     out[i] = p;
-    const int sd = seed_in ? seed_in[o] : -1;
-    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-    int idx = 0;
-    float4 nq = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (sd >= 0) { q = __ldg(tgt_pts + sd); idx = __float_as_int(q.w); nq = __ldg(tgt_aux + sd); }
+    if (!seed_in) return;                 // icp_seed_kernel fills the match
+    const int sd = seed_in[o];            // classification match (outer.cu): always a valid position
+    const float4 q = __ldg(tgt_pts + sd), nq = __ldg(tgt_aux + sd);
     cq0[i] = make_float4(q.x, q.y, q.z, __int_as_float(sd));
-    cmore[i] = make_int4(sd, sd, sd, idx);
-    cn0[i] = make_float4(nq.x, nq.y, nq.z, 0.f);
+    cn0[i] = make_float4(nq.x, nq.y, nq.z, nq_dot(nq.x, nq.y, nq.z, q.x, q.y, q.z));
 }
 
 // Iteration 0 of a source set without seeds: the plain search at full occupancy (the persistent
@@ -625,15 +606,14 @@ __global__ void src_gather_kernel(const float4* __restrict__ src, const uint32_t
 // into the candidate slots; the persistent kernel takes them as the exact answer of iteration 0.
 __global__ void __launch_bounds__(256)
 icp_seed_kernel(GridDev g, const float4* __restrict__ tgt_aux, const float4* __restrict__ src, int n,
-                float4* __restrict__ cn0, float4* __restrict__ cq0, int4* __restrict__ cmore) {
+                float4* __restrict__ cn0, float4* __restrict__ cq0) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4 p = __ldg(src + i);
     const Best b = nn_search_seeded(g, p.x, p.y, p.z, -1);
     const float4 nq = __ldg(tgt_aux + b.pos);
     cq0[i] = make_float4(b.qx, b.qy, b.qz, __int_as_float(b.pos));
-    cn0[i] = make_float4(nq.x, nq.y, nq.z, 0.f);
-    cmore[i] = make_int4(b.pos, b.pos, b.pos, b.idx);
+    cn0[i] = make_float4(nq.x, nq.y, nq.z, nq_dot(nq.x, nq.y, nq.z, b.qx, b.qy, b.qz));
 }
 
 // Sorts the source set by the target-grid cell it starts in (stable: ties keep the caller's
@@ -645,8 +625,9 @@ static int icp_sort_source(Ctx* ctx, int n, bool have_seed) {
     PW_TRY(ctx->vals.reserve(ctx, (size_t)n * 4));
     PW_TRY(ctx->keys2.reserve(ctx, (size_t)n * 8));
     PW_TRY(ctx->icp_perm.reserve(ctx, (size_t)n * 4));
-    PW_TRY(ctx->icp_sorted.reserve(ctx, (size_t)n * sizeof(float4)));
-    PW_TRY(ctx->icp_match.reserve(ctx, (size_t)n * 3 * sizeof(float4)));      // cn0, cq0, cmore
+    const int n_pad = (n + 31) / 32 * 32;            // the per-point arrays of the loop are padded to whole batches
+    PW_TRY(ctx->icp_sorted.reserve(ctx, (size_t)n_pad * sizeof(float4)));
+    PW_TRY(ctx->icp_match.reserve(ctx, (size_t)n_pad * 3 * sizeof(float4)));      // cn, cq, cmore
     const int blocks = (n + 255) / 256;
     src_key_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->icp_src.as<float4>(), n, ctx->tgt.dev.ox, ctx->tgt.dev.oy,
                                                     ctx->tgt.dev.oz, L.inv_h, L.dx, L.dy, L.dz,
@@ -661,11 +642,10 @@ static int icp_sort_source(Ctx* ctx, int n, bool have_seed) {
     size_t cap = ctx->cub_tmp.cap;
     PW_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, cap, ctx->keys.as<unsigned long long>(), ctx->keys2.as<unsigned long long>(),
                                             ctx->vals.as<uint32_t>(), ctx->icp_perm.as<uint32_t>(), n, 0, bits, ctx->stream));
-    src_gather_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->icp_src.as<float4>(), ctx->icp_perm.as<uint32_t>(), n,
+    src_gather_kernel<<<(n_pad + 255) / 256, 256, 0, ctx->stream>>>(ctx->icp_src.as<float4>(), ctx->icp_perm.as<uint32_t>(), n, n_pad,
                                                        ctx->icp_sorted.as<float4>(),
                                                        have_seed ? ctx->icp_seed.as<int>() : nullptr, ctx->tgt.dev.lv[0].pts,
-                                                       ctx->tgt_aux.as<float4>(), ctx->icp_match.as<float4>(), ctx->icp_match.as<float4>() + n,
-                                                       reinterpret_cast<int4*>(ctx->icp_match.as<float4>() + 2 * (size_t)n));
+                                                       ctx->tgt_aux.as<float4>(), ctx->icp_match.as<float4>(), ctx->icp_match.as<float4>() + n_pad);
     ctx->launches += 5;
     PW_CUDA(cudaGetLastError());
     return PWICP_OK;
@@ -678,31 +658,25 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     if (n < 3) { set_error(ctx, "icp: fewer than 3 correspondences"); return PWICP_ERR_TOO_FEW_CORR; }
     if (prm.max_iter < 1 || prm.max_iter > kMaxIcpIter) { set_error(ctx, "icp: max_iter out of range"); return PWICP_ERR_ARG; }
 
-    const size_t smem = (size_t)kIcpWarps * 2 * 4 * 32 * sizeof(float4);      // s_stage
-    PW_CUDA(cudaFuncSetAttribute(icp_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = (size_t)kIcpWarps * kStageSlots * 3 * 32 * sizeof(float4);      // s_stage
+    void* kern = idx_trace ? (void*)icp_persistent_kernel<true> : (void*)icp_persistent_kernel<false>;
+    PW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    PW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, icp_persistent_kernel, kIcpThreads, smem));
+    if (idx_trace) PW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, icp_persistent_kernel<true>, kIcpThreads, smem));
+    else PW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, icp_persistent_kernel<false>, kIcpThreads, smem));
     if (occ < 1) { set_error(ctx, "icp: kernel does not fit on an SM"); return PWICP_ERR_CUDA; }
     const long nb = ((long)n + 31) / 32;
-    // enough CTAs that every warp can own a batch, never more than can be co-resident
+    // one CTA per SM; fewer when there are not enough batches to give every warp one
     long want = (nb + kIcpWarps - 1) / kIcpWarps;
-    int grid = (int)std::min<long>((long)occ * ctx->num_sms, std::max<long>(1, want));
+    int grid = (int)std::min<long>((long)ctx->num_sms, std::max<long>(1, want));
 
-    PW_TRY(ctx->icp_work.reserve(ctx, (size_t)n * sizeof(float4)));
-    // reduction levels: level 0 = one entry per batch, then up to two levels that sum kFanIn
-    // consecutive entries each; the top level (any length) is summed in order by every CTA
-    int lcount[kMaxRedLevels], nlevels = 1;
-    lcount[0] = (int)nb;
-    while (nlevels < kMaxRedLevels && lcount[nlevels - 1] > kFanIn) {
-        lcount[nlevels] = (lcount[nlevels - 1] + kFanIn - 1) / kFanIn;
-        ++nlevels;
-    }
-    size_t part_entries = 0, done_entries = 0;
-    for (int l = 0; l < nlevels; ++l) part_entries += (size_t)lcount[l];
-    if (nlevels > 2) done_entries = (size_t)lcount[2];
-    const size_t bytes_part = part_entries * kNumVals * sizeof(double);
-    const size_t bytes_cnt = ((size_t)prm.max_iter * (kHandoutLanes * 32 + 1) + done_entries) * sizeof(int);
-    PW_TRY(ctx->icp_partials.reserve(ctx, bytes_part + bytes_cnt + 64));
+    const int n_pad = (int)(nb * 32);
+    PW_TRY(ctx->icp_work.reserve(ctx, (size_t)n_pad * sizeof(float4)));
+    // device scratch: CTA sums (double buffered) | searched[max_iter] | iter_ns[max_iter + 1]
+    const size_t bytes_part = (size_t)2 * grid * kNumVals * sizeof(double);
+    const size_t bytes_cnt = (size_t)prm.max_iter * sizeof(int);
+    const size_t off_ns = (bytes_part + bytes_cnt + 7) & ~(size_t)7;
+    PW_TRY(ctx->icp_partials.reserve(ctx, off_ns + (size_t)(prm.max_iter + 1) * 8 + 64));
     const size_t out_bytes = 64 + 16 + (size_t)prm.max_iter * (8 + 64);
     PW_TRY(ctx->icp_out.reserve(ctx, out_bytes));
     char* ob = ctx->icp_out.as<char>();
@@ -716,8 +690,7 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     if (!have_seed) {
         icp_seed_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->tgt.dev, ctx->tgt_aux.as<float4>(),
                                                                   ctx->icp_sorted.as<float4>(), n,
-                                                                  ctx->icp_match.as<float4>(), ctx->icp_match.as<float4>() + n,
-                                                                  reinterpret_cast<int4*>(ctx->icp_match.as<float4>() + 2 * (size_t)n));
+                                                                  ctx->icp_match.as<float4>(), ctx->icp_match.as<float4>() + n_pad);
         ctx->launches++;
     }
 
@@ -726,12 +699,12 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     a.aux = ctx->tgt_aux.as<float4>();
     a.src = ctx->icp_sorted.as<float4>();
     a.work = ctx->icp_work.as<float4>();
-    a.cn0 = ctx->icp_match.as<float4>();
-    a.cq0 = a.cn0 + n;
-    a.cmore = reinterpret_cast<int4*>(a.cn0 + 2 * (size_t)n);
+    a.cn = ctx->icp_match.as<float4>();
+    a.cq = a.cn + n_pad;
+    a.cmore = reinterpret_cast<int4*>(a.cn + 2 * (size_t)n_pad);
     a.seed_exact = 1;         // classification matches (outer.cu) or icp_seed_kernel
     a.slack = PWICP_SLACK_CELLS / ctx->tgt.dev.lv[0].inv_h;
-    a.build_step2 = (PWICP_BUILD_FRAC * a.slack) * (PWICP_BUILD_FRAC * a.slack);
+    a.build_step = PWICP_BUILD_FRAC * a.slack;
 
     a.n = n;
     a.max_iter = prm.max_iter;
@@ -740,40 +713,19 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     a.transl_thr = prm.tf_eps;
     a.mse_rel = prm.fit_eps;
     a.mse_abs = 1e-12;
-    {
-        double* pp = ctx->icp_partials.as<double>();
-        int* cc = reinterpret_cast<int*>(ctx->icp_partials.as<char>() + bytes_part);
-        PW_CUDA(cudaMemsetAsync(cc, 0, bytes_cnt, ctx->stream));
-        a.batch_counter = cc;
-        cc += (size_t)prm.max_iter * kHandoutLanes * 32;
-        a.fallbacks = cc;
-        cc += prm.max_iter;
-        a.done = cc;
-        for (int l = 0; l < kMaxRedLevels; ++l) { a.part[l] = nullptr; a.count[l] = 0; }
-        for (int l = 0; l < nlevels; ++l) {
-            a.part[l] = pp; pp += (size_t)lcount[l] * kNumVals;
-            a.count[l] = lcount[l];
-        }
-        a.nlevels = nlevels;
-        a.top_part = a.part[nlevels - 1];
-        a.top_count = lcount[nlevels - 1];
-    }
+    a.part = ctx->icp_partials.as<double>();
+    a.searched = reinterpret_cast<int*>(ctx->icp_partials.as<char>() + bytes_part);
+    a.iter_ns = reinterpret_cast<unsigned long long*>(ctx->icp_partials.as<char>() + off_ns);
+    PW_CUDA(cudaMemsetAsync(a.searched, 0, off_ns - bytes_part + (size_t)(prm.max_iter + 1) * 8, ctx->stream));
     a.out_T = reinterpret_cast<float*>(ob);
     a.out_state = reinterpret_cast<int*>(ob + 64);
     a.mse_trace = mse_trace ? reinterpret_cast<double*>(ob + 80) : nullptr;
     a.T_trace = T_trace ? reinterpret_cast<float*>(ob + 80 + (size_t)prm.max_iter * 8) : nullptr;
     a.idx_trace = idx_trace ? ctx->icp_idx.as<int>() : nullptr;
-    a.timing = nullptr;
-#ifdef PWICP_TIMING
-    static long long* d_timing = nullptr;
-    if (!d_timing) cudaMalloc(&d_timing, (1024 * 16 + 128) * sizeof(long long));
-    cudaMemsetAsync(d_timing, 0, (1024 * 16 + 128) * sizeof(long long), ctx->stream);
-    a.timing = d_timing;
-#endif
 
     void* kargs[] = {(void*)&a};
     PW_CUDA(cudaEventRecord(ctx->ev2, ctx->stream));
-    PW_CUDA(cudaLaunchCooperativeKernel((void*)icp_persistent_kernel, dim3(grid), dim3(kIcpThreads), kargs, smem, ctx->stream));
+    PW_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kIcpThreads), kargs, smem, ctx->stream));
     ctx->launches++;
     PW_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
 
@@ -784,31 +736,15 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     PW_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     PW_CUDA(cudaEventElapsedTime(&kms, ctx->ev2, ctx->ev1));
     ctx->last_ms = ms;
-#ifdef PWICP_TIMING
-    {
-        std::vector<long long> ht(1024 * 16 + 128);
-        cudaMemcpy(ht.data(), d_timing, ht.size() * 8, cudaMemcpyDeviceToHost);
-        // per-CTA deltas against its own first stamp (SM clocks are not synchronised)
-        double sum[16] = {0}, mx[16] = {0}, mn[16]; for (double& m : mn) m = 1e30;
-        int cnt = 0;
-        for (int b = 0; b < grid; ++b) {
-            if (!ht[b * 16]) continue;
-            ++cnt;
-            for (int k = 0; k < 9; ++k) { double v = (double)(ht[b * 16 + k] - ht[b * 16]); sum[k] += v; mx[k] = std::max(mx[k], v); mn[k] = std::min(mn[k], v); }
-        }
-        printf("FALLBACK lanes (cache builds) per iteration:");
-        for (int k = 0; k < std::min(64, host.st[0]); ++k) printf(" %lld(%lld)", ht[16 * 1024 + 2 * k], ht[16 * 1024 + 2 * k + 1]);
-        printf("\n");
-        if (cnt) { printf("TIMING it=30 n=%d cycles since iteration start (min/avg/max over %d CTAs):", n, cnt); for (int k : {1, 2, 3, 4, 8, 6, 7, 5}) printf(" [%d] %.0f/%.0f/%.0f", k, mn[k], sum[k] / cnt, mx[k]); printf("\n"); }
-    }
-#endif
     const int n_iter = host.st[0];
+    ctx->icp_prof_iters = n_iter; ctx->icp_prof_off_searched = bytes_part; ctx->icp_prof_off_ns = off_ns;
     if (T16) for (int k = 0; k < 16; ++k) T16[k] = host.T[k];
     if (res) {
         res->n_iter = n_iter; res->conv_state = host.st[1];
-        res->grid_blocks = grid; res->warps_per_block = kIcpWarps; res->group_batches = kFanIn;
+        res->grid_blocks = grid; res->warps_per_block = kIcpWarps;
+        res->group_batches = (grid * kIcpWarps) | (kIcpWarps << 16);   // reduction geometry for the oracle's reduce_mode 2
         res->device_ms = ms; res->correspondences = (long long)n_iter * n;
-        res->kernel_ms = kms; res->reserved0 = 0.f;
+        res->kernel_ms = kms; res->natural_iters = host.st[2]; res->natural_state = host.st[3];
     }
     if (mse_trace) PW_CUDA(cudaMemcpy(mse_trace, ob + 80, (size_t)n_iter * 8, cudaMemcpyDeviceToHost));
     if (T_trace) PW_CUDA(cudaMemcpy(T_trace, ob + 80 + (size_t)prm.max_iter * 8, (size_t)n_iter * 64, cudaMemcpyDeviceToHost));

@@ -442,11 +442,13 @@ void SORfilterHost(pcl::PointCloud<pcl::PointXYZ>::Ptr cloud_in, pcl::PointCloud
         meanDist[i] = kk ? (float)(s / kk) : 0.f;
     }
     double sum = 0, sq = 0;
-    for (float d : meanDist) { sum += d; sq += (double)d * d; }
+    // [PCL 1.8.1 StatisticalOutlierRemoval::applyFilterIndices] distances is a vector<float>: the square is a float
+    // product, rounded before it is widened; no clamp of the variance; a point is an outlier iff distance > threshold
+    for (float d : meanDist) { const float d_sq = d * d; sum += d; sq += d_sq; }
     const double mean = sum / n;
     const double var = (sq - sum * sum / n) / (n - 1);
-    const double thr = mean + SOR_StdMult * sqrt(max(var, 0.0));
-    for (int i = 0; i < n; ++i) if (meanDist[i] <= thr) cloud_out->push_back(pts[i]);
+    const double thr = mean + SOR_StdMult * sqrt(var);
+    for (int i = 0; i < n; ++i) if (!(meanDist[i] > thr)) cloud_out->push_back(pts[i]);
 }
 
 void PCpreprocessingHost(pcl::PointCloud<pcl::PointXYZ>::Ptr cloud_in, pcl::PointCloud<pcl::PointXYZ>::Ptr cloud_out,

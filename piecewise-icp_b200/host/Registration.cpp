@@ -496,7 +496,14 @@ bool registerEpoch(const Plan4D& pl, int startEpoch, int pairMode, int i, pcl::P
     pcl::console::TicToc time; time.tic();
     int refIdx = startEpoch;
     if (pairMode > 0) refIdx = (pairMode >= step) ? startEpoch : (i + 1 - pairMode);                // :95-97
-    else if (pairMode < 0) refIdx = pl.regPairs.at(i + 1);                                          // :98-100
+    else if (pairMode < 0) {                                                                        // :98-100
+        // the reference reads regPairs[i + 1] although calAdaptivePairSequence stores keys and targets relative to
+        // startEpoch (:563): the two agree for startEpoch == 0 only; a missing key is std::map::operator[]'s 0 there.
+        // Mirrored as is (a drop-in must pick the same pairs), without operator[]'s insertion and without a throw
+        // across the extern "C" boundary.
+        const auto it = pl.regPairs.find(i + 1);
+        refIdx = (it == pl.regPairs.end()) ? 0 : it->second;
+    }
     cout << "\n//////////////////////  Process Pair_" << step << ":  Epoch-" << pl.times[refIdx] << " and Epoch-"
          << pl.times[i + 1] << "   //////////////////////////////////////////// \n\n";
     std::string prefix = pl.cfg.FolderFilePath2 + std::to_string(pl.times[i + 1]);

@@ -3,6 +3,7 @@
 // reference's supervoxel segmentation).  Everything after that follows the reference's
 // per-patch post-processing: src/Segmentation.cpp:107-150, :195-321.
 #include "Segmentation.h"
+#include <dlfcn.h>
 #include "../../include/pwicp_host.h"
 
 #include <algorithm>
@@ -105,6 +106,26 @@ void calBPandCTSTD(pcl::PointCloud<pcl::PointXYZ>* cloudPatches, int patchNum, s
 static pwicp_segmenter_fn g_segmenter = nullptr;
 extern "C" void pwicp_host_set_segmenter(pwicp_segmenter_fn fn) { g_segmenter = fn; }
 
+// PWICP_SEGMENTER_PLUGIN=<shared object>:<symbol>: a segmentation named by the environment (include/pwicp_host.h)
+static void loadSegmenterPlugin() {
+    static bool tried = false;
+    if (tried) return;
+    tried = true;
+    const char* e = getenv("PWICP_SEGMENTER_PLUGIN");
+    if (!e || !*e) {
+        cout << "--->>> no segmenter registered: cubic-cell stand-in instead of the reference's supervoxels "
+                "(pwicp_host_set_segmenter / PWICP_SEGMENTER_PLUGIN)" << endl;
+        return;
+    }
+    const std::string spec(e);
+    const size_t colon = spec.rfind(':');
+    if (colon == std::string::npos) { cerr << "PWICP_SEGMENTER_PLUGIN: expected <shared object>:<symbol>" << endl; return; }
+    void* h = dlopen(spec.substr(0, colon).c_str(), RTLD_NOW | RTLD_LOCAL);
+    void* f = h ? dlsym(h, spec.substr(colon + 1).c_str()) : nullptr;
+    if (!f) { cerr << "PWICP_SEGMENTER_PLUGIN: cannot load " << spec << ": " << dlerror() << endl; return; }
+    g_segmenter = reinterpret_cast<pwicp_segmenter_fn>(f);
+}
+
 namespace {
 
 // src/Segmentation.cpp:107-150 for one initial patch; returns true when the patch is kept
@@ -165,10 +186,7 @@ int PatchGenerationAndRefinement(pcl::PointCloud<pcl::PointXYZ>::Ptr cloud, floa
                                  pcl::PointCloud<pcl::PointXYZ>*& cloudPatches, bool /*isVis*/) {
     cloudCentroid->clear(); cloudBoundary->clear();
     const int n = (int)cloud->size();
-    if (!g_segmenter) {
-        const char* e = getenv("PWICP_SEGMENTER");
-        if (e && std::string(e) == "supervoxel") g_segmenter = &pwicp_host_builtin_supervoxels;
-    }
+    if (!g_segmenter) loadSegmenterPlugin();
     if (g_segmenter) return patchesFromSegmenter(cloud, svResolution, cloudCentroid, cloudBoundary, cloudPatches);
     // stand-in segmentation: sort points by cubic cell of side svResolution
     float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX};

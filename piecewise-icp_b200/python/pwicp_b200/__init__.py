@@ -34,7 +34,7 @@ class IcpParams(C.Structure):
 class IcpResult(C.Structure):
     _fields_ = [("n_iter", C.c_int), ("conv_state", C.c_int), ("grid_blocks", C.c_int),
                 ("warps_per_block", C.c_int), ("group_batches", C.c_int), ("device_ms", C.c_float),
-                ("correspondences", C.c_longlong), ("kernel_ms", C.c_float), ("reserved0", C.c_float)]
+                ("correspondences", C.c_longlong), ("kernel_ms", C.c_float), ("natural_iters", C.c_int), ("natural_state", C.c_int)]
 
 
 class PairParams(C.Structure):
@@ -59,7 +59,8 @@ EXPORTS = [
     "pwicp_last_error", "pwicp_last_device_ms", "pwicp_launch_count", "pwicp_flush_l2",
     "pwicp_sync", "pwicp_set_cells_per_point", "pwicp_target_upload", "pwicp_target_rebuild", "pwicp_source_upload",
     "pwicp_clouds_upload", "pwicp_source_download", "pwicp_nn", "pwicp_icp_default_params",
-    "pwicp_icp_source_upload", "pwicp_icp_source_all", "pwicp_icp_run", "pwicp_icp_order", "pwicp_icp_p2plane",
+    "pwicp_icp_source_upload", "pwicp_icp_source_all", "pwicp_icp_run", "pwicp_icp_order", "pwicp_icp_profile",
+    "pwicp_icp_p2plane",
     "pwicp_single_iteration", "pwicp_piecewise_icp", "pwicp_percentile_nn", "pwicp_overlap_ratio",
     "pwicp_self_nn", "pwicp_vcm", "pwicp_transform", "pwicp_octree_bbox", "pwicp_bbox_corner_change",
     "pwicp_matrix2angle", "pwicp_mat4_mul", "pwicp_patch_stats", "pwicp_dmma_order_check",
@@ -104,6 +105,7 @@ def load_library(path=None):
     L.pwicp_icp_source_all.argtypes = [vp]
     L.pwicp_icp_run.argtypes = [vp, C.POINTER(IcpParams), vp, C.POINTER(IcpResult), vp, vp, vp]
     L.pwicp_icp_order.argtypes = [vp, vp]
+    L.pwicp_icp_profile.argtypes = [vp, vp, vp, C.c_int]
     L.pwicp_icp_p2plane.argtypes = [vp, vp, vp, C.c_int, vp, C.c_int, C.POINTER(IcpParams), vp,
                                     C.POINTER(IcpResult)]
     L.pwicp_single_iteration.argtypes = [vp, C.POINTER(PairParams), C.POINTER(State),
@@ -284,12 +286,20 @@ class Context:
         self._chk(self.L.pwicp_icp_run(self.h, C.byref(prm), _ptr(T), C.byref(res), _ptr(mse), _ptr(Ttr), _ptr(itr)))
         out = {"T": T.reshape(4, 4), "n_iter": res.n_iter, "state": res.conv_state,
                "grid_blocks": res.grid_blocks, "warps_per_block": res.warps_per_block,
-               "group_batches": res.group_batches,
+               "group_batches": res.group_batches, "natural_iters": res.natural_iters,
+               "natural_state": res.natural_state,
                "device_ms": res.device_ms, "kernel_ms": res.kernel_ms, "correspondences": res.correspondences}
         if trace:
             out.update(mse=mse[:res.n_iter], T_trace=Ttr[:res.n_iter].reshape(-1, 4, 4),
                        idx_trace=itr[:res.n_iter])
         return out
+
+    def icp_profile(self, cap=1024):
+        """Per-iteration profile of the last inner loop: (microseconds per iteration, queries that ran the search)."""
+        us = np.zeros(cap)
+        srch = np.zeros(cap, np.int32)
+        m = self.L.pwicp_icp_profile(self.h, _ptr(us), _ptr(srch), cap)
+        return us[:m], srch[:m]
 
     def icp_order(self):
         perm = np.zeros(self._n_icp, np.int32)
@@ -308,7 +318,8 @@ class Context:
         return {"T": T.reshape(4, 4), "n_iter": res.n_iter, "state": res.conv_state,
                 "device_ms": res.device_ms, "kernel_ms": res.kernel_ms, "correspondences": res.correspondences,
                 "grid_blocks": res.grid_blocks, "warps_per_block": res.warps_per_block,
-                "group_batches": res.group_batches}
+                "group_batches": res.group_batches, "natural_iters": res.natural_iters,
+                "natural_state": res.natural_state}
 
     # -- outer iteration / loop
     def single_iteration(self, pp, state, prm=None, want_flags=True):

@@ -33,7 +33,7 @@ def main():
     print("icp ms", r["device_ms"], "iters", r["n_iter"], "geom", r["grid_blocks"], r["warps_per_block"],
           "Gcorr/s", r["correspondences"] / r["device_ms"] / 1e6)
     perm = ctx.icp_order()
-    o = O.icp(d["ct1"], d["nrm1"], d["ct2"][perm], O.icp_params(max_iter=20, force_iters=1, reduce_mode=1,
+    o = O.icp(d["ct1"], d["nrm1"], d["ct2"][perm], O.icp_params(max_iter=20, force_iters=1, reduce_mode=2,
               group_batches=r["group_batches"]), trace=True)
     print("ICP T bit-equal", np.array_equal(r["T"], o["T"]), "idx trace equal", np.array_equal(r["idx_trace"][:, perm], o["idx_trace"]),
           "T_trace equal", np.array_equal(r["T_trace"], o["T_trace"]), "mse equal", np.array_equal(r["mse"], o["mse"]))

@@ -9,7 +9,6 @@ error the reference recorded for itself, and the difference between the two sets
 
     python scripts/refdata_4d.py stage      # here (container): copy the scans into refdata/ (git-ignored, travels with gpurun)
     python scripts/refdata_4d.py run        # on the GPU box: writes gpurun_out/refdata_4d_report.txt
-    python scripts/refdata_4d.py run --builtin [--modes 0]   # the library's own supervoxels (same labels as the reference's code)
     python scripts/refdata_4d.py run --refseg [--modes 0]
                                             # same, with the reference's own supervoxel segmentation (oracle/_ref/
                                             # libref_supervoxel.so, compiled from the reference's codelibrary) registered
@@ -66,13 +65,7 @@ def run():
     n_ep = int(sys.argv[sys.argv.index("--epochs") + 1]) if "--epochs" in sys.argv else 20      # epochs 1..n_ep
     out_root = os.path.join(ROOT, "gpurun_out", "refdata_4d_refseg" if refseg else "refdata_4d")
     rep = []
-    if "--builtin" in sys.argv:                          # the library's own supervoxels (host/Supervoxel.cpp), no oracle/_ref
-        refseg = True
-        L = host.lib()
-        L.pwicp_host_set_segmenter.argtypes = [C.c_void_p]
-        L.pwicp_host_set_segmenter(C.cast(L.pwicp_host_builtin_supervoxels, C.c_void_p))
-        rep.append("segmentation: the library's built-in supervoxels (pwicp_host_builtin_supervoxels)")
-    elif refseg:
+    if refseg:
         ref = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_supervoxel.so"))
         host.lib().pwicp_host_set_segmenter(C.cast(ref.ref_supervoxel_labels, C.c_void_p))
         rep.append("segmentation: the reference's own supervoxels (oracle/_ref/libref_supervoxel.so) through pwicp_host_set_segmenter")

@@ -8,12 +8,11 @@ CPU only.  For every pair of the reference's shipped synthetic series (data/data
 with the shipped configuration (configuration_files/configuration_4d.txt) and compares the final 4x4 with
 results/4DPCReg/<epoch>_Direct2Ref_TransMatrix.txt and with the ground truth (defined_transformations.txt).
 
-    python scripts/refdata_oracle.py [first_epoch last_epoch] [--standin | --builtin] [--mode direct|fixed|adaptive]
+    python scripts/refdata_oracle.py [first_epoch last_epoch] [--standin] [--mode direct|fixed|adaptive]
 
 --msvc-order: pcl::VoxelGrid sums the points of a voxel in the order its (unstable) std::sort leaves them; the recorded results
 come from the reference's Windows build, i.e. the Microsoft STL's order (host/msvc_sort.h) -- with it every recorded pair is
-reproduced.  --standin: the library's cubic-cell stand-in; --builtin: the library's own supervoxels (host/Supervoxel.cpp, same labels as
-the reference's code) instead of oracle/_ref.
+reproduced.  --standin: the library's cubic-cell stand-in instead of oracle/_ref.
 
 --mode fixed: the recorded <e>_Fixed_TransMatrix.txt files (interval 3: epoch e against epoch e - 3, the reference epoch
 for e <= 4; the interval is not recorded, 3 is the one that reproduces the files).  --mode adaptive: the recorded
@@ -72,9 +71,7 @@ def centroid_level_pair(pp, res=RES, sv=SV, dtmin=DTMIN):
 def register(xyz1, xyz2, use_reference_segmenter=True):
     L = host.lib()
     L.pwicp_host_set_segmenter.argtypes = [C.c_void_p]
-    if use_reference_segmenter == "builtin":            # the library's own supervoxels (host/Supervoxel.cpp)
-        L.pwicp_host_set_segmenter(C.cast(L.pwicp_host_builtin_supervoxels, C.c_void_p))
-    elif use_reference_segmenter:
+    if use_reference_segmenter:
         ref = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_supervoxel.so"))
         L.pwicp_host_set_segmenter(C.cast(ref.ref_supervoxel_labels, C.c_void_p))
     try:
@@ -128,7 +125,7 @@ def main():
     for e in range(first, last + 1):
         t0 = time.time()
         tgt = target_of(e)
-        T, res, d = register(load(tgt), load(e), "builtin" if "--builtin" in sys.argv else (not standin))
+        T, res, d = register(load(tgt), load(e), not standin)
         Tr, Vr = read_T(os.path.join(REF, "results/4DPCReg/%d_%s_TransMatrix.txt" % (e, tag)))
         a, b = pose_err(T, Tr)
         n_ok += int(a <= 1e-6 and b <= 1e-6)

@@ -154,7 +154,7 @@ def test_inner_loop_bit_exact_in_device_order(gpu_ctx, oracle, pair60k):
     perm = gpu_ctx.icp_order()
     assert sorted(perm.tolist()) == list(range(len(d["ct2"])))
     o = oracle.icp(d["ct1"], d["nrm1"], d["ct2"][perm],
-                   oracle.icp_params(max_iter=12, force_iters=1, reduce_mode=1,
+                   oracle.icp_params(max_iter=12, force_iters=1, reduce_mode=2,
                                      group_batches=r["group_batches"]),
                    trace=True)
     assert r["n_iter"] == o["n_iter"] == 12
@@ -189,7 +189,7 @@ def test_candidate_cache_adversarial_clouds(gpu_ctx, oracle):
     iters = 16
     r = gpu_ctx.icp_run(P.icp_params(max_iter=iters, force_iters=1), trace=True)
     perm = gpu_ctx.icp_order()
-    o = oracle.icp(tgt, nrm, src[perm], oracle.icp_params(max_iter=iters, force_iters=1, reduce_mode=1,
+    o = oracle.icp(tgt, nrm, src[perm], oracle.icp_params(max_iter=iters, force_iters=1, reduce_mode=2,
                                                          group_batches=r["group_batches"]), trace=True)
     assert r["n_iter"] == o["n_iter"] == iters
     assert np.array_equal(r["idx_trace"][:, perm], o["idx_trace"])
@@ -198,7 +198,7 @@ def test_candidate_cache_adversarial_clouds(gpu_ctx, oracle):
     gpu_ctx.icp_source_upload(src0)
     r = gpu_ctx.icp_run(P.icp_params(max_iter=6, force_iters=1), trace=True)
     perm = gpu_ctx.icp_order()
-    o = oracle.icp(tgt, nrm, src0[perm], oracle.icp_params(max_iter=6, force_iters=1, reduce_mode=1,
+    o = oracle.icp(tgt, nrm, src0[perm], oracle.icp_params(max_iter=6, force_iters=1, reduce_mode=2,
                                                           group_batches=r["group_batches"]), trace=True)
     assert np.array_equal(r["idx_trace"][:, perm], o["idx_trace"]) and np.array_equal(r["T_trace"], o["T_trace"])
 
@@ -362,7 +362,7 @@ def test_full_size_properties_1m(gpu_ctx, oracle):
     r = gpu_ctx.icp_run(P.icp_params(max_iter=8, force_iters=1), trace=True)
     perm = gpu_ctx.icp_order()
     o1 = oracle.icp(d["ct1"], d["nrm1"], d["ct2"][perm],
-                    oracle.icp_params(max_iter=8, force_iters=1, reduce_mode=1, group_batches=r["group_batches"]), trace=True)
+                    oracle.icp_params(max_iter=8, force_iters=1, reduce_mode=2, group_batches=r["group_batches"]), trace=True)
     assert np.array_equal(r["T_trace"], o1["T_trace"]) and np.array_equal(r["idx_trace"][:, perm], o1["idx_trace"])
     assert np.array_equal(r["mse"], o1["mse"])
     o0 = oracle.icp(d["ct1"], d["nrm1"], d["ct2"], oracle.icp_params(max_iter=8, force_iters=1))
@@ -393,7 +393,7 @@ def test_stress_10m_centroids(gpu_ctx, oracle):
     r = gpu_ctx.icp_run(P.icp_params(max_iter=6, force_iters=1), trace=True)
     perm = gpu_ctx.icp_order()
     o = oracle.icp(d["ct1"], d["nrm1"], d["ct2"][perm],
-                   oracle.icp_params(max_iter=6, force_iters=1, reduce_mode=1, group_batches=r["group_batches"]), trace=True)
+                   oracle.icp_params(max_iter=6, force_iters=1, reduce_mode=2, group_batches=r["group_batches"]), trace=True)
     assert np.array_equal(r["T_trace"], o["T_trace"]) and np.array_equal(r["mse"], o["mse"])
     assert np.array_equal(r["idx_trace"][:, perm], o["idx_trace"])
     a = gpu_ctx.icp_run(P.icp_params(max_iter=30, force_iters=1))

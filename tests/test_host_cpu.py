@@ -122,33 +122,30 @@ def test_segmenter_plugin_groups_points_like_the_reference():
     assert len(q["ct"]) > 0 and len(q["ct"]) != n or not np.array_equal(q["ct"], p["ct"])
 
 
-def test_builtin_supervoxels_give_the_references_patches(oracle):
-    """host/Supervoxel.cpp (Lin-2018 supervoxels, written from the algorithm) against the reference's own segmentation: on the
-    reference's shipped pair (tests/golden/refpair_e2.npz holds the reference's patch label of every point) the built-in
-    segmenter + the mirror's patch post-processing must select the same patches -- same centroids, same boundary points."""
-    import ctypes as C
-    from conftest import load_refpair
-    f = load_refpair(oracle.patch_stats)
-    L = host.lib()
-    L.pwicp_host_set_segmenter.argtypes = [C.c_void_p]
-    L.pwicp_host_set_segmenter(C.cast(L.pwicp_host_builtin_supervoxels, C.c_void_p))
-    try:
-        for cloud, ct_ref, bp_ref in ((f["pair"]["cloud1"], f["pair"]["ct1"], None), (f["pair"]["cloud2"], f["pair"]["ct2"], f["pair"]["bp2"])):
-            p = host.patches(cloud, f["pair"]["SVRes1"])
-            assert p["ct"].shape == ct_ref.shape and np.array_equal(p["ct"], ct_ref)
-            if bp_ref is not None:
-                assert np.array_equal(p["bp"], bp_ref)
-    finally:
-        L.pwicp_host_set_segmenter(None)
-    # labels themselves against the reference's code, when it is built here
+def test_segmenter_plugin_by_environment(oracle, tmp_path):
+    """PWICP_SEGMENTER_PLUGIN=<so>:<symbol> (include/pwicp_host.h): with the reference's own segmentation compiled where it
+    lies (oracle/_ref, test side only) the mirror's patch post-processing selects the patches the reference selected on its
+    shipped pair -- same centroids, same boundary points (tests/golden/refpair_e2.npz holds them).  Runs in a child process:
+    the plug-in is looked up once per process."""
+    import subprocess, sys
     ref_so = os.path.join(ROOT, "oracle", "_ref", "libref_supervoxel.so")
-    if os.path.exists(ref_so):
-        ref = C.CDLL(ref_so)
-        c = np.ascontiguousarray(f["pair"]["cloud2"][:50000], np.float32)
-        la, lb = np.empty(len(c), np.int32), np.empty(len(c), np.int32)
-        args = lambda out: (c.ctypes.data_as(C.c_void_p), len(c), C.c_float(0.05), 45, out.ctypes.data_as(C.c_void_p))
-        assert L.pwicp_host_builtin_supervoxels(*args(la)) == ref.ref_supervoxel_labels(*args(lb))
-        assert np.array_equal(la, lb)
+    if not os.path.exists(ref_so):
+        pytest.skip("oracle/_ref/libref_supervoxel.so not built (needs /root/reference at build time)")
+    code = (
+        "import os, sys, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, 'tests')); sys.path.insert(0, os.path.join(%r, 'piecewise-icp_b200', 'python'))\n"
+        "from conftest import load_refpair\n"
+        "from oracle import oracle_py as O\n"
+        "from pwicp_b200 import host\n"
+        "f = load_refpair(O.patch_stats)\n"
+        "for cloud, ct_ref, bp_ref in ((f['pair']['cloud1'], f['pair']['ct1'], None), (f['pair']['cloud2'], f['pair']['ct2'], f['pair']['bp2'])):\n"
+        "    p = host.patches(cloud, f['pair']['SVRes1'])\n"
+        "    assert p['ct'].shape == ct_ref.shape and np.array_equal(p['ct'], ct_ref)\n"
+        "    assert bp_ref is None or np.array_equal(p['bp'], bp_ref)\n"
+        "print('PLUGIN-OK')\n") % (ROOT, ROOT, ROOT)
+    env = dict(os.environ, PWICP_SEGMENTER_PLUGIN=ref_so + ":ref_supervoxel_labels")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert "PLUGIN-OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
 def _write_transmatrices(path, Ts, Vs):
