@@ -376,6 +376,20 @@ int pwicp_icp_run(pwicp_ctx* p, const pwicp_icp_params* prm, float* T16, pwicp_i
     return icp_run_device(ctx, prm ? *prm : d, T16, res, mse_trace, T_trace, idx_trace);
 }
 
+int pwicp_icp_phase_profile(pwicp_ctx* p, double* phase_us, int cap) {
+    Ctx* ctx = reinterpret_cast<Ctx*>(p);
+    if (!ctx || cap < 0 || !phase_us || ctx->icp_prof_iters < 1 || !ctx->icp_partials.p) { set_error(ctx, "icp_phase_profile: no inner loop has run"); return 0; }
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return 0;
+    const int m = std::min(cap, ctx->icp_prof_iters), M = ctx->icp_prof_max_iter;
+    std::vector<unsigned long long> ns((size_t)M + 1 + (size_t)M * 4);
+    cudaMemcpy(ns.data(), ctx->icp_partials.as<char>() + ctx->icp_prof_off_ns, ns.size() * 8, cudaMemcpyDeviceToHost);
+    for (int k = 0; k < m; ++k) {
+        const unsigned long long t0 = ns[k];
+        for (int j = 0; j < 4; ++j) phase_us[k * 4 + j] = (double)(ns[(size_t)M + 1 + (size_t)k * 4 + j] - t0) * 1e-3;
+    }
+    return m;
+}
+
 int pwicp_icp_profile(pwicp_ctx* p, double* iter_us, int* searched, int cap) {
     Ctx* ctx = reinterpret_cast<Ctx*>(p);
     if (!ctx || cap < 0 || ctx->icp_prof_iters < 1 || !ctx->icp_partials.p) { set_error(ctx, "icp_profile: no inner loop has run"); return 0; }

@@ -114,6 +114,7 @@ struct Ctx {
     DevBuf ct_seed, bp_seed, pp_seed, ct_order;
     bool ct_order_valid = false;
     int n_icp = 0;
+    int icp_prof_max_iter = 0;
     int icp_prof_iters = 0;                      // pwicp_icp_profile: iterations of the last run, offsets into icp_partials
     size_t icp_prof_off_searched = 0, icp_prof_off_ns = 0;
     // scratch

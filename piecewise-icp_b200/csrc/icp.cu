@@ -33,13 +33,17 @@
 #include "nn_search.cuh"
 #include "small_algebra.cuh"
 
-// candidate cache: radius beyond the NN distance (in level-0 cells) and the largest last step (as a fraction of it) at
-// which a cache is built
-#ifndef PWICP_SLACK_CELLS
-#define PWICP_SLACK_CELLS 0.03f
+// candidate cache (nn_search.cuh), in level-0 cells: how far beyond the match distance targets are collected when a
+// cache is built, how close to the match distance a target must be to be cached with the match, and the largest last
+// step (L1) after which a cache is still built (a point that has just moved several cells will move again)
+#ifndef PWICP_COLLECT_CELLS
+#define PWICP_COLLECT_CELLS 0.1f
 #endif
-#ifndef PWICP_BUILD_FRAC
-#define PWICP_BUILD_FRAC 0.25f
+#ifndef PWICP_TIE_CELLS
+#define PWICP_TIE_CELLS 0.0005f
+#endif
+#ifndef PWICP_BUILD_STEP_CELLS
+#define PWICP_BUILD_STEP_CELLS 1e30f
 #endif
 namespace cg = cooperative_groups;
 
@@ -69,7 +73,8 @@ struct IcpArgs {
     // all per-point arrays are padded to a multiple of 32 points: a pad has a zero normal (every row term and product is
     // exactly zero), a huge margin (never searches) and is excluded from the sum of squared distances
     int seed_exact;           // cq[] is the exact NN of the untransformed source (iteration 0 needs no search)
-    float slack;              // cache radius beyond the NN distance
+    float collect;            // targets within this of the match distance are looked at when a cache is built
+    float tie;                // ... and those within this of the match distance are cached with it
     float build_step;         // a cache is built only when the point moved less than this in the last step (L1 length)
     int n;
     int max_iter;
@@ -83,6 +88,7 @@ struct IcpArgs {
     float* T_trace;           // nullable
     int* idx_trace;           // nullable, [iter][n]
     unsigned long long* iter_ns;   // [max_iter + 1]: %globaltimer at the start of the loop and after every iteration (CTA 0)
+    unsigned long long* phase_ns;  // [max_iter][4]: CTA 0, warp 0: end of its batches, after the grid barrier, totals formed, solved
 };
 
 // Shared scratch of the per-iteration solve.
@@ -250,23 +256,35 @@ static __device__ __noinline__ Fallback icp_search_fallback(const IcpArgs& a, in
     const Best& bb = f.bb;
     const float4 nq = __ldg(a.aux + bb.pos);
     f.nx = nq.x; f.ny = nq.y; f.nz = nq.z;
-    CandCache cc;
-    cc.rho = 0.f;
-    if (step < a.build_step) {
-        const float rm = sqrtf(bb.d2) + a.slack;
-        cc = ball_collect(a.g.lv[0], a.g.ox, a.g.oy, a.g.oz, px, py, pz, rm * rm);
-    }
-    // the match is the primary candidate; the other cached targets follow in any order
+    // a new cache around this position (nn_search.cuh, "candidate cache"): the match, the targets within `tie` of it,
+    // and the radius just below the first target left out
     int o1 = bb.pos, o2 = bb.pos, o3 = bb.pos, k = 0;
-    if (cc.rho > 0.f) {
+    f.rho = 0.f;
+    const float d1 = sqrtf(bb.d2);
+    if (step < a.build_step) {
+        // first with the wide radius (a large gap to the second-nearest target = a long-lived cache); a query far from
+        // its match would need more than the 3x3-row scan for that: then only the ties are looked for
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            const float R = d1 + (attempt == 0 ? a.collect : 4.0f * a.tie);
+            if (R * a.g.lv[0].inv_h >= 0.95f) continue;
+            const Near5 nb = ball_collect(a.g.lv[0], a.g.ox, a.g.oy, a.g.oz, px, py, pz, R * R);
+            if (!nb.complete) continue;
+            const float lim = (d1 + a.tie) * (d1 + a.tie);
+            float rho2 = R * R;                      // complete up to the scanned radius unless a target is left out
+            bool open = true;                        // still taking targets into the cache
 #pragma unroll
-        for (int j = 0; j < kCacheCands; ++j)
-            if (cc.pos[j] != bb.pos) { if (k == 0) o1 = cc.pos[j]; else if (k == 1) o2 = cc.pos[j]; else if (k == 2) o3 = cc.pos[j]; ++k; }
-        // all four slots taken by targets other than the match cannot happen (the match is the nearest
-        // of the collected set); guard anyway: no cache rather than a wrong one
-        if (k > 3) { cc.rho = 0.f; k = 0; }
+            for (int j = 0; j <= kCacheCands; ++j) {
+                if (!open || nb.pos[j] < 0) continue;
+                if (nb.pos[j] == bb.pos) continue;   // the match itself: always cached (the primary)
+                if (nb.d2[j] < lim && k < 3) {
+                    if (k == 0) o1 = nb.pos[j]; else if (k == 1) o2 = nb.pos[j]; else o3 = nb.pos[j];
+                    ++k;
+                } else { rho2 = nb.d2[j]; open = false; }
+            }
+            f.rho = sqrtf(rho2) * 0.9999f;
+            break;
+        }
     }
-    f.rho = cc.rho;
     f.nq = nq_dot(nq.x, nq.y, nq.z, bb.qx, bb.qy, bb.qz);
     a.cq[i] = make_float4(bb.qx, bb.qy, bb.qz, __int_as_float(bb.pos | (k > 0 ? kMoreBit : 0)));
     a.cn[i] = make_float4(nq.x, nq.y, nq.z, f.nq);
@@ -481,6 +499,7 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_persistent_kernel(const Ic
             pslot = (pslot == (kStageSlots - 1) * kSlotBytes) ? 0 : pslot + kSlotBytes;
         }
 
+        if (blockIdx.x == 0 && tid == 0) a.phase_ns[it * 4] = globaltimer_ns();
         // ---- warp sums (lane v ends up with value v), CTA sum over the warps in order, published for the grid
         {
             double y[16];
@@ -499,6 +518,7 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_persistent_kernel(const Ic
             __stcg(a.part + ((size_t)(it & 1) * G + blockIdx.x) * kNumVals + lane, s);
         }
         grid.sync();
+        if (blockIdx.x == 0 && tid == 0) a.phase_ns[it * 4 + 1] = globaltimer_ns();
         // the next iteration's first two batches: their copies do not depend on the transform being solved
         // for, so they fly during the reduction and the solve
         stage_point(a.work, i0, 0);
@@ -526,10 +546,11 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_persistent_kernel(const Ic
                 s_tot[lane] = s;
             }
             __syncwarp();
+            if (blockIdx.x == 0 && lane == 0) a.phase_ns[it * 4 + 2] = globaltimer_ns();
             const int st = icp_finish_warp(a, it, s_tot, s_T, s_Tfinal, s_fin, lane);
             if (lane == 0) {
                 s_stop = st;
-                if (blockIdx.x == 0) a.iter_ns[it + 1] = globaltimer_ns();
+                if (blockIdx.x == 0) { a.iter_ns[it + 1] = globaltimer_ns(); a.phase_ns[it * 4 + 3] = a.iter_ns[it + 1]; }
             }
         }
         __syncthreads();
@@ -676,7 +697,7 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     const size_t bytes_part = (size_t)2 * grid * kNumVals * sizeof(double);
     const size_t bytes_cnt = (size_t)prm.max_iter * sizeof(int);
     const size_t off_ns = (bytes_part + bytes_cnt + 7) & ~(size_t)7;
-    PW_TRY(ctx->icp_partials.reserve(ctx, off_ns + (size_t)(prm.max_iter + 1) * 8 + 64));
+    PW_TRY(ctx->icp_partials.reserve(ctx, off_ns + (size_t)(prm.max_iter + 1) * 8 + (size_t)prm.max_iter * 32 + 64));
     const size_t out_bytes = 64 + 16 + (size_t)prm.max_iter * (8 + 64);
     PW_TRY(ctx->icp_out.reserve(ctx, out_bytes));
     char* ob = ctx->icp_out.as<char>();
@@ -703,8 +724,14 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     a.cq = a.cn + n_pad;
     a.cmore = reinterpret_cast<int4*>(a.cn + 2 * (size_t)n_pad);
     a.seed_exact = 1;         // classification matches (outer.cu) or icp_seed_kernel
-    a.slack = PWICP_SLACK_CELLS / ctx->tgt.dev.lv[0].inv_h;
-    a.build_step = PWICP_BUILD_FRAC * a.slack;
+    {
+        // tuning knobs (cells of the finest grid level); the environment overrides are for A/B runs only
+        auto knob = [](const char* name, float dflt) { const char* e = getenv(name); return e ? (float)atof(e) : dflt; };
+        const float h = 1.0f / ctx->tgt.dev.lv[0].inv_h;
+        a.collect = knob("PWICP_COLLECT_CELLS", PWICP_COLLECT_CELLS) * h;
+        a.tie = knob("PWICP_TIE_CELLS", PWICP_TIE_CELLS) * h;
+        a.build_step = knob("PWICP_BUILD_STEP_CELLS", PWICP_BUILD_STEP_CELLS) * h;
+    }
 
     a.n = n;
     a.max_iter = prm.max_iter;
@@ -716,7 +743,8 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     a.part = ctx->icp_partials.as<double>();
     a.searched = reinterpret_cast<int*>(ctx->icp_partials.as<char>() + bytes_part);
     a.iter_ns = reinterpret_cast<unsigned long long*>(ctx->icp_partials.as<char>() + off_ns);
-    PW_CUDA(cudaMemsetAsync(a.searched, 0, off_ns - bytes_part + (size_t)(prm.max_iter + 1) * 8, ctx->stream));
+    a.phase_ns = a.iter_ns + prm.max_iter + 1;
+    PW_CUDA(cudaMemsetAsync(a.searched, 0, off_ns - bytes_part + (size_t)(prm.max_iter + 1) * 8 + (size_t)prm.max_iter * 32, ctx->stream));
     a.out_T = reinterpret_cast<float*>(ob);
     a.out_state = reinterpret_cast<int*>(ob + 64);
     a.mse_trace = mse_trace ? reinterpret_cast<double*>(ob + 80) : nullptr;
@@ -737,6 +765,7 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     PW_CUDA(cudaEventElapsedTime(&kms, ctx->ev2, ctx->ev1));
     ctx->last_ms = ms;
     const int n_iter = host.st[0];
+    ctx->icp_prof_max_iter = prm.max_iter;
     ctx->icp_prof_iters = n_iter; ctx->icp_prof_off_searched = bytes_part; ctx->icp_prof_off_ns = off_ns;
     if (T16) for (int k = 0; k < 16; ++k) T16[k] = host.T[k];
     if (res) {

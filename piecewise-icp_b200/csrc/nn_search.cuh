@@ -268,29 +268,30 @@ __device__ __forceinline__ Best nn_search_seeded(const GridDev& g, float px, flo
 }
 
 // ---------------------------------------------------------------------------------------------
-// Candidate cache (inner ICP loop).  Once the incremental transforms are small a query barely
-// moves between iterations, so the set  S = { q : d2(a, q) < rho2 }  collected around an anchor a
-// (the query's position when S was built) keeps containing every target that can be its nearest
-// neighbour: if  |p - best(S)| + |p - a| < rho  then any q at least as close to p as best(S) lies
-// within rho of a, i.e. in S, and best(S) under the tie rule is the exact answer.  S is tiny (the
-// ball of radius d_nn + slack meets the sampled surface in a small disc: 1-3 targets), so an
-// iteration costs kCacheCands gathered candidates instead of a cell walk.
+// Candidate cache (inner ICP loop).  Around the position a at which a query was last searched (its anchor) the
+// targets are known in order of distance: d_1 <= d_2 <= ...  The cache holds the first m of them (the match and up to
+// three more) and the radius rho just below d_(m+1), so that S = { q : d(a, q) < rho } is exactly the cached set.
+// Later, at position p with |p - a| <= path:  if  |p - best(S)| + path < rho  then every target at least as close to
+// p as best(S) lies within rho of a, i.e. in S, and best(S) under the tie rule is the exact answer.  m is chosen per
+// query: targets within `tie` of the match (they can overtake it after a tiny move) are cached with it, the first
+// one beyond that sets rho -- for most queries m = 1 and rho - d_1 is the gap to the second-nearest target (a good
+// part of the point spacing), so a cache built right after the first, large ICP step survives the later small ones.
 constexpr int kCacheCands = 4;
 
-struct CandCache {
-    int pos[kCacheCands];   // level-0 positions; unused slots repeat pos[0]
-    float rho;              // validity radius with its safety factor applied; 0 = no cache
+struct Near5 {
+    float d2[kCacheCands + 1];   // squared distances, ascending; +inf = no such target within the scanned ball
+    int pos[kCacheCands + 1];    // level-0 positions, -1 = none
+    int complete;                // the scan covered the whole ball (else: ball too large for the 3x3-row scan)
 };
 
-// Collects the targets within sqrt(rho2max) of p on level 0: the kCacheCands nearest and the
-// radius up to which the list is complete.  Returns rho = 0 when the ball is too large for the
-// 3x3-row scan.  Out of line: runs once per query when its cache is (re)built.
-static __device__ __noinline__ CandCache ball_collect(const GridLevel& L, float ox, float oy, float oz,
-                                                      float px, float py, float pz, float rho2max) {
-    CandCache out;
+// The kCacheCands + 1 nearest targets within sqrt(rho2max) of p on level 0 (ordered by distance only; the tie rule
+// is the caller's business).  Out of line: runs once per query when its cache is (re)built.
+static __device__ __noinline__ Near5 ball_collect(const GridLevel& L, float ox, float oy, float oz,
+                                                  float px, float py, float pz, float rho2max) {
+    Near5 out;
 #pragma unroll
-    for (int k = 0; k < kCacheCands; ++k) out.pos[k] = -1;
-    out.rho = 0.f;
+    for (int k = 0; k <= kCacheCands; ++k) { out.d2[k] = __int_as_float(0x7f800000); out.pos[k] = -1; }
+    out.complete = 0;
     const float fx = (px - ox) * L.inv_h, fy = (py - oy) * L.inv_h, fz = (pz - oz) * L.inv_h;
     const float mx = 0.01f + fabsf(fx) * 4e-6f, my = 0.01f + fabsf(fy) * 4e-6f, mz = 0.01f + fabsf(fz) * 4e-6f;
     const float r = sqrtf(rho2max) * L.inv_h * 1.00001f;
@@ -316,7 +317,7 @@ static __device__ __noinline__ CandCache ball_collect(const GridLevel& L, float 
             for (uint32_t i = s; i < e; ++i) {
                 const float4 q = __ldg(L.pts + i);
                 float cd = l2_simple(px, py, pz, q.x, q.y, q.z);
-                if (cd <= rho2max) {
+                if (cd <= rho2max && cd < D[kCacheCands]) {
                     int cp = (int)i;        // sorted insertion, ascending distance
 #pragma unroll
                     for (int k = 0; k <= kCacheCands; ++k)
@@ -324,12 +325,9 @@ static __device__ __noinline__ CandCache ball_collect(const GridLevel& L, float 
                 }
             }
         }
-    if (P[0] < 0) return out;
-    // complete up to rho2max, or only below the distance of the first target left out
-    const float rho2 = (P[kCacheCands] < 0) ? rho2max : D[kCacheCands];
 #pragma unroll
-    for (int k = 0; k < kCacheCands; ++k) out.pos[k] = (P[k] >= 0) ? P[k] : P[0];
-    out.rho = sqrtf(rho2) * 0.9999f;
+    for (int k = 0; k <= kCacheCands; ++k) { out.d2[k] = D[k]; out.pos[k] = P[k]; }
+    out.complete = 1;
     return out;
 }
 

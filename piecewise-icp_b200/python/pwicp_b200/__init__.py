@@ -59,7 +59,7 @@ EXPORTS = [
     "pwicp_last_error", "pwicp_last_device_ms", "pwicp_launch_count", "pwicp_flush_l2",
     "pwicp_sync", "pwicp_set_cells_per_point", "pwicp_target_upload", "pwicp_target_rebuild", "pwicp_source_upload",
     "pwicp_clouds_upload", "pwicp_source_download", "pwicp_nn", "pwicp_icp_default_params",
-    "pwicp_icp_source_upload", "pwicp_icp_source_all", "pwicp_icp_run", "pwicp_icp_order", "pwicp_icp_profile",
+    "pwicp_icp_source_upload", "pwicp_icp_source_all", "pwicp_icp_run", "pwicp_icp_order", "pwicp_icp_profile", "pwicp_icp_phase_profile",
     "pwicp_icp_p2plane",
     "pwicp_single_iteration", "pwicp_piecewise_icp", "pwicp_percentile_nn", "pwicp_overlap_ratio",
     "pwicp_self_nn", "pwicp_vcm", "pwicp_transform", "pwicp_octree_bbox", "pwicp_bbox_corner_change",
@@ -106,6 +106,7 @@ def load_library(path=None):
     L.pwicp_icp_run.argtypes = [vp, C.POINTER(IcpParams), vp, C.POINTER(IcpResult), vp, vp, vp]
     L.pwicp_icp_order.argtypes = [vp, vp]
     L.pwicp_icp_profile.argtypes = [vp, vp, vp, C.c_int]
+    L.pwicp_icp_phase_profile.argtypes = [vp, vp, C.c_int]
     L.pwicp_icp_p2plane.argtypes = [vp, vp, vp, C.c_int, vp, C.c_int, C.POINTER(IcpParams), vp,
                                     C.POINTER(IcpResult)]
     L.pwicp_single_iteration.argtypes = [vp, C.POINTER(PairParams), C.POINTER(State),
@@ -300,6 +301,12 @@ class Context:
         srch = np.zeros(cap, np.int32)
         m = self.L.pwicp_icp_profile(self.h, _ptr(us), _ptr(srch), cap)
         return us[:m], srch[:m]
+
+    def icp_phase_profile(self, cap=1024):
+        """Where CTA 0 spent each iteration of the last inner loop: (iterations, 4) microseconds since the iteration began."""
+        us = np.zeros((cap, 4))
+        m = self.L.pwicp_icp_phase_profile(self.h, _ptr(us), cap)
+        return us[:m]
 
     def icp_order(self):
         perm = np.zeros(self._n_icp, np.int32)

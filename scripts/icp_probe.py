@@ -41,13 +41,16 @@ def timing(ctx, n, iters):
     for _ in range(5):
         ctx.flush_l2(); b = ctx.target_rebuild(); r = ctx.icp_run(prm)
         if best is None or r["device_ms"] < best[1]["device_ms"]:
-            best = (b, r, ctx.icp_profile())
-    b, r, (us, srch) = best
+            best = (b, r, ctx.icp_profile(), ctx.icp_phase_profile())
+    b, r, (us, srch), ph = best
     n2 = len(d["ct2"])
     print(f"timing n={n2} iters={iters}: build {b:.3f} ms, loop {r['device_ms']:.3f} ms, kernel {r['kernel_ms']:.3f} ms "
           f"-> {r['correspondences'] / (b + r['device_ms']) / 1e6:.2f} G corr/s resident; kernel alg. "
           f"{48 * iters * n2 / r['kernel_ms'] / 1e6:.0f} GB/s", flush=True)
     print("  iteration us :", " ".join(f"{u:.1f}" for u in us[:8]), "... median of the rest", f"{np.median(us[8:]):.2f}" if len(us) > 8 else "")
+    if len(ph) > 10:
+        print("  CTA 0 phases (median of iterations 8..): own batches done %.2f us, barrier passed %.2f, totals %.2f, solved %.2f"
+              % tuple(np.median(ph[8:], axis=0)))
     print("  searched     :", " ".join(str(s) for s in srch[:8]), "... sum of the rest", int(srch[8:].sum()))
 
 
