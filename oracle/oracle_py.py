@@ -102,6 +102,11 @@ def icp_params(max_iter=100, tf_eps=1e-8, fit_eps=1e-6, force_iters=0, reduce_mo
     return IcpParams(max_iter, tf_eps, fit_eps, force_iters, reduce_mode, group_batches, threads, rot_thr_default)
 
 
+def set_threads(n):
+    """Threads for the independent NN queries of the outer iteration / percentile (results do not depend on it)."""
+    lib().orc_set_threads(int(n))
+
+
 def nn(tgt, qry, brute=False):
     tgt, qry = _f32(tgt), _f32(qry)
     idx = np.empty(len(qry), np.int32)

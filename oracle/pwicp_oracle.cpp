@@ -509,6 +509,12 @@ orc_icp_params default_icp() {
     return p;
 }
 
+/* Threads for the INDEPENDENT nearest-neighbour queries of the outer iteration, the percentile and the VCM (1 = a plain
+ * loop, what the reference does).  Only which thread answers a query changes; every query, every sum and every
+ * selection is the same, so the results are bit-identical for any thread count (tests/test_oracle.py). */
+static int g_threads = 1;
+extern "C" void orc_set_threads(int threads) { g_threads = threads > 1 ? threads : 1; }
+
 /* i = 0..n-1 on `threads` threads in contiguous chunks (1: a plain loop, what the reference does) */
 template <typename F>
 void parallel_for(int n, int threads, F&& f) {
@@ -805,11 +811,11 @@ float orc_bbox_corner_change(const double* bb, const float* T) {
 double orc_percentile_nn(const float* cloud1, int m1, const float* cloud2, int m2, float pct) {
     KdTree t; t.build(cloud1, m1);
     std::vector<double> dist(m2);
-    for (int i = 0; i < m2; ++i) {
+    parallel_for(m2, g_threads, [&](int i) {
         int j; float d2;
         t.query(cloud2 + 3 * (size_t)i, j, d2);
         dist[i] = std::sqrt(d2);
-    }
+    });
     int leftnum = m2 * pct;                          /* int = int * float, :177 */
     if (leftnum >= m2) leftnum = m2 - 1;             /* the reference would read out of bounds */
     std::nth_element(dist.begin(), dist.begin() + leftnum, dist.end());
@@ -990,8 +996,8 @@ int orc_single_iteration(orc_pair* pr, orc_state* st, const orc_icp_params* icp_
     KdTree treeCT; treeCT.build(pr->ct1, pr->n1);
     std::vector<int> ctIdx(SVnumPC2), bpIdx(6 * (size_t)SVnumPC2);
     std::vector<float> ctD2(SVnumPC2), bpD2(6 * (size_t)SVnumPC2);
-    for (int i = 0; i < SVnumPC2; ++i) treeCT.query(pr->ct2 + 3 * (size_t)i, ctIdx[i], ctD2[i]);
-    for (int i = 0; i < 6 * SVnumPC2; ++i) treeCT.query(pr->bp2 + 3 * (size_t)i, bpIdx[i], bpD2[i]);
+    parallel_for(SVnumPC2, g_threads, [&](int i) { treeCT.query(pr->ct2 + 3 * (size_t)i, ctIdx[i], ctD2[i]); });
+    parallel_for(6 * SVnumPC2, g_threads, [&](int i) { treeCT.query(pr->bp2 + 3 * (size_t)i, bpIdx[i], bpD2[i]); });
 
     /* (2) LoDetection per patch, :750-769 */
     float max2minLoD = 2.0;

@@ -163,6 +163,10 @@ int orc_piecewise_icp(orc_pair* pr, int isManualDTinit, float DTinit, const orc_
                       int max_outer, float* DTseries, int* n_series, float* T16, double* vcm36,
                       orc_iter_stats* stats_per_iter);
 
+/* Threads for the independent NN queries of orc_single_iteration / orc_piecewise_icp / orc_percentile_nn (default 1 = the
+ * reference's single thread).  Results do not depend on it.  The inner loop takes its own count from orc_icp_params. */
+void orc_set_threads(int threads);
+
 /* 4x4 float product C = A*B, Eigen order (used for transMat = cur * transMat, :687, :319) */
 void orc_mat4_mul(const float* A, const float* B, float* C);
 

@@ -234,32 +234,71 @@ static __device__ __noinline__ int icp_finish_warp(const IcpArgs& a, int it, con
     return __shfl_sync(0xffffffffu, state, 0);
 }
 
-// The search path of a query whose candidate cache does not cover it: seeded ball search, and --
-// once the point has (nearly) stopped moving -- a new cache around its position.  Out of line on
-// purpose: it runs for every query during the first few iterations and (almost) never afterwards,
-// and the steady-state loop has to stay small enough to live in the instruction cache together
-// with the per-iteration solve (profiles/r01e_*: 6 us per iteration otherwise).
-struct Fallback {
-    Best bb;
-    float nx, ny, nz;     // normal of the match
-    float nq;             // nq_dot(normal, match)
-    float rho;            // validity radius of the cache that was written (0: none)
+// Everything a query can need beyond its inline match, out of line on purpose: the steady-state loop has to stay small
+// (instruction cache, together with the per-iteration solve: profiles/r01e_*) and, above all, keep its 28 double
+// accumulators in registers -- inlined, the live values of this path spilled them in every trip (profiles/r02j).
+//   (1) further cached candidates (cq[].w has kMoreBit): best of the cached set under the tie rule, promoted to the
+//       inline slot when it overtakes the match;
+//   (2) the certificate fails: seeded ball search and a new cache around the position (nn_search.cuh).
+struct SlowOut {
+    float d2;             // squared distance of the match
+    int pos;              // its level-0 position
+    float qx, qy, qz;     // the match
+    float nx, ny, nz, nq; // its normal, nq_dot(normal, match)
+    float margin;         // what is left of the cache radius
 };
-static __device__ __noinline__ Fallback icp_search_fallback(const IcpArgs& a, int it, int i, float px, float py, float pz,
-                                                            int seed, float step) {
+static __device__ __noinline__ SlowOut icp_slow_path(const IcpArgs& a, int it, int i, float px, float py, float pz,
+                                                     float4 q0, float4 cn, float margin, float mchk, float step) {
+    const float4* __restrict__ pts = a.g.lv[0].pts;
+    const int pos0 = __float_as_int(q0.w) & ~kMoreBit;
+    SlowOut o;
+    o.d2 = l2_simple(px, py, pz, q0.x, q0.y, q0.z);
+    o.pos = pos0; o.qx = q0.x; o.qy = q0.y; o.qz = q0.z;
+    o.nx = cn.x; o.ny = cn.y; o.nz = cn.z; o.nq = cn.w;
+    o.margin = margin;
+    if (__float_as_int(q0.w) & kMoreBit) {
+        // positions from the side array, the three loads are issued together, unused slots repeat the primary
+        const int4 cm = __ldcg(a.cmore + i);
+        int bidx = cm.w;
+        float4 q1 = q0, q2 = q0, q3 = q0;
+        if (cm.x != pos0) q1 = __ldg(pts + cm.x);
+        if (cm.y != pos0) q2 = __ldg(pts + cm.y);
+        if (cm.z != pos0) q3 = __ldg(pts + cm.z);
+#define PW_CAND(q, cp)                                                                         \
+        if ((cp) != pos0) {                                                                    \
+            const float d = l2_simple(px, py, pz, q.x, q.y, q.z);                              \
+            const int id = __float_as_int(q.w);                                                \
+            if (d < o.d2 || (d == o.d2 && id < bidx)) {                                        \
+                o.d2 = d; bidx = id; o.pos = (cp); o.qx = q.x; o.qy = q.y; o.qz = q.z;         \
+            }                                                                                  \
+        }
+        PW_CAND(q1, cm.x) PW_CAND(q2, cm.y) PW_CAND(q3, cm.z)
+#undef PW_CAND
+        if (o.pos != pos0 && mchk > 0.f && o.d2 * 1.00003f < mchk * mchk) {
+            // another cached target has become the nearest: make it the primary
+            const float4 nv = __ldg(a.aux + o.pos);
+            o.nx = nv.x; o.ny = nv.y; o.nz = nv.z;
+            o.nq = nq_dot(o.nx, o.ny, o.nz, o.qx, o.qy, o.qz);
+            a.cq[i] = make_float4(o.qx, o.qy, o.qz, __int_as_float(o.pos | kMoreBit));
+            a.cn[i] = make_float4(o.nx, o.ny, o.nz, o.nq);
+            a.cmore[i] = make_int4(cm.x == o.pos ? pos0 : cm.x, cm.y == o.pos ? pos0 : cm.y,
+                                   cm.z == o.pos ? pos0 : cm.z, bidx);
+        }
+    }
+    // |p - anchor| <= path (triangle inequality over the steps actually taken): every target at least as close to p
+    // as the best cached one lies within the cache radius of the anchor; compared as squares
+    if (mchk > 0.f && o.d2 * 1.00003f < mchk * mchk) return o;
+
     {   // queries that needed the search this iteration (diagnostic: pwicp_icp_profile)
         const unsigned m = __activemask();
         if ((int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(a.searched + it, __popc(m));
     }
-    Fallback f;
-    f.bb = nn_search_seeded<true>(a.g, px, py, pz, seed);
-    const Best& bb = f.bb;
+    const Best bb = nn_search_seeded<true>(a.g, px, py, pz, o.pos);
     const float4 nq = __ldg(a.aux + bb.pos);
-    f.nx = nq.x; f.ny = nq.y; f.nz = nq.z;
     // a new cache around this position (nn_search.cuh, "candidate cache"): the match, the targets within `tie` of it,
     // and the radius just below the first target left out
     int o1 = bb.pos, o2 = bb.pos, o3 = bb.pos, k = 0;
-    f.rho = 0.f;
+    float rho = 0.f;
     const float d1 = sqrtf(bb.d2);
     if (step < a.build_step) {
         // first with the wide radius (a large gap to the second-nearest target = a long-lived cache); a query far from
@@ -281,15 +320,18 @@ static __device__ __noinline__ Fallback icp_search_fallback(const IcpArgs& a, in
                     ++k;
                 } else { rho2 = nb.d2[j]; open = false; }
             }
-            f.rho = sqrtf(rho2) * 0.9999f;
+            rho = sqrtf(rho2) * 0.9999f;
             break;
         }
     }
-    f.nq = nq_dot(nq.x, nq.y, nq.z, bb.qx, bb.qy, bb.qz);
+    o.d2 = bb.d2; o.pos = bb.pos; o.qx = bb.qx; o.qy = bb.qy; o.qz = bb.qz;
+    o.nx = nq.x; o.ny = nq.y; o.nz = nq.z;
+    o.nq = nq_dot(nq.x, nq.y, nq.z, bb.qx, bb.qy, bb.qz);
+    o.margin = rho;
     a.cq[i] = make_float4(bb.qx, bb.qy, bb.qz, __int_as_float(bb.pos | (k > 0 ? kMoreBit : 0)));
-    a.cn[i] = make_float4(nq.x, nq.y, nq.z, f.nq);
+    a.cn[i] = make_float4(nq.x, nq.y, nq.z, o.nq);
     if (k > 0) a.cmore[i] = make_int4(o1, o2, o3, bb.idx);
-    return f;
+    return o;
 }
 
 // 16-byte asynchronous copy global -> shared (LDGSTS through L2), per-thread completion groups.
@@ -406,7 +448,6 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_persistent_kernel(const Ic
             lds128(p, s_lane_sh + slot);
             lds128(q0, s_lane_sh + slot + 512);
             lds128(cn, s_lane_sh + slot + 1024);
-            const int pos0 = __float_as_int(q0.w) & ~kMoreBit;
             float step = __int_as_float(0x7f800000);             // L1 length of the last step (>= its Euclidean length)
             float margin;                                        // cache radius left after the path travelled (lower bound)
             float mchk;                                          // ... as the certificate below uses it
@@ -426,49 +467,17 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_persistent_kernel(const Ic
                 margin = (i < a.n) ? 0.f : kPadMargin;            // no cache yet; pads never search
                 mchk = (a.seed_exact || i >= a.n) ? kPadMargin : 0.f;
             }
-            // (b) exact NN: best of the cached candidates when the cache still covers the
-            // query (nn_search.cuh, "candidate cache"), else the seeded ball search
+            // (b) exact NN: the inline match when the candidate cache still covers the query and holds nothing else
+            // (nn_search.cuh, "candidate cache"); further cached candidates and the seeded ball search are out of line
             float bd2 = l2_simple(p.x, p.y, p.z, q0.x, q0.y, q0.z);
             float qx = q0.x, qy = q0.y, qz = q0.z;
             float nx = cn.x, ny = cn.y, nz = cn.z, nq = cn.w;
-            int bpos = pos0;
-            if (__float_as_int(q0.w) & kMoreBit) {
-                // further cached candidates (a minority of the points): positions from the side array, the
-                // three loads are issued together, unused slots repeat the primary and are predicated off
-                const int4 cm = __ldcg(a.cmore + i);
-                int bidx = cm.w;
-                float4 q1 = q0, q2 = q0, q3 = q0;
-                if (cm.x != pos0) q1 = __ldg(pts + cm.x);
-                if (cm.y != pos0) q2 = __ldg(pts + cm.y);
-                if (cm.z != pos0) q3 = __ldg(pts + cm.z);
-#define PW_CAND(q, cp)                                                                         \
-                if ((cp) != pos0) {                                                            \
-                    const float d = l2_simple(p.x, p.y, p.z, q.x, q.y, q.z);                   \
-                    const int id = __float_as_int(q.w);                                        \
-                    if (d < bd2 || (d == bd2 && id < bidx)) {                                  \
-                        bd2 = d; bidx = id; bpos = (cp); qx = q.x; qy = q.y; qz = q.z;         \
-                    }                                                                          \
-                }
-                PW_CAND(q1, cm.x) PW_CAND(q2, cm.y) PW_CAND(q3, cm.z)
-#undef PW_CAND
-                if (bpos != pos0 && mchk > 0.f && bd2 * 1.00003f < mchk * mchk) {
-                    // another cached target has become the nearest: make it the primary
-                    const float4 nv = __ldg(a.aux + bpos);
-                    nx = nv.x; ny = nv.y; nz = nv.z;
-                    nq = nq_dot(nx, ny, nz, qx, qy, qz);
-                    a.cq[i] = make_float4(qx, qy, qz, __int_as_float(bpos | kMoreBit));
-                    a.cn[i] = make_float4(nx, ny, nz, nq);
-                    a.cmore[i] = make_int4(cm.x == bpos ? pos0 : cm.x, cm.y == bpos ? pos0 : cm.y,
-                                           cm.z == bpos ? pos0 : cm.z, bidx);
-                }
-            }
-            // |p - anchor| <= path (triangle inequality over the steps actually taken): every target at least as
-            // close to p as the best cached one lies within the cache radius of the anchor; compared as squares
-            if (!(mchk > 0.f && bd2 * 1.00003f < mchk * mchk)) {
-                const Fallback f = icp_search_fallback(a, it, i, p.x, p.y, p.z, bpos, step);
-                bd2 = f.bb.d2; bpos = f.bb.pos; qx = f.bb.qx; qy = f.bb.qy; qz = f.bb.qz;
-                nx = f.nx; ny = f.ny; nz = f.nz; nq = f.nq;
-                margin = f.rho;
+            int bpos = __float_as_int(q0.w);
+            if ((bpos & kMoreBit) || !(mchk > 0.f && bd2 * 1.00003f < mchk * mchk)) {
+                const SlowOut o = icp_slow_path(a, it, i, p.x, p.y, p.z, q0, cn, margin, mchk, step);
+                bd2 = o.d2; bpos = o.pos; qx = o.qx; qy = o.qy; qz = o.qz;
+                nx = o.nx; ny = o.ny; nz = o.nz; nq = o.nq;
+                margin = o.margin;
             }
             a.work[i] = make_float4(p.x, p.y, p.z, margin);
             // float expressions of TransformationEstimationPointToPlaneLLS (no FMA); nq = (nx*dx + ny*dy) + nz*dz
@@ -629,8 +638,8 @@ __global__ void __launch_bounds__(256)
 icp_seed_kernel(GridDev g, const float4* __restrict__ tgt_aux, const float4* __restrict__ src, int n,
                 float4* __restrict__ cn0, float4* __restrict__ cq0) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const float4 p = (i < n) ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     if (i >= n) return;
-    const float4 p = __ldg(src + i);
     const Best b = nn_search_seeded(g, p.x, p.y, p.z, -1);
     const float4 nq = __ldg(tgt_aux + b.pos);
     cq0[i] = make_float4(b.qx, b.qy, b.qz, __int_as_float(b.pos));

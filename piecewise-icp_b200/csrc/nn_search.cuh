@@ -22,7 +22,11 @@
 //
 // History (profiles/r01a-c): a ring search with per-lane pruning was exact but ran 8 of 32 lanes;
 // warp-cooperative group tiles (TMA-staged or read through L1) lost to load imbalance at the grid
-// barrier.  The seeded ball is both simpler and faster.
+// barrier.  Round 2 (profiles/r02j_union_search_ab.txt): one uniform scan per warp over the bounding
+// box of its 32 queries' cells (every candidate broadcast to all lanes, 32 of 32 lanes busy, no
+// divergent branch) -- the halo makes the union 3-5 times the cells a single query needs and the
+// gain in lane efficiency is eaten exactly: classification 1.03x, pre-pass 1.03x, inner-loop search
+// iterations 0.85x of this walk.  The seeded ball stays.
 #pragma once
 #include "common.cuh"
 
