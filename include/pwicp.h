@@ -111,6 +111,8 @@ typedef struct {
     float kernel_ms;        /* the persistent kernel alone (CUDA events around its launch) */
     int   natural_iters;    /* first iteration at which DefaultConvergenceCriteria was met (= n_iter unless force_iters) */
     int   natural_state;    /* ... and the PWICP_CONV_* state it reported */
+    float sort_ms;          /* Morton sort + gather of the source set (CUDA events) */
+    float prepass_ms;       /* iteration-0 search pre-pass of an unseeded source set (0 when seeded) */
 } pwicp_icp_result;
 
 /* source set of the inner loop: host upload (stand-alone use) ... */

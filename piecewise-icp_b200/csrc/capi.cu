@@ -111,7 +111,7 @@ int pwicp_ctx_create(int device, pwicp_ctx** out) {
     c->num_sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
-        cudaEventCreate(&c->ev2) != cudaSuccess) {
+        cudaEventCreate(&c->ev2) != cudaSuccess || cudaEventCreate(&c->ev3) != cudaSuccess) {
         delete c; set_error(nullptr, "stream/event creation failed"); return PWICP_ERR_CUDA;
     }
     *out = reinterpret_cast<pwicp_ctx*>(c);
@@ -130,7 +130,7 @@ void pwicp_ctx_destroy(pwicp_ctx* p) {
                       &c->scratch_b, &c->scratch_c, &c->scratch_d, &c->flags, &c->pos, &c->l2flush};
     for (DevBuf* b : bufs) b->release();
     if (c->pinned) cudaFreeHost(c->pinned);
-    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2);
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2); cudaEventDestroy(c->ev3);
     cudaStreamDestroy(c->stream);
     if (c->copy_stream) { cudaStreamDestroy(c->copy_stream); for (auto& e : c->copy_ev) if (e) cudaEventDestroy(e); }
     delete c;

@@ -256,10 +256,14 @@ static __device__ __noinline__ SlowOut icp_slow_path(const IcpArgs& a, int it, i
     o.pos = pos0; o.qx = q0.x; o.qy = q0.y; o.qz = q0.z;
     o.nx = cn.x; o.ny = cn.y; o.nz = cn.z; o.nq = cn.w;
     o.margin = margin;
+    // how close to the match a target must be to be cached with it: a quarter of the step the query has just taken
+    // (the next one is smaller), at least `tie`, at most the collection radius
+    const float tie = fminf(fmaxf(0.25f * step, a.tie), a.collect);
     if (__float_as_int(q0.w) & kMoreBit) {
         // positions from the side array, the three loads are issued together, unused slots repeat the primary
         const int4 cm = __ldcg(a.cmore + i);
         int bidx = cm.w;
+        float second = __int_as_float(0x7f800000);   // squared distance of the second-nearest cached target
         float4 q1 = q0, q2 = q0, q3 = q0;
         if (cm.x != pos0) q1 = __ldg(pts + cm.x);
         if (cm.y != pos0) q2 = __ldg(pts + cm.y);
@@ -269,20 +273,33 @@ static __device__ __noinline__ SlowOut icp_slow_path(const IcpArgs& a, int it, i
             const float d = l2_simple(px, py, pz, q.x, q.y, q.z);                              \
             const int id = __float_as_int(q.w);                                                \
             if (d < o.d2 || (d == o.d2 && id < bidx)) {                                        \
+                second = o.d2;                                                                 \
                 o.d2 = d; bidx = id; o.pos = (cp); o.qx = q.x; o.qy = q.y; o.qz = q.z;         \
-            }                                                                                  \
+            } else second = fminf(second, d);                                                  \
         }
         PW_CAND(q1, cm.x) PW_CAND(q2, cm.y) PW_CAND(q3, cm.z)
 #undef PW_CAND
-        if (o.pos != pos0 && mchk > 0.f && o.d2 * 1.00003f < mchk * mchk) {
-            // another cached target has become the nearest: make it the primary
-            const float4 nv = __ldg(a.aux + o.pos);
-            o.nx = nv.x; o.ny = nv.y; o.nz = nv.z;
-            o.nq = nq_dot(o.nx, o.ny, o.nz, o.qx, o.qy, o.qz);
-            a.cq[i] = make_float4(o.qx, o.qy, o.qz, __int_as_float(o.pos | kMoreBit));
-            a.cn[i] = make_float4(o.nx, o.ny, o.nz, o.nq);
-            a.cmore[i] = make_int4(cm.x == o.pos ? pos0 : cm.x, cm.y == o.pos ? pos0 : cm.y,
-                                   cm.z == o.pos ? pos0 : cm.z, bidx);
+        if (mchk > 0.f && o.d2 * 1.00003f < mchk * mchk) {
+            // the cache answers.  Every target within `margin` of this position is cached (the ball lies inside the
+            // cache ball around the anchor), so a NEW cache can be cut out of the old one without a search: this
+            // position as the anchor, the match alone, radius just below the second-nearest cached target.  Done as
+            // soon as that target is clear of the match: the query drops its side list and leaves this path.
+            const float d1 = sqrtf(o.d2);
+            const bool alone = second > (d1 + tie) * (d1 + tie);
+            if (o.pos != pos0 || alone) {
+                if (o.pos != pos0) {
+                    const float4 nv = __ldg(a.aux + o.pos);
+                    o.nx = nv.x; o.ny = nv.y; o.nz = nv.z;
+                    o.nq = nq_dot(o.nx, o.ny, o.nz, o.qx, o.qy, o.qz);
+                    a.cn[i] = make_float4(o.nx, o.ny, o.nz, o.nq);
+                }
+                a.cq[i] = make_float4(o.qx, o.qy, o.qz, __int_as_float(o.pos | (alone ? 0 : kMoreBit)));
+                if (!alone)      // another cached target has become the nearest: it is the primary now
+                    a.cmore[i] = make_int4(cm.x == o.pos ? pos0 : cm.x, cm.y == o.pos ? pos0 : cm.y,
+                                           cm.z == o.pos ? pos0 : cm.z, bidx);
+            }
+            if (alone) o.margin = fminf(mchk, sqrtf(second) * 0.9999f);
+            return o;
         }
     }
     // |p - anchor| <= path (triangle inequality over the steps actually taken): every target at least as close to p
@@ -304,11 +321,11 @@ static __device__ __noinline__ SlowOut icp_slow_path(const IcpArgs& a, int it, i
         // first with the wide radius (a large gap to the second-nearest target = a long-lived cache); a query far from
         // its match would need more than the 3x3-row scan for that: then only the ties are looked for
         for (int attempt = 0; attempt < 2; ++attempt) {
-            const float R = d1 + (attempt == 0 ? a.collect : 4.0f * a.tie);
+            const float R = d1 + (attempt == 0 ? a.collect : fminf(4.0f * tie, a.collect));
             if (R * a.g.lv[0].inv_h >= 0.95f) continue;
             const Near5 nb = ball_collect(a.g.lv[0], a.g.ox, a.g.oy, a.g.oz, px, py, pz, R * R);
             if (!nb.complete) continue;
-            const float lim = (d1 + a.tie) * (d1 + a.tie);
+            const float lim = (d1 + tie) * (d1 + tie);
             float rho2 = R * R;                      // complete up to the scanned radius unless a target is left out
             bool open = true;                        // still taking targets into the cache
 #pragma unroll
@@ -717,6 +734,7 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     const bool have_seed = ctx->icp_seed_valid && ctx->icp_seed.p != nullptr;
     PW_TRY(icp_sort_source(ctx, n, have_seed));
     ctx->icp_seed_valid = false;                       // seeds belong to one source set
+    PW_CUDA(cudaEventRecord(ctx->ev3, ctx->stream));
     if (!have_seed) {
         icp_seed_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->tgt.dev, ctx->tgt_aux.as<float4>(),
                                                                   ctx->icp_sorted.as<float4>(), n,
@@ -769,9 +787,11 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     struct { float T[16]; int st[4]; } host;
     PW_CUDA(cudaMemcpyAsync(&host, ob, sizeof(host), cudaMemcpyDeviceToHost, ctx->stream));
     PW_CUDA(cudaStreamSynchronize(ctx->stream));
-    float ms = 0.f, kms = 0.f;
+    float ms = 0.f, kms = 0.f, sms = 0.f, pms = 0.f;
     PW_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     PW_CUDA(cudaEventElapsedTime(&kms, ctx->ev2, ctx->ev1));
+    PW_CUDA(cudaEventElapsedTime(&sms, ctx->ev0, ctx->ev3));
+    PW_CUDA(cudaEventElapsedTime(&pms, ctx->ev3, ctx->ev2));
     ctx->last_ms = ms;
     const int n_iter = host.st[0];
     ctx->icp_prof_max_iter = prm.max_iter;
@@ -783,6 +803,7 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
         res->group_batches = (grid * kIcpWarps) | (kIcpWarps << 16);   // reduction geometry for the oracle's reduce_mode 2
         res->device_ms = ms; res->correspondences = (long long)n_iter * n;
         res->kernel_ms = kms; res->natural_iters = host.st[2]; res->natural_state = host.st[3];
+        res->sort_ms = sms; res->prepass_ms = pms;
     }
     if (mse_trace) PW_CUDA(cudaMemcpy(mse_trace, ob + 80, (size_t)n_iter * 8, cudaMemcpyDeviceToHost));
     if (T_trace) PW_CUDA(cudaMemcpy(T_trace, ob + 80 + (size_t)prm.max_iter * 8, (size_t)n_iter * 64, cudaMemcpyDeviceToHost));
