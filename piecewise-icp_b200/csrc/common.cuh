@@ -114,6 +114,7 @@ struct Ctx {
     DevBuf ct_seed, bp_seed, pp_seed, ct_order;
     bool ct_order_valid = false;
     int n_icp = 0;
+    bool icp_attr_set = false;                   // kernel attributes of the persistent kernel set for this device
     int icp_prof_max_iter = 0;
     int icp_prof_iters = 0;                      // pwicp_icp_profile: iterations of the last run, offsets into icp_partials
     size_t icp_prof_off_searched = 0, icp_prof_off_ns = 0;
@@ -134,6 +135,9 @@ int check_finite_dev(Ctx* ctx, const float* dev, size_t n_floats, bool* ok);
 int finite_accumulate_dev(Ctx* ctx, const float* dev, size_t n_floats, int* flag_dev);   // no host sync
 
 // icp.cu
+struct IcpLaunch { int grid; const char* out; int max_iter; };   // out: device: T[16] | n_iter, conv_state, natural iter, state
+int icp_enqueue(Ctx* ctx, const pwicp_icp_params& prm, int n, const int* n_dev, bool presorted,
+                bool want_mse, bool want_T, bool want_idx, IcpLaunch* L);
 int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_result* res,
                    double* mse_trace, float* T_trace, int* idx_trace);
 

@@ -76,7 +76,9 @@ struct IcpArgs {
     float collect;            // targets within this of the match distance are looked at when a cache is built
     float tie;                // ... and those within this of the match distance are cached with it
     float build_step;         // a cache is built only when the point moved less than this in the last step (L1 length)
-    int n;
+    int n;                    // number of source points ...
+    const int* n_dev;         // ... or, when not null, where the device holds it (outer loop: the stable set is counted
+                              // on the device; the launch geometry then comes from the capacity n)
     int max_iter;
     int force_iters;
     double rot_thr, transl_thr, mse_rel, mse_abs;
@@ -110,7 +112,7 @@ struct FinishSmem {
 // This code runs once per inner iteration on one warp, i.e. always from a cold instruction cache
 // (profiles/r01d_*: a straight-line version spent ~10 us mostly fetching instructions), hence the
 // rolled loops and the out-of-line placement: few instruction lines, re-used from L0.
-static __device__ __noinline__ int icp_finish_warp(const IcpArgs& a, int it, const double* s_tot, float* s_T,
+static __device__ __noinline__ int icp_finish_warp(const IcpArgs& a, int n, int it, const double* s_tot, float* s_T,
                                                    float* s_Tfinal, FinishSmem& F, int lane) {
     // ATA (mirrored) and ATb from the 28 totals
     for (int idx = lane; idx < 36; idx += 32) {
@@ -201,7 +203,7 @@ static __device__ __noinline__ int icp_finish_warp(const IcpArgs& a, int it, con
     int state = 0;
     if (lane == 0) {
         const float* Tn = F.Tn;
-        const double mse = s_tot[27] / (double)a.n;
+        const double mse = s_tot[27] / (double)n;
         const double prev_mse = F.prev_mse;
         const int iters = it + 1;
         // DefaultConvergenceCriteria<float>::hasConverged(), in PCL's order
@@ -410,7 +412,13 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_persistent_kernel(const Ic
     __shared__ FinishSmem s_fin;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nb = (a.n + 31) / 32;                              // 32-point batches
+    const int n = a.n_dev ? __ldg(a.n_dev) : a.n;                // same value in every thread of the grid
+    if (n < 3) {                                                 // pcl: min_number_correspondences_ (device-side count only)
+        if (blockIdx.x == 0 && tid < 16) a.out_T[tid] = (tid % 5 == 0) ? 1.0f : 0.0f;
+        if (blockIdx.x == 0 && tid == 0) { a.out_state[0] = 0; a.out_state[1] = PWICP_CONV_NO_CORR; }
+        return;
+    }
+    const int nb = (n + 31) / 32;                                // 32-point batches
     const int G = gridDim.x, NWT = G * kIcpWarps, ws = blockIdx.x * kIcpWarps + warp;
     const int K = (ws < nb) ? (nb - 1 - ws) / NWT + 1 : 0;       // batches ws, ws + NWT, ... of this warp
     const int per = (G + kIcpWarps - 1) / kIcpWarps;             // CTA partials per chunk of the final sum
@@ -481,8 +489,8 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_persistent_kernel(const Ic
                 mchk = margin;
                 p.x = x; p.y = y; p.z = z;
             } else {
-                margin = (i < a.n) ? 0.f : kPadMargin;            // no cache yet; pads never search
-                mchk = (a.seed_exact || i >= a.n) ? kPadMargin : 0.f;
+                margin = (i < n) ? 0.f : kPadMargin;              // no cache yet; pads never search
+                mchk = (a.seed_exact || i >= n) ? kPadMargin : 0.f;
             }
             // (b) exact NN: the inline match when the candidate cache still covers the query and holds nothing else
             // (nn_search.cuh, "candidate cache"); further cached candidates and the seeded ball search are out of line
@@ -502,10 +510,10 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_persistent_kernel(const Ic
             const float u1 = nx * p.z - nz * p.x;
             const float u2 = ny * p.x - nx * p.y;
             const float u6 = nq - nx * p.x - ny * p.y - nz * p.z;
-            const float u7 = (i < a.n) ? bd2 : 0.f;              // a pad's rows are zero through its zero normal
+            const float u7 = (i < n) ? bd2 : 0.f;                // a pad's rows are zero through its zero normal
             // traces are reported in the caller's order (src[].w = original source index)
-            if (kTrace && i < a.n)
-                a.idx_trace[(size_t)it * a.n + __float_as_int(__ldg(a.src + i).w)] = __float_as_int(__ldg(pts + bpos).w);
+            if (kTrace && i < n)
+                a.idx_trace[(size_t)it * n + __float_as_int(__ldg(a.src + i).w)] = __float_as_int(__ldg(pts + bpos).w);
             // 27 products + d2 into this lane's sums
             {
                 const double d0 = (double)u0, d1 = (double)u1, d2 = (double)u2, d3 = (double)nx, d4 = (double)ny,
@@ -573,7 +581,7 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_persistent_kernel(const Ic
             }
             __syncwarp();
             if (blockIdx.x == 0 && lane == 0) a.phase_ns[it * 4 + 2] = globaltimer_ns();
-            const int st = icp_finish_warp(a, it, s_tot, s_T, s_Tfinal, s_fin, lane);
+            const int st = icp_finish_warp(a, n, it, s_tot, s_T, s_Tfinal, s_fin, lane);
             if (lane == 0) {
                 s_stop = st;
                 if (blockIdx.x == 0) { a.iter_ns[it + 1] = globaltimer_ns(); a.phase_ns[it * 4 + 3] = a.iter_ns[it + 1]; }
@@ -698,20 +706,25 @@ static int icp_sort_source(Ctx* ctx, int n, bool have_seed) {
     return PWICP_OK;
 }
 
-int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_result* res,
-                   double* mse_trace, float* T_trace, int* idx_trace) {
-    const int n = ctx->n_icp;
+// Enqueues the inner loop on the library stream without waiting for it.  n = number of source points -- or, with
+// n_dev, the capacity (the device holds the count: outer loop).  presorted: the caller has filled icp_sorted / icp_match
+// (points in processing order + their matches, padded to whole batches) itself.
+int icp_enqueue(Ctx* ctx, const pwicp_icp_params& prm, int n, const int* n_dev, bool presorted,
+                bool want_mse, bool want_T, bool want_idx, IcpLaunch* L) {
     if (ctx->n1 < 1 || !ctx->tgt.dev.nlevels) { set_error(ctx, "icp: no target uploaded"); return PWICP_ERR_ARG; }
     if (n < 3) { set_error(ctx, "icp: fewer than 3 correspondences"); return PWICP_ERR_TOO_FEW_CORR; }
     if (prm.max_iter < 1 || prm.max_iter > kMaxIcpIter) { set_error(ctx, "icp: max_iter out of range"); return PWICP_ERR_ARG; }
 
     const size_t smem = (size_t)kIcpWarps * kStageSlots * 3 * 32 * sizeof(float4);      // s_stage
-    void* kern = idx_trace ? (void*)icp_persistent_kernel<true> : (void*)icp_persistent_kernel<false>;
-    PW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    if (idx_trace) PW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, icp_persistent_kernel<true>, kIcpThreads, smem));
-    else PW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, icp_persistent_kernel<false>, kIcpThreads, smem));
-    if (occ < 1) { set_error(ctx, "icp: kernel does not fit on an SM"); return PWICP_ERR_CUDA; }
+    void* kern = want_idx ? (void*)icp_persistent_kernel<true> : (void*)icp_persistent_kernel<false>;
+    if (!ctx->icp_attr_set) {
+        PW_CUDA(cudaFuncSetAttribute((void*)icp_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PW_CUDA(cudaFuncSetAttribute((void*)icp_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        PW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, icp_persistent_kernel<true>, kIcpThreads, smem));
+        if (occ < 1) { set_error(ctx, "icp: kernel does not fit on an SM"); return PWICP_ERR_CUDA; }
+        ctx->icp_attr_set = true;
+    }
     const long nb = ((long)n + 31) / 32;
     // one CTA per SM; fewer when there are not enough batches to give every warp one
     long want = (nb + kIcpWarps - 1) / kIcpWarps;
@@ -719,7 +732,7 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
 
     const int n_pad = (int)(nb * 32);
     PW_TRY(ctx->icp_work.reserve(ctx, (size_t)n_pad * sizeof(float4)));
-    // device scratch: CTA sums (double buffered) | searched[max_iter] | iter_ns[max_iter + 1]
+    // device scratch: CTA sums (double buffered) | searched[max_iter] | iter_ns[max_iter + 1] | phase_ns[max_iter][4]
     const size_t bytes_part = (size_t)2 * grid * kNumVals * sizeof(double);
     const size_t bytes_cnt = (size_t)prm.max_iter * sizeof(int);
     const size_t off_ns = (bytes_part + bytes_cnt + 7) & ~(size_t)7;
@@ -728,18 +741,22 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     PW_TRY(ctx->icp_out.reserve(ctx, out_bytes));
     char* ob = ctx->icp_out.as<char>();
     PW_CUDA(cudaMemsetAsync(ob, 0, out_bytes, ctx->stream));
-    if (idx_trace) PW_TRY(ctx->icp_idx.reserve(ctx, (size_t)prm.max_iter * n * sizeof(int)));
+    if (want_idx) PW_TRY(ctx->icp_idx.reserve(ctx, (size_t)prm.max_iter * n * sizeof(int)));
 
     PW_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-    const bool have_seed = ctx->icp_seed_valid && ctx->icp_seed.p != nullptr;
-    PW_TRY(icp_sort_source(ctx, n, have_seed));
-    ctx->icp_seed_valid = false;                       // seeds belong to one source set
-    PW_CUDA(cudaEventRecord(ctx->ev3, ctx->stream));
-    if (!have_seed) {
-        icp_seed_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->tgt.dev, ctx->tgt_aux.as<float4>(),
-                                                                  ctx->icp_sorted.as<float4>(), n,
-                                                                  ctx->icp_match.as<float4>(), ctx->icp_match.as<float4>() + n_pad);
-        ctx->launches++;
+    if (!presorted) {
+        const bool have_seed = ctx->icp_seed_valid && ctx->icp_seed.p != nullptr;
+        PW_TRY(icp_sort_source(ctx, n, have_seed));
+        ctx->icp_seed_valid = false;                       // seeds belong to one source set
+        PW_CUDA(cudaEventRecord(ctx->ev3, ctx->stream));
+        if (!have_seed) {
+            icp_seed_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->tgt.dev, ctx->tgt_aux.as<float4>(),
+                                                                      ctx->icp_sorted.as<float4>(), n,
+                                                                      ctx->icp_match.as<float4>(), ctx->icp_match.as<float4>() + n_pad);
+            ctx->launches++;
+        }
+    } else {
+        PW_CUDA(cudaEventRecord(ctx->ev3, ctx->stream));
     }
 
     IcpArgs a;
@@ -761,6 +778,7 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     }
 
     a.n = n;
+    a.n_dev = n_dev;
     a.max_iter = prm.max_iter;
     a.force_iters = prm.force_iters;
     a.rot_thr = prm.rot_thr_default ? 0.99999 : (1.0 - prm.tf_eps);
@@ -774,16 +792,28 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     PW_CUDA(cudaMemsetAsync(a.searched, 0, off_ns - bytes_part + (size_t)(prm.max_iter + 1) * 8 + (size_t)prm.max_iter * 32, ctx->stream));
     a.out_T = reinterpret_cast<float*>(ob);
     a.out_state = reinterpret_cast<int*>(ob + 64);
-    a.mse_trace = mse_trace ? reinterpret_cast<double*>(ob + 80) : nullptr;
-    a.T_trace = T_trace ? reinterpret_cast<float*>(ob + 80 + (size_t)prm.max_iter * 8) : nullptr;
-    a.idx_trace = idx_trace ? ctx->icp_idx.as<int>() : nullptr;
+    a.mse_trace = want_mse ? reinterpret_cast<double*>(ob + 80) : nullptr;
+    a.T_trace = want_T ? reinterpret_cast<float*>(ob + 80 + (size_t)prm.max_iter * 8) : nullptr;
+    a.idx_trace = want_idx ? ctx->icp_idx.as<int>() : nullptr;
 
     void* kargs[] = {(void*)&a};
     PW_CUDA(cudaEventRecord(ctx->ev2, ctx->stream));
     PW_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kIcpThreads), kargs, smem, ctx->stream));
     ctx->launches++;
     PW_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->icp_prof_max_iter = prm.max_iter;
+    ctx->icp_prof_off_searched = bytes_part; ctx->icp_prof_off_ns = off_ns;
+    if (L) { L->grid = grid; L->out = ob; L->max_iter = prm.max_iter; }
+    return PWICP_OK;
+}
 
+int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_result* res,
+                   double* mse_trace, float* T_trace, int* idx_trace) {
+    const int n = ctx->n_icp;
+    IcpLaunch L;
+    PW_TRY(icp_enqueue(ctx, prm, n, nullptr, false, mse_trace != nullptr, T_trace != nullptr, idx_trace != nullptr, &L));
+    const char* ob = L.out;
+    const int grid = L.grid;
     struct { float T[16]; int st[4]; } host;
     PW_CUDA(cudaMemcpyAsync(&host, ob, sizeof(host), cudaMemcpyDeviceToHost, ctx->stream));
     PW_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -794,8 +824,7 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     PW_CUDA(cudaEventElapsedTime(&pms, ctx->ev3, ctx->ev2));
     ctx->last_ms = ms;
     const int n_iter = host.st[0];
-    ctx->icp_prof_max_iter = prm.max_iter;
-    ctx->icp_prof_iters = n_iter; ctx->icp_prof_off_searched = bytes_part; ctx->icp_prof_off_ns = off_ns;
+    ctx->icp_prof_iters = n_iter;
     if (T16) for (int k = 0; k < 16; ++k) T16[k] = host.T[k];
     if (res) {
         res->n_iter = n_iter; res->conv_state = host.st[1];
