@@ -32,7 +32,8 @@ typedef enum {
     PWICP_ERR_TOO_FEW_PATCHES = -4,   /* < 4 source patches   (reference: exit, src/Registration.cpp:728-731) */
     PWICP_ERR_TOO_FEW_STABLE = -5,    /* < 4 stable patches   (reference: exit, src/Registration.cpp:864-867) */
     PWICP_ERR_TOO_FEW_CORR = -6,      /* < 3 correspondences  (PCL min_number_correspondences_) */
-    PWICP_ERR_NOMEM = -7
+    PWICP_ERR_NOMEM = -7,
+    PWICP_ERR_MAX_OUTER = -8      /* pwicp_piecewise_icp stopped by max_outer before stage 3: T16 valid, no VCM */
 } pwicp_status;
 
 /* convergence states of the inner loop (pcl::registration::DefaultConvergenceCriteria) */

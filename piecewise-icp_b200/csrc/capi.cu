@@ -111,7 +111,8 @@ int pwicp_ctx_create(int device, pwicp_ctx** out) {
     c->num_sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
-        cudaEventCreate(&c->ev2) != cudaSuccess || cudaEventCreate(&c->ev3) != cudaSuccess) {
+        cudaEventCreate(&c->ev2) != cudaSuccess || cudaEventCreate(&c->ev3) != cudaSuccess ||
+        cudaEventCreate(&c->ev_o0) != cudaSuccess || cudaEventCreate(&c->ev_o1) != cudaSuccess) {
         delete c; set_error(nullptr, "stream/event creation failed"); return PWICP_ERR_CUDA;
     }
     *out = reinterpret_cast<pwicp_ctx*>(c);
@@ -127,10 +128,11 @@ void pwicp_ctx_destroy(pwicp_ctx* p) {
     DevBuf* bufs[] = {&c->tgt_aux, &c->tgt_ok, &c->ct2, &c->bp2, &c->bpstd2, &c->patch_xyz, &c->patch_id,
                       &c->patch_off, &c->cloud2, &c->icp_src, &c->icp_work, &c->icp_partials, &c->icp_out,
                       &c->icp_idx, &c->icp_sorted, &c->icp_perm, &c->icp_seed, &c->icp_match, &c->ct_seed, &c->bp_seed, &c->pp_seed, &c->ct_order, &c->tgt_xyz, &c->tgt_nrm_raw, &c->tgt_std_raw, &c->tgt_ok_raw, &c->keys, &c->vals, &c->keys2, &c->vals2, &c->cub_tmp, &c->scratch_a,
-                      &c->scratch_b, &c->scratch_c, &c->scratch_d, &c->flags, &c->pos, &c->l2flush};
+                      &c->scratch_b, &c->scratch_c, &c->scratch_d, &c->flags, &c->pos, &c->l2flush, &c->outer_state};
     for (DevBuf* b : bufs) b->release();
     if (c->pinned) cudaFreeHost(c->pinned);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2); cudaEventDestroy(c->ev3);
+    cudaEventDestroy(c->ev_o0); cudaEventDestroy(c->ev_o1);
     cudaStreamDestroy(c->stream);
     if (c->copy_stream) { cudaStreamDestroy(c->copy_stream); for (auto& e : c->copy_ev) if (e) cudaEventDestroy(e); }
     delete c;
@@ -582,6 +584,10 @@ int pwicp_piecewise_icp(pwicp_ctx* p, const pwicp_pair_params* pp, int is_manual
     *n_series = ns;
     if (n_outer) *n_outer = count;
     memcpy(T16, transMat, sizeof(transMat));
+    if (!st.toStage3) {          // the reference loops until stage 3 (:682); max_outer is this library's guard
+        set_error(ctx, "piecewise_icp: max_outer iterations without reaching stage 3 (no VCM; T16 = transformation so far)");
+        return PWICP_ERR_MAX_OUTER;
+    }
     return PWICP_OK;
 }
 
@@ -734,7 +740,7 @@ int pwicp_vcm(pwicp_ctx* p, const float* src, int n, double* vcm36, int* singula
     PW_TRY(ctx->scratch_b.reserve(ctx, (size_t)n * sizeof(float4)));
     expand_f4_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->scratch_a.as<float>(), n, ctx->scratch_b.as<float4>());
     ctx->launches++;
-    return vcm_dev(ctx, ctx->scratch_b.as<float4>(), n, vcm36, singular, nullptr);
+    return vcm_dev(ctx, ctx->scratch_b.as<float4>(), n, vcm36, singular, nullptr, nullptr);
 }
 
 int pwicp_transform(pwicp_ctx* p, float* xyz, int n, const float* T16) {

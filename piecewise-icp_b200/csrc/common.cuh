@@ -84,6 +84,7 @@ struct Ctx {
     cudaStream_t copy_stream = nullptr;          // host-buffer calls: uploads overlap the grid build
     cudaEvent_t copy_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    cudaEvent_t ev_o0 = nullptr, ev_o1 = nullptr;   // outer iteration
     std::string err;
     float last_ms = 0.f;
     long long launches = 0;
@@ -121,6 +122,8 @@ struct Ctx {
     // scratch
     DevBuf keys, vals, keys2, vals2, cub_tmp, scratch_a, scratch_b, scratch_c, scratch_d, flags, pos;
     DevBuf l2flush;
+    DevBuf outer_state;                          // OuterDev (outer.cu): device-resident state of an outer iteration
+    bool outer_state_zeroed = false;
     void* pinned = nullptr;   // small pinned staging area
     size_t pinned_cap = 0;
 };
@@ -150,9 +153,11 @@ int percentile_dev(Ctx* ctx, const GridDev& g, const float* q_packed_dev, int nq
                    float pct, double* out, int* seeds_dev);
 float bbox_corner_change_host(const double* bb6, const float* T16);
 int icp_expand_source(Ctx* ctx, const float* packed_dev, int n);
-int vcm_dev(Ctx* ctx, const float4* src_dev, int n, double* vcm36, int* singular, int* seeds_dev);
+int vcm_dev(Ctx* ctx, const float4* src_dev, int n, double* vcm36, int* singular, int* seeds_dev,
+            const float4* cq_seed_dev);
 int transform_packed_dev(Ctx* ctx, float* xyz_dev, size_t n, const float* T16);
 int bbox_packed_dev(Ctx* ctx, const float* xyz_dev, size_t n, float* mn3, float* mx3);
+int bbox_accumulate_dev(Ctx* ctx, const float* xyz_dev, size_t n, int* out6_dev);
 void octree_cube(const float* mn, const float* mx, double res, double* bb6);
 
 // prep.cu (F4)

@@ -132,6 +132,15 @@ __global__ void bbox_init_kernel(int* out) {
     else if (threadIdx.x < 6) out[threadIdx.x] = (int)0x80000000;
 }
 
+// min / max accumulated into six ordered ints that the caller has initialised on the device (no host round trip)
+int bbox_accumulate_dev(Ctx* ctx, const float* xyz_dev, size_t n, int* out6_dev) {
+    int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)ctx->num_sms * 8);
+    bbox_kernel<<<std::max(blocks, 1), 256, 0, ctx->stream>>>(xyz_dev, n, out6_dev);
+    ctx->launches++;
+    PW_CUDA(cudaGetLastError());
+    return PWICP_OK;
+}
+
 int bbox_packed_dev(Ctx* ctx, const float* xyz_dev, size_t n, float* mn3, float* mx3) {
     PW_TRY(ensure_pinned(ctx, 4096));
     PW_TRY(ctx->scratch_d.reserve(ctx, 256));

@@ -529,3 +529,63 @@ def test_preprocess_matches_oracle(gpu_ctx, oracle):
     big = synth.make_pair(1_000_000, with_clouds=False)["ct1"]
     assert np.array_equal(gpu_ctx.knn_mean_dist(big, 14), oracle.knn_mean_dist(big, 14))
     assert np.array_equal(gpu_ctx.voxel_grid(big, 0.08), oracle.voxel_grid(big, 0.08))
+
+
+# ------------------------------------------------------------------------- round 2: parity at size
+def test_self_nn_matches_oracle_and_brute_force(gpu_ctx, oracle):
+    """pwicp_self_nn (calPCresolution, src/CommonFunc.cpp:239-263: second neighbour of nearestKSearch(i, 2)): squared distance
+    of every point to its nearest OTHER point.  Brute force in the reference's float expression at 4k points (duplicates
+    included: distance 0 to the twin), the oracle's k-NN (k = 1: float(sqrt(double(d2)))) at 200k."""
+    rng = np.random.default_rng(11)
+    p = rng.uniform(-2, 2, (4000, 3)).astype(np.float32)
+    p[100:140] = p[:40]                                                   # exact duplicates
+    d2 = gpu_ctx.self_nn(p)
+    dx = p[:, None, 0] - p[None, :, 0]; dy = p[:, None, 1] - p[None, :, 1]; dz = p[:, None, 2] - p[None, :, 2]
+    bf = (dx * dx + dy * dy) + dz * dz                                   # float32, ((dx*dx)+dy*dy)+dz*dz
+    np.fill_diagonal(bf, np.inf)
+    assert np.array_equal(d2, bf.min(1))
+    d = synth.make_pair(200_000, with_clouds=False)
+    c = d["ct1"]
+    d2 = gpu_ctx.self_nn(c)
+    md = oracle.knn_mean_dist(c, 1)                                       # [PCL] float(dist_sum / k), dist = sqrt in double
+    assert np.array_equal(np.sqrt(d2.astype(np.float64)).astype(np.float32), md)
+
+
+def test_outer_loop_full_size_matches_oracle(gpu_ctx, oracle):
+    """pwicp_piecewise_icp at BASELINE configs[1] size with clouds (1M patches, 8M patch points, 8M-point clouds) against the
+    oracle (its independent NN queries on all host threads -- results do not depend on the thread count): identical DT series
+    (the decreasing schedule of configs[4], all three stages), identical stable-set size and inner iteration count in every
+    outer iteration, pose within 1e-6, VCM relative 1e-6."""
+    d = synth.make_pair(1_000_000)
+    pp = P.PairParams(d["Res1"], d["Res2"], d["SVRes1"], d["SVRes2"], d["DTmin"])
+    gpu_ctx.upload_pair(d)
+    g = gpu_ctx.piecewise_icp(pp, 1, 0.05)
+    threads = os.cpu_count() or 1
+    oracle.set_threads(threads)
+    try:
+        o = oracle.piecewise_icp(oracle.PairData(d), 1, 0.05, oracle.icp_params(threads=threads))
+    finally:
+        oracle.set_threads(1)
+    assert g["n_outer"] == o["rc"] >= 5
+    assert np.array_equal(g["DTseries"], o["DTseries"])
+    assert (np.diff(g["DTseries"]) <= 0).all() and g["DTseries"][-1] < g["DTseries"][0]
+    assert [s.n_stable for s in g["stats"]] == [s.n_stable for s in o["stats"]]
+    assert [s.n_stable_pts for s in g["stats"]] == [s.n_stable_pts for s in o["stats"]]
+    assert [s.icp_iters for s in g["stats"]] == [s.icp_iters for s in o["stats"]]
+    p75g = [s.P75 for s in g["stats"]]; p75o = [s.P75 for s in o["stats"]]
+    assert [np.isnan(v) for v in p75g] == [np.isnan(v) for v in p75o]     # stage 1 ran in the same iterations ...
+    assert np.array_equal(np.nan_to_num(p75g), np.nan_to_num(p75o))       # ... and its percentile is the same number
+    assert any(np.isnan(v) for v in p75g) and not all(np.isnan(v) for v in p75g)     # stages 1 and 2 both ran
+    assert g["stats"][-1].vcm_written == 1                                            # stage 3 reached
+    da, dt = pose_diff(g["T"], o["T"])
+    assert da <= POSE_TOL_RAD and dt <= POSE_TOL_M
+    assert np.allclose(g["VCM"], o["VCM"], rtol=1e-6, atol=0)
+
+
+def test_max_outer_is_reported(gpu_ctx, pair2k):
+    d = pair2k
+    pp = P.PairParams(d["Res1"], d["Res2"], d["SVRes1"], d["SVRes2"], d["DTmin"])
+    gpu_ctx.upload_pair(d)
+    with pytest.raises(P.PwicpError) as e:
+        gpu_ctx.piecewise_icp(pp, 1, 0.05, max_outer=1)
+    assert e.value.status == -8                                           # PWICP_ERR_MAX_OUTER: no VCM, transformation so far
