@@ -75,6 +75,7 @@ struct IcpArgs {
     int seed_exact;           // cq[] is the exact NN of the untransformed source (iteration 0 needs no search)
     float collect;            // targets within this of the match distance are looked at when a cache is built
     float tie;                // ... and those within this of the match distance are cached with it
+    float tie_step;           // ... or within this fraction of the step the query has just taken, if that is more
     float build_step;         // a cache is built only when the point moved less than this in the last step (L1 length)
     int n;                    // number of source points ...
     const int* n_dev;         // ... or, when not null, where the device holds it (outer loop: the stable set is counted
@@ -258,9 +259,9 @@ static __device__ __noinline__ SlowOut icp_slow_path(const IcpArgs& a, int it, i
     o.pos = pos0; o.qx = q0.x; o.qy = q0.y; o.qz = q0.z;
     o.nx = cn.x; o.ny = cn.y; o.nz = cn.z; o.nq = cn.w;
     o.margin = margin;
-    // how close to the match a target must be to be cached with it: a quarter of the step the query has just taken
+    // how close to the match a target must be to be cached with it: a fraction of the step the query has just taken
     // (the next one is smaller), at least `tie`, at most the collection radius
-    const float tie = fminf(fmaxf(0.25f * step, a.tie), a.collect);
+    const float tie = fminf(fmaxf(a.tie_step * step, a.tie), a.collect);
     if (__float_as_int(q0.w) & kMoreBit) {
         // positions from the side array, the three loads are issued together, unused slots repeat the primary
         const int4 cm = __ldcg(a.cmore + i);
@@ -774,6 +775,7 @@ int icp_enqueue(Ctx* ctx, const pwicp_icp_params& prm, int n, const int* n_dev, 
         const float h = 1.0f / ctx->tgt.dev.lv[0].inv_h;
         a.collect = knob("PWICP_COLLECT_CELLS", PWICP_COLLECT_CELLS) * h;
         a.tie = knob("PWICP_TIE_CELLS", PWICP_TIE_CELLS) * h;
+        a.tie_step = knob("PWICP_TIE_STEP_FRAC", 0.25f);
         a.build_step = knob("PWICP_BUILD_STEP_CELLS", PWICP_BUILD_STEP_CELLS) * h;
     }
 

@@ -182,13 +182,14 @@ def test_preprocessing_device_equals_host_statements():
 
 
 def test_drivers_reproduce_the_references_recorded_results(tmp_path):
-    """The file-level driver PiecewiseICP_pair_call on the reference's own shipped scans (hard epochs 8, 12, 19 against the
-    reference epoch), with the reference's segmentation plugged in by environment (PWICP_SEGMENTER_PLUGIN -> oracle/_ref,
-    compiled from the reference's codelibrary where it lies; the library ships none) and the
-    within-voxel order of the reference's Windows build (PWICP_VOXEL_ORDER=msvc): the device path must land on the 4x4 the
-    reference recorded (results/4DPCReg/<e>_Direct2Ref_TransMatrix.txt) within 1e-6 rad / 1e-6 m.  Needs the staged scans
+    """The file-level 4D driver PiecewiseICP_4D_call (reference-epoch mode, the mode of the recorded run) on the reference's
+    own shipped scans -- hard epochs 8, 12, 19 against the reference epoch -- with the reference's segmentation plugged in
+    by environment (PWICP_SEGMENTER_PLUGIN -> oracle/_ref, compiled from the reference's codelibrary where it lies; the
+    library ships none) and the within-voxel order of the reference's Windows build
+    (PWICP_VOXEL_ORDER=msvc): the device path must land on the 4x4 the reference recorded
+    (results/4DPCReg/<e>_Direct2Ref_TransMatrix.txt) within 1e-6 rad / 1e-6 m.  Needs the staged scans
     (python scripts/refdata_4d.py stage: refdata/, git-ignored) and oracle/_ref; child process: the plug-in is read once."""
-    import subprocess, sys
+    import shutil, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     scans = os.path.join(root, "refdata", "scans")
     ref_so = os.path.join(root, "oracle", "_ref", "libref_supervoxel.so")
@@ -196,16 +197,17 @@ def test_drivers_reproduce_the_references_recorded_results(tmp_path):
         pytest.skip("refdata/scans or oracle/_ref/libref_supervoxel.so not present")
     for e in (8, 12, 19):
         out = str(tmp_path / ("e%d" % e)) + "/"
-        os.makedirs(out)
-        cfg = out + "configuration_pair.txt"
-        synth.write_config(cfg, os.path.join(scans, "Epoch_001.pcd"), os.path.join(scans, "Epoch_%03d.pcd" % e),
-                           res=0.005, sv=0.05, dtinit=0.05, dtmin=0.004)
-        code = ("import sys; sys.path.insert(0, %r)\nfrom pwicp_b200 import host\nassert host.pair_call(%r, %r)\nprint('PAIR-OK')\n"
-                % (os.path.join(root, "piecewise-icp_b200", "python"), cfg, out))
+        os.makedirs(out + "scans")
+        for k in (1, e):
+            shutil.copy(os.path.join(scans, "Epoch_%03d.pcd" % k), out + "scans/")
+        cfg = out + "configuration_4d.txt"
+        synth.write_config(cfg, out + "scans", out, res=0.005, sv=0.05, dtinit=0.05, dtmin=0.004)
+        code = ("import sys; sys.path.insert(0, %r)\nfrom pwicp_b200 import host\nassert host.call_4d(%r, 0, 2, 0, 0.75)\nprint('4D-OK')\n"
+                % (os.path.join(root, "piecewise-icp_b200", "python"), cfg))
         env = dict(os.environ, PWICP_SEGMENTER_PLUGIN=ref_so + ":ref_supervoxel_labels", PWICP_VOXEL_ORDER="msvc")
         r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900, cwd=out)
-        assert "PAIR-OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
-        T, V = read_transmatrix_file(out + "TransMatrix.txt")
+        assert "4D-OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+        T, V = read_transmatrix_file(out + "%d_Direct2Ref_TransMatrix.txt" % e)
         Tr, Vr = read_transmatrix_file(os.path.join(root, "refdata", "recorded", "%d_Direct2Ref_TransMatrix.txt" % e))
         da, dt = pose_err(T, Tr)
         assert da <= 1e-6 and dt <= 1e-6, (e, da, dt)
