@@ -3,8 +3,6 @@
 // One build per target replaces the reference's repeated KD-tree builds over the same cloud
 // (five per outer iteration over CTcloud1: src/Registration.cpp:738, :744, :1294 and two inside
 // pcl::IterativeClosestPoint; one per stage-1 iteration over cloud1: src/CommonFunc.cpp:269-273).
-#include <cub/cub.cuh>
-#include <thrust/iterator/reverse_iterator.h>
 #include <cfloat>
 #include <cmath>
 #include <cstring>
@@ -158,44 +156,140 @@ int bbox_packed_dev(Ctx* ctx, const float* xyz_dev, size_t n, float* mn3, float*
 }
 
 // ---- build ---------------------------------------------------------------------------------
-__global__ void cell_key_kernel(const float* __restrict__ xyz, int n, float ox, float oy, float oz,
-                                float inv_h, int dx, int dy, int dz, uint32_t* keys, uint32_t* vals) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float x = xyz[3 * (size_t)i], y = xyz[3 * (size_t)i + 1], z = xyz[3 * (size_t)i + 2];
-    // identical expression to search_level(): (p - origin) * inv_h, floor, clamp
-    float fx = (x - ox) * inv_h, fy = (y - oy) * inv_h, fz = (z - oz) * inv_h;
-    int cx = min(max((int)floorf(fx), 0), dx - 1);
-    int cy = min(max((int)floorf(fy), 0), dy - 1);
-    int cz = min(max((int)floorf(fz), 0), dz - 1);
-    uint32_t key = ((uint32_t)cz * (uint32_t)dy + (uint32_t)cy) * (uint32_t)dx + (uint32_t)cx;
-    keys[i] = key;
-    vals[i] = (uint32_t)i;
+// Counting sort by cell, hand-written (round 1 went through cub::DeviceRadixSort + DeviceScan: a third of the build was
+// the 32-bit key sort, profiles/r01j_launch_shares.txt).  Cell keys are bounded by the number of cells, so per level:
+//   count   : one atomic per (warp, distinct cell) into A[2 + cell]
+//   scan    : inclusive prefix sum of A in place (three launches)  ->  A[1 + cell] = first slot of the cell
+//   scatter : slot = A[1 + cell]++, again one atomic per (warp, distinct cell); the point goes straight into the
+//             sorted float4 array.  Afterwards A[1 + cell] is the END of the cell, i.e. A[cell] its start: A is the
+//             cell_start array the searches read (A[0] = 0, A[ncells] = n).
+// The order of the points INSIDE a cell is whatever the atomics make it.  Nothing reads it: every search compares
+// (distance, original index) explicitly, so indices and distances do not depend on it.
+__device__ __forceinline__ uint32_t cell_key_of(const float* __restrict__ xyz, int i, float ox, float oy, float oz,
+                                                float inv_h, int dx, int dy, int dz, float4& p) {
+    p.x = xyz[3 * (size_t)i]; p.y = xyz[3 * (size_t)i + 1]; p.z = xyz[3 * (size_t)i + 2];
+    // identical expression to the searches: (p - origin) * inv_h, floor, clamp
+    const float fx = (p.x - ox) * inv_h, fy = (p.y - oy) * inv_h, fz = (p.z - oz) * inv_h;
+    const int cx = min(max((int)floorf(fx), 0), dx - 1);
+    const int cy = min(max((int)floorf(fy), 0), dy - 1);
+    const int cz = min(max((int)floorf(fz), 0), dz - 1);
+    return ((uint32_t)cz * (uint32_t)dy + (uint32_t)cy) * (uint32_t)dx + (uint32_t)cx;
 }
 
-// cell_start from the SORTED keys: the first point of every non-empty cell marks its cell (no
-// atomics: a histogram by atomicAdd serialises on the coarse levels, where thousands of points
-// share a cell -- it was 2/3 of the build, profiles/r01c_*); empty cells are filled afterwards by
-// a suffix minimum (the start of the next non-empty cell).
-__global__ void cell_mark_kernel(const uint32_t* __restrict__ sorted_keys, int n, uint32_t* cells, uint32_t ncells) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) cells[ncells] = (uint32_t)n;
+__global__ void __launch_bounds__(256)
+cell_count_kernel(const float* __restrict__ xyz, int n, float ox, float oy, float oz, float inv_h, int dx, int dy, int dz,
+                  uint32_t* __restrict__ A) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint32_t k = sorted_keys[i];
-    if (i == 0 || sorted_keys[i - 1] != k) cells[k] = (uint32_t)i;
+    float4 p;
+    const uint32_t key = cell_key_of(xyz, i, ox, oy, oz, inv_h, dx, dy, dz, p);
+    // neighbours in the caller's order usually share a cell (always on the coarse levels): one atomic per group
+    const unsigned m = __match_any_sync(__activemask(), key);
+    if ((int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(A + 2 + key, (uint32_t)__popc(m));
 }
 
-__global__ void gather_sorted_kernel(const float* __restrict__ xyz, const uint32_t* __restrict__ order,
-                                     int n, float4* out, uint32_t* inv_perm) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256)
+cell_scatter_kernel(const float* __restrict__ xyz, int n, float ox, float oy, float oz, float inv_h, int dx, int dy, int dz,
+                    uint32_t* __restrict__ A, float4* __restrict__ out, uint32_t* __restrict__ inv_perm,
+                    uint32_t* __restrict__ perm) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint32_t o = order[i];
-    out[i] = make_float4(xyz[3 * (size_t)o], xyz[3 * (size_t)o + 1], xyz[3 * (size_t)o + 2],
-                         __int_as_float((int)o));
-    if (inv_perm) inv_perm[o] = (uint32_t)i;
+    float4 p;
+    const uint32_t key = cell_key_of(xyz, i, ox, oy, oz, inv_h, dx, dy, dz, p);
+    const unsigned m = __match_any_sync(__activemask(), key);
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(A + 1 + key, (uint32_t)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    const uint32_t slot = base + (uint32_t)__popc(m & ((1u << lane) - 1));
+    p.w = __int_as_float(i);
+    out[slot] = p;
+    if (inv_perm) { inv_perm[i] = slot; perm[slot] = (uint32_t)i; }
 }
 
-static int bits_for(uint64_t v) { int b = 1; while ((1ull << b) < v && b < 32) ++b; return b; }
+// inclusive prefix sum of n 32-bit counters in place: tile sums, scan of the tile sums (one block), tiles
+constexpr int kScanThreads = 512, kScanItems = 8, kScanTile = kScanThreads * kScanItems;
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_tile_sum_kernel(const uint32_t* __restrict__ a, size_t n, uint32_t* __restrict__ tsum) {
+    __shared__ uint32_t s_w[kScanThreads / 32];
+    const size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) if (base + k < n) s += a[base + k];
+    s = __reduce_add_sync(0xffffffffu, s);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t v = (threadIdx.x < kScanThreads / 32) ? s_w[threadIdx.x] : 0u;
+        v = __reduce_add_sync(0xffffffffu, v);
+        if (threadIdx.x == 0) tsum[blockIdx.x] = v;
+    }
+}
+
+// exclusive scan of the tile sums in place (one block, any count)
+__global__ void __launch_bounds__(1024)
+scan_tsum_kernel(uint32_t* __restrict__ tsum, int nt) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < nt; b0 += 1024) {
+        const int i = b0 + tid;
+        const uint32_t v = (i < nt) ? tsum[i] : 0u;
+        uint32_t x = v;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = s_warp[lane];
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const uint32_t incl = x + (warp ? s_warp[warp - 1] : 0u) + s_carry;
+        if (i < nt) tsum[i] = incl - v;
+        __syncthreads();
+        if (tid == 1023) s_carry = incl;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_tile_apply_kernel(uint32_t* __restrict__ a, size_t n, const uint32_t* __restrict__ toff) {
+    __shared__ uint32_t s_w[kScanThreads / 32];
+    const size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t v[kScanItems], s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) { v[k] = (base + k < n) ? a[base + k] : 0u; s += v[k]; v[k] = s; }
+    uint32_t x = s;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) s_w[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = (lane < kScanThreads / 32) ? s_w[lane] : 0u;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+        if (lane < kScanThreads / 32) s_w[lane] = w;
+    }
+    __syncthreads();
+    const uint32_t before = toff[blockIdx.x] + (warp ? s_w[warp - 1] : 0u) + (x - s);
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) if (base + k < n) a[base + k] = before + v[k];
+}
+
+static int scan_inclusive_inplace(Ctx* ctx, uint32_t* a, size_t n) {
+    const int nt = (int)((n + kScanTile - 1) / kScanTile);
+    PW_TRY(ctx->vals.reserve(ctx, (size_t)nt * 4));
+    uint32_t* tsum = ctx->vals.as<uint32_t>();
+    scan_tile_sum_kernel<<<nt, kScanThreads, 0, ctx->stream>>>(a, n, tsum);
+    scan_tsum_kernel<<<1, 1024, 0, ctx->stream>>>(tsum, nt);
+    scan_tile_apply_kernel<<<nt, kScanThreads, 0, ctx->stream>>>(a, n, tsum);
+    ctx->launches += 3;
+    PW_CUDA(cudaGetLastError());
+    return PWICP_OK;
+}
 
 int grid_build(Ctx* ctx, GridOwner& g, const float* xyz, int n) {
     g.dev = GridDev{};                 // invalid until the build completes; buffers are reused
@@ -231,6 +325,7 @@ int grid_build(Ctx* ctx, GridOwner& g, const float* xyz, int n) {
     g.dev.n = n;
     int nlev = 0;
     double hl = h;
+    const int blocks = (n + 255) / 256;
     for (int l = 0; l < kMaxLevels; ++l) {
         int d[3];
         for (int c = 0; c < 3; ++c) d[c] = (int)std::max(1.0, std::floor(ext[c] / hl) + 1.0);
@@ -238,36 +333,9 @@ int grid_build(Ctx* ctx, GridOwner& g, const float* xyz, int n) {
         if (ncells > 0x7fffffffull) { set_error(ctx, "grid_build: too many cells"); return PWICP_ERR_ARG; }
         float inv_h = (float)(1.0 / hl);
 
-        PW_TRY(ctx->keys.reserve(ctx, (size_t)n * 4));
-        PW_TRY(ctx->vals.reserve(ctx, (size_t)n * 4));
-        PW_TRY(ctx->keys2.reserve(ctx, (size_t)n * 4));
-        PW_TRY(ctx->vals2.reserve(ctx, (size_t)n * 4));
-        PW_TRY(g.cells[l].reserve(ctx, (ncells + 1) * sizeof(uint32_t)));
-        uint32_t* cells = g.cells[l].as<uint32_t>();
-        PW_CUDA(cudaMemsetAsync(cells, 0xff, (ncells + 1) * sizeof(uint32_t), ctx->stream));
-        int blocks = (n + 255) / 256;
-        cell_key_kernel<<<blocks, 256, 0, ctx->stream>>>(xyz, n, mn[0], mn[1], mn[2], inv_h, d[0], d[1], d[2],
-                                                         ctx->keys.as<uint32_t>(), ctx->vals.as<uint32_t>());
-        ctx->launches++;
-        auto rcells = thrust::make_reverse_iterator(cells + ncells + 1);
-        size_t tmp_bytes = 0;
-        cub::DeviceScan::InclusiveScan(nullptr, tmp_bytes, rcells, rcells, cub::Min(), (int)(ncells + 1), ctx->stream);
-        size_t tmp2 = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, tmp2, ctx->keys.as<uint32_t>(), ctx->keys2.as<uint32_t>(),
-                                        ctx->vals.as<uint32_t>(), ctx->vals2.as<uint32_t>(), n, 0,
-                                        bits_for(ncells), ctx->stream);
-        PW_TRY(ctx->cub_tmp.reserve(ctx, std::max(tmp_bytes, tmp2)));
-        // stable radix sort by cell key: points of one cell stay in ascending original index
-        size_t cap = ctx->cub_tmp.cap;
-        PW_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, cap, ctx->keys.as<uint32_t>(),
-                                                ctx->keys2.as<uint32_t>(), ctx->vals.as<uint32_t>(),
-                                                ctx->vals2.as<uint32_t>(), n, 0, bits_for(ncells), ctx->stream));
-        // cell_start: mark the first point of every non-empty cell, then suffix-min over the cells
-        cell_mark_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->keys2.as<uint32_t>(), n, cells, (uint32_t)ncells);
-        cap = ctx->cub_tmp.cap;
-        PW_CUDA(cub::DeviceScan::InclusiveScan(ctx->cub_tmp.p, cap, rcells, rcells, cub::Min(), (int)(ncells + 1), ctx->stream));
-        ctx->launches += 7;
+        PW_TRY(g.cells[l].reserve(ctx, (ncells + 2) * sizeof(uint32_t)));
         PW_TRY(g.pts[l].reserve(ctx, (size_t)n * sizeof(float4)));
+        uint32_t* A = g.cells[l].as<uint32_t>();
         float4* pts = g.pts[l].as<float4>();
         uint32_t* invp = nullptr;
         if (l == 0) {
@@ -275,13 +343,16 @@ int grid_build(Ctx* ctx, GridOwner& g, const float* xyz, int n) {
             PW_TRY(g.perm0_buf.reserve(ctx, (size_t)n * sizeof(uint32_t)));
             g.perm0 = g.perm0_buf.as<uint32_t>();
             invp = g.inv_perm.as<uint32_t>();
-            PW_CUDA(cudaMemcpyAsync(g.perm0, ctx->vals2.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
         }
-        gather_sorted_kernel<<<blocks, 256, 0, ctx->stream>>>(xyz, ctx->vals2.as<uint32_t>(), n, pts, invp);
-        ctx->launches++;
+        PW_CUDA(cudaMemsetAsync(A, 0, (ncells + 2) * sizeof(uint32_t), ctx->stream));
+        cell_count_kernel<<<blocks, 256, 0, ctx->stream>>>(xyz, n, mn[0], mn[1], mn[2], inv_h, d[0], d[1], d[2], A);
+        PW_TRY(scan_inclusive_inplace(ctx, A, (size_t)ncells + 2));
+        cell_scatter_kernel<<<blocks, 256, 0, ctx->stream>>>(xyz, n, mn[0], mn[1], mn[2], inv_h, d[0], d[1], d[2], A, pts,
+                                                            invp, g.perm0);
+        ctx->launches += 2;
 
         GridLevel& L = g.dev.lv[l];
-        L.pts = pts; L.cell_start = cells;
+        L.pts = pts; L.cell_start = A;
         L.dx = d[0]; L.dy = d[1]; L.dz = d[2];
         L.inv_h = inv_h; L.inv_h2 = inv_h * inv_h;
         nlev = l + 1;
@@ -290,6 +361,7 @@ int grid_build(Ctx* ctx, GridOwner& g, const float* xyz, int n) {
     }
     g.dev.nlevels = nlev;
     g.dev.inv_perm = g.inv_perm.as<uint32_t>();
+    PW_CUDA(cudaGetLastError());
     PW_CUDA(cudaStreamSynchronize(ctx->stream));
     return PWICP_OK;
 }

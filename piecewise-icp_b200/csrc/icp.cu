@@ -619,8 +619,9 @@ __device__ __forceinline__ unsigned long long spread21(unsigned int v) {
     return x;
 }
 
+template <typename K>
 __global__ void src_key_kernel(const float4* __restrict__ src, int n, float ox, float oy, float oz, float inv_h,
-                               int dx, int dy, int dz, unsigned long long* keys, uint32_t* vals) {
+                               int dx, int dy, int dz, K* keys, uint32_t* vals) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4 p = src[i];
@@ -628,7 +629,7 @@ __global__ void src_key_kernel(const float4* __restrict__ src, int n, float ox, 
     int cx = min(max((int)floorf(fx), 0), dx - 1);
     int cy = min(max((int)floorf(fy), 0), dy - 1);
     int cz = min(max((int)floorf(fz), 0), dz - 1);
-    keys[i] = spread21(cx) | (spread21(cy) << 1) | (spread21(cz) << 2);
+    keys[i] = (K)(spread21(cx) | (spread21(cy) << 1) | (spread21(cz) << 2));
     vals[i] = (uint32_t)i;
 }
 
@@ -685,19 +686,27 @@ static int icp_sort_source(Ctx* ctx, int n, bool have_seed) {
     PW_TRY(ctx->icp_sorted.reserve(ctx, (size_t)n_pad * sizeof(float4)));
     PW_TRY(ctx->icp_match.reserve(ctx, (size_t)n_pad * 3 * sizeof(float4)));      // cn, cq, cmore
     const int blocks = (n + 255) / 256;
-    src_key_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->icp_src.as<float4>(), n, ctx->tgt.dev.ox, ctx->tgt.dev.oy,
-                                                    ctx->tgt.dev.oz, L.inv_h, L.dx, L.dy, L.dz,
-                                                    ctx->keys.as<unsigned long long>(), ctx->vals.as<uint32_t>());
     int maxd = std::max(L.dx, std::max(L.dy, L.dz));
     int b1 = 1; while ((1 << b1) < maxd && b1 < 21) ++b1;
     const int bits = 3 * b1;
     size_t tmp = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp, ctx->keys.as<unsigned long long>(), ctx->keys2.as<unsigned long long>(),
-                                    ctx->vals.as<uint32_t>(), ctx->icp_perm.as<uint32_t>(), n, 0, bits, ctx->stream);
-    PW_TRY(ctx->cub_tmp.reserve(ctx, tmp));
-    size_t cap = ctx->cub_tmp.cap;
-    PW_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, cap, ctx->keys.as<unsigned long long>(), ctx->keys2.as<unsigned long long>(),
-                                            ctx->vals.as<uint32_t>(), ctx->icp_perm.as<uint32_t>(), n, 0, bits, ctx->stream));
+    if (bits <= 32) {                    // grids up to 1024 cells per axis: 32-bit keys, half the sort traffic
+        uint32_t* k1 = ctx->keys.as<uint32_t>(); uint32_t* k2 = ctx->keys2.as<uint32_t>();
+        src_key_kernel<uint32_t><<<blocks, 256, 0, ctx->stream>>>(ctx->icp_src.as<float4>(), n, ctx->tgt.dev.ox, ctx->tgt.dev.oy,
+                                                                 ctx->tgt.dev.oz, L.inv_h, L.dx, L.dy, L.dz, k1, ctx->vals.as<uint32_t>());
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp, k1, k2, ctx->vals.as<uint32_t>(), ctx->icp_perm.as<uint32_t>(), n, 0, bits, ctx->stream);
+        PW_TRY(ctx->cub_tmp.reserve(ctx, tmp));
+        size_t cap = ctx->cub_tmp.cap;
+        PW_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, cap, k1, k2, ctx->vals.as<uint32_t>(), ctx->icp_perm.as<uint32_t>(), n, 0, bits, ctx->stream));
+    } else {
+        unsigned long long* k1 = ctx->keys.as<unsigned long long>(); unsigned long long* k2 = ctx->keys2.as<unsigned long long>();
+        src_key_kernel<unsigned long long><<<blocks, 256, 0, ctx->stream>>>(ctx->icp_src.as<float4>(), n, ctx->tgt.dev.ox, ctx->tgt.dev.oy,
+                                                                           ctx->tgt.dev.oz, L.inv_h, L.dx, L.dy, L.dz, k1, ctx->vals.as<uint32_t>());
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp, k1, k2, ctx->vals.as<uint32_t>(), ctx->icp_perm.as<uint32_t>(), n, 0, bits, ctx->stream);
+        PW_TRY(ctx->cub_tmp.reserve(ctx, tmp));
+        size_t cap = ctx->cub_tmp.cap;
+        PW_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, cap, k1, k2, ctx->vals.as<uint32_t>(), ctx->icp_perm.as<uint32_t>(), n, 0, bits, ctx->stream));
+    }
     src_gather_kernel<<<(n_pad + 255) / 256, 256, 0, ctx->stream>>>(ctx->icp_src.as<float4>(), ctx->icp_perm.as<uint32_t>(), n, n_pad,
                                                        ctx->icp_sorted.as<float4>(),
                                                        have_seed ? ctx->icp_seed.as<int>() : nullptr, ctx->tgt.dev.lv[0].pts,

@@ -64,21 +64,19 @@ classify_dist_kernel(GridDev g, const float4* __restrict__ aux, const unsigned c
                      const float* __restrict__ bpstd2, int n2, float minLoD, float maxLoD,
                      float* __restrict__ pl, float* __restrict__ pt2pt, float* __restrict__ lod,
                      int* __restrict__ lod_minmax, const uint32_t* __restrict__ order,
-                     int* __restrict__ ct_seed, int* __restrict__ bp_seed, int first, int count) {
+                     int* __restrict__ ct_seed, int* __restrict__ bp_seed) {
     // thread u handles the u-th query of the Morton-ordered patch list (spatially compact groups);
-    // t is the query's slot in the caller's order: centroid t < n2, boundary point t - n2.  Two launches: the
-    // centroids (first = 0, count = n2), then the boundary points (first = n2, count = 6 n2), which lie within half a
-    // patch of their centroid and take its fresh match as the seed when they have none of their own (first iteration)
-    const int u = first + blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = u < first + count;
+    // t is the query's slot in the caller's order: centroid t < n2, boundary point t - n2.  (Seeding the boundary points
+    // of the first iteration with their centroid's match, in a second launch, was measured: no gain, r02r.)
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = u < 7 * n2;
     float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
     int t = 0, seed = -1;
     if (active) {
         if (u < n2) { t = (int)order[u]; p = __ldg(ct2 + t); seed = ct_seed[t]; }
         else {
-            const int v = u - n2, pt = (int)order[v / 6], bpi = 6 * pt + v % 6;
+            const int v = u - n2, bpi = 6 * (int)order[v / 6] + v % 6;
             t = n2 + bpi; p = __ldg(bp2 + bpi); seed = bp_seed[bpi];
-            if (seed < 0) seed = ct_seed[pt];
         }
     }
     if (!active) return;
@@ -692,13 +690,10 @@ int outer_single_iteration(Ctx* ctx, const pwicp_pair_params& pp, pwicp_state* s
 
     PW_TRY(ensure_patch_order(ctx));
     // (1)-(3) distances of the 7 queries of every patch, LoDetection
-    for (int pass = 0; pass < 2; ++pass) {
-        const int first = pass ? n2 : 0, count = pass ? 6 * n2 : n2;
-        classify_dist_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(
-            ctx->tgt.dev, ctx->tgt_aux.as<float4>(), ctx->tgt_ok.as<unsigned char>(), ctx->ct2.as<float4>(),
-            ctx->bp2.as<float4>(), ctx->bpstd2.as<float>(), n2, minLoD, maxLoD, pl, pt2pt, lod, &sd->lod_min,
-            ctx->ct_order.as<uint32_t>(), ctx->ct_seed.as<int>(), ctx->bp_seed.as<int>(), first, count);
-    }
+    classify_dist_kernel<<<(7 * n2 + 255) / 256, 256, 0, ctx->stream>>>(
+        ctx->tgt.dev, ctx->tgt_aux.as<float4>(), ctx->tgt_ok.as<unsigned char>(), ctx->ct2.as<float4>(),
+        ctx->bp2.as<float4>(), ctx->bpstd2.as<float>(), n2, minLoD, maxLoD, pl, pt2pt, lod, &sd->lod_min,
+        ctx->ct_order.as<uint32_t>(), ctx->ct_seed.as<int>(), ctx->bp_seed.as<int>());
     // (4) classification + compaction of the stable set straight into the inner loop's layout
     const float DTctct = st->currDT + 1 * (pp.SVRes1 + pp.SVRes2);          // :817
     classify_flag_kernel<<<nblocks, kCompactBlock, 0, ctx->stream>>>(
@@ -708,7 +703,7 @@ int outer_single_iteration(Ctx* ctx, const pwicp_pair_params& pp, pwicp_state* s
     compact_kernel<<<nblocks, kCompactBlock, 0, ctx->stream>>>(
         ctx->ct2.as<float4>(), flags, ctx->ct_order.as<uint32_t>(), block_cnt, n2, ctx->ct_seed.as<int>(),
         ctx->tgt.dev.lv[0].pts, ctx->tgt_aux.as<float4>(), sorted, cn, cq);
-    ctx->launches += 5;
+    ctx->launches += 4;
     // (5) inner ICP on the stable centroids against ALL target centroids, :877 -- the count stays on the device
     IcpLaunch L;
     PW_TRY(icp_enqueue(ctx, icp, n2, &sd->n_stable, true, false, false, false, &L));
