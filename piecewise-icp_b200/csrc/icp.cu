@@ -362,6 +362,28 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_group2() { asm volatile("cp.async.wait_group 2;" ::: "memory"); }
+// ---- bulk-copy (TMA) staging of the per-batch streams, PWICP_STAGE_TMA = 1 ------------------------------------------
+// One elected lane issues three 512-byte cp.async.bulk copies per batch (SASS UBLKCP) that complete on the slot's
+// mbarrier; the warp waits on the barrier's phase instead of a per-thread cp.async group.  A/B against the per-lane
+// LDGSTS copies: profiles/r02t_tma_ab.txt.
+#ifndef PWICP_STAGE_TMA
+#define PWICP_STAGE_TMA 0
+#endif
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra WAIT_%=;\n\t}"
+                 ::"r"(bar), "r"(parity) : "memory");
+}
+
 // 16-byte load from the shared window (volatile: never hoisted out of the loop, never cached in registers)
 __device__ __forceinline__ void lds128(float4& v, unsigned addr) {
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -411,6 +433,9 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_persistent_kernel(const Ic
     __shared__ float s_Tfinal[16];
     __shared__ int s_stop;
     __shared__ FinishSmem s_fin;
+#if PWICP_STAGE_TMA
+    __shared__ __align__(8) unsigned long long s_bar[kIcpWarps][kStageSlots];
+#endif
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = a.n_dev ? __ldg(a.n_dev) : a.n;                // same value in every thread of the grid
@@ -443,6 +468,28 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_persistent_kernel(const Ic
     // copies of point i_ of this lane (one of the batches of this warp; past the end: an empty group): point +
     // margin, matched target, its normal
     const int n_pad = nb * 32;
+#if PWICP_STAGE_TMA
+    const unsigned s_bar_sh = (unsigned)__cvta_generic_to_shared(&s_bar[warp][0]);
+    const unsigned s_warp_sh = s_lane_sh - lane * 16;            // this warp's landing zone
+    if (lane == 0) {
+        for (int k = 0; k < kStageSlots; ++k) mbar_init(s_bar_sh + 8 * k, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    unsigned phases = 0;                                         // bit s: parity the next wait on slot s expects
+    // one lane copies the three 512-byte rows of the batch that starts at point i_ - lane (past the end: nothing)
+    auto stage_point = [&](const float4* __restrict__ psrc, int i_, int slot_off) {
+        __syncwarp();                                            // every lane has read what the slot held before
+        if (lane == 0 && i_ < n_pad) {
+            const unsigned bar = s_bar_sh + 8 * (slot_off / kSlotBytes), d = s_warp_sh + slot_off;
+            asm volatile("fence.proxy.async;" ::: "memory");     // the rows were written through the generic proxy
+            mbar_expect_tx(bar, 3 * 512);
+            bulk_g2s(d, psrc + i_, 512, bar);
+            bulk_g2s(d + 512, a.cq + i_, 512, bar);
+            bulk_g2s(d + 1024, a.cn + i_, 512, bar);
+        }
+    };
+#else
     auto stage_point = [&](const float4* __restrict__ psrc, int i_, int slot_off) {
         if (i_ < n_pad) {
             const unsigned d = s_lane_sh + slot_off;
@@ -452,6 +499,7 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_persistent_kernel(const Ic
         }
         cp_async_commit();
     };
+#endif
     stage_point(a.src, i0, 0);
     stage_point(a.src, i0 + stride, kSlotBytes);
     const unsigned s_T_sh = (unsigned)__cvta_generic_to_shared(s_T);
@@ -469,7 +517,15 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_persistent_kernel(const Ic
 #pragma unroll 1
         for (int k = 0; k < K; ++k, i += stride) {
             stage_point(psrc, i + 2 * stride, pslot);
+#if PWICP_STAGE_TMA
+            {
+                const int sidx = slot / kSlotBytes;
+                mbar_wait(s_bar_sh + 8 * sidx, (phases >> sidx) & 1u);
+                phases ^= 1u << sidx;
+            }
+#else
             cp_async_wait_group2();                              // everything but the two youngest groups has landed
+#endif
             float4 p, q0, cn;
             lds128(p, s_lane_sh + slot);
             lds128(q0, s_lane_sh + slot + 512);
@@ -591,7 +647,13 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_persistent_kernel(const Ic
         __syncthreads();
         if (s_stop) break;
     }
+#if PWICP_STAGE_TMA
+    // the copies staged for an iteration that does not run must land before the CTA gives up its shared memory
+    if (K > 0) mbar_wait(s_bar_sh, phases & 1u);
+    if (K > 1) mbar_wait(s_bar_sh + 8, (phases >> 1) & 1u);
+#else
     cp_async_wait_all();
+#endif
 }
 
 __global__ void expand_xyz_kernel(const float* __restrict__ xyz, int n, float4* out) {

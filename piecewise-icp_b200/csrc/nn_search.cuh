@@ -234,33 +234,70 @@ static __device__ __noinline__ void find_seed_ool(const GridDev& g, float px, fl
     find_seed(g, px, py, pz, bd, bi, bpos);
 }
 
+// A query without a usable seed: the 3x3x3 block of finest-level cells around its home cell in ONE pass -- the home row
+// first (for overlapping clouds it holds the nearest target or one nearly as close), then the eight rows around it,
+// each pruned against the running best by the same gap / chord tests as a ball scan.  (Round 1 first took the best
+// of the home cell as a seed and then scanned the ball through it, home cell included a second time.)  Returns true
+// when the closed ball of the best distance lies inside the block (faces on the grid boundary are open: there is no
+// target beyond them), i.e. the answer is exact; else bd / bi / bpos hold a valid upper bound (or nothing).
+template <bool kWide>
+__device__ __forceinline__ bool block_scan(const GridLevel& L, float ox, float oy, float oz, float px, float py, float pz,
+                                           float& bd, int& bi, int& bpos) {
+    const float fx = (px - ox) * L.inv_h, fy = (py - oy) * L.inv_h, fz = (pz - oz) * L.inv_h;
+    const float mx = 0.01f + fabsf(fx) * 4e-6f, my = 0.01f + fabsf(fy) * 4e-6f, mz = 0.01f + fabsf(fz) * 4e-6f;
+    const int cx = min(max((int)floorf(fx), 0), L.dx - 1), cy = min(max((int)floorf(fy), 0), L.dy - 1),
+              cz = min(max((int)floorf(fz), 0), L.dz - 1);
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, L.dx - 1);
+    const int y0 = max(cy - 1, 0), y1 = min(cy + 1, L.dy - 1), z0 = max(cz - 1, 0), z1 = min(cz + 1, L.dz - 1);
+    ball_row<kWide>(L, cy, cz, fx, fy, fz, mx, my, mz, x0, x1, px, py, pz, true, bd, bi, bpos);
+    for (int kz = z0; kz <= z1; ++kz)
+        for (int ky = y0; ky <= y1; ++ky) {
+            if (ky == cy && kz == cz) continue;
+            ball_row<kWide>(L, ky, kz, fx, fy, fz, mx, my, mz, x0, x1, px, py, pz, true, bd, bi, bpos);
+        }
+    if (bpos < 0) return false;
+    const float r = sqrtf(bd) * L.inv_h * 1.00001f;
+    return (x0 == 0 || fx - r - mx >= (float)x0) && (x1 == L.dx - 1 || fx + r + mx < (float)(x1 + 1)) &&
+           (y0 == 0 || fy - r - my >= (float)y0) && (y1 == L.dy - 1 || fy + r + my < (float)(y1 + 1)) &&
+           (z0 == 0 || fz - r - mz >= (float)z0) && (z1 == L.dz - 1 || fz + r + mz < (float)(z1 + 1));
+}
+
+static __device__ __noinline__ bool block_scan_ool(const GridLevel& L, float ox, float oy, float oz, float px, float py,
+                                                   float pz, float& bd, int& bi, int& bpos) {
+    return block_scan<true>(L, ox, oy, oz, px, py, pz, bd, bi, bpos);
+}
+
 // Exact nearest neighbour.  seed_pos >= 0: level-0 position of a target known to be close
 // (normally the previous match); -1: none.
-// kLean = true (inner ICP loop): seeds come from the previous inner iteration and are never stale,
-// so the stale-seed test is dropped and the rare paths are kept out of line.
+// kLean = true (inner ICP loop): the rare paths are kept out of line.
 template <bool kLean = false>
 __device__ __forceinline__ Best nn_search_seeded(const GridDev& g, float px, float py, float pz, int seed_pos) {
     float bd = __int_as_float(0x7f800000);
     int bi = 0x7fffffff, bpos = -1;
+    bool done = false;
     if (seed_pos >= 0) {
         const float4 q = __ldg(g.lv[0].pts + seed_pos);
         bd = l2_simple(px, py, pz, q.x, q.y, q.z);
         bi = __float_as_int(q.w);
         bpos = seed_pos;
-        // a stale seed (the cloud moved by a good part of a cell since it was recorded) would make
-        // the ball large: the home cell usually holds a better candidate
-        if (kLean) { if (bd * g.lv[0].inv_h2 > PWICP_RESEED_CELLS2_LOOP) find_seed_ool(g, px, py, pz, bd, bi, bpos); }
-        else if (bd * g.lv[0].inv_h2 > PWICP_RESEED_CELLS2) find_seed(g, px, py, pz, bd, bi, bpos);
-    } else if (kLean) {
-        find_seed_ool(g, px, py, pz, bd, bi, bpos);
-    } else {
-        find_seed(g, px, py, pz, bd, bi, bpos);
     }
-    // finest level on which the ball spans only a few cells
-    int l = 0;
-    float r = sqrtf(bd) * g.lv[0].inv_h;
-    while (l < g.nlevels - 1 && r > kBallMaxCells) { ++l; r *= (1.0f / kLevelFactor); }
-    ball_scan<kLean>(g.lv[l], g.ox, g.oy, g.oz, px, py, pz, l == 0, bd, bi, bpos);
+    // no seed, or a stale one (the cloud moved by a good part of a cell since it was recorded: the ball through it
+    // would be large): the block around the home cell, with the seed as the first bound
+    const float stale = kLean ? PWICP_RESEED_CELLS2_LOOP : PWICP_RESEED_CELLS2;
+    if (seed_pos < 0 || bd * g.lv[0].inv_h2 > stale) {
+        done = kLean ? block_scan_ool(g.lv[0], g.ox, g.oy, g.oz, px, py, pz, bd, bi, bpos)
+                     : block_scan<false>(g.lv[0], g.ox, g.oy, g.oz, px, py, pz, bd, bi, bpos);
+        if (!done && bpos < 0) {             // empty block: a sampled point of the first non-empty coarser home cell
+            if (kLean) find_seed_ool(g, px, py, pz, bd, bi, bpos); else find_seed(g, px, py, pz, bd, bi, bpos);
+        }
+    }
+    if (!done) {
+        // finest level on which the ball spans only a few cells
+        int l = 0;
+        float r = sqrtf(bd) * g.lv[0].inv_h;
+        while (l < g.nlevels - 1 && r > kBallMaxCells) { ++l; r *= (1.0f / kLevelFactor); }
+        ball_scan<kLean>(g.lv[l], g.ox, g.oy, g.oz, px, py, pz, l == 0, bd, bi, bpos);
+    }
 
     Best b;
     b.d2 = bd; b.idx = bi;
