@@ -216,6 +216,12 @@ int pwicp_voxel_grid(pwicp_ctx* ctx, const float* xyz, int n, float leaf, float*
 /* first pass of pcl::StatisticalOutlierRemoval (:446-451): mean distance of every point to its k nearest other
  * points (nearestKSearch(point, k + 1) without the point itself), float(dist_sum / k).  1 <= k <= 32 < n. */
 int pwicp_knn_mean_dist(pwicp_ctx* ctx, const float* xyz, int n, int k, float* mean_dist);
+/* Front end of the supervoxel segmentation (src/Segmentation.cpp:28-46: kdtree.FindKNearestNeighbors(points[i], kNN = 45) and
+ * PCAEstimateNormal over the neighbours, per point): neighbors[n * k] = indices of the k nearest points of every point (the
+ * point itself first; squared distance in double, ties by index), normals[n * 3] = unit eigenvector of the smallest eigenvalue
+ * of the neighbours' covariance (double; orientation undefined).  Either output may be NULL.  1 <= k <= 64 <= n.  These are
+ * the inputs the reference's SupervoxelSegmentation takes; the merge itself stays with the caller (segmenter plug-in). */
+int pwicp_knn_normals(pwicp_ctx* ctx, const float* xyz, int n, int k, int* neighbors, double* normals);
 /* PCpreprocessing(cloud_in, cloud_out, isDownSamp, voxelSize, SOR_NeighborNum, SOR_StdMult) (:423-439): VoxelGrid
  * (when downsample != 0) then StatisticalOutlierRemoval; points with mean distance <= mean + std_mult * stddev are
  * kept in order.  out_xyz must hold n points. */

@@ -688,6 +688,28 @@ int pwicp_knn_mean_dist(pwicp_ctx* p, const float* xyz, int n, int k, float* mea
     return PWICP_OK;
 }
 
+// k nearest neighbours (indices, the point itself first) and PCA normals of every point: the segmentation front end
+int pwicp_knn_normals(pwicp_ctx* p, const float* xyz, int n, int k, int* neighbors, double* normals) {
+    Ctx* ctx = reinterpret_cast<Ctx*>(p);
+    if (!ctx || !xyz || n < 1 || k < 1 || k > 64 || n < k || (!neighbors && !normals)) { set_error(ctx, "knn_normals: bad arguments (1 <= k <= 64 <= n)"); return PWICP_ERR_ARG; }
+    PW_CUDA(cudaSetDevice(ctx->device));
+    PW_TRY(upload_checked(ctx, ctx->scratch_a, xyz, (size_t)3 * n, "cloud"));
+    PW_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    GridOwner& g = ctx->prep;                      // persistent buffers, rebuilt for this cloud
+    PW_TRY(grid_build(ctx, g, ctx->scratch_a.as<float>(), n));
+    PW_TRY(ctx->scratch_b.reserve(ctx, (size_t)n * k * sizeof(int)));
+    PW_TRY(ctx->scratch_c.reserve(ctx, (size_t)n * 3 * sizeof(double)));
+    PW_CUDA(cudaEventRecord(ctx->ev2, ctx->stream));
+    PW_TRY(knn_normals_dev(ctx, g.dev, k, neighbors ? ctx->scratch_b.as<int>() : nullptr, normals ? ctx->scratch_c.as<double>() : nullptr));
+    PW_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    if (neighbors) PW_CUDA(cudaMemcpyAsync(neighbors, ctx->scratch_b.p, (size_t)n * k * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (normals) PW_CUDA(cudaMemcpyAsync(normals, ctx->scratch_c.p, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    PW_CUDA(cudaStreamSynchronize(ctx->stream));
+    PW_CUDA(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));           // grid build + kernel
+    PW_CUDA(cudaEventElapsedTime(&ctx->prep_kernel_ms, ctx->ev2, ctx->ev1));    // the kernel alone
+    return PWICP_OK;
+}
+
 // VoxelGrid (optional) + StatisticalOutlierRemoval in one call: the cloud stays on the device between the two steps; the
 // selection (mean + mult * stddev of the mean distances, sequential double sums like PCL) runs on the host over the
 // downloaded 4 bytes per point.  out_xyz must hold n points.

@@ -163,6 +163,7 @@ void octree_cube(const float* mn, const float* mx, double res, double* bb6);
 // prep.cu (F4)
 int voxel_grid_dev(Ctx* ctx, const float* xyz_dev, int n, float leaf, float* out_dev, int* n_out);
 int knn_mean_dist_dev(Ctx* ctx, const GridDev& g, int k, float* out_dev);
+int knn_normals_dev(Ctx* ctx, const GridDev& g, int k, int* neighbors_dev, double* normals_dev);
 
 // patch.cu
 int patch_stats_dev(Ctx* ctx, const float* xyz_dev, const int* off_dev, int np, float* ct, float* bp, float* nrm,

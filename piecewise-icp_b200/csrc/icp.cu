@@ -482,7 +482,6 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_persistent_kernel(const Ic
         __syncwarp();                                            // every lane has read what the slot held before
         if (lane == 0 && i_ < n_pad) {
             const unsigned bar = s_bar_sh + 8 * (slot_off / kSlotBytes), d = s_warp_sh + slot_off;
-            asm volatile("fence.proxy.async;" ::: "memory");     // the rows were written through the generic proxy
             mbar_expect_tx(bar, 3 * 512);
             bulk_g2s(d, psrc + i_, 512, bar);
             bulk_g2s(d + 512, a.cq + i_, 512, bar);
@@ -609,6 +608,9 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_persistent_kernel(const Ic
             __stcg(a.part + ((size_t)(it & 1) * G + blockIdx.x) * kNumVals + lane, s);
         }
         grid.sync();
+#if PWICP_STAGE_TMA
+        asm volatile("fence.proxy.async;" ::: "memory");         // work[] was written through the generic proxy
+#endif
         if (blockIdx.x == 0 && tid == 0) a.phase_ns[it * 4 + 1] = globaltimer_ns();
         // the next iteration's first two batches: their copies do not depend on the transform being solved
         // for, so they fly during the reduction and the solve

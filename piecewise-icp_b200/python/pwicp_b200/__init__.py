@@ -60,12 +60,13 @@ EXPORTS = [
     "pwicp_last_error", "pwicp_last_device_ms", "pwicp_launch_count", "pwicp_flush_l2",
     "pwicp_sync", "pwicp_set_cells_per_point", "pwicp_target_upload", "pwicp_target_rebuild", "pwicp_source_upload",
     "pwicp_clouds_upload", "pwicp_source_download", "pwicp_nn", "pwicp_icp_default_params",
-    "pwicp_icp_source_upload", "pwicp_icp_source_all", "pwicp_icp_run", "pwicp_icp_order", "pwicp_icp_profile", "pwicp_icp_phase_profile",
+    "pwicp_icp_source_upload", "pwicp_icp_source_all", "pwicp_icp_run", "pwicp_icp_order",
     "pwicp_icp_p2plane",
     "pwicp_single_iteration", "pwicp_piecewise_icp", "pwicp_percentile_nn", "pwicp_overlap_ratio",
     "pwicp_self_nn", "pwicp_vcm", "pwicp_transform", "pwicp_octree_bbox", "pwicp_bbox_corner_change",
     "pwicp_matrix2angle", "pwicp_mat4_mul", "pwicp_patch_stats", "pwicp_dmma_order_check",
-    "pwicp_voxel_grid", "pwicp_knn_mean_dist", "pwicp_preprocess", "pwicp_last_knn_kernel_ms",
+    "pwicp_voxel_grid", "pwicp_knn_mean_dist", "pwicp_preprocess", "pwicp_last_knn_kernel_ms", "pwicp_knn_normals",
+    "pwicp_icp_profile", "pwicp_icp_phase_profile",
 ]
 
 _lib = None
@@ -120,6 +121,7 @@ def load_library(path=None):
     L.pwicp_self_nn.argtypes = [vp, vp, C.c_int, vp]
     L.pwicp_patch_stats.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp]
     L.pwicp_dmma_order_check.argtypes = [vp, vp, vp, C.c_int, C.POINTER(C.c_longlong)]
+    L.pwicp_knn_normals.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp]
     L.pwicp_last_knn_kernel_ms.argtypes = [vp]
     L.pwicp_last_knn_kernel_ms.restype = C.c_float
     L.pwicp_voxel_grid.argtypes = [vp, vp, C.c_int, C.c_float, vp, C.POINTER(C.c_int)]
@@ -364,6 +366,14 @@ class Context:
         out = C.c_float(0)
         self._chk(self.L.pwicp_overlap_ratio(self.h, _ptr(c1), len(c1), _ptr(c2), len(c2), DTinit, C.byref(out)))
         return out.value
+
+    def knn_normals(self, pts, k=45):
+        """Indices of the k nearest points of every point (itself first) and the PCA normal over them (double)."""
+        p = _f32(pts)
+        nb = np.zeros((len(p), k), np.int32)
+        nr = np.zeros((len(p), 3), np.float64)
+        self._chk(self.L.pwicp_knn_normals(self.h, _ptr(p), len(p), k, _ptr(nb), _ptr(nr)))
+        return nb, nr
 
     def self_nn(self, pts):
         p = _f32(pts)

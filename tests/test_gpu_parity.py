@@ -589,3 +589,20 @@ def test_max_outer_is_reported(gpu_ctx, pair2k):
     with pytest.raises(P.PwicpError) as e:
         gpu_ctx.piecewise_icp(pp, 1, 0.05, max_outer=1)
     assert e.value.status == -8                                           # PWICP_ERR_MAX_OUTER: no VCM, transformation so far
+
+
+def test_knn_normals_match_oracle(gpu_ctx, oracle):
+    """pwicp_knn_normals (front end of the segmentation, src/Segmentation.cpp:28-46: kNN = 45 neighbours + PCAEstimateNormal per
+    point) against the oracle's restatement (itself bit-identical to the reference's codelibrary, tests/test_oracle.py): the
+    neighbour lists index for index (double metric, ties by index, exact duplicates included), the normals within libm
+    tolerance (pow / acos / cos of the closed-form eigenvalue are not correctly rounded on either side)."""
+    pts = synth.make_scan(extent=2.0, spacing=0.01, seed=5)                  # 40k points of a dense scan
+    pts[1000:1040] = pts[:40]                                                 # exact duplicates: distance ties at 0
+    nb, nr = gpu_ctx.knn_normals(pts, 45)
+    onb, onr = oracle.knn_normals(pts, 45)
+    assert np.array_equal(nb, onb)
+    assert np.abs(nr - onr).max() <= 1e-9
+    assert np.allclose(np.linalg.norm(nr, axis=1), 1.0, atol=1e-12)
+    nb8, _ = gpu_ctx.knn_normals(pts[:5000], 8)
+    onb8, _ = oracle.knn_normals(pts[:5000], 8)
+    assert np.array_equal(nb8, onb8)
