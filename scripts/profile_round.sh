@@ -1,11 +1,14 @@
 #!/bin/bash
 # Round profile: (1) launch list of the bench command, (2) ncu --set full of the dominant kernel in the
-# bench configuration.  Run on the GPU box: gpurun -- 'bash scripts/profile_round.sh r01g'
-tag=${1:-r01x}
+# bench configuration, (3) the same at 10M (BASELINE configs[4]), (4) the bench line.
+# Run on the GPU box: gpurun -- 'bash scripts/profile_round.sh r02w'
+tag=${1:-r02x}
 mkdir -p gpurun_out
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${tag}_launches.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_bench_under_ncu.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/${tag}_launches.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-config4 > gpurun_out/${tag}_bench_under_ncu.log 2>&1
 ncu --set full --import-source on --clock-control none -k regex:icp_persistent --launch-skip 3 --launch-count 1 \
-    -o gpurun_out/${tag}_icp_bench -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_full.log 2>&1
-python bench.py > gpurun_out/${tag}_bench_line.json 2> gpurun_out/${tag}_bench.err
-tail -c 600 gpurun_out/${tag}_bench_line.json
+    -o gpurun_out/${tag}_icp_bench -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-config4 > gpurun_out/${tag}_ncu_full.log 2>&1
+ncu --set full --import-source on --clock-control none -k regex:icp_persistent --launch-skip 2 --launch-count 1 \
+    -o gpurun_out/${tag}_icp_10m -f python scripts/prof_icp_only.py 10000000 50 > gpurun_out/${tag}_ncu_10m.log 2>&1
+python bench.py --steps 20 --warmup 5 > gpurun_out/${tag}_bench_line.json 2> gpurun_out/${tag}_bench.err
+tail -c 800 gpurun_out/${tag}_bench_line.json

@@ -35,6 +35,7 @@ want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
         "launch__block_size", "launch__shared_mem_per_block_dynamic", "launch__shared_mem_per_block_static",
         "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active",
+        "sass__inst_executed_local_stores", "smsp__inst_executed_op_ldgsts.sum",
         "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
@@ -44,7 +45,7 @@ want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__
 d = {}
 with open(os.path.join(out, f"{tag}_ncu_icp.txt"), "w") as f:
     f.write("# ncu --set full --clock-control none, icp_persistent_kernel, 4th launch of python bench.py --steps 2 --warmup 3 "
-            "(1M source x 1M target, 50 forced inner iterations)\n")
+            "--no-cpu-baseline --no-config4 (1M source x 1M target, 50 forced inner iterations)\n")
     for k in want:
         if k in hdr:
             i = hdr.index(k); f.write(f"{k} [{units[i]}] = {vals[i]}\n"); d[k] = (vals[i], units[i])
@@ -58,3 +59,16 @@ print("traffic per launch", tr / 1e6, "MB")
 bl = os.path.join(src, f"{tag}_bench_line.json")
 if os.path.exists(bl) and os.path.getsize(bl):
     subprocess.run(["cp", bl, os.path.join(out, f"{tag}_bench_line.json")])
+
+# (3) the 10M capture (BASELINE configs[4]), when present
+p10 = os.path.join(src, f"{tag}_icp_10m.ncu-rep")
+if os.path.exists(p10):
+    raw = subprocess.run(["ncu", "-i", p10, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    with open(os.path.join(out, f"{tag}_ncu_icp_10m.txt"), "w") as f:
+        f.write("# ncu --set full --clock-control none, icp_persistent_kernel, 3rd launch of python scripts/prof_icp_only.py 10000000 50 "
+                "(10M source x 10M target, 50 forced inner iterations; BASELINE configs[4])\n")
+        for k in want:
+            if k in hdr:
+                i = hdr.index(k); f.write(f"{k} [{units[i]}] = {vals[i]}\n")
