@@ -196,32 +196,54 @@ def config4_leg(P, synth, torch, dist, local_rank, rank, world):
         mv = lambda a: pin((a.astype(np.float64) @ T[:3, :3].T + T[:3, 3]).astype(np.float32))
         epochs[e] = {"ct2": mv(base["ct2"]), "bp2": mv(base["bp2"]), "patch_pts2": mv(base["patch_pts2"])}
         epochs[e]["cloud2"] = epochs[e]["patch_pts2"]
-    ctx = P.Context(local_rank)
+    # two contexts per rank: while one registers epoch e, a loader thread uploads epoch e + 1 into the other (its three
+    # grid builds run on that context's stream).  ctypes drops the GIL inside the library calls.
+    ctxs = [P.Context(local_rank), P.Context(local_rank)]
     pp = P.PairParams(base["Res1"], base["Res2"], base["SVRes1"], base["SVRes2"], base["DTmin"])
+    t_up, t_icp = [0.0], [0.0]
 
-    def one(e):
+    def upload(k, e):
         d = dict(tgt); d.update(fixed); d.update(epochs[e])
-        ctx.upload_pair(d)
-        return ctx.piecewise_icp(pp, 1, 0.05)
+        t0 = time.perf_counter()
+        ctxs[k].upload_pair(d)
+        t_up[0] += time.perf_counter() - t0
 
-    one(mine[0])                                     # warm-up: allocations, first launches
+    def register(k):
+        t0 = time.perf_counter()
+        g = ctxs[k].piecewise_icp(pp, 1, 0.05)
+        t_icp[0] += time.perf_counter() - t0
+        return g
+
+    for k in (0, 1):                                 # warm-up of both contexts: allocations, first launches
+        upload(k, mine[0]); register(k)
     rec = torch.zeros((C4_EPOCHS, 96), dtype=torch.float32, device="cuda")       # 384-byte record per epoch
-    if dist:
+    if dist:                                         # ... and the first all-gather of this shape (NCCL sets up lazily)
+        allrec = torch.zeros((world,) + tuple(rec.shape), dtype=rec.dtype, device="cuda")
+        dist.all_gather_into_tensor(allrec, rec)
         dist.barrier()
+    t_up[0] = t_icp[0] = 0.0
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     dev_ms, corr, outer = 0.0, 0, 0
-    for e in mine:
-        g = one(e)
+    upload(0, mine[0])
+    for j, e in enumerate(mine):
+        loader = None
+        if j + 1 < len(mine):
+            loader = threading.Thread(target=upload, args=((j + 1) % 2, mine[j + 1]))
+            loader.start()
+        g = register(j % 2)
         dev_ms += g["device_ms"]; outer += int(g["n_outer"])
         corr += sum(int(s.icp_iters) * int(s.n_stable) for s in g["stats"])
         r = np.zeros(96, np.float32)
         r[:16] = g["T"].reshape(16); r[16:52] = g["VCM"].reshape(36).astype(np.float32); r[52] = 1.0
         rec[e] = torch.from_numpy(r).cuda()
+        if loader:
+            loader.join()
+    torch.cuda.synchronize()
+    t_loop = time.perf_counter() - t0
     if dist:
-        recs = [torch.zeros_like(rec) for _ in range(world)]
-        dist.all_gather(recs, rec)
-        rec = torch.stack(recs).sum(0)
+        dist.all_gather_into_tensor(allrec, rec)     # the one collective of the 4D mode: 384 bytes per epoch and rank
+        rec = allrec.sum(0)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     if dist:
@@ -230,6 +252,8 @@ def config4_leg(P, synth, torch, dist, local_rank, rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX); wall = float(t[0])
         c = torch.tensor([dev_ms, corr, outer], dtype=torch.float64, device="cuda")
         dist.all_reduce(c, op=dist.ReduceOp.SUM); dev_ms, corr, outer = float(c[0]), float(c[1]), int(c[2])
+        m = torch.tensor([t_up[0], t_icp[0], t_loop], dtype=torch.float64, device="cuda")
+        dist.all_reduce(m, op=dist.ReduceOp.MAX); t_up[0], t_icp[0], t_loop = float(m[0]), float(m[1]), float(m[2])
     done = int((rec[:, 52] > 0).sum().item())
     h2d_epoch = int(sum(v.nbytes for v in tgt.values()) + sum(v.nbytes for v in fixed.values()) +
                     sum(epochs[mine[0]][k].nbytes for k in ("ct2", "bp2", "patch_pts2", "cloud2")))
@@ -237,7 +261,8 @@ def config4_leg(P, synth, torch, dist, local_rank, rank, world):
     e0 = mine[0]
     T_est = rec[e0, :16].cpu().numpy().reshape(4, 4).astype(np.float64)
     resid = T_est @ synth.rigid_matrix(*motions[e0]) @ synth.rigid_matrix(*synth.DEFAULT_MOTION)   # estimate o applied motion
-    ctx.close()
+    for c_ in ctxs:
+        c_.close()
     return {"workload": "4D synthetic: 64 epochs x 2M pts each, every epoch against the reference epoch, epoch-sharded "
                         "(BASELINE configs[3])",
             "epochs": C4_EPOCHS, "patches_per_epoch": int(n2), "points_per_epoch": int(len(base["patch_pts2"])),
@@ -245,9 +270,13 @@ def config4_leg(P, synth, torch, dist, local_rank, rank, world):
             "wall_s": wall, "epochs_per_s": C4_EPOCHS / wall, "device_ms_sum_over_ranks": dev_ms,
             "outer_iterations": outer, "correspondences": corr, "correspondences_per_s": corr / wall,
             "h2d_bytes_per_epoch": h2d_epoch, "record_bytes_gathered": C4_EPOCHS * 384 * world,
+            "slowest_rank_s": {"uploads_and_grid_builds": t_up[0], "outer_loops": t_icp[0], "epoch_loop": t_loop,
+                               "gather_and_sync": wall - t_loop},
+            "upload_gbs_per_gpu_incl_grid_builds": h2d_epoch * len(mine) / max(t_up[0], 1e-9) / 1e9,
             "timed_region": "barrier | per epoch: upload of the pair from pinned host memory (pwicp_target_upload, "
-                            "pwicp_clouds_upload, pwicp_source_upload: three device grid builds) + pwicp_piecewise_icp | "
-                            "NCCL all-gather of the records | sync; wall clock, max over ranks",
+                            "pwicp_clouds_upload, pwicp_source_upload: three device grid builds) + pwicp_piecewise_icp, the "
+                            "upload of the next epoch overlapping the registration of the current one (two contexts per rank, "
+                            "a loader thread) | NCCL all-gather of the records | sync; wall clock, max over ranks",
             "sharding": "epoch e on rank e % world, as PiecewiseICP_4D_shard ((step - 1) % world == rank)",
             "residual_of_first_epoch_vs_truth": float(np.abs(resid - np.eye(4)).max())}
 
@@ -258,7 +287,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=N_CENTROIDS, help=argparse.SUPPRESS)
+    ap.add_argument("--centroids", dest="n", type=int, default=N_CENTROIDS, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-config4", action="store_true")
     args = ap.parse_args()

@@ -158,11 +158,6 @@ int pwicp_patch_stats(pwicp_ctx* ctx, const float* patch_xyz, const int* patch_o
                       float* ct3, float* bp18, float* nrm3, unsigned char* nrm_ok,
                       float* bp_std, float* ct_std);
 
-/* Self-test of the hardware property the inner loop's tensor-core batch sums rely on: chained
- * DMMA.8x8x4 over `rows` (multiple of 4) x 8 float inputs A, B equals the fma() chain in row order,
- * bit for bit.  *mismatches = number of the 64 sums that differ (0 on B200). */
-int pwicp_dmma_order_check(pwicp_ctx* ctx, const float* A, const float* B, int rows, long long* mismatches);
-
 /* ---- A2 + A7 + A8: one outer iteration / the outer loop ----------------------------------- */
 typedef struct {
     float Res1, Res2, SVRes1, SVRes2, DTmin;   /* src/Registration.cpp:706, :710 */

@@ -509,33 +509,6 @@ int pwicp_patch_stats(pwicp_ctx* p, const float* patch_xyz, const int* patch_off
     return PWICP_OK;
 }
 
-// Self-test of the hardware property the tensor-core batch sums rely on (icp.cu): D = A^T B over
-// rows x 8 float inputs by chained DMMA.8x8x4 must equal the fma() chain in row order, bit for bit.
-int pwicp_dmma_order_check(pwicp_ctx* p, const float* A, const float* B, int rows, long long* mismatches) {
-    Ctx* ctx = reinterpret_cast<Ctx*>(p);
-    if (!ctx || !A || !B || !mismatches || rows < 4 || rows % 4) { set_error(ctx, "dmma_order_check: bad arguments"); return PWICP_ERR_ARG; }
-    PW_CUDA(cudaSetDevice(ctx->device));
-    const size_t nf = (size_t)rows * 8;
-    PW_TRY(ctx->scratch_a.reserve(ctx, nf * 4));
-    PW_TRY(ctx->scratch_b.reserve(ctx, nf * 4));
-    PW_TRY(ctx->scratch_c.reserve(ctx, 64 * sizeof(double)));
-    PW_CUDA(cudaMemcpyAsync(ctx->scratch_a.p, A, nf * 4, cudaMemcpyHostToDevice, ctx->stream));
-    PW_CUDA(cudaMemcpyAsync(ctx->scratch_b.p, B, nf * 4, cudaMemcpyHostToDevice, ctx->stream));
-    PW_TRY(dmma_order_dev(ctx, ctx->scratch_a.as<float>(), ctx->scratch_b.as<float>(), ctx->scratch_c.as<double>(), rows / 4));
-    double D[64];
-    PW_CUDA(cudaMemcpyAsync(D, ctx->scratch_c.p, sizeof(D), cudaMemcpyDeviceToHost, ctx->stream));
-    PW_CUDA(cudaStreamSynchronize(ctx->stream));
-    long long bad = 0;
-    for (int m = 0; m < 8; ++m)
-        for (int n = 0; n < 8; ++n) {
-            double acc = 0.0;
-            for (int r = 0; r < rows; ++r) acc = std::fma((double)A[r * 8 + m], (double)B[r * 8 + n], acc);
-            if (memcmp(&acc, &D[m * 8 + n], sizeof(double)) != 0) ++bad;
-        }
-    *mismatches = bad;
-    return PWICP_OK;
-}
-
 // ---- outer iteration / loop -------------------------------------------------------------------
 int pwicp_single_iteration(pwicp_ctx* p, const pwicp_pair_params* pp, pwicp_state* st,
                            const pwicp_icp_params* icp, float* T16, double* vcm36,

@@ -168,6 +168,5 @@ int knn_normals_dev(Ctx* ctx, const GridDev& g, int k, int* neighbors_dev, doubl
 // patch.cu
 int patch_stats_dev(Ctx* ctx, const float* xyz_dev, const int* off_dev, int np, float* ct, float* bp, float* nrm,
                     unsigned char* ok, float* bpstd, float* ctstd);
-int dmma_order_dev(Ctx* ctx, const float* A_dev, const float* B_dev, double* D_dev, int nchunks);
 
 }  // namespace pwicp

@@ -43,6 +43,9 @@ namespace pwicp {
 #ifndef PWICP_RESEED_CELLS2_LOOP
 #define PWICP_RESEED_CELLS2_LOOP 1.0f
 #endif
+#ifndef PWICP_BLOCK_WIDE
+#define PWICP_BLOCK_WIDE 0       // stand-alone kernels: candidates of the block scan four at a time (A/B switch)
+#endif
 constexpr float kBallMaxCells = 6.0f;   // scan on the finest level whose ball radius is <= this many cells
                                         // (finer is cheaper unless the ball is mostly empty space: rows ~ (2r+1)^2)
 
@@ -286,7 +289,7 @@ __device__ __forceinline__ Best nn_search_seeded(const GridDev& g, float px, flo
     const float stale = kLean ? PWICP_RESEED_CELLS2_LOOP : PWICP_RESEED_CELLS2;
     if (seed_pos < 0 || bd * g.lv[0].inv_h2 > stale) {
         done = kLean ? block_scan_ool(g.lv[0], g.ox, g.oy, g.oz, px, py, pz, bd, bi, bpos)
-                     : block_scan<false>(g.lv[0], g.ox, g.oy, g.oz, px, py, pz, bd, bi, bpos);
+                     : block_scan<PWICP_BLOCK_WIDE != 0>(g.lv[0], g.ox, g.oy, g.oz, px, py, pz, bd, bi, bpos);
         if (!done && bpos < 0) {             // empty block: a sampled point of the first non-empty coarser home cell
             if (kLean) find_seed_ool(g, px, py, pz, bd, bi, bpos); else find_seed(g, px, py, pz, bd, bi, bpos);
         }

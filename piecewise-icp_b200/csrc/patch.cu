@@ -48,29 +48,4 @@ int patch_stats_dev(Ctx* ctx, const float* xyz_dev, const int* off_dev, int np, 
     return PWICP_OK;
 }
 
-// ---- hardware assumption check ---------------------------------------------------------------
-// The batch sums of icp_persistent_kernel rely on DMMA.8x8x4 adding its four products to the
-// accumulator one after the other in k order, each with one rounding (icp.cu).  This kernel forms
-// 8x8 sums of `nchunks * 4` products that way; pwicp_dmma_order_check compares them bit for bit with
-// a chain of fma() on the host (tests/test_gpu_parity.py keeps the assumption under test).
-__global__ void dmma_order_kernel(const float* __restrict__ A, const float* __restrict__ B, double* __restrict__ D, int nchunks) {
-    const int lane = threadIdx.x;
-    double c0 = 0.0, c1 = 0.0;
-    for (int j = 0; j < nchunks; ++j) {
-        const double a = (double)A[(j * 4 + lane % 4) * 8 + lane / 4];
-        const double b = (double)B[(j * 4 + lane % 4) * 8 + lane / 4];
-        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                     : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-    }
-    D[(lane / 4) * 8 + (lane % 4) * 2] = c0;
-    D[(lane / 4) * 8 + (lane % 4) * 2 + 1] = c1;
-}
-
-int dmma_order_dev(Ctx* ctx, const float* A_dev, const float* B_dev, double* D_dev, int nchunks) {
-    dmma_order_kernel<<<1, 32, 0, ctx->stream>>>(A_dev, B_dev, D_dev, nchunks);
-    ctx->launches++;
-    PW_CUDA(cudaGetLastError());
-    return PWICP_OK;
-}
-
 }  // namespace pwicp

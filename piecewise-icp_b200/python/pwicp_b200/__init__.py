@@ -64,7 +64,7 @@ EXPORTS = [
     "pwicp_icp_p2plane",
     "pwicp_single_iteration", "pwicp_piecewise_icp", "pwicp_percentile_nn", "pwicp_overlap_ratio",
     "pwicp_self_nn", "pwicp_vcm", "pwicp_transform", "pwicp_octree_bbox", "pwicp_bbox_corner_change",
-    "pwicp_matrix2angle", "pwicp_mat4_mul", "pwicp_patch_stats", "pwicp_dmma_order_check",
+    "pwicp_matrix2angle", "pwicp_mat4_mul", "pwicp_patch_stats",
     "pwicp_voxel_grid", "pwicp_knn_mean_dist", "pwicp_preprocess", "pwicp_last_knn_kernel_ms", "pwicp_knn_normals",
     "pwicp_icp_profile", "pwicp_icp_phase_profile",
 ]
@@ -120,7 +120,6 @@ def load_library(path=None):
     L.pwicp_overlap_ratio.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_float, C.POINTER(C.c_float)]
     L.pwicp_self_nn.argtypes = [vp, vp, C.c_int, vp]
     L.pwicp_patch_stats.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp]
-    L.pwicp_dmma_order_check.argtypes = [vp, vp, vp, C.c_int, C.POINTER(C.c_longlong)]
     L.pwicp_knn_normals.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp]
     L.pwicp_last_knn_kernel_ms.argtypes = [vp]
     L.pwicp_last_knn_kernel_ms.restype = C.c_float
@@ -380,13 +379,6 @@ class Context:
         d2 = np.zeros(len(p), np.float32)
         self._chk(self.L.pwicp_self_nn(self.h, _ptr(p), len(p), _ptr(d2)))
         return d2
-
-    def dmma_order_mismatches(self, A, B):
-        """A, B: (rows, 8) float32, rows % 4 == 0.  Number of the 64 tensor-core sums that differ from the fma chain."""
-        a, b = _f32(A), _f32(B)
-        bad = C.c_longlong(-1)
-        self._chk(self.L.pwicp_dmma_order_check(self.h, _ptr(a), _ptr(b), len(a), C.byref(bad)))
-        return bad.value
 
     def patch_stats(self, patch_xyz, patch_off):
         """Constants of every planar patch in one launch: calPatchCTandBP + calPatchNormal + calPatchSTD.

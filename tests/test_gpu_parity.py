@@ -438,18 +438,6 @@ def test_patch_stats_match_oracle(gpu_ctx, oracle):
         gpu_ctx.patch_stats(pts, off[::-1].copy())
 
 
-def test_dmma_accumulates_in_row_order(gpu_ctx):
-    """The inner loop forms its 28 batch sums with chained DMMA.8x8x4 and claims the oracle's
-    sequential order; that holds iff the tensor core adds its four products one after the other in
-    k order with one rounding each.  Checked bit for bit on wide-dynamic-range inputs."""
-    rng = np.random.default_rng(3)
-    for _ in range(200):
-        A = (rng.uniform(-0.5, 0.5, (32, 8)) * 10.0 ** rng.integers(-3, 4, (32, 8))).astype(np.float32)
-        B = (rng.uniform(-0.5, 0.5, (32, 8)) * 10.0 ** rng.integers(-3, 4, (32, 8))).astype(np.float32)
-        assert gpu_ctx.dmma_order_mismatches(A, B) == 0
-
-
-# ---------------------------------------------------------------- configs[0]: the reference's own pair and recorded result
 def test_reference_pair_reproduces_recorded_result(gpu_ctx, oracle):
     """BASELINE configs[0] on the device: the reference's shipped Epoch_001 -> Epoch_002 pair at the hot-path boundary
     (tests/golden/refpair_e2.npz, segmented by the reference's own supervoxel code), per-patch constants from the device
