@@ -246,14 +246,17 @@ def config4_leg(P, synth, torch, dist, local_rank, rank, world):
         rec = allrec.sum(0)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
+    wall_own = wall
+    t_loop_min, t_after_loop_max = t_loop, wall - t_loop
     if dist:
         dist.barrier()
         t = torch.tensor([wall], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX); wall = float(t[0])
         c = torch.tensor([dev_ms, corr, outer], dtype=torch.float64, device="cuda")
         dist.all_reduce(c, op=dist.ReduceOp.SUM); dev_ms, corr, outer = float(c[0]), float(c[1]), int(c[2])
-        m = torch.tensor([t_up[0], t_icp[0], t_loop], dtype=torch.float64, device="cuda")
-        dist.all_reduce(m, op=dist.ReduceOp.MAX); t_up[0], t_icp[0], t_loop = float(m[0]), float(m[1]), float(m[2])
+        m = torch.tensor([t_up[0], t_icp[0], t_loop, -t_loop, wall_own - t_loop], dtype=torch.float64, device="cuda")
+        dist.all_reduce(m, op=dist.ReduceOp.MAX)
+        t_up[0], t_icp[0], t_loop, t_loop_min, t_after_loop_max = float(m[0]), float(m[1]), float(m[2]), -float(m[3]), float(m[4])
     done = int((rec[:, 52] > 0).sum().item())
     h2d_epoch = int(sum(v.nbytes for v in tgt.values()) + sum(v.nbytes for v in fixed.values()) +
                     sum(epochs[mine[0]][k].nbytes for k in ("ct2", "bp2", "patch_pts2", "cloud2")))
@@ -271,7 +274,8 @@ def config4_leg(P, synth, torch, dist, local_rank, rank, world):
             "outer_iterations": outer, "correspondences": corr, "correspondences_per_s": corr / wall,
             "h2d_bytes_per_epoch": h2d_epoch, "record_bytes_gathered": C4_EPOCHS * 384 * world,
             "slowest_rank_s": {"uploads_and_grid_builds": t_up[0], "outer_loops": t_icp[0], "epoch_loop": t_loop,
-                               "gather_and_sync": wall - t_loop},
+                               "epoch_loop_fastest_rank": t_loop_min,
+                               "after_the_loop_max_over_ranks": t_after_loop_max},
             "upload_gbs_per_gpu_incl_grid_builds": h2d_epoch * len(mine) / max(t_up[0], 1e-9) / 1e9,
             "timed_region": "barrier | per epoch: upload of the pair from pinned host memory (pwicp_target_upload, "
                             "pwicp_clouds_upload, pwicp_source_upload: three device grid builds) + pwicp_piecewise_icp, the "
