@@ -71,6 +71,21 @@ static int upload_checked(Ctx* ctx, DevBuf& buf, const float* host, size_t n_flo
     return PWICP_OK;
 }
 
+// The normals of a host-buffer call have landed (or are waited for here, on the stream): finite check, level-0 order.
+int finish_deferred_aux(Ctx* ctx) {
+    if (!ctx->aux_deferred) return PWICP_OK;
+    ctx->aux_deferred = false;
+    const int n1 = ctx->aux_deferred_n1;
+    PW_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[1], 0));
+    PW_TRY(finite_accumulate_dev(ctx, ctx->tgt_nrm_raw.as<float>(), (size_t)3 * n1, ctx->aux_deferred_flag));
+    gather_aux_kernel<<<(n1 + 255) / 256, 256, 0, ctx->stream>>>(ctx->tgt_nrm_raw.as<float>(), nullptr, nullptr,
+                                                                 ctx->tgt.perm0, n1, ctx->tgt_aux.as<float4>(),
+                                                                 ctx->tgt_ok.as<unsigned char>());
+    ctx->launches++;
+    PW_CUDA(cudaGetLastError());
+    return PWICP_OK;
+}
+
 }  // namespace pwicp
 
 using namespace pwicp;
@@ -437,12 +452,14 @@ int pwicp_icp_p2plane(pwicp_ctx* p, const float* tgt_xyz, const float* tgt_nrm, 
     // earlier work on the library stream may still read these buffers
     PW_CUDA(cudaEventRecord(ctx->copy_ev[3], ctx->stream));
     PW_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[3], 0));
+    // order of the uploads = order of first use: target points (grid build), source (sort + iteration-0 search), target
+    // normals (row terms of the loop) -- the last 12 bytes per target travel while the source is sorted and searched
     PW_CUDA(cudaMemcpyAsync(ctx->tgt_xyz.p, tgt_xyz, (size_t)3 * n1 * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
     PW_CUDA(cudaEventRecord(ctx->copy_ev[0], ctx->copy_stream));
-    PW_CUDA(cudaMemcpyAsync(ctx->tgt_nrm_raw.p, tgt_nrm, (size_t)3 * n1 * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
-    PW_CUDA(cudaEventRecord(ctx->copy_ev[1], ctx->copy_stream));
     PW_CUDA(cudaMemcpyAsync(ctx->scratch_a.p, src_xyz, (size_t)3 * n2 * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
     PW_CUDA(cudaEventRecord(ctx->copy_ev[2], ctx->copy_stream));
+    PW_CUDA(cudaMemcpyAsync(ctx->tgt_nrm_raw.p, tgt_nrm, (size_t)3 * n1 * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+    PW_CUDA(cudaEventRecord(ctx->copy_ev[1], ctx->copy_stream));
 
     int* flag = ctx->scratch_d.as<int>() + 16;            // [0..5] belong to the bounding-box reduction
     PW_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
@@ -457,24 +474,25 @@ int pwicp_icp_p2plane(pwicp_ctx* p, const float* tgt_xyz, const float* tgt_nrm, 
     if (bad) { cudaStreamSynchronize(ctx->copy_stream); set_error(ctx, "target centroids: non-finite value in input"); return PWICP_ERR_NONFINITE; }
     PW_TRY(grid_build(ctx, ctx->tgt, ctx->tgt_xyz.as<float>(), n1));
     PW_TRY(reset_seeds(ctx));
-    PW_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[1], 0));
-    PW_TRY(finite_accumulate_dev(ctx, ctx->tgt_nrm_raw.as<float>(), (size_t)3 * n1, flag));
     PW_TRY(ctx->tgt_aux.reserve(ctx, (size_t)n1 * sizeof(float4)));
     PW_TRY(ctx->tgt_ok.reserve(ctx, (size_t)n1));
-    gather_aux_kernel<<<(n1 + 255) / 256, 256, 0, ctx->stream>>>(ctx->tgt_nrm_raw.as<float>(), nullptr, nullptr,
-                                                                 ctx->tgt.perm0, n1, ctx->tgt_aux.as<float4>(),
-                                                                 ctx->tgt_ok.as<unsigned char>());
-    ctx->launches++;
     PW_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[2], 0));
     PW_TRY(finite_accumulate_dev(ctx, ctx->scratch_a.as<float>(), (size_t)3 * n2, flag));
     ctx->icp_seed_valid = false;
     PW_TRY(icp_expand_source(ctx, ctx->scratch_a.as<float>(), n2));
+    ctx->n1 = n1;
+    ctx->aux_deferred = true; ctx->aux_deferred_n1 = n1; ctx->aux_deferred_flag = flag;
+    // the inner loop is enqueued without a host round trip; the verdict on the source and the normals is read with its
+    // result (non-finite values poison the arithmetic, never an address)
+    int st = pwicp_icp_run(p, prm, T16, res, nullptr, nullptr, nullptr);
+    if (ctx->aux_deferred) { const int s2 = finish_deferred_aux(ctx); if (st == PWICP_OK) st = s2; }   // the loop failed before it got there
+    if (st != PWICP_OK) { cudaStreamSynchronize(ctx->copy_stream); return st; }
     PW_CUDA(cudaMemcpyAsync(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     PW_CUDA(cudaStreamSynchronize(ctx->stream));
     if (bad) { set_error(ctx, "icp_p2plane: non-finite value in input"); return PWICP_ERR_NONFINITE; }
-    ctx->n1 = n1;
-    return pwicp_icp_run(p, prm, T16, res, nullptr, nullptr, nullptr);
+    return PWICP_OK;
 }
+
 
 // ---- F3: per-patch statistics -----------------------------------------------------------------
 int pwicp_patch_stats(pwicp_ctx* p, const float* patch_xyz, const int* patch_off, int n_patches,

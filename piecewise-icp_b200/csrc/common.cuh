@@ -111,6 +111,11 @@ struct Ctx {
     DevBuf icp_src, icp_sorted, icp_perm, icp_work, icp_partials, icp_out, icp_idx;
     DevBuf icp_seed, icp_match;   // seeds in icp_src order / matches in processing order
     bool icp_seed_valid = false;
+    // host-buffer call (pwicp_icp_p2plane): the target normals are still on their way up while the source is sorted and
+    // searched; the inner loop picks them up right before it needs them (icp_enqueue -> finish_deferred_aux)
+    bool aux_deferred = false;
+    int aux_deferred_n1 = 0;
+    int* aux_deferred_flag = nullptr;            // device flag the finite check of the normals accumulates into
     // temporal-coherence seeds of the outer iteration (level-0 positions, -1 = none)
     DevBuf ct_seed, bp_seed, pp_seed, ct_order;
     bool ct_order_valid = false;
@@ -136,6 +141,9 @@ int self_nn_dev(Ctx* ctx, const GridDev& g, float* d2_dev);
 int upload_packed(Ctx* ctx, DevBuf& buf, const float* host_xyz, size_t n_floats);
 int check_finite_dev(Ctx* ctx, const float* dev, size_t n_floats, bool* ok);
 int finite_accumulate_dev(Ctx* ctx, const float* dev, size_t n_floats, int* flag_dev);   // no host sync
+
+// capi.cu
+int finish_deferred_aux(Ctx* ctx);
 
 // icp.cu
 struct IcpLaunch { int grid; const char* out; int max_iter; };   // out: device: T[16] | n_iter, conv_state, natural iter, state

@@ -373,8 +373,8 @@ nn_kernel(GridDev g, const float* __restrict__ q, int nq, int* __restrict__ idx,
     const bool active = i < nq;
     float px = 0.f, py = 0.f, pz = 0.f;
     if (active) { px = q[3 * (size_t)i]; py = q[3 * (size_t)i + 1]; pz = q[3 * (size_t)i + 2]; }
+    const Best b = nn_search_warp(g, px, py, pz, -1, active);     // warp-collective (nn_search.cuh, team search)
     if (active) {
-        const Best b = nn_search_seeded(g, px, py, pz, -1);
         if (idx) idx[i] = b.idx;
         if (d2) d2[i] = b.d2;
     }

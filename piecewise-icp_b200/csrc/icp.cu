@@ -15,7 +15,8 @@
 // LLS system and adds its 27 products + d2 to 28 double accumulators of its own (DFMA; a product of two float
 // values is exact in double, so fma(a, b, acc) is the separately rounded acc + a*b of the reference).  At the end
 // of the iteration a warp folds its 32 lanes with a reduce-scatter butterfly (partners 16, 8, 4, 2, 1), the CTA
-// adds its warps in order, ONE grid barrier, every CTA adds the CTA sums in the same fixed order, solves the 6x6
+// adds its warps in order and posts the sum as tagged packets (no grid barrier: the readers poll for the tag), every CTA
+// adds the CTA sums in the same fixed order, solves the 6x6
 // system, builds the float transform and evaluates the convergence criteria -- identical instructions on identical
 // inputs, so all CTAs take the same decision without a second barrier or a host round trip.
 //
@@ -25,8 +26,6 @@
 // instruction of the loop) against 8 for the per-lane sums: 64 against 31 FP64-pipe cycles per batch.
 // The summation order ("reduction geometry") is fixed by (n, gridDim.x, warps per CTA) alone and the oracle's
 // reduce_mode = 2 reproduces it for the bit-exact whole-loop parity tests.
-#include <cooperative_groups.h>
-
 #include "common.cuh"
 #include <cub/cub.cuh>
 
@@ -45,7 +44,6 @@
 #ifndef PWICP_BUILD_STEP_CELLS
 #define PWICP_BUILD_STEP_CELLS 1e30f
 #endif
-namespace cg = cooperative_groups;
 
 namespace pwicp {
 
@@ -83,7 +81,7 @@ struct IcpArgs {
     int max_iter;
     int force_iters;
     double rot_thr, transl_thr, mse_rel, mse_abs;
-    double* part;             // [2][gridDim.x][28]: CTA sums of an iteration, double buffered
+    unsigned long long* part; // [2][gridDim.x][28][2]: CTA sums of an iteration as tagged 8-byte packets, double buffered
     int* searched;            // [max_iter], zeroed before the launch: queries that ran the ball search (diagnostic)
     float* out_T;             // 16: final transformation
     int* out_state;           // [0] n_iter, [1] conv_state, [2] first iteration at which the criteria were met, [3] its state
@@ -91,7 +89,7 @@ struct IcpArgs {
     float* T_trace;           // nullable
     int* idx_trace;           // nullable, [iter][n]
     unsigned long long* iter_ns;   // [max_iter + 1]: %globaltimer at the start of the loop and after every iteration (CTA 0)
-    unsigned long long* phase_ns;  // [max_iter][4]: CTA 0, warp 0: end of its batches, after the grid barrier, totals formed, solved
+    unsigned long long* phase_ns;  // [max_iter][4]: CTA 0, warp 0: end of its batches, CTA sum posted, totals formed (all packets in), solved
 };
 
 // Shared scratch of the per-iteration solve.
@@ -388,6 +386,14 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
 __device__ __forceinline__ void lds128(float4& v, unsigned addr) {
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
 }
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -420,14 +426,64 @@ __device__ __forceinline__ void fold_lanes(double (&x)[16], int lane) {
     }
 }
 
+// The grid-wide exchange of the CTA sums, without a grid barrier.  Every CTA sum travels as two 8-byte packets {half of
+// the double, iteration tag}: an aligned 8-byte store is single-copy atomic, so a reader that sees the tag sees the data
+// with it and no fence or counter is needed (the LL protocol of collective libraries).  The buffers alternate with the
+// iteration parity; a CTA can run at most one iteration ahead of the slowest one (it needs everybody's packets of
+// iteration k + 1 before it can post k + 2 into the buffer of k), so a packet is never overwritten before it has been
+// read.  The buffers are zeroed before the launch (tag 0 = nothing posted).  All CTAs are resident (cooperative launch).
+// In: s_wsum, the warp sums of this CTA (after a CTA barrier).  Out: s_csum[w] = sum of the CTA sums of chunk w, in order.
+static __device__ __noinline__ void icp_exchange(const IcpArgs& a, int it, int warp, int lane, const double* s_wsum, double* s_csum) {
+    const int G = gridDim.x;
+    const int per = (G + kIcpWarps - 1) / kIcpWarps;             // CTA sums per chunk of the final sum
+    const int nchunks = (G + per - 1) / per;
+    const unsigned tag = (unsigned)it + 1u;
+    if (lane >= kNumVals) return;
+    if (warp == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < kIcpWarps; ++w) s += s_wsum[w * kNumVals + lane];
+        unsigned long long* dst = a.part + (((size_t)(it & 1) * G + blockIdx.x) * kNumVals + lane) * 2;
+        const unsigned long long t = (unsigned long long)tag << 32;
+        st_relaxed_u64(dst, t | (unsigned)__double2loint(s));
+        st_relaxed_u64(dst + 1, t | (unsigned)__double2hiint(s));
+        if (blockIdx.x == 0 && lane == 0) a.phase_ns[it * 4 + 1] = globaltimer_ns();
+    }
+    // every CTA forms the same totals: warp w adds the CTA sums w*per .. in order (warp 0 adds the chunks afterwards)
+    if (warp < nchunks) {
+        const unsigned long long* __restrict__ src = a.part + (((size_t)(it & 1) * G + (size_t)warp * per) * kNumVals + lane) * 2;
+        const int cnt = min(per, G - warp * per);
+        double s = 0.0;
+        for (int g0 = 0; g0 < cnt; g0 += 10) {                   // loads of a round are issued before its first add
+            unsigned long long v[20];
+            bool ok;
+            do {
+                ok = true;
+#pragma unroll
+                for (int g = 0; g < 10; ++g) {
+                    const unsigned long long* q = src + (size_t)min(g0 + g, cnt - 1) * (kNumVals * 2);
+                    v[2 * g] = ld_relaxed_u64(q); v[2 * g + 1] = ld_relaxed_u64(q + 1);
+                }
+#pragma unroll
+                for (int g = 0; g < 20; ++g) ok = ok && ((unsigned)(v[g] >> 32) == tag);
+            } while (!ok);
+#pragma unroll
+            for (int g = 0; g < 10; ++g)
+                if (g0 + g < cnt) s += __hiloint2double((int)(unsigned)v[2 * g + 1], (int)(unsigned)v[2 * g]);
+        }
+        s_csum[warp * kNumVals + lane] = s;
+    }
+}
+
 // kTrace: the variant that also records the correspondence indices of every iteration (parity tests).
 template <bool kTrace>
 __global__ void __launch_bounds__(kIcpThreads, 1) icp_persistent_kernel(const IcpArgs a) {
-    cg::grid_group grid = cg::this_grid();
     // landing zone of the streamed per-point data, kStageSlots batches deep per warp, filled by cp.async; every lane
     // reads back only the 16-byte cells it copied itself: [warp][slot][point + margin, matched target, normal][lane]
     extern __shared__ __align__(16) unsigned char s_dyn[];
-    __shared__ double s_wsum[kIcpWarps][kNumVals];   // warp sums of the iteration, then the chunk sums of the CTA partials
+    __shared__ double s_wsum[kIcpWarps][kNumVals];   // warp sums of the iteration
+    __shared__ double s_csum[kIcpWarps][kNumVals];   // chunk sums of the CTA sums of the grid (a second array: the warps
+                                                     // start polling for the packets while warp 0 still adds the warp sums)
     __shared__ double s_tot[kNumVals];
     __shared__ float s_T[16];
     __shared__ float s_Tfinal[16];
@@ -447,8 +503,6 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_persistent_kernel(const Ic
     const int nb = (n + 31) / 32;                                // 32-point batches
     const int G = gridDim.x, NWT = G * kIcpWarps, ws = blockIdx.x * kIcpWarps + warp;
     const int K = (ws < nb) ? (nb - 1 - ws) / NWT + 1 : 0;       // batches ws, ws + NWT, ... of this warp
-    const int per = (G + kIcpWarps - 1) / kIcpWarps;             // CTA partials per chunk of the final sum
-    const int nchunks = (G + per - 1) / per;
     const int stride = NWT * 32;                                 // distance of this lane's consecutive points
     const int i0 = ws * 32 + lane;
     constexpr int kSlotBytes = 3 * 32 * (int)sizeof(float4);
@@ -600,42 +654,27 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_persistent_kernel(const Ic
             fold_lanes<1>(y, lane);
             if (lane < kNumVals) s_wsum[warp][lane] = y[0];
         }
-        __syncthreads();
-        if (warp == 0 && lane < kNumVals) {
-            double s = 0.0;
-#pragma unroll
-            for (int w = 0; w < kIcpWarps; ++w) s += s_wsum[w][lane];
-            __stcg(a.part + ((size_t)(it & 1) * G + blockIdx.x) * kNumVals + lane, s);
-        }
-        grid.sync();
 #if PWICP_STAGE_TMA
         asm volatile("fence.proxy.async;" ::: "memory");         // work[] was written through the generic proxy
 #endif
-        if (blockIdx.x == 0 && tid == 0) a.phase_ns[it * 4 + 1] = globaltimer_ns();
         // the next iteration's first two batches: their copies do not depend on the transform being solved
-        // for, so they fly during the reduction and the solve
+        // for, so they fly during the reduction and the solve (every slot of the ring has been consumed)
         stage_point(a.work, i0, 0);
         stage_point(a.work, i0 + stride, kSlotBytes);
-
-        // ---- every CTA forms the same totals: warp w adds the CTA sums w*per .. in order, warp 0 the chunks
-        if (warp < nchunks && lane < kNumVals) {
-            const double* __restrict__ src = a.part + ((size_t)(it & 1) * G + (size_t)warp * per) * kNumVals + lane;
-            const int cnt = min(per, G - warp * per);
-            double v[10];
-            double s = 0.0;
-            for (int g0 = 0; g0 < cnt; g0 += 10) {               // loads of a round are issued before its first add
-#pragma unroll
-                for (int g = 0; g < 10; ++g) v[g] = (g0 + g < cnt) ? __ldcg(src + (size_t)(g0 + g) * kNumVals) : 0.0;
-#pragma unroll
-                for (int g = 0; g < 10; ++g) if (g0 + g < cnt) s += v[g];
-            }
-            s_wsum[warp][lane] = s;
-        }
+        __syncthreads();
+        // ---- the grid-wide exchange of the CTA sums (icp_exchange, out of line: its address arithmetic and the twenty
+        // packets in flight per lane must not compete with the accumulators of the batch loop for registers)
+        icp_exchange(a, it, warp, lane, &s_wsum[0][0], &s_csum[0][0]);
         __syncthreads();
         if (warp == 0) {
             if (lane < kNumVals) {
+                const int per = (G + kIcpWarps - 1) / kIcpWarps, nchunks = (G + per - 1) / per;   // as icp_exchange
+                double v[kIcpWarps];                            // all loads before the first add (nchunks <= kIcpWarps)
+#pragma unroll
+                for (int c = 0; c < kIcpWarps; ++c) v[c] = s_csum[c][lane];
                 double s = 0.0;
-                for (int c = 0; c < nchunks; ++c) s += s_wsum[c][lane];
+#pragma unroll
+                for (int c = 0; c < kIcpWarps; ++c) if (c < nchunks) s += v[c];
                 s_tot[lane] = s;
             }
             __syncwarp();
@@ -730,11 +769,22 @@ icp_seed_kernel(GridDev g, const float4* __restrict__ tgt_aux, const float4* __r
                 float4* __restrict__ cn0, float4* __restrict__ cq0) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const float4 p = (i < n) ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const Best b = nn_search_warp(g, p.x, p.y, p.z, -1, i < n);   // warp-collective (nn_search.cuh, team search)
     if (i >= n) return;
-    const Best b = nn_search_seeded(g, p.x, p.y, p.z, -1);
-    const float4 nq = __ldg(tgt_aux + b.pos);
     cq0[i] = make_float4(b.qx, b.qy, b.qz, __int_as_float(b.pos));
+    if (!tgt_aux) return;                  // the normals are not on the device yet: icp_fill_cn_kernel
+    const float4 nq = __ldg(tgt_aux + b.pos);
     cn0[i] = make_float4(nq.x, nq.y, nq.z, nq_dot(nq.x, nq.y, nq.z, b.qx, b.qy, b.qz));
+}
+
+// ... the normals of the matches icp_seed_kernel found, once the normals have arrived (pwicp_icp_p2plane)
+__global__ void __launch_bounds__(256)
+icp_fill_cn_kernel(const float4* __restrict__ tgt_aux, const float4* __restrict__ cq0, int n, float4* __restrict__ cn0) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 q = cq0[i];
+    const float4 nq = __ldg(tgt_aux + __float_as_int(q.w));
+    cn0[i] = make_float4(nq.x, nq.y, nq.z, nq_dot(nq.x, nq.y, nq.z, q.x, q.y, q.z));
 }
 
 // Sorts the source set by the target-grid cell it starts in (stable: ties keep the caller's
@@ -807,7 +857,7 @@ int icp_enqueue(Ctx* ctx, const pwicp_icp_params& prm, int n, const int* n_dev, 
     const int n_pad = (int)(nb * 32);
     PW_TRY(ctx->icp_work.reserve(ctx, (size_t)n_pad * sizeof(float4)));
     // device scratch: CTA sums (double buffered) | searched[max_iter] | iter_ns[max_iter + 1] | phase_ns[max_iter][4]
-    const size_t bytes_part = (size_t)2 * grid * kNumVals * sizeof(double);
+    const size_t bytes_part = (size_t)2 * grid * kNumVals * 2 * sizeof(unsigned long long);   // tagged packets (icp_persistent_kernel)
     const size_t bytes_cnt = (size_t)prm.max_iter * sizeof(int);
     const size_t off_ns = (bytes_part + bytes_cnt + 7) & ~(size_t)7;
     PW_TRY(ctx->icp_partials.reserve(ctx, off_ns + (size_t)(prm.max_iter + 1) * 8 + (size_t)prm.max_iter * 32 + 64));
@@ -820,18 +870,27 @@ int icp_enqueue(Ctx* ctx, const pwicp_icp_params& prm, int n, const int* n_dev, 
     PW_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
     if (!presorted) {
         const bool have_seed = ctx->icp_seed_valid && ctx->icp_seed.p != nullptr;
+        if (have_seed) PW_TRY(finish_deferred_aux(ctx));   // the gather of the seeded matches reads the normals
         PW_TRY(icp_sort_source(ctx, n, have_seed));
         ctx->icp_seed_valid = false;                       // seeds belong to one source set
         PW_CUDA(cudaEventRecord(ctx->ev3, ctx->stream));
         if (!have_seed) {
-            icp_seed_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->tgt.dev, ctx->tgt_aux.as<float4>(),
+            const bool late = ctx->aux_deferred;           // normals still on their way up: search first, then wait
+            icp_seed_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->tgt.dev, late ? nullptr : ctx->tgt_aux.as<float4>(),
                                                                       ctx->icp_sorted.as<float4>(), n,
                                                                       ctx->icp_match.as<float4>(), ctx->icp_match.as<float4>() + n_pad);
             ctx->launches++;
+            if (late) {
+                PW_TRY(finish_deferred_aux(ctx));
+                icp_fill_cn_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->tgt_aux.as<float4>(), ctx->icp_match.as<float4>() + n_pad,
+                                                                            n, ctx->icp_match.as<float4>());
+                ctx->launches++;
+            }
         }
     } else {
         PW_CUDA(cudaEventRecord(ctx->ev3, ctx->stream));
     }
+    PW_TRY(finish_deferred_aux(ctx));
 
     IcpArgs a;
     a.g = ctx->tgt.dev;
@@ -860,11 +919,12 @@ int icp_enqueue(Ctx* ctx, const pwicp_icp_params& prm, int n, const int* n_dev, 
     a.transl_thr = prm.tf_eps;
     a.mse_rel = prm.fit_eps;
     a.mse_abs = 1e-12;
-    a.part = ctx->icp_partials.as<double>();
+    a.part = ctx->icp_partials.as<unsigned long long>();
     a.searched = reinterpret_cast<int*>(ctx->icp_partials.as<char>() + bytes_part);
     a.iter_ns = reinterpret_cast<unsigned long long*>(ctx->icp_partials.as<char>() + off_ns);
     a.phase_ns = a.iter_ns + prm.max_iter + 1;
-    PW_CUDA(cudaMemsetAsync(a.searched, 0, off_ns - bytes_part + (size_t)(prm.max_iter + 1) * 8 + (size_t)prm.max_iter * 32, ctx->stream));
+    // packets (tag 0 = nothing posted), search counters, timers
+    PW_CUDA(cudaMemsetAsync(a.part, 0, off_ns + (size_t)(prm.max_iter + 1) * 8 + (size_t)prm.max_iter * 32, ctx->stream));
     a.out_T = reinterpret_cast<float*>(ob);
     a.out_state = reinterpret_cast<int*>(ob + 64);
     a.mse_trace = want_mse ? reinterpret_cast<double*>(ob + 80) : nullptr;

@@ -43,6 +43,9 @@ namespace pwicp {
 #ifndef PWICP_RESEED_CELLS2_LOOP
 #define PWICP_RESEED_CELLS2_LOOP 1.0f
 #endif
+#ifndef PWICP_SKIP_DONE_BLOCK
+#define PWICP_SKIP_DONE_BLOCK 1  // a ball scan that follows a block scan leaves the block's cells out (A/B switch)
+#endif
 #ifndef PWICP_BLOCK_WIDE
 #define PWICP_BLOCK_WIDE 0       // stand-alone kernels: candidates of the block scan four at a time (A/B switch)
 #endif
@@ -101,12 +104,20 @@ __device__ __forceinline__ void scan_range(const float4* __restrict__ pts, uint3
     }
 }
 
-// One cell row (ky, kz) of the ball: chord test against the CURRENT best, then a range scan.
+// Cells of the 3x3x3 block a query has already been through (block_scan): a later ball scan skips them.  Every cell of
+// the block is settled -- scanned, or cut off by a chord of a bound that was no smaller than the present one.
+struct DoneBlock {
+    int x0, x1, y0, y1, z0, z1;      // y0 > y1: nothing has been scanned
+};
+__device__ __forceinline__ DoneBlock no_block() { return DoneBlock{0, -1, 0, -1, 0, -1}; }
+
+// One cell row (ky, kz) of the ball: chord test against the CURRENT best, then a range scan (minus the cells of the
+// row that `done` covers).
 template <bool kWide>
 __device__ __forceinline__ void ball_row(const GridLevel& L, int ky, int kz, float fx, float fy, float fz,
                                          float mx, float my, float mz, int lx, int hx,
                                          float px, float py, float pz, bool level0,
-                                         float& bd, int& bi, int& bpos) {
+                                         float& bd, int& bi, int& bpos, const DoneBlock& done = DoneBlock{0, -1, 0, -1, 0, -1}) {
     const float gy = axis_gap(fy, ky, my), gz = axis_gap(fz, kz, mz);
     const float gyz = gy * gy + gz * gz, bc = bd * L.inv_h2;
     if (gyz > bc) return;                                        // row entirely outside the ball
@@ -114,6 +125,18 @@ __device__ __forceinline__ void ball_row(const GridLevel& L, int ky, int kz, flo
     const int lxr = max(lx, (int)floorf(fx - w - mx)), hxr = min(hx, (int)floorf(fx + w + mx));
     if (lxr > hxr) return;
     const uint32_t row = ((uint32_t)kz * (uint32_t)L.dy + (uint32_t)ky) * (uint32_t)L.dx;
+    if (ky >= done.y0 && ky <= done.y1 && kz >= done.z0 && kz <= done.z1) {
+        const int hl = min(hxr, done.x0 - 1), lr = max(lxr, done.x1 + 1);
+        if (lxr <= hl) {
+            const uint32_t s = __ldg(L.cell_start + row + lxr), e = __ldg(L.cell_start + row + hl + 1);
+            scan_range<kWide>(L.pts, s, e, px, py, pz, level0, bd, bi, bpos);
+        }
+        if (lr <= hxr) {
+            const uint32_t s = __ldg(L.cell_start + row + lr), e = __ldg(L.cell_start + row + hxr + 1);
+            scan_range<kWide>(L.pts, s, e, px, py, pz, level0, bd, bi, bpos);
+        }
+        return;
+    }
     const uint32_t s = __ldg(L.cell_start + row + lxr), e = __ldg(L.cell_start + row + hxr + 1);
     scan_range<kWide>(L.pts, s, e, px, py, pz, level0, bd, bi, bpos);
 }
@@ -127,10 +150,10 @@ __device__ __forceinline__ void ball_scan_rings(const GridLevel& L, float fx, fl
                                                     float mx, float my, float mz,
                                                     int lx, int hx, int ly, int hy, int lz, int hz,
                                                     float px, float py, float pz, bool level0,
-                                                    float& bd, int& bi, int& bpos) {
+                                                    float& bd, int& bi, int& bpos, const DoneBlock& done) {
     const int cy = min(max((int)floorf(fy), ly), hy), cz = min(max((int)floorf(fz), lz), hz);
     const int R = max(max(cy - ly, hy - cy), max(cz - lz, hz - cz));
-    ball_row<kWide>(L, cy, cz, fx, fy, fz, mx, my, mz, lx, hx, px, py, pz, level0, bd, bi, bpos);
+    ball_row<kWide>(L, cy, cz, fx, fy, fz, mx, my, mz, lx, hx, px, py, pz, level0, bd, bi, bpos, done);
     for (int t = 1; t <= R; ++t) {
         // every row of ring t (and of all later rings) is at least this far away in y or z
         const float g = fminf(fminf(axis_gap(fy, cy - t, my), axis_gap(fy, cy + t, my)),
@@ -141,7 +164,7 @@ __device__ __forceinline__ void ball_scan_rings(const GridLevel& L, float fx, fl
             const bool full = (kz == cz - t || kz == cz + t);
             for (int ky = y0; ky <= y1; ++ky) {
                 if (!full && ky != cy - t && ky != cy + t) continue;
-                ball_row<kWide>(L, ky, kz, fx, fy, fz, mx, my, mz, lx, hx, px, py, pz, level0, bd, bi, bpos);
+                ball_row<kWide>(L, ky, kz, fx, fy, fz, mx, my, mz, lx, hx, px, py, pz, level0, bd, bi, bpos, done);
             }
         }
     }
@@ -152,7 +175,7 @@ static __device__ __noinline__ void ball_scan_rings_ool(const GridLevel& L, floa
                                                         int lx, int hx, int ly, int hy, int lz, int hz,
                                                         float px, float py, float pz, bool level0,
                                                         float& bd, int& bi, int& bpos) {
-    ball_scan_rings<true>(L, fx, fy, fz, mx, my, mz, lx, hx, ly, hy, lz, hz, px, py, pz, level0, bd, bi, bpos);
+    ball_scan_rings<true>(L, fx, fy, fz, mx, my, mz, lx, hx, ly, hy, lz, hz, px, py, pz, level0, bd, bi, bpos, no_block());
 }
 
 // Scans every cell of level L that the closed ball of radius sqrt(bd) around p touches.
@@ -162,7 +185,7 @@ static __device__ __noinline__ void ball_scan_rings_ool(const GridLevel& L, floa
 template <bool kLean>
 __device__ __forceinline__ void ball_scan(const GridLevel& L, float ox, float oy, float oz,
                                           float px, float py, float pz, bool level0,
-                                          float& bd, int& bi, int& bpos) {
+                                          float& bd, int& bi, int& bpos, const DoneBlock& done = DoneBlock{0, -1, 0, -1, 0, -1}) {
     const float fx = (px - ox) * L.inv_h, fy = (py - oy) * L.inv_h, fz = (pz - oz) * L.inv_h;
     const float mx = 0.01f + fabsf(fx) * 4e-6f, my = 0.01f + fabsf(fy) * 4e-6f, mz = 0.01f + fabsf(fz) * 4e-6f;
     // radius in cell units, rounded up generously (float sqrt/mul errors are ~1e-7 relative)
@@ -175,12 +198,14 @@ __device__ __forceinline__ void ball_scan(const GridLevel& L, float ox, float oy
         // variants (one state-machine loop; row list in shared memory + one candidate loop) were
         // measured and were not faster: the batch time is a chain of dependent L2 round trips.
         for (int kz = lz; kz <= hz; ++kz)
-            for (int ky = ly; ky <= hy; ++ky)
-                ball_row<kLean>(L, ky, kz, fx, fy, fz, mx, my, mz, lx, hx, px, py, pz, level0, bd, bi, bpos);
+            for (int ky = ly; ky <= hy; ++ky) {
+                if (kLean) ball_row<true>(L, ky, kz, fx, fy, fz, mx, my, mz, lx, hx, px, py, pz, level0, bd, bi, bpos);
+                else ball_row<false>(L, ky, kz, fx, fy, fz, mx, my, mz, lx, hx, px, py, pz, level0, bd, bi, bpos, done);
+            }
     } else if (kLean) {
         ball_scan_rings_ool(L, fx, fy, fz, mx, my, mz, lx, hx, ly, hy, lz, hz, px, py, pz, level0, bd, bi, bpos);
     } else {
-        ball_scan_rings<false>(L, fx, fy, fz, mx, my, mz, lx, hx, ly, hy, lz, hz, px, py, pz, level0, bd, bi, bpos);
+        ball_scan_rings<false>(L, fx, fy, fz, mx, my, mz, lx, hx, ly, hy, lz, hz, px, py, pz, level0, bd, bi, bpos, done);
     }
 }
 
@@ -265,6 +290,13 @@ __device__ __forceinline__ bool block_scan(const GridLevel& L, float ox, float o
            (z0 == 0 || fz - r - mz >= (float)z0) && (z1 == L.dz - 1 || fz + r + mz < (float)(z1 + 1));
 }
 
+// the cells block_scan() goes through for this query (level 0)
+__device__ __forceinline__ DoneBlock block_extent(const GridLevel& L, float ox, float oy, float oz, float px, float py, float pz) {
+    const int cx = min(max((int)floorf((px - ox) * L.inv_h), 0), L.dx - 1), cy = min(max((int)floorf((py - oy) * L.inv_h), 0), L.dy - 1),
+              cz = min(max((int)floorf((pz - oz) * L.inv_h), 0), L.dz - 1);
+    return DoneBlock{max(cx - 1, 0), min(cx + 1, L.dx - 1), max(cy - 1, 0), min(cy + 1, L.dy - 1), max(cz - 1, 0), min(cz + 1, L.dz - 1)};
+}
+
 static __device__ __noinline__ bool block_scan_ool(const GridLevel& L, float ox, float oy, float oz, float px, float py,
                                                    float pz, float& bd, int& bi, int& bpos) {
     return block_scan<true>(L, ox, oy, oz, px, py, pz, bd, bi, bpos);
@@ -277,7 +309,7 @@ template <bool kLean = false>
 __device__ __forceinline__ Best nn_search_seeded(const GridDev& g, float px, float py, float pz, int seed_pos) {
     float bd = __int_as_float(0x7f800000);
     int bi = 0x7fffffff, bpos = -1;
-    bool done = false;
+    bool done = false, blocked = false;
     if (seed_pos >= 0) {
         const float4 q = __ldg(g.lv[0].pts + seed_pos);
         bd = l2_simple(px, py, pz, q.x, q.y, q.z);
@@ -290,6 +322,7 @@ __device__ __forceinline__ Best nn_search_seeded(const GridDev& g, float px, flo
     if (seed_pos < 0 || bd * g.lv[0].inv_h2 > stale) {
         done = kLean ? block_scan_ool(g.lv[0], g.ox, g.oy, g.oz, px, py, pz, bd, bi, bpos)
                      : block_scan<PWICP_BLOCK_WIDE != 0>(g.lv[0], g.ox, g.oy, g.oz, px, py, pz, bd, bi, bpos);
+        blocked = true;
         if (!done && bpos < 0) {             // empty block: a sampled point of the first non-empty coarser home cell
             if (kLean) find_seed_ool(g, px, py, pz, bd, bi, bpos); else find_seed(g, px, py, pz, bd, bi, bpos);
         }
@@ -299,7 +332,13 @@ __device__ __forceinline__ Best nn_search_seeded(const GridDev& g, float px, flo
         int l = 0;
         float r = sqrtf(bd) * g.lv[0].inv_h;
         while (l < g.nlevels - 1 && r > kBallMaxCells) { ++l; r *= (1.0f / kLevelFactor); }
-        ball_scan<kLean>(g.lv[l], g.ox, g.oy, g.oz, px, py, pz, l == 0, bd, bi, bpos);
+        // the block's cells are settled: the ball scan on the same level leaves them out (stand-alone kernels; in the
+        // register-capped inner loop a block scan is followed by a ball scan only for queries far from the surface)
+        if (kLean) ball_scan<true>(g.lv[l], g.ox, g.oy, g.oz, px, py, pz, l == 0, bd, bi, bpos);
+        else {
+            const DoneBlock db = (blocked && l == 0 && PWICP_SKIP_DONE_BLOCK) ? block_extent(g.lv[0], g.ox, g.oy, g.oz, px, py, pz) : no_block();
+            ball_scan<false>(g.lv[l], g.ox, g.oy, g.oz, px, py, pz, l == 0, bd, bi, bpos, db);
+        }
     }
 
     Best b;
@@ -308,6 +347,176 @@ __device__ __forceinline__ Best nn_search_seeded(const GridDev& g, float px, flo
     b.pos = bpos;
     const float4 q = __ldg(g.lv[0].pts + bpos);
     b.qx = q.x; b.qy = q.y; b.qz = q.z;
+    return b;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Team search (round 2): kTeam adjacent lanes work on ONE query at a time.
+//
+// The thread-per-query walk above spends its time in divergence: the 32 lanes of a warp scan rows of different
+// lengths and prune at different points, so a warp issues ~8000 instructions for 32 queries of ~70 candidates each
+// (ncu, round 1: 11 of 32 lanes active) and every query is a chain of up to 18 dependent L2 round trips.  Two
+// warp-wide formulations lost (one tile / one union box per warp: the halo of 32 queries is 3-5x what one needs).
+// Here the unit of cooperation is a team of kTeam lanes and the unit of work is still ONE query's own 3x3x3 block:
+//   step 1  the home row (three cells, one contiguous range): candidate j of the range goes to lane j mod kTeam,
+//           arg-min over the team by xor shuffles -> an upper bound bd;
+//   step 2  the eight rows around it, one (or two) per lane: gap test and chord cut against bd -- most rows die
+//           here without a memory access; the surviving ranges are scanned by the whole team, one after the other;
+//   step 3  arg-min again; the answer is exact when the ball of the result lies inside the block.
+// Four dependent memory round trips per query instead of eighteen, every candidate load a coalesced row of kTeam
+// 16-byte cells, and the rows are pruned against a bound exactly as before, so the candidate count does not grow.
+// The rounds of the 32 / kTeam teams of a warp run independently (team masks on every shuffle).
+// Pruning never changes the result: a row or chord is skipped only when its lower bound exceeds an upper bound of
+// the NN distance, and the arg-min is over (distance, original index) pairs, which is order-independent.
+#ifndef PWICP_TEAM_SEARCH
+#define PWICP_TEAM_SEARCH 0      // measured (profiles/r02ab_team_search_ab.txt): loses to the thread-per-query walk
+#endif
+#ifndef PWICP_TEAM
+#define PWICP_TEAM 8
+#endif
+constexpr int kTeam = PWICP_TEAM;
+
+template <int kT>
+__device__ __forceinline__ void team_argmin(unsigned tmask, float& bd, int& bi, int& bpos) {
+#pragma unroll
+    for (int o = kT / 2; o > 0; o >>= 1) {
+        const float od = __shfl_xor_sync(tmask, bd, o);
+        const int oi = __shfl_xor_sync(tmask, bi, o), op = __shfl_xor_sync(tmask, bpos, o);
+        if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; bpos = op; }
+    }
+}
+
+// candidates [s, e) against the lane's own best, candidate s + sub + k * kT for lane `sub` of the team
+template <int kT>
+__device__ __forceinline__ void team_scan_range(const float4* __restrict__ pts, uint32_t s, uint32_t e, int sub,
+                                                float px, float py, float pz, float& bd, int& bi, int& bpos) {
+    for (uint32_t i = s + (uint32_t)sub; i < e; i += kT) {
+        const float4 q = __ldg(pts + i);
+        const float d = l2_simple(px, py, pz, q.x, q.y, q.z);
+        const int id = __float_as_int(q.w);
+        if (d < bd || (d == bd && id < bi)) { bd = d; bi = id; bpos = (int)i; }
+    }
+}
+
+// One query (the same px, py, pz and the same incoming bound in all lanes of the team), its 3x3x3 block on level 0.
+// All lanes return the same bd / bi / bpos; true = the result is exact (see block_scan).
+template <int kT>
+__device__ __forceinline__ bool team_block_scan(const GridLevel& L, float ox, float oy, float oz, float px, float py,
+                                                float pz, unsigned tmask, int tbase, int sub,
+                                                float& bd, int& bi, int& bpos) {
+    const float fx = (px - ox) * L.inv_h, fy = (py - oy) * L.inv_h, fz = (pz - oz) * L.inv_h;
+    const float mx = 0.01f + fabsf(fx) * 4e-6f, my = 0.01f + fabsf(fy) * 4e-6f, mz = 0.01f + fabsf(fz) * 4e-6f;
+    const int cx = min(max((int)floorf(fx), 0), L.dx - 1), cy = min(max((int)floorf(fy), 0), L.dy - 1),
+              cz = min(max((int)floorf(fz), 0), L.dz - 1);
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, L.dx - 1);
+    const int y0 = max(cy - 1, 0), y1 = min(cy + 1, L.dy - 1), z0 = max(cz - 1, 0), z1 = min(cz + 1, L.dz - 1);
+    // step 1: the home row, cut by the incoming bound if there is one (a stale seed)
+    {
+        uint32_t s = 0, e = 0;
+        const float gy = axis_gap(fy, cy, my), gz = axis_gap(fz, cz, mz);
+        const float gyz = gy * gy + gz * gz, bc = bd * L.inv_h2;
+        if (gyz <= bc) {
+            const float w = sqrtf(bc - gyz) * 1.00001f;
+            const int lxr = max(x0, (int)floorf(fx - w - mx)), hxr = min(x1, (int)floorf(fx + w + mx));
+            if (lxr <= hxr) {
+                const uint32_t row = ((uint32_t)cz * (uint32_t)L.dy + (uint32_t)cy) * (uint32_t)L.dx;
+                s = __ldg(L.cell_start + row + lxr); e = __ldg(L.cell_start + row + hxr + 1);
+            }
+        }
+        team_scan_range<kT>(L.pts, s, e, sub, px, py, pz, bd, bi, bpos);
+        team_argmin<kT>(tmask, bd, bi, bpos);
+    }
+    // step 2: the eight rows around it; lane `sub` tests rows sub, sub + kT, ... against the bound of step 1
+    constexpr int kSlots = (8 + kT - 1) / kT;
+    uint32_t rs[kSlots], re[kSlots];
+    const float bc = bd * L.inv_h2;
+#pragma unroll
+    for (int k = 0; k < kSlots; ++k) {
+        rs[k] = 0; re[k] = 0;
+        const int r = sub + k * kT;                      // 0..7 -> the eight (dy, dz) != (0, 0)
+        const int r9 = r + (r >= 4 ? 1 : 0);
+        const int ky = cy + r9 % 3 - 1, kz = cz + r9 / 3 - 1;
+        if (r < 8 && ky >= y0 && ky <= y1 && kz >= z0 && kz <= z1) {
+            const float gy = axis_gap(fy, ky, my), gz = axis_gap(fz, kz, mz);
+            const float gyz = gy * gy + gz * gz;
+            if (gyz <= bc) {
+                const float w = sqrtf(bc - gyz) * 1.00001f;
+                const int lxr = max(x0, (int)floorf(fx - w - mx)), hxr = min(x1, (int)floorf(fx + w + mx));
+                if (lxr <= hxr) {
+                    const uint32_t row = ((uint32_t)kz * (uint32_t)L.dy + (uint32_t)ky) * (uint32_t)L.dx;
+                    rs[k] = __ldg(L.cell_start + row + lxr); re[k] = __ldg(L.cell_start + row + hxr + 1);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kSlots; ++k) {
+        unsigned live = (__ballot_sync(tmask, re[k] > rs[k]) >> tbase) & ((kT == 32) ? 0xffffffffu : ((1u << kT) - 1u));
+        while (live) {
+            const int j = __ffs(live) - 1;
+            live &= live - 1;
+            const uint32_t s = __shfl_sync(tmask, rs[k], tbase + j), e = __shfl_sync(tmask, re[k], tbase + j);
+            team_scan_range<kT>(L.pts, s, e, sub, px, py, pz, bd, bi, bpos);
+        }
+    }
+    team_argmin<kT>(tmask, bd, bi, bpos);
+    if (bpos < 0) return false;
+    const float r = sqrtf(bd) * L.inv_h * 1.00001f;
+    return (x0 == 0 || fx - r - mx >= (float)x0) && (x1 == L.dx - 1 || fx + r + mx < (float)(x1 + 1)) &&
+           (y0 == 0 || fy - r - my >= (float)y0) && (y1 == L.dy - 1 || fy + r + my < (float)(y1 + 1)) &&
+           (z0 == 0 || fz - r - mz >= (float)z0) && (z1 == L.dz - 1 || fz + r + mz < (float)(z1 + 1));
+}
+
+// Exact nearest neighbour for every lane of a warp (a warp-collective call: ALL 32 lanes must arrive; lanes without a
+// query pass active = false).  Queries with a fresh seed run the seeded ball as before (one to nine short rows, the
+// same trip counts across the warp); queries without a usable seed go through the team block scan, the teams taking
+// the queries of their own kT lanes one after the other; what the block does not settle (empty block, ball beyond
+// the block) finishes on the serial path from the bound reached.
+template <int kT = kTeam>
+__device__ __forceinline__ Best nn_search_warp(const GridDev& g, float px, float py, float pz, int seed_pos, bool active) {
+#if !PWICP_TEAM_SEARCH
+    if (!active) { Best none; none.d2 = 0.f; none.idx = 0; none.pos = 0; none.qx = none.qy = none.qz = 0.f; return none; }
+    return nn_search_seeded(g, px, py, pz, seed_pos);
+#endif
+    const int lane = (int)(threadIdx.x & 31), sub = lane % kT, tbase = lane - sub;
+    const unsigned tmask = ((kT == 32) ? 0xffffffffu : ((1u << kT) - 1u)) << tbase;
+    float bd = __int_as_float(0x7f800000);
+    int bi = 0x7fffffff, bpos = -1;
+    if (active && seed_pos >= 0) {
+        const float4 q = __ldg(g.lv[0].pts + seed_pos);
+        bd = l2_simple(px, py, pz, q.x, q.y, q.z);
+        bi = __float_as_int(q.w);
+        bpos = seed_pos;
+    }
+    const bool want_block = active && (seed_pos < 0 || bd * g.lv[0].inv_h2 > PWICP_RESEED_CELLS2);
+    bool done = false;
+    unsigned todo = (__ballot_sync(0xffffffffu, want_block) >> tbase) & ((kT == 32) ? 0xffffffffu : ((1u << kT) - 1u));
+    while (todo) {                                       // team-uniform
+        const int j = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int owner = tbase + j;
+        const float qx = __shfl_sync(tmask, px, owner), qy = __shfl_sync(tmask, py, owner), qz = __shfl_sync(tmask, pz, owner);
+        float tbd = __shfl_sync(tmask, bd, owner);
+        int tbi = __shfl_sync(tmask, bi, owner), tbp = __shfl_sync(tmask, bpos, owner);
+        const bool ok = team_block_scan<kT>(g.lv[0], g.ox, g.oy, g.oz, qx, qy, qz, tmask, tbase, sub, tbd, tbi, tbp);
+        if (sub == j) { bd = tbd; bi = tbi; bpos = tbp; done = ok; }
+    }
+    __syncwarp();
+    if (active && !done) {
+        if (bpos < 0) find_seed(g, px, py, pz, bd, bi, bpos);
+        int l = 0;
+        float r = sqrtf(bd) * g.lv[0].inv_h;
+        while (l < g.nlevels - 1 && r > kBallMaxCells) { ++l; r *= (1.0f / kLevelFactor); }
+        ball_scan<false>(g.lv[l], g.ox, g.oy, g.oz, px, py, pz, l == 0, bd, bi, bpos);
+    }
+    Best b;
+    b.d2 = bd; b.idx = bi; b.pos = 0; b.qx = b.qy = b.qz = 0.f;
+    if (active) {
+        if (bpos < 0) bpos = (int)__ldg(g.inv_perm + bi);
+        b.pos = bpos;
+        const float4 q = __ldg(g.lv[0].pts + bpos);
+        b.qx = q.x; b.qy = q.y; b.qz = q.z;
+    }
     return b;
 }
 

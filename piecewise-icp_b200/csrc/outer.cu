@@ -79,8 +79,8 @@ classify_dist_kernel(GridDev g, const float4* __restrict__ aux, const unsigned c
             t = n2 + bpi; p = __ldg(bp2 + bpi); seed = bp_seed[bpi];
         }
     }
+    const Best b = nn_search_warp(g, p.x, p.y, p.z, seed, active);   // warp-collective (nn_search.cuh, team search)
     if (!active) return;
-    const Best b = nn_search_seeded(g, p.x, p.y, p.z, seed);
     if (t < n2) ct_seed[t] = b.pos; else bp_seed[t - n2] = b.pos;
     const float4 a = __ldg(aux + b.pos);
     float resDis;
@@ -283,8 +283,8 @@ percentile_d2_kernel(GridDev g, const float* __restrict__ q, int nq, const int* 
     if (active) { px = q[3 * (size_t)i]; py = q[3 * (size_t)i + 1]; pz = q[3 * (size_t)i + 2]; }
     const int seed = (active && seeds) ? seeds[i] : -1;
     float dist2 = __int_as_float(0x7f800000);
+    const Best b = nn_search_warp(g, px, py, pz, seed, active);      // warp-collective (nn_search.cuh, team search)
     if (active) {
-        const Best b = nn_search_seeded(g, px, py, pz, seed);
         if (seeds) seeds[i] = b.pos;
         dist2 = b.d2;
     }
