@@ -248,9 +248,36 @@ struct SlowOut {
     float nx, ny, nz, nq; // its normal, nq_dot(normal, match)
     float margin;         // what is left of the cache radius
 };
+// a new cache around the position of a query that has just searched (nn_search.cuh, "candidate cache"): the match, the
+// targets within `tie` of it (o1..o3, k of them), and the radius just below the first target left out
+__device__ __forceinline__ float compose_cache(const Near5& nb, int match_pos, float d1, float tie, float R,
+                                               int& o1, int& o2, int& o3, int& k) {
+    const float lim = (d1 + tie) * (d1 + tie);
+    float rho2 = R * R;                      // complete up to the scanned radius unless a target is left out
+    bool open = true;                        // still taking targets into the cache
+#pragma unroll
+    for (int j = 0; j <= kCacheCands; ++j) {
+        if (!open || nb.pos[j] < 0) continue;
+        if (nb.pos[j] == match_pos) continue;   // the match itself: always cached (the primary)
+        if (nb.d2[j] < lim && k < 3) {
+            if (k == 0) o1 = nb.pos[j]; else if (k == 1) o2 = nb.pos[j]; else o3 = nb.pos[j];
+            ++k;
+        } else { rho2 = nb.d2[j]; open = false; }
+    }
+    return sqrtf(rho2) * 0.9999f;
+}
+
+// A warp-uniform call (all 32 lanes; need = this lane's query is on the slow path).  When at most kCoopQueries queries
+// of the batch have to search, the WHOLE WARP searches for each of them in turn (warp_search_seeded / warp_collect:
+// one cell row per lane) -- a lone lane walking its rows one after the other held the other 31 up for ~15 us
+// (iteration 2 at 1M: 1.5 % of the queries search, the iteration took 99 us against 17 us for a cached one).
+#ifndef PWICP_COOP_QUERIES
+#define PWICP_COOP_QUERIES 4
+#endif
 static __device__ __noinline__ SlowOut icp_slow_path(const IcpArgs& a, int it, int i, float px, float py, float pz,
-                                                     float4 q0, float4 cn, float margin, float mchk, float step) {
+                                                     float4 q0, float4 cn, float margin, float mchk, float step, bool need) {
     const float4* __restrict__ pts = a.g.lv[0].pts;
+    const int lane = (int)(threadIdx.x & 31);
     const int pos0 = __float_as_int(q0.w) & ~kMoreBit;
     SlowOut o;
     o.d2 = l2_simple(px, py, pz, q0.x, q0.y, q0.z);
@@ -260,7 +287,8 @@ static __device__ __noinline__ SlowOut icp_slow_path(const IcpArgs& a, int it, i
     // how close to the match a target must be to be cached with it: a fraction of the step the query has just taken
     // (the next one is smaller), at least `tie`, at most the collection radius
     const float tie = fminf(fmaxf(a.tie_step * step, a.tie), a.collect);
-    if (__float_as_int(q0.w) & kMoreBit) {
+    bool search = need;
+    if (need && (__float_as_int(q0.w) & kMoreBit)) {
         // positions from the side array, the three loads are issued together, unused slots repeat the primary
         const int4 cm = __ldcg(a.cmore + i);
         int bidx = cm.w;
@@ -300,55 +328,76 @@ static __device__ __noinline__ SlowOut icp_slow_path(const IcpArgs& a, int it, i
                                            cm.z == o.pos ? pos0 : cm.z, bidx);
             }
             if (alone) o.margin = fminf(mchk, sqrtf(second) * 0.9999f);
-            return o;
+            search = false;
         }
     }
     // |p - anchor| <= path (triangle inequality over the steps actually taken): every target at least as close to p
     // as the best cached one lies within the cache radius of the anchor; compared as squares
-    if (mchk > 0.f && o.d2 * 1.00003f < mchk * mchk) return o;
+    if (search && mchk > 0.f && o.d2 * 1.00003f < mchk * mchk) search = false;
 
-    {   // queries that needed the search this iteration (diagnostic: pwicp_icp_profile)
-        const unsigned m = __activemask();
-        if ((int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(a.searched + it, __popc(m));
-    }
-    const Best bb = nn_search_seeded<true>(a.g, px, py, pz, o.pos);
-    const float4 nq = __ldg(a.aux + bb.pos);
-    // a new cache around this position (nn_search.cuh, "candidate cache"): the match, the targets within `tie` of it,
-    // and the radius just below the first target left out
-    int o1 = bb.pos, o2 = bb.pos, o3 = bb.pos, k = 0;
+    const unsigned sm = __ballot_sync(0xffffffffu, search);
+    if (sm == 0) return o;
+    // queries that needed the search this iteration (diagnostic: pwicp_icp_profile)
+    if (lane == __ffs(sm) - 1) atomicAdd(a.searched + it, __popc(sm));
+
+    const GridLevel& L0 = a.g.lv[0];
+    Best bb;
+    bb.d2 = 0.f; bb.idx = 0; bb.pos = 0; bb.qx = bb.qy = bb.qz = 0.f;
+    int o1 = 0, o2 = 0, o3 = 0, k = 0;
     float rho = 0.f;
-    const float d1 = sqrtf(bb.d2);
-    if (step < a.build_step) {
-        // first with the wide radius (a large gap to the second-nearest target = a long-lived cache); a query far from
-        // its match would need more than the 3x3-row scan for that: then only the ties are looked for
-        for (int attempt = 0; attempt < 2; ++attempt) {
-            const float R = d1 + (attempt == 0 ? a.collect : fminf(4.0f * tie, a.collect));
-            if (R * a.g.lv[0].inv_h >= 0.95f) continue;
-            const Near5 nb = ball_collect(a.g.lv[0], a.g.ox, a.g.oy, a.g.oz, px, py, pz, R * R);
-            if (!nb.complete) continue;
-            const float lim = (d1 + tie) * (d1 + tie);
-            float rho2 = R * R;                      // complete up to the scanned radius unless a target is left out
-            bool open = true;                        // still taking targets into the cache
-#pragma unroll
-            for (int j = 0; j <= kCacheCands; ++j) {
-                if (!open || nb.pos[j] < 0) continue;
-                if (nb.pos[j] == bb.pos) continue;   // the match itself: always cached (the primary)
-                if (nb.d2[j] < lim && k < 3) {
-                    if (k == 0) o1 = nb.pos[j]; else if (k == 1) o2 = nb.pos[j]; else o3 = nb.pos[j];
-                    ++k;
-                } else { rho2 = nb.d2[j]; open = false; }
+    bool settled = false;
+    if (__popc(sm) <= PWICP_COOP_QUERIES) {
+        for (unsigned rest = sm; rest; rest &= rest - 1) {       // warp-uniform
+            const int j = __ffs(rest) - 1;
+            const float wx = __shfl_sync(0xffffffffu, px, j), wy = __shfl_sync(0xffffffffu, py, j), wz = __shfl_sync(0xffffffffu, pz, j);
+            const float wstep = __shfl_sync(0xffffffffu, step, j), wtie = __shfl_sync(0xffffffffu, tie, j);
+            const int wseed = __shfl_sync(0xffffffffu, o.pos, j);
+            Best tb;
+            if (!warp_search_seeded(a.g, wx, wy, wz, wseed, tb)) continue;       // ball too large: the owner walks it alone
+            int t1 = tb.pos, t2 = tb.pos, t3 = tb.pos, tk = 0;
+            float trho = 0.f;
+            const float d1 = sqrtf(tb.d2);
+            if (wstep < a.build_step) {
+                for (int attempt = 0; attempt < 2; ++attempt) {
+                    const float R = d1 + (attempt == 0 ? a.collect : fminf(4.0f * wtie, a.collect));
+                    if (R * L0.inv_h >= 0.95f) continue;
+                    Near5 nb;
+                    warp_collect(L0, a.g.ox, a.g.oy, a.g.oz, wx, wy, wz, R * R, nb);
+                    if (!nb.complete) continue;
+                    trho = compose_cache(nb, tb.pos, d1, wtie, R, t1, t2, t3, tk);
+                    break;
+                }
             }
-            rho = sqrtf(rho2) * 0.9999f;
-            break;
+            if (lane == j) { bb = tb; o1 = t1; o2 = t2; o3 = t3; k = tk; rho = trho; settled = true; }
         }
     }
-    o.d2 = bb.d2; o.pos = bb.pos; o.qx = bb.qx; o.qy = bb.qy; o.qz = bb.qz;
-    o.nx = nq.x; o.ny = nq.y; o.nz = nq.z;
-    o.nq = nq_dot(nq.x, nq.y, nq.z, bb.qx, bb.qy, bb.qz);
-    o.margin = rho;
-    a.cq[i] = make_float4(bb.qx, bb.qy, bb.qz, __int_as_float(bb.pos | (k > 0 ? kMoreBit : 0)));
-    a.cn[i] = make_float4(nq.x, nq.y, nq.z, o.nq);
-    if (k > 0) a.cmore[i] = make_int4(o1, o2, o3, bb.idx);
+    if (search && !settled) {
+        bb = nn_search_seeded<true>(a.g, px, py, pz, o.pos);
+        o1 = bb.pos; o2 = bb.pos; o3 = bb.pos; k = 0; rho = 0.f;
+        const float d1 = sqrtf(bb.d2);
+        if (step < a.build_step) {
+            // first with the wide radius (a large gap to the second-nearest target = a long-lived cache); a query far from
+            // its match would need more than the 3x3-row scan for that: then only the ties are looked for
+            for (int attempt = 0; attempt < 2; ++attempt) {
+                const float R = d1 + (attempt == 0 ? a.collect : fminf(4.0f * tie, a.collect));
+                if (R * L0.inv_h >= 0.95f) continue;
+                const Near5 nb = ball_collect(L0, a.g.ox, a.g.oy, a.g.oz, px, py, pz, R * R);
+                if (!nb.complete) continue;
+                rho = compose_cache(nb, bb.pos, d1, tie, R, o1, o2, o3, k);
+                break;
+            }
+        }
+    }
+    if (search) {
+        const float4 nq = __ldg(a.aux + bb.pos);
+        o.d2 = bb.d2; o.pos = bb.pos; o.qx = bb.qx; o.qy = bb.qy; o.qz = bb.qz;
+        o.nx = nq.x; o.ny = nq.y; o.nz = nq.z;
+        o.nq = nq_dot(nq.x, nq.y, nq.z, bb.qx, bb.qy, bb.qz);
+        o.margin = rho;
+        a.cq[i] = make_float4(bb.qx, bb.qy, bb.qz, __int_as_float(bb.pos | (k > 0 ? kMoreBit : 0)));
+        a.cn[i] = make_float4(nq.x, nq.y, nq.z, o.nq);
+        if (k > 0) a.cmore[i] = make_int4(o1, o2, o3, bb.idx);
+    }
     return o;
 }
 
@@ -608,11 +657,22 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_persistent_kernel(const Ic
             float qx = q0.x, qy = q0.y, qz = q0.z;
             float nx = cn.x, ny = cn.y, nz = cn.z, nq = cn.w;
             int bpos = __float_as_int(q0.w);
-            if ((bpos & kMoreBit) || !(mchk > 0.f && bd2 * 1.00003f < mchk * mchk)) {
-                const SlowOut o = icp_slow_path(a, it, i, p.x, p.y, p.z, q0, cn, margin, mchk, step);
-                bd2 = o.d2; bpos = o.pos; qx = o.qx; qy = o.qy; qz = o.qz;
-                nx = o.nx; ny = o.ny; nz = o.nz; nq = o.nq;
-                margin = o.margin;
+            const bool slow = (bpos & kMoreBit) || !(mchk > 0.f && bd2 * 1.00003f < mchk * mchk);
+            if (__any_sync(0xffffffffu, slow)) {                 // warp-uniform: the slow path may search as a warp
+                // the accumulators are parked in local memory around the call, explicitly: left to the register
+                // allocator, those that share registers with the callee were stored and reloaded in EVERY trip of the
+                // loop, call or no call (seven of them with this slow path, 14 + 14 local accesses per batch)
+                volatile double parked[kNumVals];
+#pragma unroll
+                for (int v = 0; v < kNumVals; ++v) parked[v] = acc[v];
+                const SlowOut o = icp_slow_path(a, it, i, p.x, p.y, p.z, q0, cn, margin, mchk, step, slow);
+#pragma unroll
+                for (int v = 0; v < kNumVals; ++v) acc[v] = parked[v];
+                if (slow) {
+                    bd2 = o.d2; bpos = o.pos; qx = o.qx; qy = o.qy; qz = o.qz;
+                    nx = o.nx; ny = o.ny; nz = o.nz; nq = o.nq;
+                    margin = o.margin;
+                }
             }
             a.work[i] = make_float4(p.x, p.y, p.z, margin);
             // float expressions of TransformationEstimationPointToPlaneLLS (no FMA); nq = (nx*dx + ny*dy) + nz*dz
