@@ -109,11 +109,12 @@ typedef struct {
                                the summation order is a function of (n_source, this) alone */
     float device_ms;        /* whole inner loop (source sort, iteration-0 pre-pass, persistent kernel), CUDA events */
     long long correspondences;  /* n_iter * n_source */
-    float kernel_ms;        /* the persistent kernel alone (CUDA events around its launch) */
+    float kernel_ms;        /* the persistent kernel alone (CUDA events around its launches, summed) */
     int   natural_iters;    /* first iteration at which DefaultConvergenceCriteria was met (= n_iter unless force_iters) */
     int   natural_state;    /* ... and the PWICP_CONV_* state it reported */
     float sort_ms;          /* Morton sort + gather of the source set (CUDA events) */
     float prepass_ms;       /* iteration-0 search pre-pass of an unseeded source set (0 when seeded) */
+    float research_ms;      /* the stand-alone search of iteration 1 between the two launches of the persistent kernel */
 } pwicp_icp_result;
 
 /* source set of the inner loop: host upload (stand-alone use) ... */

@@ -127,6 +127,7 @@ int pwicp_ctx_create(int device, pwicp_ctx** out) {
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
         cudaEventCreate(&c->ev2) != cudaSuccess || cudaEventCreate(&c->ev3) != cudaSuccess ||
+        cudaEventCreate(&c->ev4) != cudaSuccess || cudaEventCreate(&c->ev5) != cudaSuccess ||
         cudaEventCreate(&c->ev_o0) != cudaSuccess || cudaEventCreate(&c->ev_o1) != cudaSuccess) {
         delete c; set_error(nullptr, "stream/event creation failed"); return PWICP_ERR_CUDA;
     }
@@ -146,7 +147,7 @@ void pwicp_ctx_destroy(pwicp_ctx* p) {
                       &c->scratch_b, &c->scratch_c, &c->scratch_d, &c->flags, &c->pos, &c->l2flush, &c->outer_state};
     for (DevBuf* b : bufs) b->release();
     if (c->pinned) cudaFreeHost(c->pinned);
-    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2); cudaEventDestroy(c->ev3);
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2); cudaEventDestroy(c->ev3); cudaEventDestroy(c->ev4); cudaEventDestroy(c->ev5);
     cudaEventDestroy(c->ev_o0); cudaEventDestroy(c->ev_o1);
     cudaStreamDestroy(c->stream);
     if (c->copy_stream) { cudaStreamDestroy(c->copy_stream); for (auto& e : c->copy_ev) if (e) cudaEventDestroy(e); }

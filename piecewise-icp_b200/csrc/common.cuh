@@ -83,7 +83,7 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;          // host-buffer calls: uploads overlap the grid build
     cudaEvent_t copy_ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev4 = nullptr, ev5 = nullptr;
     cudaEvent_t ev_o0 = nullptr, ev_o1 = nullptr;   // outer iteration
     std::string err;
     float last_ms = 0.f;

@@ -80,6 +80,11 @@ struct IcpArgs {
                               // on the device; the launch geometry then comes from the capacity n)
     int max_iter;
     int force_iters;
+    // the loop runs as two launches with a stand-alone search in between (icp_research_kernel): this launch does the
+    // iterations [it_begin, it_end); it_begin > 0: the points in work[] are already where this iteration wants them and
+    // carry their fresh caches, the state of the loop so far comes from *carry
+    int it_begin, it_end;
+    struct IcpCarry* carry;
     double rot_thr, transl_thr, mse_rel, mse_abs;
     unsigned long long* part; // [2][gridDim.x][28][2]: CTA sums of an iteration as tagged 8-byte packets, double buffered
     int* searched;            // [max_iter], zeroed before the launch: queries that ran the ball search (diagnostic)
@@ -90,6 +95,15 @@ struct IcpArgs {
     int* idx_trace;           // nullable, [iter][n]
     unsigned long long* iter_ns;   // [max_iter + 1]: %globaltimer at the start of the loop and after every iteration (CTA 0)
     unsigned long long* phase_ns;  // [max_iter][4]: CTA 0, warp 0: end of its batches, CTA sum posted, totals formed (all packets in), solved
+};
+
+// What a launch that ends before the loop does hands to the next one (written by CTA 0).
+struct IcpCarry {
+    float T[16];         // the incremental transform of the last iteration done
+    float Tfinal[16];    // the accumulated one
+    double prev_mse;
+    int met;             // the convergence criteria have been met before
+    int stop;            // conv_state != 0: the loop is over, the launches that follow return at once
 };
 
 // Shared scratch of the per-iteration solve.
@@ -248,36 +262,9 @@ struct SlowOut {
     float nx, ny, nz, nq; // its normal, nq_dot(normal, match)
     float margin;         // what is left of the cache radius
 };
-// a new cache around the position of a query that has just searched (nn_search.cuh, "candidate cache"): the match, the
-// targets within `tie` of it (o1..o3, k of them), and the radius just below the first target left out
-__device__ __forceinline__ float compose_cache(const Near5& nb, int match_pos, float d1, float tie, float R,
-                                               int& o1, int& o2, int& o3, int& k) {
-    const float lim = (d1 + tie) * (d1 + tie);
-    float rho2 = R * R;                      // complete up to the scanned radius unless a target is left out
-    bool open = true;                        // still taking targets into the cache
-#pragma unroll
-    for (int j = 0; j <= kCacheCands; ++j) {
-        if (!open || nb.pos[j] < 0) continue;
-        if (nb.pos[j] == match_pos) continue;   // the match itself: always cached (the primary)
-        if (nb.d2[j] < lim && k < 3) {
-            if (k == 0) o1 = nb.pos[j]; else if (k == 1) o2 = nb.pos[j]; else o3 = nb.pos[j];
-            ++k;
-        } else { rho2 = nb.d2[j]; open = false; }
-    }
-    return sqrtf(rho2) * 0.9999f;
-}
-
-// A warp-uniform call (all 32 lanes; need = this lane's query is on the slow path).  When at most kCoopQueries queries
-// of the batch have to search, the WHOLE WARP searches for each of them in turn (warp_search_seeded / warp_collect:
-// one cell row per lane) -- a lone lane walking its rows one after the other held the other 31 up for ~15 us
-// (iteration 2 at 1M: 1.5 % of the queries search, the iteration took 99 us against 17 us for a cached one).
-#ifndef PWICP_COOP_QUERIES
-#define PWICP_COOP_QUERIES 4
-#endif
 static __device__ __noinline__ SlowOut icp_slow_path(const IcpArgs& a, int it, int i, float px, float py, float pz,
-                                                     float4 q0, float4 cn, float margin, float mchk, float step, bool need) {
+                                                     float4 q0, float4 cn, float margin, float mchk, float step) {
     const float4* __restrict__ pts = a.g.lv[0].pts;
-    const int lane = (int)(threadIdx.x & 31);
     const int pos0 = __float_as_int(q0.w) & ~kMoreBit;
     SlowOut o;
     o.d2 = l2_simple(px, py, pz, q0.x, q0.y, q0.z);
@@ -287,8 +274,7 @@ static __device__ __noinline__ SlowOut icp_slow_path(const IcpArgs& a, int it, i
     // how close to the match a target must be to be cached with it: a fraction of the step the query has just taken
     // (the next one is smaller), at least `tie`, at most the collection radius
     const float tie = fminf(fmaxf(a.tie_step * step, a.tie), a.collect);
-    bool search = need;
-    if (need && (__float_as_int(q0.w) & kMoreBit)) {
+    if (__float_as_int(q0.w) & kMoreBit) {
         // positions from the side array, the three loads are issued together, unused slots repeat the primary
         const int4 cm = __ldcg(a.cmore + i);
         int bidx = cm.w;
@@ -328,76 +314,55 @@ static __device__ __noinline__ SlowOut icp_slow_path(const IcpArgs& a, int it, i
                                            cm.z == o.pos ? pos0 : cm.z, bidx);
             }
             if (alone) o.margin = fminf(mchk, sqrtf(second) * 0.9999f);
-            search = false;
+            return o;
         }
     }
     // |p - anchor| <= path (triangle inequality over the steps actually taken): every target at least as close to p
     // as the best cached one lies within the cache radius of the anchor; compared as squares
-    if (search && mchk > 0.f && o.d2 * 1.00003f < mchk * mchk) search = false;
+    if (mchk > 0.f && o.d2 * 1.00003f < mchk * mchk) return o;
 
-    const unsigned sm = __ballot_sync(0xffffffffu, search);
-    if (sm == 0) return o;
-    // queries that needed the search this iteration (diagnostic: pwicp_icp_profile)
-    if (lane == __ffs(sm) - 1) atomicAdd(a.searched + it, __popc(sm));
-
-    const GridLevel& L0 = a.g.lv[0];
-    Best bb;
-    bb.d2 = 0.f; bb.idx = 0; bb.pos = 0; bb.qx = bb.qy = bb.qz = 0.f;
-    int o1 = 0, o2 = 0, o3 = 0, k = 0;
+    {   // queries that needed the search this iteration (diagnostic: pwicp_icp_profile)
+        const unsigned m = __activemask();
+        if ((int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(a.searched + it, __popc(m));
+    }
+    const Best bb = nn_search_seeded<true>(a.g, px, py, pz, o.pos);
+    const float4 nq = __ldg(a.aux + bb.pos);
+    // a new cache around this position (nn_search.cuh, "candidate cache"): the match, the targets within `tie` of it,
+    // and the radius just below the first target left out
+    int o1 = bb.pos, o2 = bb.pos, o3 = bb.pos, k = 0;
     float rho = 0.f;
-    bool settled = false;
-    if (__popc(sm) <= PWICP_COOP_QUERIES) {
-        for (unsigned rest = sm; rest; rest &= rest - 1) {       // warp-uniform
-            const int j = __ffs(rest) - 1;
-            const float wx = __shfl_sync(0xffffffffu, px, j), wy = __shfl_sync(0xffffffffu, py, j), wz = __shfl_sync(0xffffffffu, pz, j);
-            const float wstep = __shfl_sync(0xffffffffu, step, j), wtie = __shfl_sync(0xffffffffu, tie, j);
-            const int wseed = __shfl_sync(0xffffffffu, o.pos, j);
-            Best tb;
-            if (!warp_search_seeded(a.g, wx, wy, wz, wseed, tb)) continue;       // ball too large: the owner walks it alone
-            int t1 = tb.pos, t2 = tb.pos, t3 = tb.pos, tk = 0;
-            float trho = 0.f;
-            const float d1 = sqrtf(tb.d2);
-            if (wstep < a.build_step) {
-                for (int attempt = 0; attempt < 2; ++attempt) {
-                    const float R = d1 + (attempt == 0 ? a.collect : fminf(4.0f * wtie, a.collect));
-                    if (R * L0.inv_h >= 0.95f) continue;
-                    Near5 nb;
-                    warp_collect(L0, a.g.ox, a.g.oy, a.g.oz, wx, wy, wz, R * R, nb);
-                    if (!nb.complete) continue;
-                    trho = compose_cache(nb, tb.pos, d1, wtie, R, t1, t2, t3, tk);
-                    break;
-                }
+    const float d1 = sqrtf(bb.d2);
+    if (step < a.build_step) {
+        // first with the wide radius (a large gap to the second-nearest target = a long-lived cache); a query far from
+        // its match would need more than the 3x3-row scan for that: then only the ties are looked for
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            const float R = d1 + (attempt == 0 ? a.collect : fminf(4.0f * tie, a.collect));
+            if (R * a.g.lv[0].inv_h >= 0.95f) continue;
+            const Near5 nb = ball_collect(a.g.lv[0], a.g.ox, a.g.oy, a.g.oz, px, py, pz, R * R);
+            if (!nb.complete) continue;
+            const float lim = (d1 + tie) * (d1 + tie);
+            float rho2 = R * R;                      // complete up to the scanned radius unless a target is left out
+            bool open = true;                        // still taking targets into the cache
+#pragma unroll
+            for (int j = 0; j <= kCacheCands; ++j) {
+                if (!open || nb.pos[j] < 0) continue;
+                if (nb.pos[j] == bb.pos) continue;   // the match itself: always cached (the primary)
+                if (nb.d2[j] < lim && k < 3) {
+                    if (k == 0) o1 = nb.pos[j]; else if (k == 1) o2 = nb.pos[j]; else o3 = nb.pos[j];
+                    ++k;
+                } else { rho2 = nb.d2[j]; open = false; }
             }
-            if (lane == j) { bb = tb; o1 = t1; o2 = t2; o3 = t3; k = tk; rho = trho; settled = true; }
+            rho = sqrtf(rho2) * 0.9999f;
+            break;
         }
     }
-    if (search && !settled) {
-        bb = nn_search_seeded<true>(a.g, px, py, pz, o.pos);
-        o1 = bb.pos; o2 = bb.pos; o3 = bb.pos; k = 0; rho = 0.f;
-        const float d1 = sqrtf(bb.d2);
-        if (step < a.build_step) {
-            // first with the wide radius (a large gap to the second-nearest target = a long-lived cache); a query far from
-            // its match would need more than the 3x3-row scan for that: then only the ties are looked for
-            for (int attempt = 0; attempt < 2; ++attempt) {
-                const float R = d1 + (attempt == 0 ? a.collect : fminf(4.0f * tie, a.collect));
-                if (R * L0.inv_h >= 0.95f) continue;
-                const Near5 nb = ball_collect(L0, a.g.ox, a.g.oy, a.g.oz, px, py, pz, R * R);
-                if (!nb.complete) continue;
-                rho = compose_cache(nb, bb.pos, d1, tie, R, o1, o2, o3, k);
-                break;
-            }
-        }
-    }
-    if (search) {
-        const float4 nq = __ldg(a.aux + bb.pos);
-        o.d2 = bb.d2; o.pos = bb.pos; o.qx = bb.qx; o.qy = bb.qy; o.qz = bb.qz;
-        o.nx = nq.x; o.ny = nq.y; o.nz = nq.z;
-        o.nq = nq_dot(nq.x, nq.y, nq.z, bb.qx, bb.qy, bb.qz);
-        o.margin = rho;
-        a.cq[i] = make_float4(bb.qx, bb.qy, bb.qz, __int_as_float(bb.pos | (k > 0 ? kMoreBit : 0)));
-        a.cn[i] = make_float4(nq.x, nq.y, nq.z, o.nq);
-        if (k > 0) a.cmore[i] = make_int4(o1, o2, o3, bb.idx);
-    }
+    o.d2 = bb.d2; o.pos = bb.pos; o.qx = bb.qx; o.qy = bb.qy; o.qz = bb.qz;
+    o.nx = nq.x; o.ny = nq.y; o.nz = nq.z;
+    o.nq = nq_dot(nq.x, nq.y, nq.z, bb.qx, bb.qy, bb.qz);
+    o.margin = rho;
+    a.cq[i] = make_float4(bb.qx, bb.qy, bb.qz, __int_as_float(bb.pos | (k > 0 ? kMoreBit : 0)));
+    a.cn[i] = make_float4(nq.x, nq.y, nq.z, o.nq);
+    if (k > 0) a.cmore[i] = make_int4(o1, o2, o3, bb.idx);
     return o;
 }
 
@@ -545,6 +510,8 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_persistent_kernel(const Ic
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = a.n_dev ? __ldg(a.n_dev) : a.n;                // same value in every thread of the grid
     if (n < 3) {                                                 // pcl: min_number_correspondences_ (device-side count only)
+        if (a.it_begin > 0) return;
+        if (blockIdx.x == 0 && tid == 0 && a.carry) a.carry->stop = PWICP_CONV_NO_CORR;
         if (blockIdx.x == 0 && tid < 16) a.out_T[tid] = (tid % 5 == 0) ? 1.0f : 0.0f;
         if (blockIdx.x == 0 && tid == 0) { a.out_state[0] = 0; a.out_state[1] = PWICP_CONV_NO_CORR; }
         return;
@@ -563,9 +530,15 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_persistent_kernel(const Ic
         asm volatile("mov.u32 %0, %1;" : "=r"(s_lane_sh) : "r"(v));
     }
 
-    if (tid < 16) { s_T[tid] = (tid % 5 == 0) ? 1.0f : 0.0f; s_Tfinal[tid] = s_T[tid]; }
-    if (tid == 0) { s_stop = 0; s_fin.prev_mse = 1.7976931348623157e308; s_fin.met = 0; }   // DBL_MAX
-    if (blockIdx.x == 0 && tid == 0) a.iter_ns[0] = globaltimer_ns();
+    if (a.it_begin == 0) {
+        if (tid < 16) { s_T[tid] = (tid % 5 == 0) ? 1.0f : 0.0f; s_Tfinal[tid] = s_T[tid]; }
+        if (tid == 0) { s_stop = 0; s_fin.prev_mse = 1.7976931348623157e308; s_fin.met = 0; }   // DBL_MAX
+        if (blockIdx.x == 0 && tid == 0) a.iter_ns[0] = globaltimer_ns();
+    } else {
+        if (__ldcg(&a.carry->stop)) return;                      // the loop ended in the previous launch (every thread)
+        if (tid < 16) { s_T[tid] = __ldcg(&a.carry->T[tid]); s_Tfinal[tid] = __ldcg(&a.carry->Tfinal[tid]); }
+        if (tid == 0) { s_stop = 0; s_fin.prev_mse = __ldcg(&a.carry->prev_mse); s_fin.met = __ldcg(&a.carry->met); }
+    }
     __syncthreads();
 
     // copies of point i_ of this lane (one of the batches of this warp; past the end: an empty group): point +
@@ -602,17 +575,18 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_persistent_kernel(const Ic
         cp_async_commit();
     };
 #endif
-    stage_point(a.src, i0, 0);
-    stage_point(a.src, i0 + stride, kSlotBytes);
+    stage_point(a.it_begin == 0 ? a.src : a.work, i0, 0);
+    stage_point(a.it_begin == 0 ? a.src : a.work, i0 + stride, kSlotBytes);
     const unsigned s_T_sh = (unsigned)__cvta_generic_to_shared(s_T);
 
-    for (int it = 0;; ++it) {
+    for (int it = a.it_begin;; ++it) {
         double acc[kNumVals];
 #pragma unroll
         for (int v = 0; v < kNumVals; ++v) acc[v] = 0.0;
         const float4* __restrict__ psrc = (it == 0) ? a.src : a.work;
         const float4* __restrict__ pts = a.g.lv[0].pts;
         const bool first = it == 0;
+        const bool resumed = it > 0 && it == a.it_begin;         // work[] holds this iteration's positions and caches
 
         // ---- phase A: this warp's batches, two batches of copies in flight ahead of the one being processed
         int slot = 0, pslot = 2 * kSlotBytes, i = i0;            // byte offsets of the ring slots
@@ -635,7 +609,10 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_persistent_kernel(const Ic
             float step = __int_as_float(0x7f800000);             // L1 length of the last step (>= its Euclidean length)
             float margin;                                        // cache radius left after the path travelled (lower bound)
             float mchk;                                          // ... as the certificate below uses it
-            if (!first) {
+            if (resumed) {
+                margin = p.w;
+                mchk = margin;
+            } else if (!first) {
                 // the transform is read from shared memory where it is used (three broadcast loads): twelve more
                 // live registers across the loop would spill the accumulators
                 float4 r0, r1, r2;
@@ -657,22 +634,11 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_persistent_kernel(const Ic
             float qx = q0.x, qy = q0.y, qz = q0.z;
             float nx = cn.x, ny = cn.y, nz = cn.z, nq = cn.w;
             int bpos = __float_as_int(q0.w);
-            const bool slow = (bpos & kMoreBit) || !(mchk > 0.f && bd2 * 1.00003f < mchk * mchk);
-            if (__any_sync(0xffffffffu, slow)) {                 // warp-uniform: the slow path may search as a warp
-                // the accumulators are parked in local memory around the call, explicitly: left to the register
-                // allocator, those that share registers with the callee were stored and reloaded in EVERY trip of the
-                // loop, call or no call (seven of them with this slow path, 14 + 14 local accesses per batch)
-                volatile double parked[kNumVals];
-#pragma unroll
-                for (int v = 0; v < kNumVals; ++v) parked[v] = acc[v];
-                const SlowOut o = icp_slow_path(a, it, i, p.x, p.y, p.z, q0, cn, margin, mchk, step, slow);
-#pragma unroll
-                for (int v = 0; v < kNumVals; ++v) acc[v] = parked[v];
-                if (slow) {
-                    bd2 = o.d2; bpos = o.pos; qx = o.qx; qy = o.qy; qz = o.qz;
-                    nx = o.nx; ny = o.ny; nz = o.nz; nq = o.nq;
-                    margin = o.margin;
-                }
+            if ((bpos & kMoreBit) || !(mchk > 0.f && bd2 * 1.00003f < mchk * mchk)) {
+                const SlowOut o = icp_slow_path(a, it, i, p.x, p.y, p.z, q0, cn, margin, mchk, step);
+                bd2 = o.d2; bpos = o.pos; qx = o.qx; qy = o.qy; qz = o.qz;
+                nx = o.nx; ny = o.ny; nz = o.nz; nq = o.nq;
+                margin = o.margin;
             }
             a.work[i] = make_float4(p.x, p.y, p.z, margin);
             // float expressions of TransformationEstimationPointToPlaneLLS (no FMA); nq = (nx*dx + ny*dy) + nz*dz
@@ -740,13 +706,17 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_persistent_kernel(const Ic
             __syncwarp();
             if (blockIdx.x == 0 && lane == 0) a.phase_ns[it * 4 + 2] = globaltimer_ns();
             const int st = icp_finish_warp(a, n, it, s_tot, s_T, s_Tfinal, s_fin, lane);
+            if (blockIdx.x == 0 && a.carry && it + 1 == a.it_end) {   // hand-over to the next launch
+                if (lane < 16) { a.carry->T[lane] = s_T[lane]; a.carry->Tfinal[lane] = s_Tfinal[lane]; }
+                if (lane == 0) { a.carry->prev_mse = s_fin.prev_mse; a.carry->met = s_fin.met; a.carry->stop = st; }
+            }
             if (lane == 0) {
                 s_stop = st;
                 if (blockIdx.x == 0) { a.iter_ns[it + 1] = globaltimer_ns(); a.phase_ns[it * 4 + 3] = a.iter_ns[it + 1]; }
             }
         }
         __syncthreads();
-        if (s_stop) break;
+        if (s_stop || it + 1 >= a.it_end) break;
     }
 #if PWICP_STAGE_TMA
     // the copies staged for an iteration that does not run must land before the CTA gives up its shared memory
@@ -847,6 +817,65 @@ icp_fill_cn_kernel(const float4* __restrict__ tgt_aux, const float4* __restrict_
     cn0[i] = make_float4(nq.x, nq.y, nq.z, nq_dot(nq.x, nq.y, nq.z, q.x, q.y, q.z));
 }
 
+// Iteration 1 of the loop searches for EVERY query (no cache exists yet; after the first, large ICP step the matches of
+// iteration 0 are stale) -- 0.43 of the 1.39 ms the persistent kernel took at 1M, at 16 warps per SM and 128 registers.
+// This kernel does that iteration's per-point work up to the match at full occupancy, between two launches of the
+// persistent kernel: the transform of iteration 0 applied to the point (the same float expression), the seeded search,
+// the candidate cache around the new position (what icp_slow_path does for a query without a cache).  The second
+// launch finds work[] = the transformed point + the radius of its fresh cache and cq / cn / cmore = the match, and
+// starts with the row terms of iteration 1.
+__global__ void __launch_bounds__(256)
+icp_research_kernel(const IcpArgs a) {
+    const int n = a.n_dev ? __ldg(a.n_dev) : a.n;
+    if (n < 3 || __ldcg(&a.carry->stop)) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_pad = (n + 31) / 32 * 32;
+    if (i >= n_pad) return;
+    const float* T = a.carry->T;
+    const float4 p = a.work[i];
+    const float x = __ldcg(T + 0) * p.x + __ldcg(T + 1) * p.y + __ldcg(T + 2) * p.z + __ldcg(T + 3);     // xform_point (small_algebra.cuh)
+    const float y = __ldcg(T + 4) * p.x + __ldcg(T + 5) * p.y + __ldcg(T + 6) * p.z + __ldcg(T + 7);
+    const float z = __ldcg(T + 8) * p.x + __ldcg(T + 9) * p.y + __ldcg(T + 10) * p.z + __ldcg(T + 11);
+    if (i >= n) { a.work[i] = make_float4(x, y, z, kPadMargin); return; }
+    const float step = (fabsf(x - p.x) + fabsf(y - p.y)) + fabsf(z - p.z);
+    const float tie = fminf(fmaxf(a.tie_step * step, a.tie), a.collect);
+    {
+        const unsigned m = __activemask();
+        if ((int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(a.searched + 1, __popc(m));
+    }
+    const Best bb = nn_search_seeded<false>(a.g, x, y, z, __float_as_int(a.cq[i].w) & ~kMoreBit);
+    const float4 nq = __ldg(a.aux + bb.pos);
+    int o1 = bb.pos, o2 = bb.pos, o3 = bb.pos, k = 0;
+    float rho = 0.f;
+    const float d1 = sqrtf(bb.d2);
+    if (step < a.build_step) {
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            const float R = d1 + (attempt == 0 ? a.collect : fminf(4.0f * tie, a.collect));
+            if (R * a.g.lv[0].inv_h >= 0.95f) continue;
+            const Near5 nb = ball_collect(a.g.lv[0], a.g.ox, a.g.oy, a.g.oz, x, y, z, R * R);
+            if (!nb.complete) continue;
+            const float lim = (d1 + tie) * (d1 + tie);
+            float rho2 = R * R;
+            bool open = true;
+#pragma unroll
+            for (int j = 0; j <= kCacheCands; ++j) {
+                if (!open || nb.pos[j] < 0) continue;
+                if (nb.pos[j] == bb.pos) continue;
+                if (nb.d2[j] < lim && k < 3) {
+                    if (k == 0) o1 = nb.pos[j]; else if (k == 1) o2 = nb.pos[j]; else o3 = nb.pos[j];
+                    ++k;
+                } else { rho2 = nb.d2[j]; open = false; }
+            }
+            rho = sqrtf(rho2) * 0.9999f;
+            break;
+        }
+    }
+    a.work[i] = make_float4(x, y, z, rho);
+    a.cq[i] = make_float4(bb.qx, bb.qy, bb.qz, __int_as_float(bb.pos | (k > 0 ? kMoreBit : 0)));
+    a.cn[i] = make_float4(nq.x, nq.y, nq.z, nq_dot(nq.x, nq.y, nq.z, bb.qx, bb.qy, bb.qz));
+    if (k > 0) a.cmore[i] = make_int4(o1, o2, o3, bb.idx);
+}
+
 // Sorts the source set by the target-grid cell it starts in (stable: ties keep the caller's
 // order), so that the 8 queries of a tile group share a small candidate block.  The processing
 // order only affects the order of the double sums (DESIGN.md "reduction geometry").
@@ -920,7 +949,8 @@ int icp_enqueue(Ctx* ctx, const pwicp_icp_params& prm, int n, const int* n_dev, 
     const size_t bytes_part = (size_t)2 * grid * kNumVals * 2 * sizeof(unsigned long long);   // tagged packets (icp_persistent_kernel)
     const size_t bytes_cnt = (size_t)prm.max_iter * sizeof(int);
     const size_t off_ns = (bytes_part + bytes_cnt + 7) & ~(size_t)7;
-    PW_TRY(ctx->icp_partials.reserve(ctx, off_ns + (size_t)(prm.max_iter + 1) * 8 + (size_t)prm.max_iter * 32 + 64));
+    const size_t off_carry = (off_ns + (size_t)(prm.max_iter + 1) * 8 + (size_t)prm.max_iter * 32 + 15) & ~(size_t)15;
+    PW_TRY(ctx->icp_partials.reserve(ctx, off_carry + sizeof(IcpCarry) + 64));
     const size_t out_bytes = 64 + 16 + (size_t)prm.max_iter * (8 + 64);
     PW_TRY(ctx->icp_out.reserve(ctx, out_bytes));
     char* ob = ctx->icp_out.as<char>();
@@ -984,17 +1014,34 @@ int icp_enqueue(Ctx* ctx, const pwicp_icp_params& prm, int n, const int* n_dev, 
     a.iter_ns = reinterpret_cast<unsigned long long*>(ctx->icp_partials.as<char>() + off_ns);
     a.phase_ns = a.iter_ns + prm.max_iter + 1;
     // packets (tag 0 = nothing posted), search counters, timers
-    PW_CUDA(cudaMemsetAsync(a.part, 0, off_ns + (size_t)(prm.max_iter + 1) * 8 + (size_t)prm.max_iter * 32, ctx->stream));
+    PW_CUDA(cudaMemsetAsync(a.part, 0, off_carry + sizeof(IcpCarry), ctx->stream));
+    a.carry = reinterpret_cast<IcpCarry*>(ctx->icp_partials.as<char>() + off_carry);
     a.out_T = reinterpret_cast<float*>(ob);
     a.out_state = reinterpret_cast<int*>(ob + 64);
     a.mse_trace = want_mse ? reinterpret_cast<double*>(ob + 80) : nullptr;
     a.T_trace = want_T ? reinterpret_cast<float*>(ob + 80 + (size_t)prm.max_iter * 8) : nullptr;
     a.idx_trace = want_idx ? ctx->icp_idx.as<int>() : nullptr;
 
+    // Two launches with the search of iteration 1 between them (icp_research_kernel) -- or one, when there is no
+    // iteration 1 or the A/B switch says so.  (Cooperative launches: every CTA must be resident, the CTA sums are
+    // exchanged by polling.)
+    static const bool split_env = [] { const char* e = getenv("PWICP_SPLIT_ITER1"); return !e || atoi(e) != 0; }();
+    const bool split = split_env && prm.max_iter > 1;
     void* kargs[] = {(void*)&a};
+    a.it_begin = 0; a.it_end = split ? 1 : prm.max_iter;
     PW_CUDA(cudaEventRecord(ctx->ev2, ctx->stream));
     PW_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kIcpThreads), kargs, smem, ctx->stream));
     ctx->launches++;
+    PW_CUDA(cudaEventRecord(ctx->ev4, ctx->stream));
+    if (split) {
+        icp_research_kernel<<<(n_pad + 255) / 256, 256, 0, ctx->stream>>>(a);
+        PW_CUDA(cudaEventRecord(ctx->ev5, ctx->stream));
+        a.it_begin = 1; a.it_end = prm.max_iter;
+        PW_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kIcpThreads), kargs, smem, ctx->stream));
+        ctx->launches += 2;
+    } else {
+        PW_CUDA(cudaEventRecord(ctx->ev5, ctx->stream));
+    }
     PW_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->icp_prof_max_iter = prm.max_iter;
     ctx->icp_prof_off_searched = bytes_part; ctx->icp_prof_off_ns = off_ns;
@@ -1012,9 +1059,12 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     struct { float T[16]; int st[4]; } host;
     PW_CUDA(cudaMemcpyAsync(&host, ob, sizeof(host), cudaMemcpyDeviceToHost, ctx->stream));
     PW_CUDA(cudaStreamSynchronize(ctx->stream));
-    float ms = 0.f, kms = 0.f, sms = 0.f, pms = 0.f;
+    float ms = 0.f, kms = 0.f, kms2 = 0.f, rms = 0.f, sms = 0.f, pms = 0.f;
     PW_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-    PW_CUDA(cudaEventElapsedTime(&kms, ctx->ev2, ctx->ev1));
+    PW_CUDA(cudaEventElapsedTime(&kms, ctx->ev2, ctx->ev4));     // the persistent kernel: first launch ...
+    PW_CUDA(cudaEventElapsedTime(&kms2, ctx->ev5, ctx->ev1));    // ... and second
+    PW_CUDA(cudaEventElapsedTime(&rms, ctx->ev4, ctx->ev5));     // the search of iteration 1 between them
+    kms += kms2;
     PW_CUDA(cudaEventElapsedTime(&sms, ctx->ev0, ctx->ev3));
     PW_CUDA(cudaEventElapsedTime(&pms, ctx->ev3, ctx->ev2));
     ctx->last_ms = ms;
@@ -1027,7 +1077,7 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
         res->group_batches = (grid * kIcpWarps) | (kIcpWarps << 16);   // reduction geometry for the oracle's reduce_mode 2
         res->device_ms = ms; res->correspondences = (long long)n_iter * n;
         res->kernel_ms = kms; res->natural_iters = host.st[2]; res->natural_state = host.st[3];
-        res->sort_ms = sms; res->prepass_ms = pms;
+        res->sort_ms = sms; res->prepass_ms = pms; res->research_ms = rms;
     }
     if (mse_trace) PW_CUDA(cudaMemcpy(mse_trace, ob + 80, (size_t)n_iter * 8, cudaMemcpyDeviceToHost));
     if (T_trace) PW_CUDA(cudaMemcpy(T_trace, ob + 80 + (size_t)prm.max_iter * 8, (size_t)n_iter * 64, cudaMemcpyDeviceToHost));

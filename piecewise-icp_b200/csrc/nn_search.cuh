@@ -584,101 +584,8 @@ static __device__ __noinline__ Near5 ball_collect(const GridLevel& L, float ox, 
     return out;
 }
 
-// ---------------------------------------------------------------------------------------------
-// One query, the whole warp (inner ICP loop, iterations in which only a few queries of a batch miss their cache: the
-// other lanes would idle through a chain of ~35 dependent L2 round trips).  Every lane takes ONE cell row of the ball
-// through the seed -- gap test, chord cut, cell_start loads and the candidates of the row, all rows in flight at once
-// -- and the warp folds the results: four round trips instead of ~35.  Exact for the same reason as ball_scan (the rows
-// cover the ball of the seed distance; pruning is against that bound); false when the ball needs more than 32 rows
-// (the caller falls back to the serial walk).  All 32 lanes must call with the same arguments.
-static __device__ __noinline__ bool warp_search_seeded(const GridDev& g, float px, float py, float pz, int seed_pos, Best& out) {
-    const GridLevel& L = g.lv[0];
-    const int lane = (int)(threadIdx.x & 31);
-    const float4 sq = __ldg(L.pts + seed_pos);
-    float bd = l2_simple(px, py, pz, sq.x, sq.y, sq.z);
-    int bi = __float_as_int(sq.w), bpos = seed_pos;
-    const float fx = (px - g.ox) * L.inv_h, fy = (py - g.oy) * L.inv_h, fz = (pz - g.oz) * L.inv_h;
-    const float mx = 0.01f + fabsf(fx) * 4e-6f, my = 0.01f + fabsf(fy) * 4e-6f, mz = 0.01f + fabsf(fz) * 4e-6f;
-    const float r = sqrtf(bd) * L.inv_h * 1.00001f;
-    if (!(r < 16.0f)) return false;
-    const int lx = min(max((int)floorf(fx - r - mx), 0), L.dx - 1), hx = min(max((int)floorf(fx + r + mx), 0), L.dx - 1);
-    const int ly = min(max((int)floorf(fy - r - my), 0), L.dy - 1), hy = min(max((int)floorf(fy + r + my), 0), L.dy - 1);
-    const int lz = min(max((int)floorf(fz - r - mz), 0), L.dz - 1), hz = min(max((int)floorf(fz + r + mz), 0), L.dz - 1);
-    const int ny = hy - ly + 1, nz = hz - lz + 1;
-    if (ny * nz > 32) return false;
-    if (lane < ny * nz)
-        ball_row<true>(L, ly + lane % ny, lz + lane / ny, fx, fy, fz, mx, my, mz, lx, hx, px, py, pz, true, bd, bi, bpos);
-    // arg-min over (distance, original index); a non-negative float orders like its bit pattern
-    const unsigned db = __float_as_uint(bd), m = __reduce_min_sync(0xffffffffu, db);
-    const int mi = __reduce_min_sync(0xffffffffu, db == m ? bi : 0x7fffffff);
-    const int src = __ffs(__ballot_sync(0xffffffffu, db == m && bi == mi)) - 1;
-    bpos = __shfl_sync(0xffffffffu, bpos, src);
-    const float4 q = __ldg(L.pts + bpos);
-    out.d2 = __uint_as_float(m); out.idx = mi; out.pos = bpos; out.qx = q.x; out.qy = q.y; out.qz = q.z;
-    return true;
-}
-
-// ball_collect() by the whole warp: one row per lane, the per-lane lists merged by five rounds of warp minimum.  Among
-// targets at exactly the same distance the order is by lane, not by scan position (the cache does not depend on it:
-// nn_search.cuh, "candidate cache").  All 32 lanes must call with the same arguments; all return the same lists.
-static __device__ __noinline__ void warp_collect(const GridLevel& L, float ox, float oy, float oz,
-                                                 float px, float py, float pz, float rho2max, Near5& out) {
-    const int lane = (int)(threadIdx.x & 31);
-    const unsigned kInf = 0x7f800000u;
-#pragma unroll
-    for (int k = 0; k <= kCacheCands; ++k) { out.d2[k] = __uint_as_float(kInf); out.pos[k] = -1; }
-    out.complete = 0;
-    const float fx = (px - ox) * L.inv_h, fy = (py - oy) * L.inv_h, fz = (pz - oz) * L.inv_h;
-    const float mx = 0.01f + fabsf(fx) * 4e-6f, my = 0.01f + fabsf(fy) * 4e-6f, mz = 0.01f + fabsf(fz) * 4e-6f;
-    const float r = sqrtf(rho2max) * L.inv_h * 1.00001f;
-    const int lx = min(max((int)floorf(fx - r - mx), 0), L.dx - 1), hx = min(max((int)floorf(fx + r + mx), 0), L.dx - 1);
-    const int ly = min(max((int)floorf(fy - r - my), 0), L.dy - 1), hy = min(max((int)floorf(fy + r + my), 0), L.dy - 1);
-    const int lz = min(max((int)floorf(fz - r - mz), 0), L.dz - 1), hz = min(max((int)floorf(fz + r + mz), 0), L.dz - 1);
-    if (hy - ly > 2 || hz - lz > 2) return;
-    const int ny = hy - ly + 1, nz = hz - lz + 1;
-    float D[kCacheCands + 1];
-    int P[kCacheCands + 1];
-#pragma unroll
-    for (int k = 0; k <= kCacheCands; ++k) { D[k] = __uint_as_float(kInf); P[k] = -1; }
-    if (lane < ny * nz) {
-        const int ky = ly + lane % ny, kz = lz + lane / ny;
-        const float bc = rho2max * L.inv_h2;
-        const float gy = axis_gap(fy, ky, my), gz = axis_gap(fz, kz, mz);
-        const float gyz = gy * gy + gz * gz;
-        if (gyz <= bc) {
-            const float w = sqrtf(bc - gyz) * 1.00001f;
-            const int lxr = max(lx, (int)floorf(fx - w - mx)), hxr = min(hx, (int)floorf(fx + w + mx));
-            if (lxr <= hxr) {
-                const uint32_t row = ((uint32_t)kz * (uint32_t)L.dy + (uint32_t)ky) * (uint32_t)L.dx;
-                const uint32_t s = __ldg(L.cell_start + row + lxr), e = __ldg(L.cell_start + row + hxr + 1);
-                for (uint32_t i = s; i < e; ++i) {
-                    const float4 q = __ldg(L.pts + i);
-                    float cd = l2_simple(px, py, pz, q.x, q.y, q.z);
-                    if (cd <= rho2max && cd < D[kCacheCands]) {
-                        int cp = (int)i;        // sorted insertion, ascending distance
-#pragma unroll
-                        for (int k = 0; k <= kCacheCands; ++k)
-                            if (cd < D[k]) { const float td = D[k]; const int tp = P[k]; D[k] = cd; P[k] = cp; cd = td; cp = tp; }
-                    }
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int k = 0; k <= kCacheCands; ++k) {
-        const unsigned h = __float_as_uint(D[0]), m = __reduce_min_sync(0xffffffffu, h);
-        const int src = __ffs(__ballot_sync(0xffffffffu, h == m)) - 1;
-        const int pp = __shfl_sync(0xffffffffu, P[0], src);
-        if (m != kInf) { out.d2[k] = __uint_as_float(m); out.pos[k] = pp; }
-        if (lane == src && m != kInf) {
-#pragma unroll
-            for (int j = 0; j < kCacheCands; ++j) { D[j] = D[j + 1]; P[j] = P[j + 1]; }
-            D[kCacheCands] = __uint_as_float(kInf); P[kCacheCands] = -1;
-        }
-    }
-    out.complete = 1;
-}
-
+// (A whole-warp version of the seeded search + collect for batches in which only a few queries miss their cache was
+// measured and rejected: profiles/r02ae_warp_search_ab.txt.)
 __device__ __forceinline__ Best nn_search(const GridDev& g, float px, float py, float pz) {
     return nn_search_seeded(g, px, py, pz, -1);
 }

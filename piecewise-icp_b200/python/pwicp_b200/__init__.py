@@ -35,7 +35,7 @@ class IcpResult(C.Structure):
     _fields_ = [("n_iter", C.c_int), ("conv_state", C.c_int), ("grid_blocks", C.c_int),
                 ("warps_per_block", C.c_int), ("group_batches", C.c_int), ("device_ms", C.c_float),
                 ("correspondences", C.c_longlong), ("kernel_ms", C.c_float), ("natural_iters", C.c_int), ("natural_state", C.c_int),
-                ("sort_ms", C.c_float), ("prepass_ms", C.c_float)]
+                ("sort_ms", C.c_float), ("prepass_ms", C.c_float), ("research_ms", C.c_float)]
 
 
 class PairParams(C.Structure):
@@ -290,7 +290,7 @@ class Context:
         out = {"T": T.reshape(4, 4), "n_iter": res.n_iter, "state": res.conv_state,
                "grid_blocks": res.grid_blocks, "warps_per_block": res.warps_per_block,
                "group_batches": res.group_batches, "natural_iters": res.natural_iters,
-               "natural_state": res.natural_state, "sort_ms": res.sort_ms, "prepass_ms": res.prepass_ms,
+               "natural_state": res.natural_state, "sort_ms": res.sort_ms, "prepass_ms": res.prepass_ms, "research_ms": res.research_ms,
                "device_ms": res.device_ms, "kernel_ms": res.kernel_ms, "correspondences": res.correspondences}
         if trace:
             out.update(mse=mse[:res.n_iter], T_trace=Ttr[:res.n_iter].reshape(-1, 4, 4),
@@ -328,7 +328,7 @@ class Context:
                 "device_ms": res.device_ms, "kernel_ms": res.kernel_ms, "correspondences": res.correspondences,
                 "grid_blocks": res.grid_blocks, "warps_per_block": res.warps_per_block,
                 "group_batches": res.group_batches, "natural_iters": res.natural_iters,
-                "natural_state": res.natural_state, "sort_ms": res.sort_ms, "prepass_ms": res.prepass_ms}
+                "natural_state": res.natural_state, "sort_ms": res.sort_ms, "prepass_ms": res.prepass_ms, "research_ms": res.research_ms}
 
     # -- outer iteration / loop
     def single_iteration(self, pp, state, prm=None, want_flags=True):

@@ -44,7 +44,7 @@ def timing(ctx, n, iters):
             best = (b, r, ctx.icp_profile(), ctx.icp_phase_profile())
     b, r, (us, srch), ph = best
     n2 = len(d["ct2"])
-    print(f"timing n={n2} iters={iters}: build {b:.3f} ms, loop {r['device_ms']:.3f} ms, kernel {r['kernel_ms']:.3f} ms "
+    print(f"timing n={n2} iters={iters}: build {b:.3f} ms, loop {r['device_ms']:.3f} ms, kernel {r['kernel_ms']:.3f} ms + iteration-1 search {r['research_ms']:.3f} ms "
           f"-> {r['correspondences'] / (b + r['device_ms']) / 1e6:.2f} G corr/s resident; kernel alg. "
           f"{48 * iters * n2 / r['kernel_ms'] / 1e6:.0f} GB/s", flush=True)
     print("  iteration us :", " ".join(f"{u:.1f}" for u in us[:8]), "... median of the rest", f"{np.median(us[8:]):.2f}" if len(us) > 8 else "")
