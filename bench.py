@@ -202,10 +202,16 @@ def config4_leg(P, synth, torch, dist, local_rank, rank, world):
     pp = P.PairParams(base["Res1"], base["Res2"], base["SVRes1"], base["SVRes2"], base["DTmin"])
     t_up, t_icp = [0.0], [0.0]
 
+    have_ref = [False, False]
+
     def upload(k, e):
+        # the reference epoch goes up once per context (inside the timed region), every other upload is the moving epoch
         d = dict(tgt); d.update(fixed); d.update(epochs[e])
         t0 = time.perf_counter()
-        ctxs[k].upload_pair(d)
+        if have_ref[k]:
+            ctxs[k].upload_source_side(d)
+        else:
+            ctxs[k].upload_pair(d); have_ref[k] = True
         t_up[0] += time.perf_counter() - t0
 
     def register(k):
@@ -222,6 +228,7 @@ def config4_leg(P, synth, torch, dist, local_rank, rank, world):
         dist.all_gather_into_tensor(allrec, rec)
         dist.barrier()
     t_up[0] = t_icp[0] = 0.0
+    have_ref[0] = have_ref[1] = False                # the warm-up's reference uploads do not count
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     dev_ms, corr, outer = 0.0, 0, 0
@@ -258,7 +265,8 @@ def config4_leg(P, synth, torch, dist, local_rank, rank, world):
         dist.all_reduce(m, op=dist.ReduceOp.MAX)
         t_up[0], t_icp[0], t_loop, t_loop_min, t_after_loop_max = float(m[0]), float(m[1]), float(m[2]), -float(m[3]), float(m[4])
     done = int((rec[:, 52] > 0).sum().item())
-    h2d_epoch = int(sum(v.nbytes for v in tgt.values()) + sum(v.nbytes for v in fixed.values()) +
+    h2d_ref = int(sum(v.nbytes for v in tgt.values()))
+    h2d_epoch = int(sum(v.nbytes for v in fixed.values()) +
                     sum(epochs[mine[0]][k].nbytes for k in ("ct2", "bp2", "patch_pts2", "cloud2")))
     # ground truth: epoch e was moved by motions[e]; the estimate maps it back
     e0 = mine[0]
@@ -272,13 +280,14 @@ def config4_leg(P, synth, torch, dist, local_rank, rank, world):
             "scaling": "strong", "n_gpus": world, "epochs_registered": done,
             "wall_s": wall, "epochs_per_s": C4_EPOCHS / wall, "device_ms_sum_over_ranks": dev_ms,
             "outer_iterations": outer, "correspondences": corr, "correspondences_per_s": corr / wall,
-            "h2d_bytes_per_epoch": h2d_epoch, "record_bytes_gathered": C4_EPOCHS * 384 * world,
+            "h2d_bytes_per_epoch": h2d_epoch, "h2d_bytes_reference_epoch_once_per_context": h2d_ref, "record_bytes_gathered": C4_EPOCHS * 384 * world,
             "slowest_rank_s": {"uploads_and_grid_builds": t_up[0], "outer_loops": t_icp[0], "epoch_loop": t_loop,
                                "epoch_loop_fastest_rank": t_loop_min,
                                "after_the_loop_max_over_ranks": t_after_loop_max},
-            "upload_gbs_per_gpu_incl_grid_builds": h2d_epoch * len(mine) / max(t_up[0], 1e-9) / 1e9,
-            "timed_region": "barrier | per epoch: upload of the pair from pinned host memory (pwicp_target_upload, "
-                            "pwicp_clouds_upload, pwicp_source_upload: three device grid builds) + pwicp_piecewise_icp, the "
+            "upload_gbs_per_gpu_incl_grid_builds": (h2d_epoch * len(mine) + h2d_ref * min(2, len(mine))) / max(t_up[0], 1e-9) / 1e9,
+            "timed_region": "barrier | the reference epoch once per context (pwicp_target_upload + cloud1: two device grid "
+                            "builds) | per epoch: upload of the moving epoch from pinned host memory (pwicp_source_upload, "
+                            "pwicp_clouds_upload with the resident cloud1) + pwicp_piecewise_icp, the "
                             "upload of the next epoch overlapping the registration of the current one (two contexts per rank, "
                             "a loader thread) | NCCL all-gather of the records | sync; wall clock, max over ranks",
             "sharding": "epoch e on rank e % world, as PiecewiseICP_4D_shard ((step - 1) % world == rank)",

@@ -78,7 +78,9 @@ int pwicp_target_rebuild(pwicp_ctx* ctx);
 int pwicp_source_upload(pwicp_ctx* ctx, const float* ct_xyz, const float* bp_xyz,
                         const float* bp_std, const int* patch_off, const float* patch_xyz, int n2);
 /* the pre-processed full clouds cloud1 / cloud2 of Piecewise_ICP (src/Registration.cpp:618);
- * cloud1 gets its own grid (replaces the tree build of src/CommonFunc.cpp:269-273). */
+ * cloud1 gets its own grid (replaces the tree build of src/CommonFunc.cpp:269-273).
+ * cloud1 = NULL keeps the resident cloud1 and its grid (a 4D series registers every epoch against the same reference
+ * epoch, src/Registration.cpp:95-97: the reference side is uploaded once, pwicp_target_upload likewise). */
 int pwicp_clouds_upload(pwicp_ctx* ctx, const float* cloud1, int m1, const float* cloud2, int m2);
 /* current (transformed) source-side data back to the host; any pointer may be NULL */
 int pwicp_source_download(pwicp_ctx* ctx, float* cloud2, float* ct_xyz, float* bp_xyz, float* patch_xyz);

@@ -128,6 +128,7 @@ int pwicp_ctx_create(int device, pwicp_ctx** out) {
         cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
         cudaEventCreate(&c->ev2) != cudaSuccess || cudaEventCreate(&c->ev3) != cudaSuccess ||
         cudaEventCreate(&c->ev4) != cudaSuccess || cudaEventCreate(&c->ev5) != cudaSuccess ||
+        cudaEventCreate(&c->ev6) != cudaSuccess || cudaEventCreate(&c->ev7) != cudaSuccess ||
         cudaEventCreate(&c->ev_o0) != cudaSuccess || cudaEventCreate(&c->ev_o1) != cudaSuccess) {
         delete c; set_error(nullptr, "stream/event creation failed"); return PWICP_ERR_CUDA;
     }
@@ -147,7 +148,7 @@ void pwicp_ctx_destroy(pwicp_ctx* p) {
                       &c->scratch_b, &c->scratch_c, &c->scratch_d, &c->flags, &c->pos, &c->l2flush, &c->outer_state};
     for (DevBuf* b : bufs) b->release();
     if (c->pinned) cudaFreeHost(c->pinned);
-    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2); cudaEventDestroy(c->ev3); cudaEventDestroy(c->ev4); cudaEventDestroy(c->ev5);
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2); cudaEventDestroy(c->ev3); cudaEventDestroy(c->ev4); cudaEventDestroy(c->ev5); cudaEventDestroy(c->ev6); cudaEventDestroy(c->ev7);
     cudaEventDestroy(c->ev_o0); cudaEventDestroy(c->ev_o1);
     cudaStreamDestroy(c->stream);
     if (c->copy_stream) { cudaStreamDestroy(c->copy_stream); for (auto& e : c->copy_ev) if (e) cudaEventDestroy(e); }
@@ -304,11 +305,18 @@ int pwicp_source_upload(pwicp_ctx* p, const float* ct_xyz, const float* bp_xyz, 
 
 int pwicp_clouds_upload(pwicp_ctx* p, const float* cloud1, int m1, const float* cloud2, int m2) {
     Ctx* ctx = reinterpret_cast<Ctx*>(p);
-    if (!ctx || m1 < 1 || m2 < 1 || !cloud1 || !cloud2) { set_error(ctx, "clouds_upload: bad arguments"); return PWICP_ERR_ARG; }
+    if (!ctx || m2 < 1 || !cloud2 || (cloud1 && m1 < 1)) { set_error(ctx, "clouds_upload: bad arguments"); return PWICP_ERR_ARG; }
     PW_CUDA(cudaSetDevice(ctx->device));
-    ctx->m1 = ctx->m2 = 0;
-    PW_TRY(upload_checked(ctx, ctx->scratch_a, cloud1, (size_t)3 * m1, "cloud1"));
-    PW_TRY(grid_build(ctx, ctx->c1, ctx->scratch_a.as<float>(), m1));
+    if (!cloud1) {
+        // the reference epoch of a series stays resident: cloud1 and its grid are kept, only cloud2 is replaced
+        if (ctx->m1 < 1 || !ctx->c1.dev.nlevels) { set_error(ctx, "clouds_upload: no resident cloud1 to keep"); return PWICP_ERR_ARG; }
+        m1 = ctx->m1;
+        ctx->m2 = 0;
+    } else {
+        ctx->m1 = ctx->m2 = 0;
+        PW_TRY(upload_checked(ctx, ctx->scratch_a, cloud1, (size_t)3 * m1, "cloud1"));
+        PW_TRY(grid_build(ctx, ctx->c1, ctx->scratch_a.as<float>(), m1));
+    }
     PW_TRY(reset_seeds(ctx));
     PW_TRY(upload_checked(ctx, ctx->cloud2, cloud2, (size_t)3 * m2, "cloud2"));
     ctx->m1 = m1; ctx->m2 = m2;
@@ -481,10 +489,13 @@ int pwicp_icp_p2plane(pwicp_ctx* p, const float* tgt_xyz, const float* tgt_nrm, 
     PW_TRY(finite_accumulate_dev(ctx, ctx->scratch_a.as<float>(), (size_t)3 * n2, flag));
     ctx->icp_seed_valid = false;
     PW_TRY(icp_expand_source(ctx, ctx->scratch_a.as<float>(), n2));
+    // a non-finite source coordinate would send the search to an invalid address: the verdict on the source is read
+    // before the loop is enqueued (the normals are still travelling; theirs only poison arithmetic and is read last)
+    PW_CUDA(cudaMemcpyAsync(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PW_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (bad) { cudaStreamSynchronize(ctx->copy_stream); set_error(ctx, "icp_p2plane: non-finite value in input"); return PWICP_ERR_NONFINITE; }
     ctx->n1 = n1;
     ctx->aux_deferred = true; ctx->aux_deferred_n1 = n1; ctx->aux_deferred_flag = flag;
-    // the inner loop is enqueued without a host round trip; the verdict on the source and the normals is read with its
-    // result (non-finite values poison the arithmetic, never an address)
     int st = pwicp_icp_run(p, prm, T16, res, nullptr, nullptr, nullptr);
     if (ctx->aux_deferred) { const int s2 = finish_deferred_aux(ctx); if (st == PWICP_OK) st = s2; }   // the loop failed before it got there
     if (st != PWICP_OK) { cudaStreamSynchronize(ctx->copy_stream); return st; }

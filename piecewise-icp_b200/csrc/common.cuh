@@ -83,7 +83,7 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;          // host-buffer calls: uploads overlap the grid build
     cudaEvent_t copy_ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev4 = nullptr, ev5 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev4 = nullptr, ev5 = nullptr, ev6 = nullptr, ev7 = nullptr;
     cudaEvent_t ev_o0 = nullptr, ev_o1 = nullptr;   // outer iteration
     std::string err;
     float last_ms = 0.f;
@@ -120,6 +120,7 @@ struct Ctx {
     DevBuf ct_seed, bp_seed, pp_seed, ct_order;
     bool ct_order_valid = false;
     int n_icp = 0;
+    int icp_nsplit = 0;                          // stand-alone search passes of the last inner loop (icp_enqueue)
     bool icp_attr_set = false;                   // kernel attributes of the persistent kernel set for this device
     int icp_prof_max_iter = 0;
     int icp_prof_iters = 0;                      // pwicp_icp_profile: iterations of the last run, offsets into icp_partials

@@ -41,12 +41,16 @@
 #ifndef PWICP_TIE_CELLS
 #define PWICP_TIE_CELLS 0.0005f
 #endif
+#ifndef PWICP_RESEARCH_ALWAYS_BLOCK
+#define PWICP_RESEARCH_ALWAYS_BLOCK 1     // icp_research_kernel: one code path for fresh and stale seeds (A/B switch)
+#endif
 #ifndef PWICP_BUILD_STEP_CELLS
 #define PWICP_BUILD_STEP_CELLS 1e30f
 #endif
 
 namespace pwicp {
 
+constexpr int kSplitMinPoints = 500000;   // icp_enqueue: source sets from this size on run iteration 1's search as its own kernel
 constexpr int kMoreBit = 0x40000000;      // in cq[].w: further cached candidates in cmore[]
 constexpr float kPadMargin = 1e18f;       // margin of a padding point: its square is finite, no step ever uses it up
 
@@ -839,11 +843,20 @@ icp_research_kernel(const IcpArgs a) {
     if (i >= n) { a.work[i] = make_float4(x, y, z, kPadMargin); return; }
     const float step = (fabsf(x - p.x) + fabsf(y - p.y)) + fabsf(z - p.z);
     const float tie = fminf(fmaxf(a.tie_step * step, a.tie), a.collect);
+    // a query whose cache still covers it (second pass, before iteration 2: most of them) only moves; one with further
+    // cached candidates is left to the loop (icp_slow_path, (1))
+    const float margin = __fmaf_rn(step, -1.00001f, p.w);
+    const float4 q0 = a.cq[i];
+    if ((__float_as_int(q0.w) & kMoreBit) ||
+        (margin > 0.f && l2_simple(x, y, z, q0.x, q0.y, q0.z) * 1.00003f < margin * margin)) {
+        a.work[i] = make_float4(x, y, z, margin);
+        return;
+    }
     {
         const unsigned m = __activemask();
-        if ((int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(a.searched + 1, __popc(m));
+        if ((int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(a.searched + a.it_begin, __popc(m));
     }
-    const Best bb = nn_search_seeded<false>(a.g, x, y, z, __float_as_int(a.cq[i].w) & ~kMoreBit);
+    const Best bb = nn_search_seeded<false>(a.g, x, y, z, __float_as_int(q0.w), PWICP_RESEARCH_ALWAYS_BLOCK != 0);
     const float4 nq = __ldg(a.aux + bb.pos);
     int o1 = bb.pos, o2 = bb.pos, o3 = bb.pos, k = 0;
     float rho = 0.f;
@@ -1025,24 +1038,28 @@ int icp_enqueue(Ctx* ctx, const pwicp_icp_params& prm, int n, const int* n_dev, 
     // Two launches with the search of iteration 1 between them (icp_research_kernel) -- or one, when there is no
     // iteration 1 or the A/B switch says so.  (Cooperative launches: every CTA must be resident, the CTA sums are
     // exchanged by polling.)
-    static const bool split_env = [] { const char* e = getenv("PWICP_SPLIT_ITER1"); return !e || atoi(e) != 0; }();
-    const bool split = split_env && prm.max_iter > 1;
+    // PWICP_SPLIT_ITER1 = number of leading iterations whose search runs as its own kernel (A/B: 0, 1, 2).  One: a second
+    // pass before iteration 2 -- 1.5 % of the queries search there -- loses (1M: iteration 2 105 -> 209 us and weaker
+    // caches afterwards, profiles/r02ak_split2_ab.txt)
+    static const int split_env = [] { const char* e = getenv("PWICP_SPLIT_ITER1"); return e ? atoi(e) : 1; }();
+    // worth it for large source sets only: below ~half a million points the extra launches cost more than the
+    // occupancy gains (outer loop at 300k patches: 4.86 -> 5.06 ms with the split, profiles/r02af_split_launch_ab.txt)
+    const int nsplit = (n >= kSplitMinPoints) ? std::max(0, std::min(std::min(split_env, 2), prm.max_iter - 1)) : 0;     // searches taken out: before iterations 1 .. nsplit
     void* kargs[] = {(void*)&a};
-    a.it_begin = 0; a.it_end = split ? 1 : prm.max_iter;
-    PW_CUDA(cudaEventRecord(ctx->ev2, ctx->stream));
-    PW_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kIcpThreads), kargs, smem, ctx->stream));
-    ctx->launches++;
-    PW_CUDA(cudaEventRecord(ctx->ev4, ctx->stream));
-    if (split) {
-        icp_research_kernel<<<(n_pad + 255) / 256, 256, 0, ctx->stream>>>(a);
-        PW_CUDA(cudaEventRecord(ctx->ev5, ctx->stream));
-        a.it_begin = 1; a.it_end = prm.max_iter;
+    cudaEvent_t ev_k[4] = {ctx->ev2, ctx->ev5, ctx->ev7, nullptr}, ev_r[3] = {ctx->ev4, ctx->ev6, nullptr};
+    for (int part = 0; part <= nsplit; ++part) {
+        a.it_begin = part; a.it_end = (part < nsplit) ? part + 1 : prm.max_iter;
+        if (part > 0) {
+            icp_research_kernel<<<(n_pad + 255) / 256, 256, 0, ctx->stream>>>(a);           // the search of iteration `part`
+            ctx->launches++;
+        }
+        PW_CUDA(cudaEventRecord(ev_k[part], ctx->stream));
         PW_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kIcpThreads), kargs, smem, ctx->stream));
-        ctx->launches += 2;
-    } else {
-        PW_CUDA(cudaEventRecord(ctx->ev5, ctx->stream));
+        ctx->launches++;
+        if (part < nsplit) PW_CUDA(cudaEventRecord(ev_r[part], ctx->stream));
     }
     PW_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->icp_nsplit = nsplit;
     ctx->icp_prof_max_iter = prm.max_iter;
     ctx->icp_prof_off_searched = bytes_part; ctx->icp_prof_off_ns = off_ns;
     if (L) { L->grid = grid; L->out = ob; L->max_iter = prm.max_iter; }
@@ -1059,12 +1076,17 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     struct { float T[16]; int st[4]; } host;
     PW_CUDA(cudaMemcpyAsync(&host, ob, sizeof(host), cudaMemcpyDeviceToHost, ctx->stream));
     PW_CUDA(cudaStreamSynchronize(ctx->stream));
-    float ms = 0.f, kms = 0.f, kms2 = 0.f, rms = 0.f, sms = 0.f, pms = 0.f;
+    float ms = 0.f, kms = 0.f, rms = 0.f, sms = 0.f, pms = 0.f;
     PW_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-    PW_CUDA(cudaEventElapsedTime(&kms, ctx->ev2, ctx->ev4));     // the persistent kernel: first launch ...
-    PW_CUDA(cudaEventElapsedTime(&kms2, ctx->ev5, ctx->ev1));    // ... and second
-    PW_CUDA(cudaEventElapsedTime(&rms, ctx->ev4, ctx->ev5));     // the search of iteration 1 between them
-    kms += kms2;
+    {   // the persistent kernel (its launches summed) and the stand-alone searches between them
+        cudaEvent_t ev_k[3] = {ctx->ev2, ctx->ev5, ctx->ev7}, ev_r[3] = {ctx->ev4, ctx->ev6, ctx->ev1};
+        for (int part = 0; part <= ctx->icp_nsplit; ++part) {
+            float t = 0.f;
+            PW_CUDA(cudaEventElapsedTime(&t, ev_k[part], part < ctx->icp_nsplit ? ev_r[part] : ctx->ev1));
+            kms += t;
+            if (part < ctx->icp_nsplit) { PW_CUDA(cudaEventElapsedTime(&t, ev_r[part], ev_k[part + 1])); rms += t; }
+        }
+    }
     PW_CUDA(cudaEventElapsedTime(&sms, ctx->ev0, ctx->ev3));
     PW_CUDA(cudaEventElapsedTime(&pms, ctx->ev3, ctx->ev2));
     ctx->last_ms = ms;

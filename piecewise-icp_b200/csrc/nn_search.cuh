@@ -43,9 +43,6 @@ namespace pwicp {
 #ifndef PWICP_RESEED_CELLS2_LOOP
 #define PWICP_RESEED_CELLS2_LOOP 1.0f
 #endif
-#ifndef PWICP_SKIP_DONE_BLOCK
-#define PWICP_SKIP_DONE_BLOCK 1  // a ball scan that follows a block scan leaves the block's cells out (A/B switch)
-#endif
 #ifndef PWICP_BLOCK_WIDE
 #define PWICP_BLOCK_WIDE 0       // stand-alone kernels: candidates of the block scan four at a time (A/B switch)
 #endif
@@ -104,20 +101,12 @@ __device__ __forceinline__ void scan_range(const float4* __restrict__ pts, uint3
     }
 }
 
-// Cells of the 3x3x3 block a query has already been through (block_scan): a later ball scan skips them.  Every cell of
-// the block is settled -- scanned, or cut off by a chord of a bound that was no smaller than the present one.
-struct DoneBlock {
-    int x0, x1, y0, y1, z0, z1;      // y0 > y1: nothing has been scanned
-};
-__device__ __forceinline__ DoneBlock no_block() { return DoneBlock{0, -1, 0, -1, 0, -1}; }
-
-// One cell row (ky, kz) of the ball: chord test against the CURRENT best, then a range scan (minus the cells of the
-// row that `done` covers).
+// One cell row (ky, kz) of the ball: chord test against the CURRENT best, then a range scan.
 template <bool kWide>
 __device__ __forceinline__ void ball_row(const GridLevel& L, int ky, int kz, float fx, float fy, float fz,
                                          float mx, float my, float mz, int lx, int hx,
                                          float px, float py, float pz, bool level0,
-                                         float& bd, int& bi, int& bpos, const DoneBlock& done = DoneBlock{0, -1, 0, -1, 0, -1}) {
+                                         float& bd, int& bi, int& bpos) {
     const float gy = axis_gap(fy, ky, my), gz = axis_gap(fz, kz, mz);
     const float gyz = gy * gy + gz * gz, bc = bd * L.inv_h2;
     if (gyz > bc) return;                                        // row entirely outside the ball
@@ -125,20 +114,65 @@ __device__ __forceinline__ void ball_row(const GridLevel& L, int ky, int kz, flo
     const int lxr = max(lx, (int)floorf(fx - w - mx)), hxr = min(hx, (int)floorf(fx + w + mx));
     if (lxr > hxr) return;
     const uint32_t row = ((uint32_t)kz * (uint32_t)L.dy + (uint32_t)ky) * (uint32_t)L.dx;
-    if (ky >= done.y0 && ky <= done.y1 && kz >= done.z0 && kz <= done.z1) {
-        const int hl = min(hxr, done.x0 - 1), lr = max(lxr, done.x1 + 1);
-        if (lxr <= hl) {
-            const uint32_t s = __ldg(L.cell_start + row + lxr), e = __ldg(L.cell_start + row + hl + 1);
-            scan_range<kWide>(L.pts, s, e, px, py, pz, level0, bd, bi, bpos);
-        }
-        if (lr <= hxr) {
-            const uint32_t s = __ldg(L.cell_start + row + lr), e = __ldg(L.cell_start + row + hxr + 1);
-            scan_range<kWide>(L.pts, s, e, px, py, pz, level0, bd, bi, bpos);
-        }
-        return;
-    }
     const uint32_t s = __ldg(L.cell_start + row + lxr), e = __ldg(L.cell_start + row + hxr + 1);
     scan_range<kWide>(L.pts, s, e, px, py, pz, level0, bd, bi, bpos);
+}
+
+// Up to 3 x 3 cell rows in one flattened pass (stand-alone search kernels; PWICP_FLAT_ROWS).  The nested walk -- row
+// after row, every lane with its own trip counts -- keeps 11 of 32 lanes busy in the candidate loop and is issue-bound
+// (ncu: profiles/r02ac_ncu_nn_kernel_bw.txt).  Here every lane (1) tests all its rows against the bound it has --
+// gap, chord, and the cell_start loads of all surviving rows in flight together, one round trip instead of up to nine --
+// (2) queues the non-empty ranges in a small local array and (3) runs ONE candidate loop over the queue: the warp's
+// trip count is the largest per-lane candidate total instead of the sum of the per-row maxima.  The chords are cut
+// against the incoming bound only (it is not tightened between rows), which is still exact: a row or cell is left
+// out only when its lower bound exceeds an upper bound of the NN distance.  (cy, cz): a row to leave out (already
+// scanned), or outside the box for none.
+// Measured (profiles/r02ag_flat_rows_ab.txt): loses 5-8 % -- without the bound tightening from row to row the lanes look
+// at more candidates than the flattening saves.  Off.
+#ifndef PWICP_FLAT_ROWS
+#define PWICP_FLAT_ROWS 0
+#endif
+__device__ __forceinline__ void rows_flat(const GridLevel& L, float fx, float fy, float fz, float mx, float my, float mz,
+                                          int lx, int hx, int ly, int hy, int lz, int hz, int cy, int cz,
+                                          float px, float py, float pz, float& bd, int& bi, int& bpos) {
+    uint32_t rs[9], re[9];
+    const float bc = bd * L.inv_h2;
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+        rs[r] = 0; re[r] = 0;
+        const int ky = ly + r % 3, kz = lz + r / 3;
+        if (ky <= hy && kz <= hz && !(ky == cy && kz == cz)) {
+            const float gy = axis_gap(fy, ky, my), gz = axis_gap(fz, kz, mz);
+            const float gyz = gy * gy + gz * gz;
+            if (gyz <= bc) {
+                const float w = sqrtf(bc - gyz) * 1.00001f;
+                const int lxr = max(lx, (int)floorf(fx - w - mx)), hxr = min(hx, (int)floorf(fx + w + mx));
+                if (lxr <= hxr) {
+                    const uint32_t row = ((uint32_t)kz * (uint32_t)L.dy + (uint32_t)ky) * (uint32_t)L.dx;
+                    rs[r] = __ldg(L.cell_start + row + lxr); re[r] = __ldg(L.cell_start + row + hxr + 1);
+                }
+            }
+        }
+    }
+    uint2 queue[9];
+    int nr = 0;
+#pragma unroll
+    for (int r = 0; r < 9; ++r)
+        if (re[r] > rs[r]) queue[nr++] = make_uint2(rs[r], re[r]);
+    int r = 0;
+    uint32_t i = 0, e = 0;
+    for (;;) {
+        if (i >= e) {
+            if (r >= nr) break;
+            const uint2 t = queue[r++];
+            i = t.x; e = t.y;
+        }
+        const float4 q = __ldg(L.pts + i);
+        const float d = l2_simple(px, py, pz, q.x, q.y, q.z);
+        const int id = __float_as_int(q.w);
+        if (d < bd || (d == bd && id < bi)) { bd = d; bi = id; bpos = (int)i; }
+        ++i;
+    }
 }
 
 // Large balls (more than 3x3 rows): rows nearest-first, as square rings in y/z around the home
@@ -150,10 +184,10 @@ __device__ __forceinline__ void ball_scan_rings(const GridLevel& L, float fx, fl
                                                     float mx, float my, float mz,
                                                     int lx, int hx, int ly, int hy, int lz, int hz,
                                                     float px, float py, float pz, bool level0,
-                                                    float& bd, int& bi, int& bpos, const DoneBlock& done) {
+                                                    float& bd, int& bi, int& bpos) {
     const int cy = min(max((int)floorf(fy), ly), hy), cz = min(max((int)floorf(fz), lz), hz);
     const int R = max(max(cy - ly, hy - cy), max(cz - lz, hz - cz));
-    ball_row<kWide>(L, cy, cz, fx, fy, fz, mx, my, mz, lx, hx, px, py, pz, level0, bd, bi, bpos, done);
+    ball_row<kWide>(L, cy, cz, fx, fy, fz, mx, my, mz, lx, hx, px, py, pz, level0, bd, bi, bpos);
     for (int t = 1; t <= R; ++t) {
         // every row of ring t (and of all later rings) is at least this far away in y or z
         const float g = fminf(fminf(axis_gap(fy, cy - t, my), axis_gap(fy, cy + t, my)),
@@ -164,7 +198,7 @@ __device__ __forceinline__ void ball_scan_rings(const GridLevel& L, float fx, fl
             const bool full = (kz == cz - t || kz == cz + t);
             for (int ky = y0; ky <= y1; ++ky) {
                 if (!full && ky != cy - t && ky != cy + t) continue;
-                ball_row<kWide>(L, ky, kz, fx, fy, fz, mx, my, mz, lx, hx, px, py, pz, level0, bd, bi, bpos, done);
+                ball_row<kWide>(L, ky, kz, fx, fy, fz, mx, my, mz, lx, hx, px, py, pz, level0, bd, bi, bpos);
             }
         }
     }
@@ -175,7 +209,7 @@ static __device__ __noinline__ void ball_scan_rings_ool(const GridLevel& L, floa
                                                         int lx, int hx, int ly, int hy, int lz, int hz,
                                                         float px, float py, float pz, bool level0,
                                                         float& bd, int& bi, int& bpos) {
-    ball_scan_rings<true>(L, fx, fy, fz, mx, my, mz, lx, hx, ly, hy, lz, hz, px, py, pz, level0, bd, bi, bpos, no_block());
+    ball_scan_rings<true>(L, fx, fy, fz, mx, my, mz, lx, hx, ly, hy, lz, hz, px, py, pz, level0, bd, bi, bpos);
 }
 
 // Scans every cell of level L that the closed ball of radius sqrt(bd) around p touches.
@@ -185,7 +219,7 @@ static __device__ __noinline__ void ball_scan_rings_ool(const GridLevel& L, floa
 template <bool kLean>
 __device__ __forceinline__ void ball_scan(const GridLevel& L, float ox, float oy, float oz,
                                           float px, float py, float pz, bool level0,
-                                          float& bd, int& bi, int& bpos, const DoneBlock& done = DoneBlock{0, -1, 0, -1, 0, -1}) {
+                                          float& bd, int& bi, int& bpos) {
     const float fx = (px - ox) * L.inv_h, fy = (py - oy) * L.inv_h, fz = (pz - oz) * L.inv_h;
     const float mx = 0.01f + fabsf(fx) * 4e-6f, my = 0.01f + fabsf(fy) * 4e-6f, mz = 0.01f + fabsf(fz) * 4e-6f;
     // radius in cell units, rounded up generously (float sqrt/mul errors are ~1e-7 relative)
@@ -197,15 +231,17 @@ __device__ __forceinline__ void ball_scan(const GridLevel& L, float ox, float oy
         // one to nine rows (the common case of a seeded query): plain nested loops.  Two flattened
         // variants (one state-machine loop; row list in shared memory + one candidate loop) were
         // measured and were not faster: the batch time is a chain of dependent L2 round trips.
-        for (int kz = lz; kz <= hz; ++kz)
-            for (int ky = ly; ky <= hy; ++ky) {
-                if (kLean) ball_row<true>(L, ky, kz, fx, fy, fz, mx, my, mz, lx, hx, px, py, pz, level0, bd, bi, bpos);
-                else ball_row<false>(L, ky, kz, fx, fy, fz, mx, my, mz, lx, hx, px, py, pz, level0, bd, bi, bpos, done);
-            }
+        if (!kLean && PWICP_FLAT_ROWS && level0) {
+            rows_flat(L, fx, fy, fz, mx, my, mz, lx, hx, ly, hy, lz, hz, -1, -1, px, py, pz, bd, bi, bpos);
+        } else {
+            for (int kz = lz; kz <= hz; ++kz)
+                for (int ky = ly; ky <= hy; ++ky)
+                    ball_row<kLean>(L, ky, kz, fx, fy, fz, mx, my, mz, lx, hx, px, py, pz, level0, bd, bi, bpos);
+        }
     } else if (kLean) {
         ball_scan_rings_ool(L, fx, fy, fz, mx, my, mz, lx, hx, ly, hy, lz, hz, px, py, pz, level0, bd, bi, bpos);
     } else {
-        ball_scan_rings<false>(L, fx, fy, fz, mx, my, mz, lx, hx, ly, hy, lz, hz, px, py, pz, level0, bd, bi, bpos, done);
+        ball_scan_rings<false>(L, fx, fy, fz, mx, my, mz, lx, hx, ly, hy, lz, hz, px, py, pz, level0, bd, bi, bpos);
     }
 }
 
@@ -268,7 +304,7 @@ static __device__ __noinline__ void find_seed_ool(const GridDev& g, float px, fl
 // of the home cell as a seed and then scanned the ball through it, home cell included a second time.)  Returns true
 // when the closed ball of the best distance lies inside the block (faces on the grid boundary are open: there is no
 // target beyond them), i.e. the answer is exact; else bd / bi / bpos hold a valid upper bound (or nothing).
-template <bool kWide>
+template <bool kWide, bool kFlat = false>
 __device__ __forceinline__ bool block_scan(const GridLevel& L, float ox, float oy, float oz, float px, float py, float pz,
                                            float& bd, int& bi, int& bpos) {
     const float fx = (px - ox) * L.inv_h, fy = (py - oy) * L.inv_h, fz = (pz - oz) * L.inv_h;
@@ -278,23 +314,20 @@ __device__ __forceinline__ bool block_scan(const GridLevel& L, float ox, float o
     const int x0 = max(cx - 1, 0), x1 = min(cx + 1, L.dx - 1);
     const int y0 = max(cy - 1, 0), y1 = min(cy + 1, L.dy - 1), z0 = max(cz - 1, 0), z1 = min(cz + 1, L.dz - 1);
     ball_row<kWide>(L, cy, cz, fx, fy, fz, mx, my, mz, x0, x1, px, py, pz, true, bd, bi, bpos);
-    for (int kz = z0; kz <= z1; ++kz)
-        for (int ky = y0; ky <= y1; ++ky) {
-            if (ky == cy && kz == cz) continue;
-            ball_row<kWide>(L, ky, kz, fx, fy, fz, mx, my, mz, x0, x1, px, py, pz, true, bd, bi, bpos);
-        }
+    if (kFlat) {
+        rows_flat(L, fx, fy, fz, mx, my, mz, x0, x1, y0, y1, z0, z1, cy, cz, px, py, pz, bd, bi, bpos);
+    } else {
+        for (int kz = z0; kz <= z1; ++kz)
+            for (int ky = y0; ky <= y1; ++ky) {
+                if (ky == cy && kz == cz) continue;
+                ball_row<kWide>(L, ky, kz, fx, fy, fz, mx, my, mz, x0, x1, px, py, pz, true, bd, bi, bpos);
+            }
+    }
     if (bpos < 0) return false;
     const float r = sqrtf(bd) * L.inv_h * 1.00001f;
     return (x0 == 0 || fx - r - mx >= (float)x0) && (x1 == L.dx - 1 || fx + r + mx < (float)(x1 + 1)) &&
            (y0 == 0 || fy - r - my >= (float)y0) && (y1 == L.dy - 1 || fy + r + my < (float)(y1 + 1)) &&
            (z0 == 0 || fz - r - mz >= (float)z0) && (z1 == L.dz - 1 || fz + r + mz < (float)(z1 + 1));
-}
-
-// the cells block_scan() goes through for this query (level 0)
-__device__ __forceinline__ DoneBlock block_extent(const GridLevel& L, float ox, float oy, float oz, float px, float py, float pz) {
-    const int cx = min(max((int)floorf((px - ox) * L.inv_h), 0), L.dx - 1), cy = min(max((int)floorf((py - oy) * L.inv_h), 0), L.dy - 1),
-              cz = min(max((int)floorf((pz - oz) * L.inv_h), 0), L.dz - 1);
-    return DoneBlock{max(cx - 1, 0), min(cx + 1, L.dx - 1), max(cy - 1, 0), min(cy + 1, L.dy - 1), max(cz - 1, 0), min(cz + 1, L.dz - 1)};
 }
 
 static __device__ __noinline__ bool block_scan_ool(const GridLevel& L, float ox, float oy, float oz, float px, float py,
@@ -306,10 +339,11 @@ static __device__ __noinline__ bool block_scan_ool(const GridLevel& L, float ox,
 // (normally the previous match); -1: none.
 // kLean = true (inner ICP loop): the rare paths are kept out of line.
 template <bool kLean = false>
-__device__ __forceinline__ Best nn_search_seeded(const GridDev& g, float px, float py, float pz, int seed_pos) {
+__device__ __forceinline__ Best nn_search_seeded(const GridDev& g, float px, float py, float pz, int seed_pos,
+                                                 bool always_block = false) {
     float bd = __int_as_float(0x7f800000);
     int bi = 0x7fffffff, bpos = -1;
-    bool done = false, blocked = false;
+    bool done = false;
     if (seed_pos >= 0) {
         const float4 q = __ldg(g.lv[0].pts + seed_pos);
         bd = l2_simple(px, py, pz, q.x, q.y, q.z);
@@ -319,10 +353,11 @@ __device__ __forceinline__ Best nn_search_seeded(const GridDev& g, float px, flo
     // no seed, or a stale one (the cloud moved by a good part of a cell since it was recorded: the ball through it
     // would be large): the block around the home cell, with the seed as the first bound
     const float stale = kLean ? PWICP_RESEED_CELLS2_LOOP : PWICP_RESEED_CELLS2;
-    if (seed_pos < 0 || bd * g.lv[0].inv_h2 > stale) {
+    // always_block: every lane takes the block scan, the seed only bounds it (callers whose seeds are a mix of fresh
+    // and stale ones: two code paths in one warp run one after the other)
+    if (seed_pos < 0 || always_block || bd * g.lv[0].inv_h2 > stale) {
         done = kLean ? block_scan_ool(g.lv[0], g.ox, g.oy, g.oz, px, py, pz, bd, bi, bpos)
-                     : block_scan<PWICP_BLOCK_WIDE != 0>(g.lv[0], g.ox, g.oy, g.oz, px, py, pz, bd, bi, bpos);
-        blocked = true;
+                     : block_scan<PWICP_BLOCK_WIDE != 0, PWICP_FLAT_ROWS != 0>(g.lv[0], g.ox, g.oy, g.oz, px, py, pz, bd, bi, bpos);
         if (!done && bpos < 0) {             // empty block: a sampled point of the first non-empty coarser home cell
             if (kLean) find_seed_ool(g, px, py, pz, bd, bi, bpos); else find_seed(g, px, py, pz, bd, bi, bpos);
         }
@@ -332,13 +367,7 @@ __device__ __forceinline__ Best nn_search_seeded(const GridDev& g, float px, flo
         int l = 0;
         float r = sqrtf(bd) * g.lv[0].inv_h;
         while (l < g.nlevels - 1 && r > kBallMaxCells) { ++l; r *= (1.0f / kLevelFactor); }
-        // the block's cells are settled: the ball scan on the same level leaves them out (stand-alone kernels; in the
-        // register-capped inner loop a block scan is followed by a ball scan only for queries far from the surface)
-        if (kLean) ball_scan<true>(g.lv[l], g.ox, g.oy, g.oz, px, py, pz, l == 0, bd, bi, bpos);
-        else {
-            const DoneBlock db = (blocked && l == 0 && PWICP_SKIP_DONE_BLOCK) ? block_extent(g.lv[0], g.ox, g.oy, g.oz, px, py, pz) : no_block();
-            ball_scan<false>(g.lv[l], g.ox, g.oy, g.oz, px, py, pz, l == 0, bd, bi, bpos, db);
-        }
+        ball_scan<kLean>(g.lv[l], g.ox, g.oy, g.oz, px, py, pz, l == 0, bd, bi, bpos);
     }
 
     Best b;
@@ -557,6 +586,25 @@ static __device__ __noinline__ Near5 ball_collect(const GridLevel& L, float ox, 
 #pragma unroll
     for (int k = 0; k <= kCacheCands; ++k) { D[k] = __int_as_float(0x7f800000); P[k] = -1; }
     const float bc = rho2max * L.inv_h2;
+    // Targets inside the radius are rare (one to three per query).  Sorting each one into the list where it is met ran
+    // the 25-instruction insertion with two lanes of the warp active (16 % of the instructions of icp_research_kernel,
+    // profiles/r02x): hits are parked in a small local list in scan order and sorted in after the walk, when the lanes
+    // are back together.  Same list as before, same order among equal distances.
+    constexpr int kPark = 8;
+    float LD[kPark];
+    int LP[kPark], cnt = 0;
+    auto flush = [&]() {
+        for (int j = 0; j < cnt; ++j) {
+            float cd = LD[j];
+            int cp = LP[j];
+            if (cd < D[kCacheCands]) {          // sorted insertion, ascending distance
+#pragma unroll
+                for (int k = 0; k <= kCacheCands; ++k)
+                    if (cd < D[k]) { const float td = D[k]; const int tp = P[k]; D[k] = cd; P[k] = cp; cd = td; cp = tp; }
+            }
+        }
+        cnt = 0;
+    };
     for (int kz = lz; kz <= hz; ++kz)
         for (int ky = ly; ky <= hy; ++ky) {
             const float gy = axis_gap(fy, ky, my), gz = axis_gap(fz, kz, mz);
@@ -569,15 +617,14 @@ static __device__ __noinline__ Near5 ball_collect(const GridLevel& L, float ox, 
             const uint32_t s = __ldg(L.cell_start + row + lxr), e = __ldg(L.cell_start + row + hxr + 1);
             for (uint32_t i = s; i < e; ++i) {
                 const float4 q = __ldg(L.pts + i);
-                float cd = l2_simple(px, py, pz, q.x, q.y, q.z);
-                if (cd <= rho2max && cd < D[kCacheCands]) {
-                    int cp = (int)i;        // sorted insertion, ascending distance
-#pragma unroll
-                    for (int k = 0; k <= kCacheCands; ++k)
-                        if (cd < D[k]) { const float td = D[k]; const int tp = P[k]; D[k] = cd; P[k] = cp; cd = td; cp = tp; }
+                const float cd = l2_simple(px, py, pz, q.x, q.y, q.z);
+                if (cd <= rho2max) {
+                    if (cnt == kPark) flush();
+                    LD[cnt] = cd; LP[cnt] = (int)i; ++cnt;
                 }
             }
         }
+    flush();
 #pragma unroll
     for (int k = 0; k <= kCacheCands; ++k) { out.d2[k] = D[k]; out.pos[k] = P[k]; }
     out.complete = 1;

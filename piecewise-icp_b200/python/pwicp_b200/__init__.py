@@ -242,14 +242,25 @@ class Context:
         self.mp2 = 0 if off is None else int(off[-1])
 
     def clouds_upload(self, cloud1, cloud2):
-        c1, c2 = _f32(cloud1), _f32(cloud2)
-        self._chk(self.L.pwicp_clouds_upload(self.h, _ptr(c1), len(c1), _ptr(c2), len(c2)))
-        self.m1, self.m2 = len(c1), len(c2)
+        """cloud1 = None keeps the resident cloud1 and its grid (the reference epoch of a series)."""
+        c2 = _f32(cloud2)
+        if cloud1 is None:
+            self._chk(self.L.pwicp_clouds_upload(self.h, None, 0, _ptr(c2), len(c2)))
+        else:
+            c1 = _f32(cloud1)
+            self._chk(self.L.pwicp_clouds_upload(self.h, _ptr(c1), len(c1), _ptr(c2), len(c2)))
+            self.m1 = len(c1)
+        self.m2 = len(c2)
 
     def upload_pair(self, d):
         self.target_upload(d["ct1"], d["nrm1"], d["ctstd1"], d.get("nrm1_ok"))
         self.source_upload(d["ct2"], d["bp2"], d["bpstd2"], d["patch_off2"], d["patch_pts2"])
         self.clouds_upload(d["cloud1"], d["cloud2"])
+
+    def upload_source_side(self, d):
+        """The moving epoch of a pair whose reference side (pwicp_target_upload, cloud1) is already resident."""
+        self.source_upload(d["ct2"], d["bp2"], d["bpstd2"], d["patch_off2"], d["patch_pts2"])
+        self.clouds_upload(None, d["cloud2"])
 
     def source_download(self):
         cloud2 = np.zeros((self.m2, 3), np.float32)

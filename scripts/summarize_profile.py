@@ -26,7 +26,11 @@ subprocess.run(["cp", os.path.join(src, f"{tag}_launches.csv"), os.path.join(out
 raw = subprocess.run(["ncu", "-i", os.path.join(src, f"{tag}_icp_bench.ncu-rep"), "--page", "raw", "--csv"],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
-hdr, units, vals = rows[0], rows[1], rows[2]
+hdr, units = rows[0], rows[1]
+ikn, idur = hdr.index("Kernel Name"), hdr.index("gpu__time_duration.sum")
+captured = [r for r in rows[2:] if len(r) == len(hdr)]
+pers = [r for r in captured if "icp_persistent" in r[ikn]]
+vals = max(pers, key=lambda r: float(r[idur].replace(",", "")))      # the long launch (iterations 1..49)
 want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
         "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
@@ -44,14 +48,21 @@ want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__
         "sass__inst_executed_local_loads", "sass__inst_executed_global_loads", "sass__inst_executed_shared_loads"]
 d = {}
 with open(os.path.join(out, f"{tag}_ncu_icp.txt"), "w") as f:
-    f.write("# ncu --set full --clock-control none, icp_persistent_kernel, 4th launch of python bench.py --steps 2 --warmup 3 "
-            "--no-cpu-baseline --no-config4 (1M source x 1M target, 50 forced inner iterations)\n")
+    f.write("# ncu --set full --clock-control none, python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-config4 (1M source x 1M "
+            "target, 50 forced inner iterations): the kernels of the inner loop of one step; the full list of metrics is for "
+            "the long launch of icp_persistent_kernel (iterations 1..49)\n")
+    for r in captured:
+        f.write(f"#   {r[ikn][:60]:60s} {r[idur]} {units[idur]}, dram read {r[hdr.index('dram__bytes_read.sum')]} "
+                f"{units[hdr.index('dram__bytes_read.sum')]}, write {r[hdr.index('dram__bytes_write.sum')]} {units[hdr.index('dram__bytes_write.sum')]}, "
+                f"lanes/inst {r[hdr.index('smsp__thread_inst_executed_per_inst_executed.ratio')]}, issue active "
+                f"{r[hdr.index('smsp__issue_active.avg.pct_of_peak_sustained_active')]} %\n")
     for k in want:
         if k in hdr:
             i = hdr.index(k); f.write(f"{k} [{units[i]}] = {vals[i]}\n"); d[k] = (vals[i], units[i])
 def to_bytes(v, u):
     v = float(v.replace(",", "")); return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
-tr = to_bytes(*d["dram__bytes_read.sum"]) + to_bytes(*d["dram__bytes_write.sum"])
+ird, iwr = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")      # both launches of the persistent kernel
+tr = sum(to_bytes(r[ird], units[ird]) + to_bytes(r[iwr], units[iwr]) for r in pers)
 json.dump({"kernel": "icp_persistent_kernel", "config": "1M x 1M, 50 forced inner iterations (bench.py)",
            "dram_bytes_per_launch": tr, "source": f"profiles/{tag}_ncu_icp.txt"},
           open(os.path.join(out, "traffic.json"), "w"))
@@ -67,7 +78,7 @@ if os.path.exists(p10):
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, vals = rows[0], rows[1], rows[2]
     with open(os.path.join(out, f"{tag}_ncu_icp_10m.txt"), "w") as f:
-        f.write("# ncu --set full --clock-control none, icp_persistent_kernel, 3rd launch of python scripts/prof_icp_only.py 10000000 50 "
+        f.write("# ncu --set full --clock-control none, icp_persistent_kernel, the long launch (iterations 1..49) of the 3rd run of python scripts/prof_icp_only.py 10000000 50 "
                 "(10M source x 10M target, 50 forced inner iterations; BASELINE configs[4])\n")
         for k in want:
             if k in hdr:

@@ -233,6 +233,16 @@ def test_inner_loop_host_buffer_call_and_errors(gpu_ctx, oracle, pair2k):
     assert e.value.status == -6
     r1 = gpu_ctx.icp_p2plane(d["ct1"], d["nrm1"], d["ct2"][:3], P.icp_params(max_iter=1))
     assert r1["n_iter"] == 1 and r1["state"] == 1
+    # the normals travel last and are checked on the device while the loop is already enqueued: the verdict must still
+    # arrive with the result, for each of the three arrays, and the context must stay usable
+    for key in ("nrm1", "ct2", "ct1"):
+        bad = {k: d[k].copy() for k in ("ct1", "nrm1", "ct2")}
+        bad[key][len(bad[key]) // 2, 1] = np.nan
+        with pytest.raises(P.PwicpError) as e:
+            gpu_ctx.icp_p2plane(bad["ct1"], bad["nrm1"], bad["ct2"])
+        assert e.value.status == -3
+    r2 = gpu_ctx.icp_p2plane(d["ct1"], d["nrm1"], d["ct2"])
+    assert np.array_equal(r2["T"], r["T"]) and r2["n_iter"] == r["n_iter"]
 
 
 # ------------------------------------------------------------------------------- A2, A7, A8, A10
@@ -282,6 +292,18 @@ def test_outer_loop_matches_oracle_and_golden(gpu_ctx, oracle, gold, pair2k):
         assert [s.icp_iters for s in g["stats"]] == [s.icp_iters for s in o["stats"]]
         assert np.allclose(g["VCM"], o["VCM"], rtol=1e-6, atol=0)      # relative 1e-6
     assert np.allclose(g["VCM"], g["VCM"].T, rtol=1e-9)
+    # a series against one reference epoch: the reference side stays resident, only the moving epoch is uploaded again
+    # (pwicp_clouds_upload with cloud1 = NULL) -- same result, bit for bit
+    gpu_ctx.upload_source_side(d)
+    g2 = gpu_ctx.piecewise_icp(pp, 0, 0.0)
+    assert np.array_equal(g2["T"], g["T"]) and np.array_equal(g2["DTseries"], g["DTseries"]) and np.array_equal(g2["VCM"], g["VCM"])
+    fresh = P.Context(0)
+    try:
+        with pytest.raises(P.PwicpError) as e:
+            fresh.clouds_upload(None, d["cloud2"])
+        assert e.value.status == -2
+    finally:
+        fresh.close()
 
 
 def test_outer_loop_error_codes(gpu_ctx, pair2k):
