@@ -225,7 +225,11 @@ def config4_leg(P, synth, torch, dist, local_rank, rank, world):
     rec = torch.zeros((C4_EPOCHS, 96), dtype=torch.float32, device="cuda")       # 384-byte record per epoch
     if dist:                                         # ... and the first all-gather of this shape (NCCL sets up lazily)
         allrec = torch.zeros((world,) + tuple(rec.shape), dtype=rec.dtype, device="cuda")
-        dist.all_gather_into_tensor(allrec, rec)
+        for _ in range(2):                           # every kernel of the tail once before the clock starts: CUDA loads
+            dist.all_gather_into_tensor(allrec, rec)  # a module at its first launch (the reduction over the ranks cost
+            _ = allrec.sum(0)                         # 9 ms in the timed region of r02x at 8 GPUs)
+            rec[0] = torch.from_numpy(np.zeros(96, np.float32)).cuda()
+            torch.cuda.synchronize()
         dist.barrier()
     t_up[0] = t_icp[0] = 0.0
     have_ref[0] = have_ref[1] = False                # the warm-up's reference uploads do not count

@@ -1,11 +1,19 @@
 """Per-instruction stall samples of an ncu capture taken with --import-source on: the hottest SASS instructions and the
-share of the samples by code region.  python scripts/hot_sass.py <file.ncu-rep> <out.txt> '<title>'"""
+share of the samples by code region.  python scripts/hot_sass.py <file.ncu-rep> <out.txt> '<title>' [ncu import filters, e.g. --launch-skip 3 --launch-count 1]"""
 import csv, subprocess, sys
 from collections import defaultdict
 rep, out, title = sys.argv[1], sys.argv[2], sys.argv[3]
+pick = sys.argv[4] if len(sys.argv) > 4 else ""      # substring of the kernel name; of several matches the one with the most samples
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
-hdr = rows[1]; data = rows[2:]
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]
+best = None
+for a, b in zip(starts[:-1], starts[1:]):
+    if pick not in rows[a][1]: continue
+    h = rows[a + 1]; dd = [r for r in rows[a + 2:b] if len(r) == len(h)]
+    n = sum(int(r[h.index("# Samples")]) for r in dd)
+    if best is None or n > best[0]: best = (n, h, dd)
+hdr, data = best[1], best[2]
 iS, iE, isrc, iA = hdr.index("# Samples"), hdr.index("Instructions Executed"), hdr.index("Source"), hdr.index("Address")
 stall = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
 tot = sum(int(r[iS]) for r in data)
