@@ -445,7 +445,7 @@ def main():
                        "pairs_per_step": world},
             "icp_iters_per_s": args.steps * INNER_ITERS * world / dev_s,
             "build_ms": float(np.mean(build_ms)), "icp_ms": icp_avg_ms,
-            "phases_ms": {"grid_build": float(np.mean(build_ms)), "morton_sort_of_source": float(np.mean(sort_ms)),
+            "phases_ms": {"grid_build": float(np.mean(build_ms)), "spatial_order_of_source": float(np.mean(sort_ms)),
                           "iteration0_search_prepass": float(np.mean(pre_ms)), "persistent_kernel": kern_avg_ms,
                           "iteration1_search_kernel": float(np.mean(res_ms)),
                           "kernel_search_iterations": float(np.mean(it_search)),
@@ -476,7 +476,7 @@ def main():
                                  "summed: iteration 0 | iterations 1..49); between them icp_research_kernel does the "
                                  "search of iteration 1 (every query searches there) at full occupancy -- "
                                  "achieved_incl_iteration1_search_kernel counts its time as well; the rest of a step is "
-                                 "the grid build, the Morton sort of the source and the iteration-0 search pre-pass "
+                                 "the grid build, the spatial ordering of the source and the iteration-0 search pre-pass "
                                  "(icp_seed_kernel); peak = measured copy bandwidth "
                                  "(MEASURED_PEAKS.json); traffic = dram read+write bytes of one launch (ncu)"},
         }

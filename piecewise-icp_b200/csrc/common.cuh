@@ -141,6 +141,8 @@ int nn_query_packed(Ctx* ctx, const GridDev& g, const float* q_dev_packed, int n
 int self_nn_dev(Ctx* ctx, const GridDev& g, float* d2_dev);
 int upload_packed(Ctx* ctx, DevBuf& buf, const float* host_xyz, size_t n_floats);
 int check_finite_dev(Ctx* ctx, const float* dev, size_t n_floats, bool* ok);
+int scan_inclusive_inplace(Ctx* ctx, uint32_t* a, size_t n);               // a[i] = a[0] + .. + a[i], any n
+int spatial_order_dev(Ctx* ctx, const GridDev& g, const float4* pts, int n, uint32_t* order);   // processing order of a query set
 int finite_accumulate_dev(Ctx* ctx, const float* dev, size_t n_floats, int* flag_dev);   // no host sync
 
 // capi.cu

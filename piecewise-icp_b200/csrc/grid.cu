@@ -279,13 +279,95 @@ scan_tile_apply_kernel(uint32_t* __restrict__ a, size_t n, const uint32_t* __res
     for (int k = 0; k < kScanItems; ++k) if (base + k < n) a[base + k] = before + v[k];
 }
 
-static int scan_inclusive_inplace(Ctx* ctx, uint32_t* a, size_t n) {
+int scan_inclusive_inplace(Ctx* ctx, uint32_t* a, size_t n) {
     const int nt = (int)((n + kScanTile - 1) / kScanTile);
     PW_TRY(ctx->vals.reserve(ctx, (size_t)nt * 4));
     uint32_t* tsum = ctx->vals.as<uint32_t>();
     scan_tile_sum_kernel<<<nt, kScanThreads, 0, ctx->stream>>>(a, n, tsum);
     scan_tsum_kernel<<<1, 1024, 0, ctx->stream>>>(tsum, nt);
     scan_tile_apply_kernel<<<nt, kScanThreads, 0, ctx->stream>>>(a, n, tsum);
+    ctx->launches += 3;
+    PW_CUDA(cudaGetLastError());
+    return PWICP_OK;
+}
+
+// ---- processing order of a query set -----------------------------------------------------------
+// The inner loop and the classification work through their queries in an order in which consecutive queries are
+// spatial neighbours (the 32 lanes of a warp then walk the same few cell rows).  Round 1 and the first half of round
+// 2 sorted Morton codes of the target-grid cell with cub::DeviceRadixSort (four onesweep passes, 3 % of a bench
+// step); the keys are bounded, so this is a counting sort like the grid build's: bins = cells of twice the finest
+// cell size, enumerated block by block (8 x 8 x 8 bins, Morton order inside a block, blocks row-major), one
+// warp-aggregated atomic per bin for the count and for the slot, and a last pass that ranks the points of a bin by
+// their index in the caller's order -- the order is a function of the input alone, whatever the atomics do (the
+// summation order of the inner loop depends on it).
+__device__ __forceinline__ uint32_t order_key_of(float x, float y, float z, float ox, float oy, float oz, float inv_h,
+                                                 int dx, int dy, int dz, int nbx, int nby) {
+    const int cx = min(max((int)floorf((x - ox) * inv_h), 0), dx - 1) >> 1;
+    const int cy = min(max((int)floorf((y - oy) * inv_h), 0), dy - 1) >> 1;
+    const int cz = min(max((int)floorf((z - oz) * inv_h), 0), dz - 1) >> 1;
+    const uint32_t lx = cx & 7, ly = cy & 7, lz = cz & 7;
+    auto spread3 = [](uint32_t v) { return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4); };
+    const uint32_t m = spread3(lx) | (spread3(ly) << 1) | (spread3(lz) << 2);
+    return (((uint32_t)(cz >> 3) * (uint32_t)nby + (uint32_t)(cy >> 3)) * (uint32_t)nbx + (uint32_t)(cx >> 3)) * 512u + m;
+}
+
+__global__ void __launch_bounds__(256)
+order_count_kernel(const float4* __restrict__ pts, int n, float ox, float oy, float oz, float inv_h, int dx, int dy, int dz,
+                   int nbx, int nby, uint32_t* __restrict__ A) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = pts[i];
+    const uint32_t key = order_key_of(p.x, p.y, p.z, ox, oy, oz, inv_h, dx, dy, dz, nbx, nby);
+    const unsigned m = __match_any_sync(__activemask(), key);
+    if ((int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(A + 2 + key, (uint32_t)__popc(m));
+}
+
+__global__ void __launch_bounds__(256)
+order_scatter_kernel(const float4* __restrict__ pts, int n, float ox, float oy, float oz, float inv_h, int dx, int dy, int dz,
+                     int nbx, int nby, uint32_t* __restrict__ A, uint32_t* __restrict__ slots) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = pts[i];
+    const uint32_t key = order_key_of(p.x, p.y, p.z, ox, oy, oz, inv_h, dx, dy, dz, nbx, nby);
+    const unsigned m = __match_any_sync(__activemask(), key);
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(A + 1 + key, (uint32_t)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    slots[base + (uint32_t)__popc(m & ((1u << lane) - 1))] = (uint32_t)i;
+}
+
+// after the scatter A[key] .. A[key + 1] is the bin of `key`; the point takes the place of its rank among the bin's
+// points by index in the caller's order
+__global__ void __launch_bounds__(256)
+order_rank_kernel(const float4* __restrict__ pts, int n, float ox, float oy, float oz, float inv_h, int dx, int dy, int dz,
+                  int nbx, int nby, const uint32_t* __restrict__ A, const uint32_t* __restrict__ slots,
+                  uint32_t* __restrict__ order) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = pts[i];
+    const uint32_t key = order_key_of(p.x, p.y, p.z, ox, oy, oz, inv_h, dx, dy, dz, nbx, nby);
+    const uint32_t s = A[key], e = A[key + 1];
+    uint32_t rank = 0;
+    for (uint32_t j = s; j < e; ++j) rank += (slots[j] < (uint32_t)i) ? 1u : 0u;
+    order[s + rank] = (uint32_t)i;
+}
+
+int spatial_order_dev(Ctx* ctx, const GridDev& g, const float4* pts, int n, uint32_t* order) {
+    const GridLevel& L = g.lv[0];
+    const int nbx = (((L.dx - 1) >> 1) >> 3) + 1, nby = (((L.dy - 1) >> 1) >> 3) + 1, nbz = (((L.dz - 1) >> 1) >> 3) + 1;
+    const uint64_t nbins = (uint64_t)nbx * nby * nbz * 512ull;
+    if (nbins > 0x7ffffff0ull) { set_error(ctx, "spatial_order: too many bins"); return PWICP_ERR_ARG; }
+    PW_TRY(ctx->keys.reserve(ctx, (nbins + 2) * sizeof(uint32_t)));
+    PW_TRY(ctx->keys2.reserve(ctx, (size_t)n * sizeof(uint32_t)));
+    uint32_t* A = ctx->keys.as<uint32_t>();
+    uint32_t* slots = ctx->keys2.as<uint32_t>();
+    const int blocks = (n + 255) / 256;
+    PW_CUDA(cudaMemsetAsync(A, 0, (nbins + 2) * sizeof(uint32_t), ctx->stream));
+    order_count_kernel<<<blocks, 256, 0, ctx->stream>>>(pts, n, g.ox, g.oy, g.oz, L.inv_h, L.dx, L.dy, L.dz, nbx, nby, A);
+    PW_TRY(scan_inclusive_inplace(ctx, A, (size_t)nbins + 2));
+    order_scatter_kernel<<<blocks, 256, 0, ctx->stream>>>(pts, n, g.ox, g.oy, g.oz, L.inv_h, L.dx, L.dy, L.dz, nbx, nby, A, slots);
+    order_rank_kernel<<<blocks, 256, 0, ctx->stream>>>(pts, n, g.ox, g.oy, g.oz, L.inv_h, L.dx, L.dy, L.dz, nbx, nby, A, slots, order);
     ctx->launches += 3;
     PW_CUDA(cudaGetLastError());
     return PWICP_OK;

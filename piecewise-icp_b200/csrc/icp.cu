@@ -27,7 +27,6 @@
 // The summation order ("reduction geometry") is fixed by (n, gridDim.x, warps per CTA) alone and the oracle's
 // reduce_mode = 2 reproduces it for the bit-exact whole-loop parity tests.
 #include "common.cuh"
-#include <cub/cub.cuh>
 
 #include "nn_search.cuh"
 #include "small_algebra.cuh"
@@ -744,32 +743,6 @@ int icp_expand_source(Ctx* ctx, const float* packed_dev, int n) {
     return PWICP_OK;
 }
 
-// key = Morton code of the finest-level cell of the source point (same cell expression as the
-// grid build), so that consecutive points of the sorted order sit in a compact 3-D neighbourhood
-__device__ __forceinline__ unsigned long long spread21(unsigned int v) {
-    unsigned long long x = v & 0x1fffffu;
-    x = (x | x << 32) & 0x1f00000000ffffull;
-    x = (x | x << 16) & 0x1f0000ff0000ffull;
-    x = (x | x << 8) & 0x100f00f00f00f00full;
-    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
-    x = (x | x << 2) & 0x1249249249249249ull;
-    return x;
-}
-
-template <typename K>
-__global__ void src_key_kernel(const float4* __restrict__ src, int n, float ox, float oy, float oz, float inv_h,
-                               int dx, int dy, int dz, K* keys, uint32_t* vals) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float4 p = src[i];
-    float fx = (p.x - ox) * inv_h, fy = (p.y - oy) * inv_h, fz = (p.z - oz) * inv_h;
-    int cx = min(max((int)floorf(fx), 0), dx - 1);
-    int cy = min(max((int)floorf(fy), 0), dy - 1);
-    int cz = min(max((int)floorf(fz), 0), dz - 1);
-    keys[i] = (K)(spread21(cx) | (spread21(cy) << 1) | (spread21(cz) << 2));
-    vals[i] = (uint32_t)i;
-}
-
 // a padding point (i >= n, up to the next multiple of 32): zero normal, see IcpArgs
 __device__ __forceinline__ void write_pad(int i, float4* out, float4* cn0, float4* cq0) {
     out[i] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
@@ -889,45 +862,20 @@ icp_research_kernel(const IcpArgs a) {
     if (k > 0) a.cmore[i] = make_int4(o1, o2, o3, bb.idx);
 }
 
-// Sorts the source set by the target-grid cell it starts in (stable: ties keep the caller's
-// order), so that the 8 queries of a tile group share a small candidate block.  The processing
-// order only affects the order of the double sums (DESIGN.md "reduction geometry").
+// Puts the source set into a spatially compact processing order (spatial_order_dev, grid.cu: bins of the target grid,
+// ties in the caller's order) so that the lanes of a warp walk the same few cell rows.  The processing order only
+// affects the order of the double sums (DESIGN.md "reduction geometry").
 static int icp_sort_source(Ctx* ctx, int n, bool have_seed) {
-    const GridLevel& L = ctx->tgt.dev.lv[0];
-    PW_TRY(ctx->keys.reserve(ctx, (size_t)n * 8));
-    PW_TRY(ctx->vals.reserve(ctx, (size_t)n * 4));
-    PW_TRY(ctx->keys2.reserve(ctx, (size_t)n * 8));
     PW_TRY(ctx->icp_perm.reserve(ctx, (size_t)n * 4));
     const int n_pad = (n + 31) / 32 * 32;            // the per-point arrays of the loop are padded to whole batches
     PW_TRY(ctx->icp_sorted.reserve(ctx, (size_t)n_pad * sizeof(float4)));
     PW_TRY(ctx->icp_match.reserve(ctx, (size_t)n_pad * 3 * sizeof(float4)));      // cn, cq, cmore
-    const int blocks = (n + 255) / 256;
-    int maxd = std::max(L.dx, std::max(L.dy, L.dz));
-    int b1 = 1; while ((1 << b1) < maxd && b1 < 21) ++b1;
-    const int bits = 3 * b1;
-    size_t tmp = 0;
-    if (bits <= 32) {                    // grids up to 1024 cells per axis: 32-bit keys, half the sort traffic
-        uint32_t* k1 = ctx->keys.as<uint32_t>(); uint32_t* k2 = ctx->keys2.as<uint32_t>();
-        src_key_kernel<uint32_t><<<blocks, 256, 0, ctx->stream>>>(ctx->icp_src.as<float4>(), n, ctx->tgt.dev.ox, ctx->tgt.dev.oy,
-                                                                 ctx->tgt.dev.oz, L.inv_h, L.dx, L.dy, L.dz, k1, ctx->vals.as<uint32_t>());
-        cub::DeviceRadixSort::SortPairs(nullptr, tmp, k1, k2, ctx->vals.as<uint32_t>(), ctx->icp_perm.as<uint32_t>(), n, 0, bits, ctx->stream);
-        PW_TRY(ctx->cub_tmp.reserve(ctx, tmp));
-        size_t cap = ctx->cub_tmp.cap;
-        PW_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, cap, k1, k2, ctx->vals.as<uint32_t>(), ctx->icp_perm.as<uint32_t>(), n, 0, bits, ctx->stream));
-    } else {
-        unsigned long long* k1 = ctx->keys.as<unsigned long long>(); unsigned long long* k2 = ctx->keys2.as<unsigned long long>();
-        src_key_kernel<unsigned long long><<<blocks, 256, 0, ctx->stream>>>(ctx->icp_src.as<float4>(), n, ctx->tgt.dev.ox, ctx->tgt.dev.oy,
-                                                                           ctx->tgt.dev.oz, L.inv_h, L.dx, L.dy, L.dz, k1, ctx->vals.as<uint32_t>());
-        cub::DeviceRadixSort::SortPairs(nullptr, tmp, k1, k2, ctx->vals.as<uint32_t>(), ctx->icp_perm.as<uint32_t>(), n, 0, bits, ctx->stream);
-        PW_TRY(ctx->cub_tmp.reserve(ctx, tmp));
-        size_t cap = ctx->cub_tmp.cap;
-        PW_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, cap, k1, k2, ctx->vals.as<uint32_t>(), ctx->icp_perm.as<uint32_t>(), n, 0, bits, ctx->stream));
-    }
+    PW_TRY(spatial_order_dev(ctx, ctx->tgt.dev, ctx->icp_src.as<float4>(), n, ctx->icp_perm.as<uint32_t>()));
     src_gather_kernel<<<(n_pad + 255) / 256, 256, 0, ctx->stream>>>(ctx->icp_src.as<float4>(), ctx->icp_perm.as<uint32_t>(), n, n_pad,
                                                        ctx->icp_sorted.as<float4>(),
                                                        have_seed ? ctx->icp_seed.as<int>() : nullptr, ctx->tgt.dev.lv[0].pts,
                                                        ctx->tgt_aux.as<float4>(), ctx->icp_match.as<float4>(), ctx->icp_match.as<float4>() + n_pad);
-    ctx->launches += 5;
+    ctx->launches += 1;
     PW_CUDA(cudaGetLastError());
     return PWICP_OK;
 }

@@ -5,7 +5,6 @@
 // distances, (4) stable/unstable classification + order-preserving compaction, (5) inner ICP,
 // (6) bounding-cube corner change, (7) DT schedule incl. the stage-1 percentile, (8) transform of
 // cloud2 / CT2 / BP2 / patches, (9) VCM on the pre-update stable centroids.
-#include <cub/cub.cuh>
 #include <cfloat>
 #include <cmath>
 #include <cstddef>
@@ -581,52 +580,14 @@ int vcm_dev(Ctx* ctx, const float4* src, int n, double* vcm36, int* singular, in
 }
 
 // ---- Morton order of the source patches (once per pair) ------------------------------------
-__device__ __forceinline__ unsigned long long spread21_o(unsigned int v) {
-    unsigned long long x = v & 0x1fffffu;
-    x = (x | x << 32) & 0x1f00000000ffffull;
-    x = (x | x << 16) & 0x1f0000ff0000ffull;
-    x = (x | x << 8) & 0x100f00f00f00f00full;
-    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
-    x = (x | x << 2) & 0x1249249249249249ull;
-    return x;
-}
 
-__global__ void patch_key_kernel(const float4* __restrict__ ct2, int n, float ox, float oy, float oz, float inv_h,
-                                 int dx, int dy, int dz, unsigned long long* keys, uint32_t* vals) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float4 p = ct2[i];
-    int cx = min(max((int)floorf((p.x - ox) * inv_h), 0), dx - 1);
-    int cy = min(max((int)floorf((p.y - oy) * inv_h), 0), dy - 1);
-    int cz = min(max((int)floorf((p.z - oz) * inv_h), 0), dz - 1);
-    keys[i] = spread21_o(cx) | (spread21_o(cy) << 1) | (spread21_o(cz) << 2);
-    vals[i] = (uint32_t)i;
-}
-
-// Processing order of the classification queries: patches sorted by the Morton code of the
-// target-grid cell of their centroid.  Results are written back in the caller's order, so the
-// order only shapes the query groups of the tile search.
+// Processing order of the classification queries: patches in the spatial order of their centroid (spatial_order_dev,
+// grid.cu).  Results are written back in the caller's order, so the order only shapes the warps of the search.
 static int ensure_patch_order(Ctx* ctx) {
     if (ctx->ct_order_valid) return PWICP_OK;
     const int n = ctx->n2;
-    const GridLevel& L = ctx->tgt.dev.lv[0];
-    PW_TRY(ctx->keys.reserve(ctx, (size_t)n * 8));
-    PW_TRY(ctx->vals.reserve(ctx, (size_t)n * 4));
-    PW_TRY(ctx->keys2.reserve(ctx, (size_t)n * 8));
     PW_TRY(ctx->ct_order.reserve(ctx, (size_t)n * 4));
-    patch_key_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->ct2.as<float4>(), n, ctx->tgt.dev.ox, ctx->tgt.dev.oy,
-                                                             ctx->tgt.dev.oz, L.inv_h, L.dx, L.dy, L.dz,
-                                                             ctx->keys.as<unsigned long long>(), ctx->vals.as<uint32_t>());
-    int maxd = std::max(L.dx, std::max(L.dy, L.dz));
-    int b1 = 1; while ((1 << b1) < maxd && b1 < 21) ++b1;
-    size_t tmp = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp, ctx->keys.as<unsigned long long>(), ctx->keys2.as<unsigned long long>(),
-                                    ctx->vals.as<uint32_t>(), ctx->ct_order.as<uint32_t>(), n, 0, 3 * b1, ctx->stream);
-    PW_TRY(ctx->cub_tmp.reserve(ctx, tmp));
-    size_t cap = ctx->cub_tmp.cap;
-    PW_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, cap, ctx->keys.as<unsigned long long>(), ctx->keys2.as<unsigned long long>(),
-                                            ctx->vals.as<uint32_t>(), ctx->ct_order.as<uint32_t>(), n, 0, 3 * b1, ctx->stream));
-    ctx->launches += 4;
+    PW_TRY(spatial_order_dev(ctx, ctx->tgt.dev, ctx->ct2.as<float4>(), n, ctx->ct_order.as<uint32_t>()));
     ctx->ct_order_valid = true;
     return PWICP_OK;
 }
