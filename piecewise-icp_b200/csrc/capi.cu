@@ -476,12 +476,17 @@ int pwicp_icp_p2plane(pwicp_ctx* p, const float* tgt_xyz, const float* tgt_nrm, 
     PW_TRY(finite_accumulate_dev(ctx, ctx->tgt_xyz.as<float>(), (size_t)3 * n1, flag));
     ctx->tgt_has_std = false;
     ctx->tgt_has_ok = false;
-    // a non-finite coordinate would poison the bounding box: the build needs the verdict on the target
+    // a non-finite coordinate would poison the bounding box: the verdict on the target comes back with the box (one
+    // round trip), and the build does not wait for its own kernels at the end
     int bad = 0;
-    PW_CUDA(cudaMemcpyAsync(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    PW_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (bad) { cudaStreamSynchronize(ctx->copy_stream); set_error(ctx, "target centroids: non-finite value in input"); return PWICP_ERR_NONFINITE; }
-    PW_TRY(grid_build(ctx, ctx->tgt, ctx->tgt_xyz.as<float>(), n1));
+    {
+        const int rc = grid_build(ctx, ctx->tgt, ctx->tgt_xyz.as<float>(), n1, flag, false);
+        if (rc != PWICP_OK) {
+            cudaStreamSynchronize(ctx->copy_stream);
+            if (rc == PWICP_ERR_NONFINITE) set_error(ctx, "target centroids: non-finite value in input");
+            return rc;
+        }
+    }
     PW_TRY(reset_seeds(ctx));
     PW_TRY(ctx->tgt_aux.reserve(ctx, (size_t)n1 * sizeof(float4)));
     PW_TRY(ctx->tgt_ok.reserve(ctx, (size_t)n1));
@@ -496,12 +501,12 @@ int pwicp_icp_p2plane(pwicp_ctx* p, const float* tgt_xyz, const float* tgt_nrm, 
     if (bad) { cudaStreamSynchronize(ctx->copy_stream); set_error(ctx, "icp_p2plane: non-finite value in input"); return PWICP_ERR_NONFINITE; }
     ctx->n1 = n1;
     ctx->aux_deferred = true; ctx->aux_deferred_n1 = n1; ctx->aux_deferred_flag = flag;
+    ctx->tail_flag_dev = flag; ctx->tail_flag_host = 0;      // the verdict on the normals comes back with the result
     int st = pwicp_icp_run(p, prm, T16, res, nullptr, nullptr, nullptr);
+    ctx->tail_flag_dev = nullptr;
     if (ctx->aux_deferred) { const int s2 = finish_deferred_aux(ctx); if (st == PWICP_OK) st = s2; }   // the loop failed before it got there
-    if (st != PWICP_OK) { cudaStreamSynchronize(ctx->copy_stream); return st; }
-    PW_CUDA(cudaMemcpyAsync(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    PW_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (bad) { set_error(ctx, "icp_p2plane: non-finite value in input"); return PWICP_ERR_NONFINITE; }
+    if (st != PWICP_OK) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->stream); return st; }
+    if (ctx->tail_flag_host) { set_error(ctx, "icp_p2plane: non-finite value in input"); return PWICP_ERR_NONFINITE; }
     return PWICP_OK;
 }
 

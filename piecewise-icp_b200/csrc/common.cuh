@@ -116,6 +116,8 @@ struct Ctx {
     bool aux_deferred = false;
     int aux_deferred_n1 = 0;
     int* aux_deferred_flag = nullptr;            // device flag the finite check of the normals accumulates into
+    const int* tail_flag_dev = nullptr;          // ... read back with the result of the loop (icp_run_device) ...
+    int tail_flag_host = 0;                      // ... into this
     // temporal-coherence seeds of the outer iteration (level-0 positions, -1 = none)
     DevBuf ct_seed, bp_seed, pp_seed, ct_order;
     bool ct_order_valid = false;
@@ -135,7 +137,8 @@ struct Ctx {
 };
 
 // grid.cu
-int grid_build(Ctx* ctx, GridOwner& g, const float* xyz_dev_packed, int n);
+int grid_build(Ctx* ctx, GridOwner& g, const float* xyz_dev_packed, int n, const int* bad_flag_dev = nullptr,
+               bool sync_at_end = true);
 int nn_query_packed(Ctx* ctx, const GridDev& g, const float* q_dev_packed, int nq, int* idx_dev,
                     float* d2_dev);
 int self_nn_dev(Ctx* ctx, const GridDev& g, float* d2_dev);
@@ -167,7 +170,8 @@ int icp_expand_source(Ctx* ctx, const float* packed_dev, int n);
 int vcm_dev(Ctx* ctx, const float4* src_dev, int n, double* vcm36, int* singular, int* seeds_dev,
             const float4* cq_seed_dev);
 int transform_packed_dev(Ctx* ctx, float* xyz_dev, size_t n, const float* T16);
-int bbox_packed_dev(Ctx* ctx, const float* xyz_dev, size_t n, float* mn3, float* mx3);
+int bbox_packed_dev(Ctx* ctx, const float* xyz_dev, size_t n, float* mn3, float* mx3, const int* flag_dev = nullptr,
+                    int* flag_out = nullptr);
 int bbox_accumulate_dev(Ctx* ctx, const float* xyz_dev, size_t n, int* out6_dev);
 void octree_cube(const float* mn, const float* mx, double res, double* bb6);
 

@@ -139,7 +139,7 @@ int bbox_accumulate_dev(Ctx* ctx, const float* xyz_dev, size_t n, int* out6_dev)
     return PWICP_OK;
 }
 
-int bbox_packed_dev(Ctx* ctx, const float* xyz_dev, size_t n, float* mn3, float* mx3) {
+int bbox_packed_dev(Ctx* ctx, const float* xyz_dev, size_t n, float* mn3, float* mx3, const int* flag_dev, int* flag_out) {
     PW_TRY(ensure_pinned(ctx, 4096));
     PW_TRY(ctx->scratch_d.reserve(ctx, 256));
     int* out = ctx->scratch_d.as<int>();
@@ -149,9 +149,12 @@ int bbox_packed_dev(Ctx* ctx, const float* xyz_dev, size_t n, float* mn3, float*
     bbox_kernel<<<blocks, 256, 0, ctx->stream>>>(xyz_dev, n, out);
     ctx->launches += 2;
     PW_CUDA(cudaMemcpyAsync(ctx->pinned, out, 6 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    // a device flag of the caller (the verdict of a finite check) rides on the same round trip
+    if (flag_dev) PW_CUDA(cudaMemcpyAsync((int*)ctx->pinned + 8, flag_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     PW_CUDA(cudaStreamSynchronize(ctx->stream));
     const int* h = (const int*)ctx->pinned;
     for (int c = 0; c < 3; ++c) { mn3[c] = ordered_to_float(h[c]); mx3[c] = ordered_to_float(h[3 + c]); }
+    if (flag_dev && flag_out) *flag_out = h[8];
     return PWICP_OK;
 }
 
@@ -373,12 +376,17 @@ int spatial_order_dev(Ctx* ctx, const GridDev& g, const float4* pts, int n, uint
     return PWICP_OK;
 }
 
-int grid_build(Ctx* ctx, GridOwner& g, const float* xyz, int n) {
+// bad_flag_dev: a device flag that a finite check of xyz accumulates into (enqueued before this call); it is read with
+// the bounding box, and a set flag ends the build with PWICP_ERR_NONFINITE before the box is used.  sync_at_end = false:
+// the caller keeps enqueuing on the library stream (host-buffer call of the inner loop).
+int grid_build(Ctx* ctx, GridOwner& g, const float* xyz, int n, const int* bad_flag_dev, bool sync_at_end) {
     g.dev = GridDev{};                 // invalid until the build completes; buffers are reused
     g.n = 0;
     if (n < 1) { set_error(ctx, "grid_build: empty target"); return PWICP_ERR_ARG; }
     float mn[3], mx[3];
-    PW_TRY(bbox_packed_dev(ctx, xyz, (size_t)n, mn, mx));
+    int bad = 0;
+    PW_TRY(bbox_packed_dev(ctx, xyz, (size_t)n, mn, mx, bad_flag_dev, &bad));
+    if (bad) { set_error(ctx, "non-finite value in input"); return PWICP_ERR_NONFINITE; }
     double ext[3];
     for (int c = 0; c < 3; ++c) ext[c] = std::max((double)mx[c] - (double)mn[c], 0.0);
     double emax = std::max(ext[0], std::max(ext[1], ext[2]));
@@ -444,7 +452,7 @@ int grid_build(Ctx* ctx, GridOwner& g, const float* xyz, int n) {
     g.dev.nlevels = nlev;
     g.dev.inv_perm = g.inv_perm.as<uint32_t>();
     PW_CUDA(cudaGetLastError());
-    PW_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (sync_at_end) PW_CUDA(cudaStreamSynchronize(ctx->stream));
     return PWICP_OK;
 }
 

@@ -1023,6 +1023,8 @@ int icp_run_device(Ctx* ctx, const pwicp_icp_params& prm, float* T16, pwicp_icp_
     const int grid = L.grid;
     struct { float T[16]; int st[4]; } host;
     PW_CUDA(cudaMemcpyAsync(&host, ob, sizeof(host), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->tail_flag_dev)                                  // host-buffer call: the finite verdict rides on the same round trip
+        PW_CUDA(cudaMemcpyAsync(&ctx->tail_flag_host, ctx->tail_flag_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     PW_CUDA(cudaStreamSynchronize(ctx->stream));
     float ms = 0.f, kms = 0.f, rms = 0.f, sms = 0.f, pms = 0.f;
     PW_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
