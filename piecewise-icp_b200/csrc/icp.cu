@@ -4,7 +4,7 @@
 // pcl::IterativeClosestPointWithNormals::align with TransformationEstimationPointToPlaneLLS and
 // DefaultConvergenceCriteria.
 //
-// Layout (round 2).  One CTA of 16 warps per SM.  The 32-point batches of the Morton-ordered source
+// Layout (round 2).  One CTA of 16 warps per SM.  The 32-point batches of the spatially ordered source
 // are dealt out round robin to the warps of the whole grid (batch b belongs to warp b mod NWT) and stay with that
 // warp for the whole loop: every piece of per-point state -- the transformed point, its matched target and normal,
 // the candidate cache -- is read and written by one thread only, so no iteration needs a grid-wide fence for it, and

@@ -64,7 +64,7 @@ classify_dist_kernel(GridDev g, const float4* __restrict__ aux, const unsigned c
                      float* __restrict__ pl, float* __restrict__ pt2pt, float* __restrict__ lod,
                      int* __restrict__ lod_minmax, const uint32_t* __restrict__ order,
                      int* __restrict__ ct_seed, int* __restrict__ bp_seed) {
-    // thread u handles the u-th query of the Morton-ordered patch list (spatially compact groups);
+    // thread u handles the u-th query of the spatially ordered patch list (spatial_order_dev) (spatially compact groups);
     // t is the query's slot in the caller's order: centroid t < n2, boundary point t - n2.  (Seeding the boundary points
     // of the first iteration with their centroid's match, in a second launch, was measured: no gain, r02r.)
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
@@ -103,7 +103,7 @@ classify_dist_kernel(GridDev g, const float4* __restrict__ aux, const unsigned c
 }
 
 // ---- (4) classification, src/Registration.cpp:815-862 ---------------------------------------
-// Thread u handles the u-th patch of the Morton order (t = order[u]); the flags are stored in the caller's order, the
+// Thread u handles the u-th patch of the processing order (t = order[u]); the flags are stored in the caller's order, the
 // number of stable patches per 256-thread block in processing order (first level of the compaction scan).
 constexpr int kCompactBlock = 256;
 __global__ void __launch_bounds__(kCompactBlock)
@@ -178,7 +178,7 @@ scan_blocks_kernel(int* __restrict__ block_cnt, int nblocks, OuterDev* st, float
 
 // third level: position of every stable patch, and the stable set written in the layout of the inner loop
 // (icp.cu): point (w = its rank), its classification match and that match's normal inline.  The stable set is in
-// Morton order of the patches, so the inner loop needs no sort of its own.
+// processing order of the patches, so the inner loop needs no sort of its own.
 __global__ void __launch_bounds__(kCompactBlock)
 compact_kernel(const float4* __restrict__ ct2, const int* __restrict__ flags, const uint32_t* __restrict__ order,
                const int* __restrict__ block_off, int n2, const int* __restrict__ ct_seed,
@@ -579,7 +579,7 @@ int vcm_dev(Ctx* ctx, const float4* src, int n, double* vcm36, int* singular, in
     return PWICP_OK;
 }
 
-// ---- Morton order of the source patches (once per pair) ------------------------------------
+// ---- processing order of the source patches (once per pair) --------------------------------
 
 // Processing order of the classification queries: patches in the spatial order of their centroid (spatial_order_dev,
 // grid.cu).  Results are written back in the caller's order, so the order only shapes the warps of the search.
