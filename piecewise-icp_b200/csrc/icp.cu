@@ -989,10 +989,12 @@ int icp_enqueue(Ctx* ctx, const pwicp_icp_params& prm, int n, const int* n_dev, 
     // PWICP_SPLIT_ITER1 = number of leading iterations whose search runs as its own kernel (A/B: 0, 1, 2).  One: a second
     // pass before iteration 2 -- 1.5 % of the queries search there -- loses (1M: iteration 2 105 -> 209 us and weaker
     // caches afterwards, profiles/r02ak_split2_ab.txt)
-    static const int split_env = [] { const char* e = getenv("PWICP_SPLIT_ITER1"); return e ? atoi(e) : 1; }();
+    // (read at every call: the tests switch it)  PWICP_SPLIT_MIN_POINTS overrides the size from which the split is used.
+    const int split_env = [] { const char* e = getenv("PWICP_SPLIT_ITER1"); return e ? atoi(e) : 1; }();
+    const int split_min = [] { const char* e = getenv("PWICP_SPLIT_MIN_POINTS"); return e ? atoi(e) : kSplitMinPoints; }();
     // worth it for large source sets only: below ~half a million points the extra launches cost more than the
     // occupancy gains (outer loop at 300k patches: 4.86 -> 5.06 ms with the split, profiles/r02af_split_launch_ab.txt)
-    const int nsplit = (n >= kSplitMinPoints) ? std::max(0, std::min(std::min(split_env, 2), prm.max_iter - 1)) : 0;     // searches taken out: before iterations 1 .. nsplit
+    const int nsplit = (n >= split_min) ? std::max(0, std::min(std::min(split_env, 2), prm.max_iter - 1)) : 0;     // searches taken out: before iterations 1 .. nsplit
     void* kargs[] = {(void*)&a};
     cudaEvent_t ev_k[4] = {ctx->ev2, ctx->ev5, ctx->ev7, nullptr}, ev_r[3] = {ctx->ev4, ctx->ev6, nullptr};
     for (int part = 0; part <= nsplit; ++part) {

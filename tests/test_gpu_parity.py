@@ -164,6 +164,32 @@ def test_inner_loop_bit_exact_in_device_order(gpu_ctx, oracle, pair60k):
     assert np.array_equal(r["T"], o["T"])
 
 
+def test_inner_loop_split_launch_small_set(gpu_ctx, oracle, pair60k, monkeypatch):
+    """The two-launch form of the loop (stand-alone search of iteration 1; used from 500k points on) at a size the
+    oracle finishes in seconds: bit-exact against the oracle and against the single launch."""
+    d = pair60k
+    gpu_ctx.target_upload(d["ct1"], d["nrm1"], d["ctstd1"])
+    gpu_ctx.icp_source_upload(d["ct2"])
+    one = gpu_ctx.icp_run(P.icp_params(max_iter=12, force_iters=1), trace=True)
+    monkeypatch.setenv("PWICP_SPLIT_MIN_POINTS", "0")
+    two = gpu_ctx.icp_run(P.icp_params(max_iter=12, force_iters=1), trace=True)
+    assert two["research_ms"] > 0.0 and one["research_ms"] == 0.0
+    for k in ("idx_trace", "T_trace", "mse", "T"):
+        assert np.array_equal(one[k], two[k]), k
+    perm = gpu_ctx.icp_order()
+    o = oracle.icp(d["ct1"], d["nrm1"], d["ct2"][perm],
+                   oracle.icp_params(max_iter=12, force_iters=1, reduce_mode=2, group_batches=two["group_batches"], threads=8), trace=True)
+    assert np.array_equal(two["idx_trace"][:, perm], o["idx_trace"])
+    assert np.array_equal(two["T_trace"], o["T_trace"]) and np.array_equal(two["mse"], o["mse"])
+    nat = gpu_ctx.icp_run()                                            # criteria in charge: the loop may end in either launch
+    monkeypatch.delenv("PWICP_SPLIT_MIN_POINTS")
+    ref = gpu_ctx.icp_run()
+    assert nat["n_iter"] == ref["n_iter"] and nat["state"] == ref["state"] and np.array_equal(nat["T"], ref["T"])
+    monkeypatch.setenv("PWICP_SPLIT_MIN_POINTS", "0")
+    m1 = gpu_ctx.icp_run(P.icp_params(max_iter=1))                     # one iteration: nothing to split
+    assert m1["n_iter"] == 1 and m1["research_ms"] == 0.0
+
+
 def test_candidate_cache_adversarial_clouds(gpu_ctx, oracle):
     """The per-query candidate cache of the inner loop (exact by a ball-coverage certificate) on
     inputs that are not a sampled surface: a volume-filling random cloud, exact duplicates, and a
