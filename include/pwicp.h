@@ -136,7 +136,7 @@ int pwicp_icp_run(pwicp_ctx* ctx, const pwicp_icp_params* prm, float* T16, pwicp
  * returns the number of iterations written. */
 int pwicp_icp_profile(pwicp_ctx* ctx, double* iter_us, int* searched, int cap);
 /* ... and where CTA 0 spent each iteration: phase_us[4 k + j] = microseconds from the start of iteration k to the end of
- * its own batches (j = 0), the grid barrier passed (1), the totals formed (2), the 6x6 system solved (3). */
+ * its own batches (j = 0), its CTA sum posted (1), the packets of all CTAs in and the totals formed (2), the 6x6 system solved (3). */
 int pwicp_icp_phase_profile(pwicp_ctx* ctx, double* phase_us, int cap);
 /* Processing order of the last pwicp_icp_run: perm[k] = index (in the uploaded source set) of the
  * k-th point in the order the device accumulated the normal equations (source points are sorted

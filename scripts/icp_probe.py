@@ -49,7 +49,7 @@ def timing(ctx, n, iters):
           f"{48 * iters * n2 / r['kernel_ms'] / 1e6:.0f} GB/s", flush=True)
     print("  iteration us :", " ".join(f"{u:.1f}" for u in us[:8]), "... median of the rest", f"{np.median(us[8:]):.2f}" if len(us) > 8 else "")
     if len(ph) > 10:
-        print("  CTA 0 phases (median of iterations 8..): own batches done %.2f us, barrier passed %.2f, totals %.2f, solved %.2f"
+        print("  CTA 0 phases (median of iterations 8..): own batches done %.2f us, CTA sum posted %.2f, totals %.2f, solved %.2f"
               % tuple(np.median(ph[8:], axis=0)))
     print("  searched     :", " ".join(str(s) for s in srch[:8]), "... sum of the rest", int(srch[8:].sum()))
 
