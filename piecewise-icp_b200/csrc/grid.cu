@@ -179,8 +179,41 @@ __device__ __forceinline__ uint32_t cell_key_of(const float* __restrict__ xyz, i
     return ((uint32_t)cz * (uint32_t)dy + (uint32_t)cy) * (uint32_t)dx + (uint32_t)cx;
 }
 
+// one level per launch (large clouds, see grid_build)
+__global__ void __launch_bounds__(256)
+cell_count_kernel(const float* __restrict__ xyz, int n, float ox, float oy, float oz, float inv_h, int dx, int dy, int dz,
+                  uint32_t* __restrict__ A) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 p;
+    const uint32_t key = cell_key_of(xyz, i, ox, oy, oz, inv_h, dx, dy, dz, p);
+    // neighbours in the caller's order usually share a cell (always on the coarse levels): one atomic per group
+    const unsigned m = __match_any_sync(__activemask(), key);
+    if ((int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(A + 2 + key, (uint32_t)__popc(m));
+}
+
+__global__ void __launch_bounds__(256)
+cell_scatter_kernel(const float* __restrict__ xyz, int n, float ox, float oy, float oz, float inv_h, int dx, int dy, int dz,
+                    uint32_t* __restrict__ A, float4* __restrict__ out, uint32_t* __restrict__ inv_perm,
+                    uint32_t* __restrict__ perm) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 p;
+    const uint32_t key = cell_key_of(xyz, i, ox, oy, oz, inv_h, dx, dy, dz, p);
+    const unsigned m = __match_any_sync(__activemask(), key);
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(A + 1 + key, (uint32_t)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    const uint32_t slot = base + (uint32_t)__popc(m & ((1u << lane) - 1));
+    p.w = __int_as_float(i);
+    out[slot] = p;
+    if (inv_perm) { inv_perm[i] = slot; perm[slot] = (uint32_t)i; }
+}
+
 // all levels of a grid in one pass over the points: one count launch, one segmented scan (three launches), one scatter
 // launch -- 8 launches for three levels where a loop over the levels took 18 (0.245 -> see DESIGN.md 2)
+constexpr int kFuseLevelsMaxPoints = 2000000;   // grid_build: up to this size all levels share the count / scan / scatter launches
 struct LevelBuild { float inv_h; int dx, dy, dz; uint32_t* A; float4* pts; };
 struct LevelsBuild { LevelBuild lv[kMaxLevels]; int nlev; };
 
@@ -509,10 +542,23 @@ int grid_build(Ctx* ctx, GridOwner& g, const float* xyz, int n, const int* bad_f
     }
     // count, scan, scatter: every level in the same three steps (8 launches for three levels instead of 18)
     B.nlev = nlev;
-    cell_count_levels_kernel<<<blocks, 256, 0, ctx->stream>>>(xyz, n, mn[0], mn[1], mn[2], B);
-    PW_TRY(scan_inclusive_inplace_segs(ctx, Aseg, nseg, nlev));
-    cell_scatter_levels_kernel<<<blocks, 256, 0, ctx->stream>>>(xyz, n, mn[0], mn[1], mn[2], B, g.inv_perm.as<uint32_t>(), g.perm0);
-    ctx->launches += 2;
+    if (n <= kFuseLevelsMaxPoints) {
+        // count, scan, scatter: every level in the same three steps (8 launches for three levels instead of 18)
+        cell_count_levels_kernel<<<blocks, 256, 0, ctx->stream>>>(xyz, n, mn[0], mn[1], mn[2], B);
+        PW_TRY(scan_inclusive_inplace_segs(ctx, Aseg, nseg, nlev));
+        cell_scatter_levels_kernel<<<blocks, 256, 0, ctx->stream>>>(xyz, n, mn[0], mn[1], mn[2], B, g.inv_perm.as<uint32_t>(), g.perm0);
+        ctx->launches += 2;
+    } else {
+        // large clouds: level after level (at 10M the shared launches are 45 % slower, profiles/r02as_build_ab.txt)
+        for (int l = 0; l < nlev; ++l) {
+            const LevelBuild& V = B.lv[l];
+            cell_count_kernel<<<blocks, 256, 0, ctx->stream>>>(xyz, n, mn[0], mn[1], mn[2], V.inv_h, V.dx, V.dy, V.dz, V.A);
+            PW_TRY(scan_inclusive_inplace(ctx, V.A, nseg[l]));
+            cell_scatter_kernel<<<blocks, 256, 0, ctx->stream>>>(xyz, n, mn[0], mn[1], mn[2], V.inv_h, V.dx, V.dy, V.dz, V.A, V.pts,
+                                                                l == 0 ? g.inv_perm.as<uint32_t>() : nullptr, g.perm0);
+            ctx->launches += 2;
+        }
+    }
     g.dev.nlevels = nlev;
     g.dev.inv_perm = g.inv_perm.as<uint32_t>();
     PW_CUDA(cudaGetLastError());
