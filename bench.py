@@ -9,12 +9,13 @@ build included, one-time uploads excluded).
   value  : correspondences/s with inputs already resident in HBM (CUDA events on the library stream)
   e2e    : the same metric through the host-buffer C-ABI call pwicp_icp_p2plane (the call shape of
            P2PICPwithPatchNormal), H2D of both clouds from pinned memory and D2H of the 4x4 inside the timed region
-  phases : where a resident step goes (grid build / Morton sort / iteration-0 search pre-pass / search iterations /
-           cached iterations), `natural`: the same pair with the convergence criteria allowed to stop the loop
+  phases : where a resident step goes (grid build / processing order / iteration-0 search pre-pass / stand-alone search of
+           iteration 1 / persistent kernel: search iterations, cached iterations), `natural`: the same pair with the convergence criteria allowed to stop the loop
   N > 1  : the headline repeats per rank (one pair per rank, no data-path collective: weak scaling); the sharded
            workload that can fail to scale is `config4` below
   config4: BASELINE configs[3], "4D synthetic: 64 epochs x 2M pts, epoch-sharded": every epoch is registered against the
-           reference epoch through the product's outer loop (upload of the pair from pinned host memory + pwicp_piecewise_icp),
+           reference epoch through the product's outer loop (the reference epoch resident, upload of the moving epoch from pinned
+           host memory + pwicp_piecewise_icp),
            epochs dealt out as PiecewiseICP_4D_shard does ((step - 1) % world == rank), the fixed 384-byte records
            all-gathered over NCCL -- all inside one barrier-bracketed timed region (strong scaling; runs at every N, 1 included)
 
