@@ -103,26 +103,42 @@ __host__ __device__ __forceinline__ float ordered_to_float(int i) {
 }
 
 // min/max over packed xyz.  out[0..2] = ordered-int min, out[3..5] = ordered-int max.
-__global__ void bbox_kernel(const float* __restrict__ xyz, size_t n, int* out) {
+// Four points = three 16-byte loads per thread and trip (the arrays come from cudaMalloc: 16-byte aligned), the warps of
+// a block folded in shared memory before the six atomics (round 1 / 2: scalar loads, six atomics per warp -- 43 us per
+// 2.4M points in the ncu launch list of the outer loop, 7 % of it).
+__global__ void __launch_bounds__(256)
+bbox_kernel(const float* __restrict__ xyz, size_t n, int* out) {
+    __shared__ float s_mn[8][3], s_mx[8][3];
     float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) {
-        float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+    auto take = [&](float x, float y, float z) {
         mn[0] = fminf(mn[0], x); mx[0] = fmaxf(mx[0], x);
         mn[1] = fminf(mn[1], y); mx[1] = fmaxf(mx[1], y);
         mn[2] = fminf(mn[2], z); mx[2] = fmaxf(mx[2], z);
+    };
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    const size_t nq = (reinterpret_cast<uintptr_t>(xyz) & 15) ? 0 : n / 4;   // groups of four points (an unaligned array: scalar loads)
+    const float4* __restrict__ v = reinterpret_cast<const float4*>(xyz);
+    for (size_t g = tid; g < nq; g += stride) {
+        const float4 a = v[3 * g], b = v[3 * g + 1], c = v[3 * g + 2];
+        take(a.x, a.y, a.z); take(a.w, b.x, b.y); take(b.z, b.w, c.x); take(c.y, c.z, c.w);
     }
+    for (size_t i = 4 * nq + tid; i < n; i += stride) take(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
     for (int c = 0; c < 3; ++c)
         for (int o = 16; o; o >>= 1) {
             mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
             mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
         }
-    if ((threadIdx.x & 31) == 0)
-        for (int c = 0; c < 3; ++c) {
-            atomicMin(out + c, float_to_ordered(mn[c]));
-            atomicMax(out + 3 + c, float_to_ordered(mx[c]));
-        }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0)
+        for (int c = 0; c < 3; ++c) { s_mn[warp][c] = mn[c]; s_mx[warp][c] = mx[c]; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        const int c = threadIdx.x;
+        float a = s_mn[0][c], b = s_mx[0][c];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { a = fminf(a, s_mn[w][c]); b = fmaxf(b, s_mx[w][c]); }
+        atomicMin(out + c, float_to_ordered(a));
+        atomicMax(out + 3 + c, float_to_ordered(b));
+    }
 }
 
 __global__ void bbox_init_kernel(int* out) {
