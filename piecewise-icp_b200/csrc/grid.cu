@@ -413,7 +413,9 @@ static int scan_inclusive_inplace_segs(Ctx* ctx, uint32_t* const* a, const size_
 // cell size, enumerated block by block (8 x 8 x 8 bins, Morton order inside a block, blocks row-major), one
 // warp-aggregated atomic per bin for the count and for the slot, and a last pass that ranks the points of a bin by
 // their index in the caller's order -- the order is a function of the input alone, whatever the atomics do (the
-// summation order of the inner loop depends on it).
+// summation order of the inner loop depends on it); only bins of more than 512 points, i.e. degenerate inputs, keep
+// the order of the atomics.
+constexpr uint32_t kRankMaxBin = 512;   // order_rank_kernel: bins up to this size are ranked by index in the caller's order
 __device__ __forceinline__ uint32_t order_key_of(float x, float y, float z, float ox, float oy, float oz, float inv_h,
                                                  int dx, int dy, int dz, int nbx, int nby) {
     const int cx = min(max((int)floorf((x - ox) * inv_h), 0), dx - 1) >> 1;
@@ -438,7 +440,7 @@ order_count_kernel(const float4* __restrict__ pts, int n, float ox, float oy, fl
 
 __global__ void __launch_bounds__(256)
 order_scatter_kernel(const float4* __restrict__ pts, int n, float ox, float oy, float oz, float inv_h, int dx, int dy, int dz,
-                     int nbx, int nby, uint32_t* __restrict__ A, uint32_t* __restrict__ slots) {
+                     int nbx, int nby, uint32_t* __restrict__ A, uint32_t* __restrict__ slots, uint32_t* __restrict__ myslot) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4 p = pts[i];
@@ -448,7 +450,9 @@ order_scatter_kernel(const float4* __restrict__ pts, int n, float ox, float oy, 
     uint32_t base = 0;
     if (lane == leader) base = atomicAdd(A + 1 + key, (uint32_t)__popc(m));
     base = __shfl_sync(m, base, leader);
-    slots[base + (uint32_t)__popc(m & ((1u << lane) - 1))] = (uint32_t)i;
+    const uint32_t slot = base + (uint32_t)__popc(m & ((1u << lane) - 1));
+    slots[slot] = (uint32_t)i;
+    myslot[i] = slot;
 }
 
 // after the scatter A[key] .. A[key + 1] is the bin of `key`; the point takes the place of its rank among the bin's
@@ -456,12 +460,15 @@ order_scatter_kernel(const float4* __restrict__ pts, int n, float ox, float oy, 
 __global__ void __launch_bounds__(256)
 order_rank_kernel(const float4* __restrict__ pts, int n, float ox, float oy, float oz, float inv_h, int dx, int dy, int dz,
                   int nbx, int nby, const uint32_t* __restrict__ A, const uint32_t* __restrict__ slots,
-                  uint32_t* __restrict__ order) {
+                  const uint32_t* __restrict__ myslot, uint32_t* __restrict__ order) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4 p = pts[i];
     const uint32_t key = order_key_of(p.x, p.y, p.z, ox, oy, oz, inv_h, dx, dy, dz, nbx, nby);
     const uint32_t s = A[key], e = A[key + 1];
+    // a bin that holds more than kRankMaxBin points (a degenerate input: a source far outside the target's box clamps
+    // into one boundary cell) keeps the order the atomics made -- the quadratic ranking would take minutes at 1M
+    if (e - s > kRankMaxBin) { order[myslot[i]] = (uint32_t)i; return; }
     uint32_t rank = 0;
     for (uint32_t j = s; j < e; ++j) rank += (slots[j] < (uint32_t)i) ? 1u : 0u;
     order[s + rank] = (uint32_t)i;
@@ -473,15 +480,16 @@ int spatial_order_dev(Ctx* ctx, const GridDev& g, const float4* pts, int n, uint
     const uint64_t nbins = (uint64_t)nbx * nby * nbz * 512ull;
     if (nbins > 0x7ffffff0ull) { set_error(ctx, "spatial_order: too many bins"); return PWICP_ERR_ARG; }
     PW_TRY(ctx->keys.reserve(ctx, (nbins + 2) * sizeof(uint32_t)));
-    PW_TRY(ctx->keys2.reserve(ctx, (size_t)n * sizeof(uint32_t)));
+    PW_TRY(ctx->keys2.reserve(ctx, (size_t)2 * n * sizeof(uint32_t)));
     uint32_t* A = ctx->keys.as<uint32_t>();
     uint32_t* slots = ctx->keys2.as<uint32_t>();
+    uint32_t* myslot = slots + n;
     const int blocks = (n + 255) / 256;
     PW_CUDA(cudaMemsetAsync(A, 0, (nbins + 2) * sizeof(uint32_t), ctx->stream));
     order_count_kernel<<<blocks, 256, 0, ctx->stream>>>(pts, n, g.ox, g.oy, g.oz, L.inv_h, L.dx, L.dy, L.dz, nbx, nby, A);
     PW_TRY(scan_inclusive_inplace(ctx, A, (size_t)nbins + 2));
-    order_scatter_kernel<<<blocks, 256, 0, ctx->stream>>>(pts, n, g.ox, g.oy, g.oz, L.inv_h, L.dx, L.dy, L.dz, nbx, nby, A, slots);
-    order_rank_kernel<<<blocks, 256, 0, ctx->stream>>>(pts, n, g.ox, g.oy, g.oz, L.inv_h, L.dx, L.dy, L.dz, nbx, nby, A, slots, order);
+    order_scatter_kernel<<<blocks, 256, 0, ctx->stream>>>(pts, n, g.ox, g.oy, g.oz, L.inv_h, L.dx, L.dy, L.dz, nbx, nby, A, slots, myslot);
+    order_rank_kernel<<<blocks, 256, 0, ctx->stream>>>(pts, n, g.ox, g.oy, g.oz, L.inv_h, L.dx, L.dy, L.dz, nbx, nby, A, slots, myslot, order);
     ctx->launches += 3;
     PW_CUDA(cudaGetLastError());
     return PWICP_OK;

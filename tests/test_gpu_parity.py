@@ -8,6 +8,8 @@ loop bit-exact against the oracle run in the device's summation order.
 """
 import os
 
+import time
+
 import numpy as np
 import pytest
 
@@ -188,6 +190,24 @@ def test_inner_loop_split_launch_small_set(gpu_ctx, oracle, pair60k, monkeypatch
     monkeypatch.setenv("PWICP_SPLIT_MIN_POINTS", "0")
     m1 = gpu_ctx.icp_run(P.icp_params(max_iter=1))                     # one iteration: nothing to split
     assert m1["n_iter"] == 1 and m1["research_ms"] == 0.0
+
+
+def test_inner_loop_source_outside_the_target_box(gpu_ctx, oracle, pair60k):
+    """A source set far outside the target's bounding box: every point clamps into boundary cells of the target grid
+    (one huge bin of the processing order, balls that span the whole grid).  Must stay fast and exact."""
+    d = pair60k
+    src = (d["ct2"][:20000] + np.array([0.0, 0.0, 60.0], np.float32)).astype(np.float32)
+    gpu_ctx.target_upload(d["ct1"], d["nrm1"], d["ctstd1"])
+    gpu_ctx.icp_source_upload(src)
+    t0 = time.perf_counter()
+    r = gpu_ctx.icp_run(P.icp_params(max_iter=3, force_iters=1), trace=True)
+    assert time.perf_counter() - t0 < 20.0
+    perm = gpu_ctx.icp_order()
+    assert np.array_equal(np.sort(perm), np.arange(len(src)))
+    o = oracle.icp(d["ct1"], d["nrm1"], src[perm],
+                   oracle.icp_params(max_iter=3, force_iters=1, reduce_mode=2, group_batches=r["group_batches"], threads=8), trace=True)
+    assert np.array_equal(r["idx_trace"][:, perm], o["idx_trace"])
+    assert np.array_equal(r["T_trace"], o["T_trace"]) and np.array_equal(r["mse"], o["mse"])
 
 
 def test_candidate_cache_adversarial_clouds(gpu_ctx, oracle):
